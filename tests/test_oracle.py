@@ -1,0 +1,141 @@
+"""Oracle self-checks: SA/LCP vs naive, literal restatement (A1) == A3 == brute-force clean spec (A2),
+decode round trip, reference quirks, committed golden fixtures."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from tests.util import brute_parse, naive_sa, random_case
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.mark.parametrize("alphabet", [b"AC", b"ACGT", b"ACGTN", b"A"])
+def test_sa_lcp_vs_naive(alphabet):
+    rng = np.random.default_rng(len(alphabet))
+    for _ in range(150):
+        n = int(rng.integers(1, 200))
+        d = bytes(rng.choice(list(alphabet), size=n).astype(np.uint8))
+        sa = orc.sa_build(d)
+        ref = naive_sa(d)
+        assert sa.tolist() == ref
+        lcp = orc.lcp_build(d, sa)
+        for k in range(1, n):
+            a, b = d[ref[k - 1]:], d[ref[k]:]
+            l = 0
+            while l < min(len(a), len(b)) and a[l] == b[l]:
+                l += 1
+            assert lcp[k] == l
+
+
+def test_sa_repetitive_medium():
+    rng = np.random.default_rng(7)
+    unit = bytes(rng.choice(list(b"ACGT"), size=37).astype(np.uint8))
+    d = unit * 300 + b"ACGT" * 500 + b"A" * 3000 + unit * 20
+    sa = orc.sa_build(d)
+    assert sorted(sa.tolist()) == list(range(len(d)))
+    dd = np.frombuffer(d, dtype=np.uint8)
+    # adjacent suffixes must be in order
+    for k in range(1, len(d), 7):
+        assert d[sa[k - 1]:] < d[sa[k]:]
+    assert dd.size == sa.size
+
+
+@pytest.mark.parametrize("alphabet,seed", [(b"AC", 1), (b"ACGT", 2), (b"ACGTN", 3)])
+def test_a1_equals_a3_equals_brute(alphabet, seed):
+    rng = np.random.default_rng(seed)
+    checked = thrown = 0
+    for _ in range(700):
+        d, x = random_case(rng, alphabet, 30, 30)
+        sa = orc.sa_build(d)
+        lcp = orc.lcp_build(d, sa)
+        a1, wt = orc.encode_literal(d, sa, x)
+        a3 = orc.encode_a3(d, sa, lcp, x)
+        a2 = brute_parse(d, x)
+        # A3 == A2 always (both are the clean spec)
+        assert a3.tolist() == a2.tolist(), (d, x)
+        # A1 == clean spec; where the Scala would throw (Q2) the oracle continues as a mismatch
+        assert a1.tolist() == a2.tolist(), (d, x, wt)
+        thrown += wt > 0
+        checked += 1
+        assert orc.decode(d, a1) == x
+    assert checked == 700
+    assert thrown > 0   # the crash site is reachable with random inputs
+
+
+def test_literals_and_empty():
+    d = b"ACGTACGTTTGA"
+    sa = orc.sa_build(d)
+    # Q8 empty haplotype => no phrases
+    a1, _ = orc.encode_literal(d, sa, b"")
+    assert a1.shape == (0, 2)
+    # bytes absent from the reference become literals (pos = byte value, len = 0)
+    a1, _ = orc.encode_literal(d, sa, b"NNACGTN")
+    assert a1.tolist()[0] == [ord("N"), 0] and a1.tolist()[1] == [ord("N"), 0]
+    assert a1.tolist()[-1] == [ord("N"), 0]
+    assert orc.decode(d, a1) == b"NNACGTN"
+    # record layout: int64 LE pairs
+    b = orc.lz_bytes(np.array([[5, 3], [78, 0]]))
+    assert b == (5).to_bytes(8, "little") + (3).to_bytes(8, "little") + (78).to_bytes(8, "little") + bytes(8)
+
+
+def test_q1_tiebreak_is_lexicographically_smallest_suffix():
+    # "ACG" occurs at 0, 4, 8; suffix order: ACG (8) < ACGAACG (4) < ACGTACGAACG (0)
+    d = b"ACGTACGAACG"
+    sa = orc.sa_build(d)
+    a1, _ = orc.encode_literal(d, sa, b"ACG")
+    assert a1.tolist() == [[8, 3]]
+    a1, _ = orc.encode_literal(d, sa, b"ACGC")
+    assert a1.tolist()[0] == [8, 3]
+
+
+def test_q2_flagged():
+    d = b"ACGT"
+    sa = orc.sa_build(d)
+    a1, wt = orc.encode_literal(d, sa, b"ACGTA")   # haplotype = ref + trailing insertion
+    assert wt > 0
+    assert a1.tolist() == [[0, 4], [0, 1]]
+
+
+def test_strip_gaps():
+    assert orc.strip_gaps(b"A--C-G\n").tobytes() == b"ACG"
+    assert orc.strip_gaps(b"----").tobytes() == b""
+    assert orc.strip_gaps(b"").tobytes() == b""
+
+
+def test_synth_shape_and_determinism():
+    seed = orc.seed_for(1)
+    d = orc.syn_reference(seed, 20000)
+    assert set(np.unique(d).tolist()) <= set(b"ACGT")
+    rows = orc.syn_rows(seed, d, 0, 4, 1e-2, 1e-3, 1e-3)
+    rows2 = orc.syn_rows(seed, d, 0, 4, 1e-2, 1e-3, 1e-3)
+    assert (rows == rows2).all()
+    # row 0 is the reference with gaps
+    assert orc.strip_gaps(rows[0]).tobytes() == d.tobytes()
+    # every row decodes against its own parse
+    sa = orc.sa_build(d)
+    res, m, wt, sec = orc.encode_rows_mt(d, sa, list(rows), 2)
+    for h in range(4):
+        assert orc.decode(d, res[h]) == orc.strip_gaps(rows[h]).tobytes()
+        assert m[h] == orc.strip_gaps(rows[h]).size
+    assert res[0].tolist() == [[0, 20000]]
+    # slices are independent of batch start
+    r23 = orc.syn_rows(seed, d, 2, 2, 1e-2, 1e-3, 1e-3)
+    assert (r23 == rows[2:4]).all()
+
+
+def test_golden_fixtures():
+    """tests/golden/*.npz were produced by tests/golden/make_golden.py from this oracle (the reference
+    has no vectors of its own); they pin the oracle against accidental drift."""
+    files = sorted(f for f in os.listdir(GOLD) if f.endswith(".npz"))
+    assert files, "no golden fixtures"
+    for f in files:
+        z = np.load(os.path.join(GOLD, f))
+        d = z["ref"].tobytes()
+        sa = orc.sa_build(d)
+        assert sa.tolist() == z["sa"].tolist()
+        for h in range(int(z["nrows"])):
+            x = orc.strip_gaps(z[f"row{h}"])
+            a1, _ = orc.encode_literal(d, sa, x)
+            assert orc.lz_bytes(a1) == z[f"lz{h}"].tobytes()
