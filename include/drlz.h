@@ -1,0 +1,109 @@
+/*
+ * drlz.h -- C ABI of libdrlz.so: the B200-native drop-in for PanGenSpark's distributed RLZ parse.
+ *
+ * The reference has no FFI for this path: its only boundary is the process boundary
+ *     spark-submit --class org.ngseq.pangenspark.DistributedRLZ <jar> localradix localref dataGlob fsURI outDir gaplessOut
+ * (drlz.sh:15, DistributedRLZ.scala:37-43) and the arithmetic lives in three local closures
+ * (binarySearch :108-164, factor :176-217, encode :222-242).  This header is the interface a maintainer binds
+ * from Java (JNI / Panama), from the native `drlz` CLI, or from Python (ctypes).
+ * Each entry point names the reference code it replaces.
+ *
+ * Conventions: plain pointers and sizes; the caller owns every buffer; 0 = success, negative = DRLZ_E_*;
+ * no exceptions or exit() cross this boundary; one context per GPU (one process per GPU).  A context may be
+ * used from one thread at a time.  There is no CPU fallback: without a CUDA device drlz_create fails.
+ */
+#ifndef DRLZ_H
+#define DRLZ_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DRLZ_OK 0
+#define DRLZ_E_ARG (-1)        /* bad argument */
+#define DRLZ_E_CUDA (-2)       /* CUDA runtime error (see drlz_last_error) */
+#define DRLZ_E_NOMEM (-3)
+#define DRLZ_E_NOSPACE (-4)    /* pairs_cap too small; required count returned */
+#define DRLZ_E_ALPHABET (-5)   /* reference contains bytes outside {A,C,G,T} (2-bit path) */
+#define DRLZ_E_STATE (-6)      /* index not built / wrong call order */
+#define DRLZ_E_LIMIT (-7)      /* n or m >= 2^32 - 1024, or more than 65535 rows in one batch */
+#define DRLZ_E_INTERNAL (-8)
+
+typedef struct drlz_ctx drlz_ctx;
+
+/* ---- lifecycle -------------------------------------------------------------------------------------- */
+int drlz_create(drlz_ctx** out, int device);
+void drlz_destroy(drlz_ctx* ctx);
+const char* drlz_last_error(const drlz_ctx* ctx);
+/* Run all kernels of this context on the caller's CUDA stream (cudaStream_t as void*), e.g. torch's current
+ * stream, so that caller-side CUDA events bracket them.  NULL restores the context's own stream. */
+int drlz_set_stream(drlz_ctx* ctx, void* cuda_stream);
+/* options: "kmer" (jump-table k, 0 = auto), "chunk" (bases per parse chunk, 0 = default 2048),
+ *          "group_bytes" (host-path pipeline granularity), "lcp" (1 = also build the LCP array) */
+int drlz_set_option(drlz_ctx* ctx, const char* key, int64_t value);
+
+/* pinned host memory for the streaming path (cudaHostAlloc); plain malloc memory also works, slower */
+void* drlz_host_alloc(size_t bytes);
+void drlz_host_free(void* p);
+
+/* ---- index: replaces `./radixSA localref localradix` + the SA text load + both broadcasts -------------
+ * (DistributedRLZ.scala:45,52,55,58,61,63).  ref = exactly n sequence bytes (no header, no newline). */
+int drlz_build_index(drlz_ctx* ctx, const uint8_t* ref, uint64_t n);
+/* copy index arrays to the host.  what: 0 = SA (uint32[n]), 1 = inverse SA (uint32[n]), 2 = LCP (uint32[n],
+ * needs option lcp=1), 3 = k-mer table (uint32[4^k+1]), 4 = packed text (uint64[(n+31)/32]).  */
+int drlz_index_get(drlz_ctx* ctx, int what, void* host_out, uint64_t bytes);
+/* info[0]=n, [1]=k, [2]=prefix-doubling rounds, [3]=index bytes on device */
+int drlz_index_info(const drlz_ctx* ctx, uint64_t info[4]);
+/* time of the last drlz_build_index in ms: [0] total, [1] pack, [2] suffix array, [3] k-mer table, [4] lcp */
+int drlz_index_timings(const drlz_ctx* ctx, double ms[5]);
+
+/* Multi-GPU: rank 0 builds, the others call drlz_index_reserve(n, k) and receive the three buffers by an
+ * NCCL broadcast (done by the caller, e.g. torch.distributed) into the device pointers returned by
+ * drlz_index_buffers, then call drlz_index_commit.  bufs: [0] packed text, [1] SA, [2] k-mer table. */
+int drlz_index_reserve(drlz_ctx* ctx, uint64_t n, int k);
+int drlz_index_buffers(drlz_ctx* ctx, void* dev_ptrs[3], uint64_t bytes[3]);
+int drlz_index_commit(drlz_ctx* ctx);
+
+/* ---- parse: replaces the gap strip (:72,86) + encode (:222-242) + record encoding (:263-284) ----------
+ * One MSA row (one haplotype).  strip_gaps != 0 removes every '-' first.  A trailing "\n" / "\r\n" is ignored
+ * (Spark's text reader drops it).  pairs_out receives n_pairs records of (int64 pos, int64 len), i.e. the exact
+ * bytes of <outDir>/<basename>.lz on a little-endian host.  gapless_out (nullable, >= cols bytes) receives the
+ * gapless sequence (the body of the gapless FASTA record, :75-80).  If pairs_cap is too small the call
+ * returns DRLZ_E_NOSPACE with the required count in *n_pairs. */
+int drlz_parse(drlz_ctx* ctx, const uint8_t* msa_row, uint64_t cols, int strip_gaps, uint8_t* gapless_out,
+               uint64_t* m_out, int64_t* pairs_out, uint64_t pairs_cap, uint64_t* n_pairs);
+
+/* H rows at once (the data-parallel axis of the Spark job, :247-248).  Phrase records of row h start at
+ * pairs_out + 2 * (n_pairs[0] + ... + n_pairs[h-1]).  gapless_out (nullable) is an array of H row buffers
+ * (entries may be NULL).  Host->device copies of the rows are pipelined with the kernels. */
+int drlz_parse_batch(drlz_ctx* ctx, const uint8_t* const* rows, const uint64_t* cols, uint32_t H, int strip_gaps,
+                     uint8_t* const* gapless_out, uint64_t* m_out, int64_t* pairs_out, uint64_t pairs_cap,
+                     uint64_t* n_pairs);
+
+/* Same with the rows already resident in device memory: row h = rows_dev + row_off[h]; every row_off is a
+ * multiple of 16 and the buffer is readable up to the next multiple of 16 past each row's end; cols excludes
+ * any line terminator.  The phrase records stay on the device: *pairs_dev points into context-owned memory
+ * valid until the next parse call (layout as in drlz_parse_batch). */
+int drlz_parse_batch_device(drlz_ctx* ctx, const uint8_t* rows_dev, const uint64_t* row_off, const uint64_t* cols,
+                            uint32_t H, int strip_gaps, uint64_t* m_out, const int64_t** pairs_dev,
+                            uint64_t* n_pairs);
+
+/* Copy bytes from device memory owned by the context (e.g. *pairs_dev) to the host, on the context's stream. */
+int drlz_copy_to_host(drlz_ctx* ctx, void* dst_host, const void* src_dev, uint64_t bytes);
+
+/* Stage timings (ms, CUDA events on the context's stream) of the last parse call:
+ * [0] strip+pack, [1] speculative parse, [2] fix-up rounds, [3] pointer jumping + compaction, [4] emission,
+ * [5] whole device pipeline, [6] fix-up rounds executed, [7] kernels launched.  */
+int drlz_parse_timings(const drlz_ctx* ctx, double ms[8]);
+
+/* Dense matching statistics of one gapless, pure-ACGT sequence in host memory: for every position i
+ * ms[i] = longest match length of x[i..] in the reference and pos[i] = SA[leftmost index of its interval]
+ * (literal => ms 0, pos = byte value).  Diagnostic / validation entry point. */
+int drlz_matching_stats(drlz_ctx* ctx, const uint8_t* x, uint64_t m, uint32_t* ms_out, uint32_t* pos_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

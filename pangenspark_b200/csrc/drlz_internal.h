@@ -1,0 +1,83 @@
+// drlz_internal.h -- host-side declarations shared by the .cu translation units of libdrlz.so
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "rlz_core.cuh"
+
+namespace drlz {
+
+extern unsigned long long g_launches;
+
+static const int kPackTileBytes = 4096;      // MSA bytes per CTA in the strip/pack kernels
+
+// ---- strip + pack (pack.cu) --------------------------------------------------------------------
+struct PackJob {
+    const uint8_t* rows;          // device; row h starts at rows + row_off[h] (16-byte aligned, readable up to
+                                  // the next multiple of 16 past cols[h])
+    const uint64_t* row_off;      // [H] device
+    const uint64_t* cols;         // [H] device
+    uint32_t H;
+    uint32_t tiles_per_row;       // ceil(max cols / kPackTileBytes)
+    int strip;                    // 1: '-' is a gap column (DistributedRLZ.scala:72,86); 0: keep it (a literal)
+    uint32_t* tile_cnt;           // [H*tiles_per_row] non-gap bytes per tile
+    uint32_t* tile_exc;           // [H*tiles_per_row] non-ACGT non-gap bytes per tile
+    uint64_t* tile_off;           // [H*tiles_per_row] exclusive prefix of tile_cnt over the whole batch
+    uint64_t* tile_excoff;        // same for tile_exc
+    uint64_t* scan_tmp;           // scan_tmp_elems(H*tiles_per_row) * 2
+    uint64_t* X;                  // packed output, zero-filled by the caller
+    const uint64_t* xoff;         // [H] word offset of haplotype h inside X (device)
+    uint64_t* m_out;              // [H] gapless lengths (device)
+    uint64_t* exc_off;            // [H+1] exception offsets (device)
+    uint32_t* exc_pos;            // [exc_cap]
+    uint8_t* exc_byte;            // [exc_cap]
+    uint64_t exc_cap;
+    uint32_t* flags;              // bit 0: exception capacity exceeded
+    uint8_t* gapless;             // optional gapless bytes out (device) or null
+    const uint64_t* gapless_off;  // [H] byte offsets into gapless
+};
+void launch_pack(const PackJob& job, cudaStream_t s);
+
+// ---- suffix array + k-mer table (sa_build.cu) ---------------------------------------------------
+struct SaWorkspace;   // opaque
+// Builds SA (uint32[n]) of the packed text and, when isa != null, the inverse.  Returns 0 or a cudaError.
+int build_suffix_array(const uint64_t* text, uint64_t n, uint32_t* sa, uint32_t* isa, cudaStream_t s,
+                       int* rounds_out, char* err, int errlen);
+// tab: 4^k + 1 entries
+int build_kmer_table(const uint64_t* text, uint64_t n, const uint32_t* sa, int k, uint32_t* tab, cudaStream_t s);
+// LCP[j] = lcp(suffix SA[j-1], suffix SA[j]), LCP[0] = 0
+int build_lcp(const uint64_t* text, uint64_t n, const uint32_t* sa, const uint32_t* isa, uint32_t* lcp,
+              cudaStream_t s);
+
+// ---- parse pipeline (parse.cu) -----------------------------------------------------------------
+struct ParseBuffers {
+    ParseView pv;                 // device pointers (see rlz_core.cuh)
+    uint32_t H;
+    uint32_t max_chunks_per_hap;
+    uint32_t* jump_a;             // [NC*(kAltSlots+1)]
+    uint32_t* jump_b;
+    uint8_t* mark;                // [NC*(kAltSlots+1)]
+    uint32_t* true_cnt;           // [NC]
+    uint32_t* true_entry;         // [NC]
+    uint64_t* true_off;           // [NC]
+    uint64_t* scan_tmp;           // scan_tmp_elems(NC)
+    uint64_t* hap_pairs;          // [H+1]: [h] phrases of haplotype h's start offset, [H] = total
+    uint32_t* host_counters;      // pinned host mirror of pv.counters (2 + kMaxRounds)
+    uint64_t* host_total;         // pinned host: total phrase count
+};
+// Stage A: speculative parse, fix-up rounds, pointer jumping, per-chunk counts and offsets.
+// Synchronises the stream (reads round counters and the phrase total).  Returns 0, or 2 on overflow.
+// ev (nullable): 4 events recorded before P1, after P1, after the fix-up rounds, after compaction.
+int parse_stage_count(ParseBuffers& pb, cudaStream_t s, int* rounds_out, cudaEvent_t* ev);
+// Stage B: emission into `out` (device, >= 2*total int64).
+void parse_stage_emit(ParseBuffers& pb, int64_t* out, cudaStream_t s);
+
+void launch_make_hapviews(HapView* haps, const uint64_t* X, const uint64_t* xoff, const uint64_t* m,
+                          const uint32_t* exc_pos, const uint8_t* exc_byte, const uint64_t* exc_off, uint32_t H,
+                          cudaStream_t s);
+
+}  // namespace drlz
+
+namespace drlz {
+void launch_fill_chunk_hap(uint32_t* chunk_hap, const uint32_t* hap_chunk_base, uint32_t H, uint32_t NC, cudaStream_t s);
+void launch_ms_dense(const IndexView& ix, const uint64_t* X, uint64_t m, uint32_t* ms, uint32_t* pos, cudaStream_t s);
+}

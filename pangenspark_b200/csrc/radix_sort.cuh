@@ -1,0 +1,116 @@
+// radix_sort.cuh -- hand-written LSD radix sort of (key, uint32 value) pairs, 8-bit digits.
+//
+// Per pass: (1) per-tile digit histograms in shared memory -> digit-major matrix in HBM,
+//           (2) exclusive scan of the matrix (scan.cuh),
+//           (3) stable scatter: warp-level multisplit with __match_any_sync, warp-private digit
+//               counters in shared memory, cross-warp prefix per digit, then coalesced-as-possible
+//               stores (a tile of 4096 keys puts ~16 consecutive keys into each of the 256 runs).
+// Passes whose digit is constant over all keys are skipped by the caller through the bit range.
+// Used by the suffix-array prefix doubling (sa_build.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "scan.cuh"
+
+namespace drlz {
+
+static const int kSortThreads = 256;
+static const int kSortItems = 16;
+static const int kSortTile = kSortThreads * kSortItems;   // 4096 keys per CTA
+static const int kSortWarps = kSortThreads / 32;
+
+template <typename K>
+__global__ void __launch_bounds__(kSortThreads)
+k_sort_hist(const K* __restrict__ keys, uint64_t n, int shift, uint32_t* __restrict__ hist, uint32_t ntiles) {
+    __shared__ uint32_t h[256];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    uint64_t base = (uint64_t)blockIdx.x * kSortTile;
+#pragma unroll
+    for (int k = 0; k < kSortItems; ++k) {
+        uint64_t i = base + (uint64_t)k * kSortThreads + threadIdx.x;
+        if (i < n) atomicAdd(&h[(unsigned)(keys[i] >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    hist[(uint64_t)threadIdx.x * ntiles + blockIdx.x] = h[threadIdx.x];
+}
+
+template <typename K>
+__global__ void __launch_bounds__(kSortThreads)
+k_sort_scatter(const K* __restrict__ keys, const uint32_t* __restrict__ vals, K* __restrict__ okeys,
+               uint32_t* __restrict__ ovals, uint64_t n, int shift, const uint32_t* __restrict__ offs,
+               uint32_t ntiles) {
+    __shared__ uint32_t wcnt[kSortWarps][256];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < kSortWarps * 256; i += kSortThreads) (&wcnt[0][0])[i] = 0;
+    __syncthreads();
+    // warp w owns the contiguous slice [w*512, w*512+512) of the tile; item k of lane l sits at k*32+l,
+    // so (k, lane) order == memory order == stable order.
+    uint64_t base = (uint64_t)blockIdx.x * kSortTile + (uint64_t)warp * (32 * kSortItems);
+    K key[kSortItems];
+    uint32_t rank[kSortItems];
+    const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+    for (int k = 0; k < kSortItems; ++k) {
+        uint64_t i = base + (uint64_t)k * 32 + lane;
+        bool valid = i < n;
+        key[k] = valid ? keys[i] : (K)0;
+        unsigned d = valid ? ((unsigned)(key[k] >> shift) & 255u) : 256u;
+        unsigned peers = __match_any_sync(0xffffffffu, d);
+        uint32_t before = 0;
+        if (valid) before = wcnt[warp][d];
+        __syncwarp();
+        rank[k] = before + __popc(peers & lt);
+        if (valid && (peers & lt) == 0) wcnt[warp][d] = before + __popc(peers);
+        __syncwarp();
+    }
+    __syncthreads();
+    {   // digit t: exclusive prefix over warps + global offset of (digit, tile)
+        int t = threadIdx.x;
+        uint32_t run = offs[(uint64_t)t * ntiles + blockIdx.x];
+#pragma unroll
+        for (int w = 0; w < kSortWarps; ++w) { uint32_t c = wcnt[w][t]; wcnt[w][t] = run; run += c; }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kSortItems; ++k) {
+        uint64_t i = base + (uint64_t)k * 32 + lane;
+        if (i < n) {
+            unsigned d = (unsigned)(key[k] >> shift) & 255u;
+            uint32_t dst = wcnt[warp][d] + rank[k];
+            okeys[dst] = key[k];
+            ovals[dst] = vals[i];
+        }
+    }
+}
+
+struct SortWorkspace {
+    uint32_t* hist;      // 256 * ntiles (+ scan tmp behind it)
+    uint32_t* scan_tmp;
+};
+
+static inline uint64_t sort_hist_elems(uint64_t n) { return 256ull * ((n + kSortTile - 1) / kSortTile); }
+
+// Sorts by bits [begin_bit, end_bit) of the key.  Result lands in (*keys_a, *vals_a) (pointers are swapped
+// as needed).  n < 2^32.  Returns the number of passes executed.
+template <typename K>
+int radix_sort_pairs(K** keys_a, K** keys_b, uint32_t** vals_a, uint32_t** vals_b, uint64_t n, int begin_bit,
+                     int end_bit, uint32_t* hist, uint32_t* scan_tmp, cudaStream_t s) {
+    if (n <= 1) return 0;
+    uint32_t ntiles = (uint32_t)((n + kSortTile - 1) / kSortTile);
+    uint64_t hn = 256ull * ntiles;
+    int passes = 0;
+    for (int shift = begin_bit; shift < end_bit; shift += 8) {
+        g_launches += 2;
+        k_sort_hist<K><<<ntiles, kSortThreads, 0, s>>>(*keys_a, n, shift, hist, ntiles);
+        device_scan<uint32_t, LoadArr<uint32_t, uint32_t>, StoreArr<uint32_t>, OpSum, false>(
+            LoadArr<uint32_t, uint32_t>{hist}, StoreArr<uint32_t>{hist}, hn, scan_tmp, OpSum(), 0u, s);
+        k_sort_scatter<K><<<ntiles, kSortThreads, 0, s>>>(*keys_a, *vals_a, *keys_b, *vals_b, n, shift, hist, ntiles);
+        K* tk = *keys_a; *keys_a = *keys_b; *keys_b = tk;
+        uint32_t* tv = *vals_a; *vals_a = *vals_b; *vals_b = tv;
+        ++passes;
+    }
+    return passes;
+}
+
+}  // namespace drlz

@@ -1,0 +1,353 @@
+// rlz_core.cuh -- per-thread RLZ logic shared by every parse kernel.
+//
+// Everything here is __host__ __device__ so that tests/emu (a test-only host harness) can run the
+// exact same statements on the CPU; the product (libdrlz.so) only ever calls them from kernels.
+//
+// Semantics reproduced (DistributedRLZ.scala:108-242, SURVEY.md 8(a) "clean spec"):
+//   at haplotype position i:  L = longest l such that x[i..i+l) occurs in d
+//                             pos = SA[leftmost index of the SA interval of x[i..i+L)]      (quirk Q1)
+//                             L == 0  =>  literal (pos = byte value, len = 0)               (:210-211)
+//   greedy: i += max(1, L)                                                                  (:226-240)
+//
+// Data layout (all in HBM):
+//   text / haplotypes : 2 bits per base (A,C,G,T -> 0..3), 32 bases per 64-bit word, first base in the
+//                       most significant bits, so integer order of words == lexicographic order of bases;
+//                       arrays carry >= 2 zero pad words.
+//   SA                : uint32 suffix array of the reference (n < 2^32 - 64)
+//   tab               : 4^k + 1 entries; tab[K] = #suffixes whose zero-padded k-mer key is < K
+//                       (a jump table replacing the top ~2k levels of the SA binary search)
+//   exceptions        : sorted positions (+ bytes) of haplotype bytes outside {A,C,G,T}; such a byte can
+//                       never match a pure-ACGT reference, so it ends the running phrase and is a literal.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define DRLZ_HD __host__ __device__ __forceinline__
+#else
+#define DRLZ_HD inline
+#endif
+
+namespace drlz {
+
+typedef uint32_t pos_t;                   // positions in reference / haplotype
+static const uint32_t kEmpty = 0xFFFFFFFFu;
+static const int kAltSlots = 3;           // alternative entry records per chunk (see parse pipeline)
+
+DRLZ_HD int clz64(uint64_t v) {
+#if defined(__CUDA_ARCH__)
+    return __clzll((long long)v);
+#else
+    return __builtin_clzll(v);
+#endif
+}
+
+// 32 bases starting at base `pos`
+DRLZ_HD uint64_t get64(const uint64_t* __restrict__ w, uint64_t pos) {
+    uint64_t wi = pos >> 5;
+    unsigned sh = (unsigned)(pos & 31) * 2;
+    uint64_t a = w[wi];
+    if (sh == 0) return a;
+    return (a << sh) | (w[wi + 1] >> (64 - sh));
+}
+
+DRLZ_HD unsigned base_at(const uint64_t* __restrict__ w, uint64_t pos) {
+    return (unsigned)(w[pos >> 5] >> (62 - 2 * (pos & 31))) & 3u;
+}
+
+struct IndexView {
+    const uint64_t* text;   // packed reference
+    const uint32_t* sa;
+    const uint32_t* tab;    // 4^k + 1
+    uint64_t n;
+    int k;
+};
+
+struct HapView {
+    const uint64_t* x;        // packed haplotype
+    uint64_t m;               // gapless length
+    const uint32_t* exc_pos;  // sorted exception positions (may be null when n_exc == 0)
+    const uint8_t* exc_byte;
+    uint32_t n_exc;
+};
+
+struct Match {
+    uint32_t len;   // 0 => literal
+    uint32_t pos;   // SA[leftmost] or the literal byte
+};
+
+// lcp(x[i..i+maxlen), d[p..n)) and whether the suffix d[p..] sorts before the pattern.
+DRLZ_HD uint32_t cmp_suffix(const uint64_t* __restrict__ X, uint64_t i, const uint64_t* __restrict__ D,
+                            uint64_t p, uint64_t n, uint32_t maxlen, bool* less) {
+    uint64_t rem = n - p;
+    uint32_t lim = rem < (uint64_t)maxlen ? (uint32_t)rem : maxlen;
+    uint32_t l = 0;
+    bool diff_less = false;
+    while (l < lim) {
+        uint64_t a = get64(X, i + l), b = get64(D, p + l);
+        uint64_t xr = a ^ b;
+        if (xr) {
+            l += (uint32_t)(clz64(xr) >> 1);
+            diff_less = b < a;
+            break;
+        }
+        l += 32;
+    }
+    if (l >= lim) {
+        l = lim;
+        // pattern exhausted => suffix >= pattern; else the suffix ran out => suffix < pattern
+        *less = (lim != maxlen);
+    } else {
+        *less = diff_less;
+    }
+    return l;
+}
+
+// Longest match of x[i..i+maxlen) in d with the reference's tie-break.  maxlen >= 1.
+DRLZ_HD Match lookup(const IndexView& ix, const uint64_t* __restrict__ X, uint64_t i, uint32_t maxlen) {
+    const int k = ix.k;
+    const uint64_t n = ix.n;
+    uint64_t xw = get64(X, i);
+    uint32_t kk = maxlen < (uint32_t)k ? maxlen : (uint32_t)k;
+    uint64_t kmer = xw >> (64 - 2 * k);
+    uint64_t lowmask = (1ull << (2 * (k - (int)kk))) - 1;
+    uint64_t lokey = kmer & ~lowmask, hikey = kmer | lowmask;
+    uint32_t lo = ix.tab[lokey], hi = ix.tab[hikey + 1];
+    // r = #suffixes < pattern lies in [lo, hi]
+    uint32_t l = lo, h = hi;
+    uint32_t lcp_left = 0, lcp_right = 0;
+    bool have_left = false, have_right = false;
+    while (l < h) {
+        uint32_t mid = l + ((h - l) >> 1);
+        bool less;
+        uint32_t c = cmp_suffix(X, i, ix.text, ix.sa[mid], n, maxlen, &less);
+        if (less) { l = mid + 1; lcp_left = c; have_left = true; }
+        else { h = mid; lcp_right = c; have_right = true; }
+    }
+    uint32_t r = l;
+    bool dummy;
+    uint32_t l1 = 0, l2 = 0;
+    if (r > 0) l1 = have_left ? lcp_left : cmp_suffix(X, i, ix.text, ix.sa[r - 1], n, maxlen, &dummy);
+    uint32_t sar = 0;
+    if ((uint64_t)r < n) {
+        sar = ix.sa[r];
+        l2 = have_right ? lcp_right : cmp_suffix(X, i, ix.text, sar, n, maxlen, &dummy);
+    }
+    Match mt;
+    if (l2 > l1) { mt.len = l2; mt.pos = sar; return mt; }
+    if (l1 == 0) { mt.len = 0; mt.pos = 0; return mt; }
+    // leftmost index whose suffix shares >= L bases with the pattern; it lies in [tab[key(L)], r-1]
+    uint32_t L = l1;
+    uint32_t Lk = L < (uint32_t)k ? L : (uint32_t)k;
+    uint32_t a = lo;
+    if (Lk != kk) {
+        uint64_t m2 = (1ull << (2 * (k - (int)Lk))) - 1;
+        a = ix.tab[kmer & ~m2];
+    }
+    uint32_t b = r - 1;
+    while (a < b) {
+        uint32_t mid = a + ((b - a) >> 1);
+        uint32_t c = cmp_suffix(X, i, ix.text, ix.sa[mid], n, L, &dummy);
+        if (c >= L) b = mid; else a = mid + 1;
+    }
+    mt.len = L; mt.pos = ix.sa[a];
+    return mt;
+}
+
+// index of the first exception at or after position i (binary search)
+DRLZ_HD uint32_t exc_lower_bound(const HapView& hv, uint64_t i) {
+    uint32_t a = 0, b = hv.n_exc;
+    while (a < b) {
+        uint32_t mid = a + ((b - a) >> 1);
+        if ((uint64_t)hv.exc_pos[mid] < i) a = mid + 1; else b = mid;
+    }
+    return a;
+}
+
+// One greedy step at position i.  *cursor = index of the first exception >= i (kept monotone by the caller
+// through this function).  Literals carry their byte in .pos.
+DRLZ_HD Match phrase_at(const IndexView& ix, const HapView& hv, uint64_t i, uint32_t* cursor) {
+    uint64_t stop = hv.m;
+    if (hv.n_exc) {
+        uint32_t c = *cursor;
+        while (c < hv.n_exc && (uint64_t)hv.exc_pos[c] < i) ++c;
+        *cursor = c;
+        if (c < hv.n_exc) stop = hv.exc_pos[c];
+        if (stop == i) { Match mt; mt.len = 0; mt.pos = hv.exc_byte[c]; return mt; }
+    }
+    uint32_t maxlen = (uint32_t)(stop - i);
+    Match mt = lookup(ix, hv.x, i, maxlen);
+    if (mt.len == 0) mt.pos = (uint32_t)("ACGT"[base_at(hv.x, i)]);
+    return mt;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Chunk-parallel exact greedy parse.
+//
+// The greedy parse is a deterministic function of its start position, so two parses that ever share
+// a phrase start coincide from there on.  Each haplotype is cut into chunks of C bases:
+//   P1  every chunk parses speculatively from its first base            -> spec_cnt, spec_exit
+//   R   every exit position e is registered as an "alternative entry" of the chunk containing e
+//   F   every new alternative entry is parsed in tandem with the chunk's speculative parse until the
+//       two share a phrase start (merge) or the chunk ends              -> alt_cnt, alt_exit
+//       (R and F repeat until no new entry appears; two rounds in practice)
+//   J   records form a functional graph (record -> record entered at its exit); pointer jumping from
+//       (chunk 0, speculative record) marks the true chain
+//   E   per chunk the marked record's phrase count is prefix-summed (stream compaction) and the chunk is
+//       parsed once more from its true entry straight into the output slots.
+// ---------------------------------------------------------------------------------------------
+
+struct ParseView {
+    IndexView ix;
+    const HapView* haps;            // [H]
+    const uint32_t* chunk_hap;      // [NC] haplotype of global chunk g
+    const uint32_t* hap_chunk_base; // [H+1]
+    uint32_t chunk_bases;           // C
+    uint32_t n_chunks;              // NC
+    uint32_t* spec_cnt;             // [NC]
+    uint32_t* spec_exit;            // [NC]
+    uint32_t* alt_entry;            // [NC*kAltSlots], kEmpty when unused
+    uint32_t* alt_cnt;              // [NC*kAltSlots]
+    uint32_t* alt_exit;             // [NC*kAltSlots]
+    uint32_t* alt_round;            // [NC*kAltSlots] round in which the record must be fix-parsed
+    uint32_t* counters;             // [0] overflow flag, [1 + r] records created for round r
+};
+
+DRLZ_HD uint32_t atomic_cas_u32(uint32_t* p, uint32_t cmp, uint32_t val) {
+#if defined(__CUDA_ARCH__)
+    return atomicCAS(p, cmp, val);
+#else
+    uint32_t old = *p; if (old == cmp) *p = val; return old;
+#endif
+}
+DRLZ_HD void atomic_inc_u32(uint32_t* p) {
+#if defined(__CUDA_ARCH__)
+    atomicAdd(p, 1u);
+#else
+    ++*p;
+#endif
+}
+
+static const int kMaxRounds = 30;
+
+// R: register exit position x of haplotype h as an entry; new records are scheduled for `next_round`.
+DRLZ_HD void register_exit(const ParseView& pv, uint32_t h, uint64_t x, uint32_t next_round) {
+    const HapView& hv = pv.haps[h];
+    if (x >= hv.m) return;                                   // parse finished
+    uint32_t C = pv.chunk_bases;
+    if (x % C == 0) return;                                  // that is the chunk's speculative record
+    uint32_t g = pv.hap_chunk_base[h] + (uint32_t)(x / C);
+    for (int s = 0; s < kAltSlots; ++s) {
+        uint32_t old = atomic_cas_u32(&pv.alt_entry[g * kAltSlots + s], kEmpty, (uint32_t)x);
+        if (old == kEmpty) {
+            pv.alt_round[g * kAltSlots + s] = next_round;
+            atomic_inc_u32(&pv.counters[1 + (next_round < (uint32_t)kMaxRounds ? next_round : kMaxRounds)]);
+            return;
+        }
+        if (old == (uint32_t)x) return;
+    }
+    pv.counters[0] = 1;                                      // more distinct entries than slots
+}
+
+// P1 for global chunk g
+DRLZ_HD void spec_parse_chunk(const ParseView& pv, uint32_t g) {
+    uint32_t h = pv.chunk_hap[g];
+    const HapView& hv = pv.haps[h];
+    uint64_t s = (uint64_t)(g - pv.hap_chunk_base[h]) * pv.chunk_bases;
+    uint64_t e = s + pv.chunk_bases; if (e > hv.m) e = hv.m;
+    uint64_t i = s; uint32_t cnt = 0;
+    uint32_t cur = hv.n_exc ? exc_lower_bound(hv, i) : 0;
+    while (i < e) {
+        Match mt = phrase_at(pv.ix, hv, i, &cur);
+        ++cnt;
+        i += mt.len ? mt.len : 1;
+    }
+    pv.spec_cnt[g] = cnt;
+    pv.spec_exit[g] = (uint32_t)i;
+    register_exit(pv, h, i, 1);
+}
+
+// F for alternative record (g, slot) scheduled for `round`
+DRLZ_HD void fix_parse_record(const ParseView& pv, uint32_t g, int slot, uint32_t round) {
+    uint32_t rid = g * kAltSlots + slot;
+    if (pv.alt_entry[rid] == kEmpty || pv.alt_round[rid] != round) return;
+    uint32_t h = pv.chunk_hap[g];
+    const HapView& hv = pv.haps[h];
+    uint64_t s = (uint64_t)(g - pv.hap_chunk_base[h]) * pv.chunk_bases;
+    uint64_t e = s + pv.chunk_bases; if (e > hv.m) e = hv.m;
+    uint64_t iA = s, iB = pv.alt_entry[rid];
+    uint32_t cntA = 0, cntB = 0;
+    uint32_t curA = hv.n_exc ? exc_lower_bound(hv, iA) : 0;
+    uint32_t curB = hv.n_exc ? exc_lower_bound(hv, iB) : 0;
+    bool merged = false;
+    while (iB < e) {
+        while (iA < iB) {
+            Match mt = phrase_at(pv.ix, hv, iA, &curA);
+            ++cntA;
+            iA += mt.len ? mt.len : 1;
+        }
+        if (iA == iB) { merged = true; break; }
+        Match mt = phrase_at(pv.ix, hv, iB, &curB);
+        ++cntB;
+        iB += mt.len ? mt.len : 1;
+    }
+    if (merged) {
+        pv.alt_cnt[rid] = cntB + (pv.spec_cnt[g] - cntA);
+        pv.alt_exit[rid] = pv.spec_exit[g];                  // already registered by P1
+    } else {
+        pv.alt_cnt[rid] = cntB;
+        pv.alt_exit[rid] = (uint32_t)iB;
+        register_exit(pv, h, iB, round + 1);
+    }
+}
+
+// J: node ids.  node = g*(kAltSlots+1) + 0 (speculative) | 1+slot (alternative)
+DRLZ_HD uint32_t node_succ(const ParseView& pv, uint32_t node) {
+    uint32_t g = node / (kAltSlots + 1);
+    int r = (int)(node % (kAltSlots + 1));
+    uint32_t h = pv.chunk_hap[g];
+    const HapView& hv = pv.haps[h];
+    uint64_t x;
+    if (r == 0) x = pv.spec_exit[g];
+    else {
+        if (pv.alt_entry[g * kAltSlots + r - 1] == kEmpty) return node;
+        x = pv.alt_exit[g * kAltSlots + r - 1];
+    }
+    if (x >= hv.m) return node;                              // terminal: self loop
+    uint32_t C = pv.chunk_bases;
+    uint32_t g2 = pv.hap_chunk_base[h] + (uint32_t)(x / C);
+    if (x % C == 0) return g2 * (kAltSlots + 1);
+    for (int s = 0; s < kAltSlots; ++s)
+        if (pv.alt_entry[g2 * kAltSlots + s] == (uint32_t)x) return g2 * (kAltSlots + 1) + 1 + s;
+    pv.counters[0] = 2;                                      // unresolved link (cannot happen after convergence)
+    return node;
+}
+
+// E: after marking, pick the chunk's true record: returns phrase count, *entry = true entry position
+DRLZ_HD uint32_t chunk_true_record(const ParseView& pv, const uint8_t* mark, uint32_t g, uint32_t* entry) {
+    uint32_t base = g * (kAltSlots + 1);
+    if (mark[base]) {
+        uint32_t h = pv.chunk_hap[g];
+        *entry = (g - pv.hap_chunk_base[h]) * pv.chunk_bases;
+        return pv.spec_cnt[g];
+    }
+    for (int s = 0; s < kAltSlots; ++s)
+        if (mark[base + 1 + s]) { *entry = pv.alt_entry[g * kAltSlots + s]; return pv.alt_cnt[g * kAltSlots + s]; }
+    *entry = 0;
+    return 0;
+}
+
+// E: write `cnt` phrases of chunk g starting at `entry` as (int64 pos, int64 len) records
+DRLZ_HD void emit_chunk(const ParseView& pv, uint32_t g, uint32_t entry, uint32_t cnt, int64_t* out) {
+    uint32_t h = pv.chunk_hap[g];
+    const HapView& hv = pv.haps[h];
+    uint64_t i = entry;
+    uint32_t cur = hv.n_exc ? exc_lower_bound(hv, i) : 0;
+    for (uint32_t t = 0; t < cnt; ++t) {
+        Match mt = phrase_at(pv.ix, hv, i, &cur);
+        out[2 * (uint64_t)t] = (int64_t)mt.pos;
+        out[2 * (uint64_t)t + 1] = (int64_t)mt.len;
+        i += mt.len ? mt.len : 1;
+    }
+}
+
+}  // namespace drlz

@@ -1,0 +1,267 @@
+// sa_build.cu -- suffix array of the 2-bit packed reference by radix-sort prefix doubling, the k-mer jump
+// table derived from it, and the LCP array.  Replaces the external `radixSA` binary
+// (DistributedRLZ.scala:45,52) and the text SA load (:55).
+//
+//   round 0 : key = first 29 bases (58 bits) | min(remaining, 29) (6 bits)  -> 8-pass LSD radix sort.
+//             The length field makes every suffix shorter than 29 unique and sorts a proper prefix first,
+//             which is exactly the "shorter suffix first" order of the reference's SA.
+//   round r : only suffixes whose group is not yet a singleton stay active (early retirement);
+//             key = (group head index << 32) | (rank of suffix i+h, 0 past the end), radix sorted over the
+//             significant bits only; positions come back through the (sorted) list of active SA slots.
+//             h = 29, 58, 116, ...   One 8-byte device->host read per round decides termination.
+//   rank[]  is the inverse suffix array once every group is a singleton.
+#include <stdio.h>
+#include "drlz_internal.h"
+#include "radix_sort.cuh"
+#include "scan.cuh"
+
+namespace drlz {
+
+static const int kH0 = 29;
+
+#define SA_CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { snprintf(err, errlen, "%s: %s", #x, cudaGetErrorString(e_)); rc = (int)e_; goto done; } } while (0)
+
+__global__ void k_sa_init_keys(const uint64_t* __restrict__ text, uint64_t n, uint64_t* keys, uint32_t* vals) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t rem = n - i;
+    uint64_t len = rem < (uint64_t)kH0 ? rem : (uint64_t)kH0;
+    keys[i] = (get64(text, i) & ~0x3Full) | len;
+    vals[i] = (uint32_t)i;
+}
+
+// head flag of sorted position j
+struct LoadHeadIdx {
+    const uint64_t* keys;
+    __device__ __forceinline__ uint32_t operator()(uint64_t j) const {
+        return (j == 0 || keys[j] != keys[j - 1]) ? (uint32_t)j : 0u;
+    }
+};
+// ISA[sa[j]] = group head; also copies the sorted values into SA
+struct StoreRank {
+    const uint32_t* vals; uint32_t* sa; uint32_t* isa;
+    __device__ __forceinline__ void operator()(uint64_t j, uint32_t head) const {
+        uint32_t s = vals[j];
+        sa[j] = s; isa[s] = head;
+    }
+};
+// active flag: position j is in a group of size > 1  (keys = sorted keys of the element list, nel elements)
+struct LoadActive {
+    const uint64_t* keys; uint64_t nel;
+    __device__ __forceinline__ uint32_t operator()(uint64_t j) const {
+        bool head = j == 0 || keys[j] != keys[j - 1];
+        bool next_head = j + 1 >= nel || keys[j + 1] != keys[j];
+        return (head && next_head) ? 0u : 1u;
+    }
+};
+// compaction: active element j of the current list -> slot list of the next round
+struct StoreCompact {
+    const uint64_t* keys; uint64_t nel; const uint32_t* cur_slots; /* null in round 0: slot == j */ uint32_t* next_slots;
+    __device__ __forceinline__ void operator()(uint64_t j, uint32_t dst) const {
+        bool head = j == 0 || keys[j] != keys[j - 1];
+        bool next_head = j + 1 >= nel || keys[j + 1] != keys[j];
+        if (!(head && next_head)) next_slots[dst] = cur_slots ? cur_slots[j] : (uint32_t)j;
+    }
+};
+
+__global__ void k_sa_round_keys(const uint32_t* __restrict__ slots, uint64_t na, const uint32_t* __restrict__ sa,
+                                const uint32_t* __restrict__ isa, uint64_t n, uint64_t h, uint64_t* keys, uint32_t* vals) {
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= na) return;
+    uint32_t j = slots[t];
+    uint32_t s = sa[j];
+    uint64_t g = isa[s];
+    uint64_t p = (uint64_t)s + h;
+    uint64_t r2 = p < n ? (uint64_t)isa[p] + 1 : 0;
+    keys[t] = (g << 32) | r2;
+    vals[t] = s;
+}
+
+// new group head (as an index t into the sorted active list) by running maximum
+struct LoadHeadT {
+    const uint64_t* keys;
+    __device__ __forceinline__ uint32_t operator()(uint64_t t) const {
+        return (t == 0 || keys[t] != keys[t - 1]) ? (uint32_t)t : 0u;
+    }
+};
+struct StoreRound {
+    const uint32_t* slots; const uint32_t* vals; uint32_t* sa; uint32_t* isa;
+    __device__ __forceinline__ void operator()(uint64_t t, uint32_t head_t) const {
+        uint32_t s = vals[t];
+        sa[slots[t]] = s;
+        isa[s] = slots[head_t];
+    }
+};
+
+static int bits_for(uint64_t v) { int b = 0; while (v) { ++b; v >>= 1; } return b ? b : 1; }
+
+int build_suffix_array(const uint64_t* text, uint64_t n, uint32_t* sa, uint32_t* isa_out, cudaStream_t s,
+                       int* rounds_out, char* err, int errlen) {
+    int rc = 0;
+    if (rounds_out) *rounds_out = 0;
+    if (n == 0) return 0;
+    uint64_t *keys_a = nullptr, *keys_b = nullptr, *tot_host = nullptr;
+    uint32_t *vals_a = nullptr, *vals_b = nullptr, *hist = nullptr, *scan_tmp = nullptr, *slots_a = nullptr,
+             *slots_b = nullptr, *isa = nullptr;
+    uint64_t hist_n = sort_hist_elems(n);
+    uint64_t tmp_n = scan_tmp_elems(hist_n > n ? hist_n : n) + 8;
+    SA_CK(cudaMalloc(&keys_a, n * 8));
+    SA_CK(cudaMalloc(&keys_b, n * 8));
+    SA_CK(cudaMalloc(&vals_a, n * 4));
+    SA_CK(cudaMalloc(&vals_b, n * 4));
+    SA_CK(cudaMalloc(&hist, hist_n * 4 + 64));
+    SA_CK(cudaMalloc(&scan_tmp, tmp_n * 4));
+    SA_CK(cudaMalloc(&slots_a, n * 4));
+    SA_CK(cudaMalloc(&slots_b, n * 4));
+    if (isa_out) isa = isa_out; else SA_CK(cudaMalloc(&isa, n * 4));
+    SA_CK(cudaMallocHost(&tot_host, 8));
+    {
+        const unsigned T = 256;
+        unsigned nb = (unsigned)((n + T - 1) / T);
+        g_launches += 1;
+        k_sa_init_keys<<<nb, T, 0, s>>>(text, n, keys_a, vals_a);
+        radix_sort_pairs<uint64_t>(&keys_a, &keys_b, &vals_a, &vals_b, n, 0, 64, hist, scan_tmp, s);
+        // ranks = group head index (inclusive running max of head indices); SA = sorted values
+        device_scan<uint32_t, LoadHeadIdx, StoreRank, OpMax, true>(LoadHeadIdx{keys_a}, StoreRank{vals_a, sa, isa}, n,
+                                                                   scan_tmp, OpMax(), 0u, s);
+        // active slots
+        device_scan<uint32_t, LoadActive, StoreCompact, OpSum, false>(
+            LoadActive{keys_a, n}, StoreCompact{keys_a, n, nullptr, slots_a}, n, scan_tmp, OpSum(), 0u, s);
+        uint64_t ntile = (n + kScanTile - 1) / kScanTile;
+        uint32_t na32 = 0;
+        SA_CK(cudaMemcpyAsync(tot_host, scan_tmp + ntile, 4, cudaMemcpyDeviceToHost, s));
+        SA_CK(cudaStreamSynchronize(s));
+        na32 = *(uint32_t*)tot_host;
+        uint64_t na = na32;
+        uint64_t h = kH0;
+        int rounds = 0;
+        int rank_bits = bits_for(n);        // ranks+1 <= n
+        while (na > 0) {
+            ++rounds;
+            unsigned nba = (unsigned)((na + T - 1) / T);
+            g_launches += 1;
+            k_sa_round_keys<<<nba, T, 0, s>>>(slots_a, na, sa, isa, n, h, keys_a, vals_a);
+            // low half: rank of i+h; high half: group head.  Only the significant bytes are sorted.
+            radix_sort_pairs<uint64_t>(&keys_a, &keys_b, &vals_a, &vals_b, na, 0, rank_bits, hist, scan_tmp, s);
+            radix_sort_pairs<uint64_t>(&keys_a, &keys_b, &vals_a, &vals_b, na, 32, 32 + rank_bits, hist, scan_tmp, s);
+            device_scan<uint32_t, LoadHeadT, StoreRound, OpMax, true>(LoadHeadT{keys_a}, StoreRound{slots_a, vals_a, sa, isa},
+                                                                     na, scan_tmp, OpMax(), 0u, s);
+            device_scan<uint32_t, LoadActive, StoreCompact, OpSum, false>(
+                LoadActive{keys_a, na}, StoreCompact{keys_a, na, slots_a, slots_b}, na, scan_tmp, OpSum(), 0u, s);
+            uint64_t nt = (na + kScanTile - 1) / kScanTile;
+            SA_CK(cudaMemcpyAsync(tot_host, scan_tmp + nt, 4, cudaMemcpyDeviceToHost, s));
+            SA_CK(cudaStreamSynchronize(s));
+            na = *(uint32_t*)tot_host;
+            uint32_t* tsl = slots_a; slots_a = slots_b; slots_b = tsl;
+            h *= 2;
+            if (rounds > 40) { snprintf(err, errlen, "prefix doubling did not converge"); rc = -1; goto done; }
+        }
+        if (rounds_out) *rounds_out = rounds;
+        SA_CK(cudaGetLastError());
+    }
+done:
+    cudaFree(keys_a); cudaFree(keys_b); cudaFree(vals_a); cudaFree(vals_b); cudaFree(hist); cudaFree(scan_tmp);
+    cudaFree(slots_a); cudaFree(slots_b);
+    if (!isa_out) cudaFree(isa);
+    if (tot_host) cudaFreeHost(tot_host);
+    return rc;
+}
+
+// ---- k-mer jump table ---------------------------------------------------------------------------
+__global__ void k_tab_fill(uint32_t* tab, uint64_t cnt, uint32_t v) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < cnt) tab[i] = v;
+}
+__global__ void k_tab_mark(const uint64_t* __restrict__ text, uint64_t n, const uint32_t* __restrict__ sa, int k, uint32_t* tab) {
+    uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    uint64_t key = get64(text, sa[j]) >> (64 - 2 * k);
+    bool first = j == 0 || (get64(text, sa[j - 1]) >> (64 - 2 * k)) != key;
+    if (first) tab[key] = (uint32_t)j;
+}
+// right-to-left running minimum: element e of the scan is table entry (cnt-1-e)
+struct LoadRev { const uint32_t* tab; uint64_t cnt; __device__ __forceinline__ uint32_t operator()(uint64_t e) const { return tab[cnt - 1 - e]; } };
+struct StoreRev { uint32_t* tab; uint64_t cnt; __device__ __forceinline__ void operator()(uint64_t e, uint32_t v) const { tab[cnt - 1 - e] = v; } };
+
+int build_kmer_table(const uint64_t* text, uint64_t n, const uint32_t* sa, int k, uint32_t* tab, cudaStream_t s) {
+    uint64_t cnt = (1ull << (2 * k)) + 1;
+    uint32_t* tmp = nullptr;
+    cudaError_t e = cudaMalloc(&tmp, scan_tmp_elems(cnt) * 4 + 64);
+    if (e != cudaSuccess) return (int)e;
+    g_launches += 2;
+    k_tab_fill<<<(unsigned)((cnt + 255) / 256), 256, 0, s>>>(tab, cnt, (uint32_t)n);
+    if (n) k_tab_mark<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(text, n, sa, k, tab);
+    device_scan<uint32_t, LoadRev, StoreRev, OpMin, true>(LoadRev{tab, cnt}, StoreRev{tab, cnt}, cnt, tmp, OpMin(),
+                                                          0xFFFFFFFFu, s);
+    e = cudaStreamSynchronize(s);
+    cudaFree(tmp);
+    return (int)e;
+}
+
+// ---- LCP (Kasai order inside fixed blocks of text positions) ----------------------------------------
+static const int kLcpBlock = 64;
+__global__ void k_lcp(const uint64_t* __restrict__ text, uint64_t n, const uint32_t* __restrict__ sa,
+                      const uint32_t* __restrict__ isa, uint32_t* __restrict__ lcp) {
+    uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t i0 = b * kLcpBlock;
+    if (i0 >= n) return;
+    uint64_t i1 = i0 + kLcpBlock < n ? i0 + kLcpBlock : n;
+    uint64_t hh = 0;
+    for (uint64_t i = i0; i < i1; ++i) {
+        uint32_t r = isa[i];
+        if (r == 0) { lcp[0] = 0; hh = 0; continue; }
+        uint64_t j = sa[r - 1];
+        // extend from hh (Kasai: lcp of the successor suffix is at least lcp-1)
+        uint64_t lim = n - (i > j ? i : j);
+        while (hh < lim) {
+            uint64_t xr = get64(text, i + hh) ^ get64(text, j + hh);
+            if (xr) { hh += (uint64_t)(clz64(xr) >> 1); break; }
+            hh += 32;
+        }
+        if (hh > lim) hh = lim;
+        lcp[r] = (uint32_t)hh;
+        if (hh) --hh;
+    }
+}
+
+int build_lcp(const uint64_t* text, uint64_t n, const uint32_t* sa, const uint32_t* isa, uint32_t* lcp, cudaStream_t s) {
+    if (n == 0) return 0;
+    uint64_t nb = (n + kLcpBlock - 1) / kLcpBlock;
+    g_launches += 1;
+    k_lcp<<<(unsigned)((nb + 127) / 128), 128, 0, s>>>(text, n, sa, isa, lcp);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace drlz
+
+// ---- debug/test entry points (not part of include/drlz.h): exercise the primitives in isolation ----
+extern "C" int drlz_debug_sort_pairs(uint64_t* keys_host, uint32_t* vals_host, uint64_t n, int begin_bit, int end_bit) {
+    using namespace drlz;
+    if (n == 0) return 0;
+    uint64_t *ka = nullptr, *kb = nullptr; uint32_t *va = nullptr, *vb = nullptr, *hist = nullptr, *tmp = nullptr;
+    uint64_t hist_n = sort_hist_elems(n);
+    if (cudaMalloc(&ka, n * 8) || cudaMalloc(&kb, n * 8) || cudaMalloc(&va, n * 4) || cudaMalloc(&vb, n * 4) ||
+        cudaMalloc(&hist, hist_n * 4 + 64) || cudaMalloc(&tmp, (scan_tmp_elems(hist_n) + 8) * 4)) return -1;
+    cudaMemcpy(ka, keys_host, n * 8, cudaMemcpyHostToDevice);
+    cudaMemcpy(va, vals_host, n * 4, cudaMemcpyHostToDevice);
+    radix_sort_pairs<uint64_t>(&ka, &kb, &va, &vb, n, begin_bit, end_bit, hist, tmp, 0);
+    cudaError_t e = cudaDeviceSynchronize();
+    cudaMemcpy(keys_host, ka, n * 8, cudaMemcpyDeviceToHost);
+    cudaMemcpy(vals_host, va, n * 4, cudaMemcpyDeviceToHost);
+    cudaFree(ka); cudaFree(kb); cudaFree(va); cudaFree(vb); cudaFree(hist); cudaFree(tmp);
+    return (int)e;
+}
+
+extern "C" int drlz_debug_scan_u32(const uint32_t* in_host, uint64_t* out_host, uint64_t n, uint64_t* total) {
+    using namespace drlz;
+    uint32_t* din = nullptr; uint64_t *dout = nullptr, *tmp = nullptr;
+    if (cudaMalloc(&din, n * 4 + 4) || cudaMalloc(&dout, n * 8 + 8) || cudaMalloc(&tmp, scan_tmp_elems(n) * 8)) return -1;
+    cudaMemcpy(din, in_host, n * 4, cudaMemcpyHostToDevice);
+    device_scan<uint64_t, LoadArr<uint32_t, uint64_t>, StoreArr<uint64_t>, OpSum, false>(
+        LoadArr<uint32_t, uint64_t>{din}, StoreArr<uint64_t>{dout}, n, tmp, OpSum(), 0ull, 0);
+    cudaError_t e = cudaDeviceSynchronize();
+    cudaMemcpy(out_host, dout, n * 8, cudaMemcpyDeviceToHost);
+    cudaMemcpy(total, tmp + (n + kScanTile - 1) / kScanTile, 8, cudaMemcpyDeviceToHost);
+    cudaFree(din); cudaFree(dout); cudaFree(tmp);
+    return (int)e;
+}

@@ -1,0 +1,107 @@
+// emu.cpp -- TEST-ONLY host harness that runs the statements of pangenspark_b200/csrc/rlz_core.cuh
+// on the CPU (sequentially, one "thread" after another) so the chunk-parallel parse logic can be checked
+// against the oracle without a GPU.  It is never linked into libdrlz.so and nothing in the product calls it.
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include "../../pangenspark_b200/csrc/rlz_core.cuh"
+
+using namespace drlz;
+
+static int code_of(uint8_t b) { return b == 'A' ? 0 : b == 'C' ? 1 : b == 'G' ? 2 : b == 'T' ? 3 : -1; }
+
+static void pack_seq(const uint8_t* s, uint64_t m, std::vector<uint64_t>& w, std::vector<uint32_t>* ep,
+                     std::vector<uint8_t>* eb) {
+    w.assign(m / 32 + 3, 0);
+    for (uint64_t i = 0; i < m; ++i) {
+        int c = code_of(s[i]);
+        if (c < 0) { if (ep) { ep->push_back((uint32_t)i); eb->push_back(s[i]); } c = 0; }
+        w[i >> 5] |= (uint64_t)c << (62 - 2 * (i & 31));
+    }
+}
+
+static void build_tab(const std::vector<uint64_t>& text, uint64_t n, const std::vector<uint32_t>& sa, int k,
+                      std::vector<uint32_t>& tab) {
+    uint64_t nk = 1ull << (2 * k);
+    tab.assign(nk + 1, (uint32_t)n);
+    uint64_t prev = 0;  // next K to fill
+    for (uint64_t j = 0; j < n; ++j) {
+        uint64_t key = get64(text.data(), sa[j]) >> (64 - 2 * k);
+        // bases past n are zero in `text`, i.e. the zero-padded key
+        for (uint64_t K = prev; K <= key; ++K) tab[K] = (uint32_t)j;
+        if (key + 1 > prev) prev = key + 1;
+    }
+}
+
+extern "C" {
+
+void emu_free(void* p) { free(p); }
+
+// returns 0 ok, 1 reference not ACGT, 2 overflow/unresolved
+int emu_parse(const uint8_t* ref, uint64_t n, const int64_t* sa64, int k, uint32_t chunk, int H,
+              const uint8_t* const* rows, const uint64_t* cols, int64_t** pairs_out, uint64_t* npairs,
+              uint64_t* m_out, int* rounds_out) {
+    for (uint64_t i = 0; i < n; ++i) if (code_of(ref[i]) < 0) return 1;
+    std::vector<uint64_t> text; pack_seq(ref, n, text, nullptr, nullptr);
+    std::vector<uint32_t> sa(n); for (uint64_t i = 0; i < n; ++i) sa[i] = (uint32_t)sa64[i];
+    std::vector<uint32_t> tab; build_tab(text, n, sa, k, tab);
+    IndexView ix{text.data(), sa.data(), tab.data(), n, k};
+
+    std::vector<std::vector<uint64_t>> xs(H);
+    std::vector<std::vector<uint32_t>> eps(H);
+    std::vector<std::vector<uint8_t>> ebs(H);
+    std::vector<HapView> haps(H);
+    std::vector<uint32_t> base(H + 1, 0);
+    for (int h = 0; h < H; ++h) {
+        std::vector<uint8_t> g; g.reserve(cols[h]);
+        uint64_t c = cols[h];
+        while (c > 0 && (rows[h][c - 1] == '\n' || rows[h][c - 1] == '\r')) --c;
+        for (uint64_t t = 0; t < c; ++t) if (rows[h][t] != '-') g.push_back(rows[h][t]);
+        pack_seq(g.data(), g.size(), xs[h], &eps[h], &ebs[h]);
+        haps[h] = HapView{xs[h].data(), (uint64_t)g.size(), eps[h].data(), ebs[h].data(), (uint32_t)eps[h].size()};
+        m_out[h] = g.size();
+        base[h + 1] = base[h] + (uint32_t)((g.size() + chunk - 1) / chunk);
+    }
+    uint32_t NC = base[H];
+    std::vector<uint32_t> chunk_hap(NC);
+    for (int h = 0; h < H; ++h) for (uint32_t g = base[h]; g < base[h + 1]; ++g) chunk_hap[g] = h;
+    std::vector<uint32_t> spec_cnt(NC), spec_exit(NC), alt_entry((size_t)NC * kAltSlots, kEmpty),
+        alt_cnt((size_t)NC * kAltSlots, 0), alt_exit((size_t)NC * kAltSlots, 0), alt_round((size_t)NC * kAltSlots, 0),
+        counters(2 + kMaxRounds, 0);
+    ParseView pv{ix, haps.data(), chunk_hap.data(), base.data(), chunk, NC, spec_cnt.data(), spec_exit.data(),
+                 alt_entry.data(), alt_cnt.data(), alt_exit.data(), alt_round.data(), counters.data()};
+    for (uint32_t g = 0; g < NC; ++g) spec_parse_chunk(pv, g);
+    int round = 1;
+    while (counters[1 + round] > 0 && round < kMaxRounds) {
+        for (uint32_t g = 0; g < NC; ++g) for (int s = 0; s < kAltSlots; ++s) fix_parse_record(pv, g, s, round);
+        ++round;
+    }
+    *rounds_out = round;
+    if (counters[0] || round >= kMaxRounds) return 2;
+    uint32_t NN = NC * (kAltSlots + 1);
+    std::vector<uint32_t> jump(NN), jump2(NN);
+    std::vector<uint8_t> mark(NN, 0);
+    for (uint32_t v = 0; v < NN; ++v) jump[v] = node_succ(pv, v);
+    if (counters[0]) return 2;
+    uint32_t maxc = 1;
+    for (int h = 0; h < H; ++h) { if (base[h + 1] > base[h]) mark[base[h] * (kAltSlots + 1)] = 1; if (base[h+1]-base[h] > maxc) maxc = base[h+1]-base[h]; }
+    for (uint32_t span = 1; span < 2 * maxc; span *= 2) {
+        for (uint32_t v = 0; v < NN; ++v) { uint32_t j = jump[v]; if (mark[v]) mark[j] = 1; jump2[v] = jump[j]; }
+        jump.swap(jump2);
+    }
+    std::vector<uint64_t> off(NC + 1, 0);
+    std::vector<uint32_t> ent(NC), cnt(NC);
+    for (uint32_t g = 0; g < NC; ++g) { cnt[g] = chunk_true_record(pv, mark.data(), g, &ent[g]); off[g + 1] = off[g] + cnt[g]; }
+    std::vector<int64_t> out(2 * off[NC] + 2);
+    for (uint32_t g = 0; g < NC; ++g) if (cnt[g]) emit_chunk(pv, g, ent[g], cnt[g], out.data() + 2 * off[g]);
+    for (int h = 0; h < H; ++h) {
+        uint64_t a = off[base[h]], b = off[base[h + 1]];
+        npairs[h] = b - a;
+        pairs_out[h] = (int64_t*)malloc(sizeof(int64_t) * 2 * (b - a) + 16);
+        memcpy(pairs_out[h], out.data() + 2 * a, sizeof(int64_t) * 2 * (b - a));
+    }
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,73 @@
+"""The chunk-parallel parse logic of rlz_core.cuh (run on the host by the test-only harness tests/emu)
+must reproduce the oracle's literal restatement of DistributedRLZ.scala bit for bit."""
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from tests.emu import emu
+from tests.util import random_case
+
+
+def check(d, rows, k, chunk):
+    sa = orc.sa_build(d)
+    rc, res, m, rounds = emu.parse(d, sa, rows, k, chunk)
+    assert rc == 0, (rc, rounds)
+    for h, r in enumerate(rows):
+        x = orc.strip_gaps(r).tobytes()
+        a1, _ = orc.encode_literal(d, sa, x)
+        assert m[h] == len(x)
+        assert res[h].tolist() == a1.tolist(), (d, r, k, chunk)
+    return rounds
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_random_small(seed):
+    rng = np.random.default_rng(seed)
+    for it in range(400):
+        d, x = random_case(rng, b"ACGT", 60, 80)
+        if rng.random() < 0.3:   # haplotype bytes outside the reference alphabet and gaps
+            xb = bytearray(x)
+            for _ in range(int(rng.integers(1, 4))):
+                xb.insert(int(rng.integers(0, len(xb) + 1)), int(rng.choice(list(b"N-n"))))
+            x = bytes(xb)
+        k = int(rng.integers(1, 6))
+        chunk = int(rng.choice([1, 2, 3, 5, 8, 16, 64]))
+        check(d, [x, x[::-1], b""], k, chunk)
+
+
+def test_low_complexity_never_merging():
+    # parses started at different offsets of a homopolymer never share a phrase start:
+    # the fix-up must still converge (one extra record per round) or report overflow, never be wrong
+    d = b"A" * 63 + b"C"
+    x = b"A" * 1000
+    sa = orc.sa_build(d)
+    rc, res, m, rounds = emu.parse(d, sa, [x], 3, 256)
+    a1, _ = orc.encode_literal(d, sa, x)
+    if rc == 0:
+        assert res[0].tolist() == a1.tolist()
+    else:
+        assert rc == 2
+
+
+def test_synth_medium():
+    seed = orc.seed_for(1)
+    d = orc.syn_reference(seed, 200_000, repeats=20)
+    rows = orc.syn_rows(seed, d, 0, 4, 2e-3, 1e-4, 1e-4)
+    rounds = check(d.tobytes(), [r.tobytes() for r in rows], 8, 512)
+    assert rounds <= 4
+
+
+def test_golden():
+    import os
+    gold = os.path.join(os.path.dirname(__file__), "golden")
+    for f in sorted(os.listdir(gold)):
+        if not f.endswith(".npz"):
+            continue
+        z = np.load(os.path.join(gold, f))
+        d = z["ref"].tobytes()
+        rows = [z[f"row{h}"].tobytes() for h in range(int(z["nrows"]))]
+        sa = z["sa"]
+        rc, res, m, rounds = emu.parse(d, sa, rows, 4, 16)
+        assert rc == 0
+        for h in range(len(rows)):
+            assert orc.lz_bytes(res[h]) == z[f"lz{h}"].tobytes()

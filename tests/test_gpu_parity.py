@@ -1,0 +1,251 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle.  Run on the B200 box: pytest -m gpu."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from pangenspark_b200 import drlz as D
+from tests.util import random_case
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = D.Drlz(0)
+    yield c
+    c.close()
+
+
+def test_scan_primitive():
+    L = D.load_library()
+    rng = np.random.default_rng(0)
+    for n in (1, 5, 4095, 4096, 4097, 100_000, 3_000_001):
+        a = rng.integers(0, 1000, size=n).astype(np.uint32)
+        out = np.zeros(n, dtype=np.uint64)
+        tot = C.c_uint64(0)
+        rc = L.drlz_debug_scan_u32(a.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), C.c_uint64(n), C.byref(tot))
+        assert rc == 0
+        ref = np.concatenate([[0], np.cumsum(a.astype(np.uint64))])
+        assert (out == ref[:-1]).all()
+        assert tot.value == ref[-1]
+
+
+def test_radix_sort_primitive():
+    L = D.load_library()
+    rng = np.random.default_rng(1)
+    for n, bits in ((1, 64), (2, 64), (777, 64), (4096, 64), (4097, 24), (250_000, 64), (1_000_003, 40)):
+        keys = rng.integers(0, 2 ** 63, size=n, dtype=np.uint64) * 2 + rng.integers(0, 2, size=n).astype(np.uint64)
+        if bits < 64:
+            keys &= np.uint64((1 << bits) - 1)
+        keys[: n // 3] = keys[0]                       # many duplicates: stability
+        vals = np.arange(n, dtype=np.uint32)
+        k2, v2 = keys.copy(), vals.copy()
+        rc = L.drlz_debug_sort_pairs(k2.ctypes.data_as(C.c_void_p), v2.ctypes.data_as(C.c_void_p), C.c_uint64(n), 0, bits)
+        assert rc == 0
+        order = np.argsort(keys, kind="stable")
+        assert (k2 == keys[order]).all()
+        assert (v2 == vals[order]).all()
+
+
+def _check_index(ctx, d: bytes, k=None):
+    if k is not None:
+        ctx.set_option("kmer", k)
+    ctx.set_option("lcp", 1)
+    ctx.build_index(d)
+    ctx.set_option("kmer", 0)
+    sa_ref = orc.sa_build(d)
+    sa = ctx.index_get("sa")
+    assert (sa.astype(np.int64) == sa_ref).all()
+    isa = ctx.index_get("isa")
+    if len(d):
+        assert (isa[sa] == np.arange(len(d))).all()
+        lcp = ctx.index_get("lcp")
+        assert (lcp.astype(np.int64) == orc.lcp_build(d, sa_ref)).all()
+    return sa_ref
+
+
+@pytest.mark.parametrize("alphabet", [b"ACGT", b"AC", b"A"])
+def test_suffix_array_small(ctx, alphabet):
+    rng = np.random.default_rng(len(alphabet))
+    for n in list(range(1, 70)) + [100, 257, 1000, 4097, 20000]:
+        d = bytes(rng.choice(list(alphabet), size=n).astype(np.uint8))
+        _check_index(ctx, d, k=int(rng.integers(1, 7)))
+
+
+def test_suffix_array_repeats(ctx):
+    rng = np.random.default_rng(9)
+    unit = bytes(rng.choice(list(b"ACGT"), size=37).astype(np.uint8))
+    d = unit * 300 + b"ACGT" * 500 + b"A" * 3000 + unit * 20 + bytes(rng.choice(list(b"ACGT"), size=50000).astype(np.uint8))
+    _check_index(ctx, d)
+    d2 = orc.syn_reference(orc.seed_for(3), 1_500_000, repeats=40).tobytes()
+    _check_index(ctx, d2)
+    assert ctx.index_info()["sa_rounds"] >= 1
+
+
+def test_kmer_table_and_text(ctx):
+    d = orc.syn_reference(orc.seed_for(2), 100_000).tobytes()
+    ctx.set_option("kmer", 6)
+    ctx.build_index(d)
+    ctx.set_option("kmer", 0)
+    k = ctx.index_info()["k"]
+    assert k == 6
+    sa = ctx.index_get("sa").astype(np.int64)
+    codes = np.frombuffer(d.translate(bytes.maketrans(b"ACGT", b"\x00\x01\x02\x03")), dtype=np.uint8).astype(np.int64)
+    pad = np.concatenate([codes, np.zeros(k, dtype=np.int64)])
+    keys = np.zeros(len(d), dtype=np.int64)
+    for t in range(k):
+        keys = keys * 4 + pad[sa + t] * (sa + t < len(d))
+    tab = ctx.index_get("tab").astype(np.int64)
+    expect = np.searchsorted(keys, np.arange(4 ** k + 1), side="left")
+    assert (tab == expect).all()
+    text = ctx.index_get("text")
+    w0 = 0
+    for t in range(32):
+        w0 = (w0 << 2) | int(codes[t])
+    assert int(text[0]) == w0
+
+
+def _check_rows(ctx, d: bytes, rows, sa=None):
+    if sa is None:
+        sa = orc.sa_build(d)
+    res, m, gl = ctx.parse_batch(rows, strip_gaps=True, want_gapless=True)
+    for h, r in enumerate(rows):
+        x = orc.strip_gaps(r).tobytes()
+        a1, _ = orc.encode_literal(d, sa, x)
+        assert int(m[h]) == len(x)
+        assert gl[h].tobytes() == x
+        assert orc.lz_bytes(res[h]) == orc.lz_bytes(a1), (h, len(x), res[h][:5], a1[:5])
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_parse_random_small(ctx, seed):
+    rng = np.random.default_rng(100 + seed)
+    for it in range(60):
+        d, x = random_case(rng, b"ACGT", 200, 300)
+        xb = bytearray(x)
+        if rng.random() < 0.5:
+            for _ in range(int(rng.integers(1, 5))):
+                xb.insert(int(rng.integers(0, len(xb) + 1)), int(rng.choice(list(b"N-n-"))))
+        ctx.set_option("kmer", int(rng.integers(1, 6)))
+        ctx.set_option("chunk", int(rng.choice([1, 2, 3, 7, 16, 64, 2048])))
+        ctx.build_index(d)
+        _check_rows(ctx, d, [bytes(xb), bytes(xb)[::-1], b"", b"----", bytes(xb) + b"\n"])
+    ctx.set_option("kmer", 0)
+    ctx.set_option("chunk", 0)
+
+
+def test_parse_golden(ctx):
+    for f in sorted(os.listdir(GOLD)):
+        if not f.endswith(".npz"):
+            continue
+        z = np.load(os.path.join(GOLD, f))
+        d = z["ref"].tobytes()
+        for chunk in (16, 2048):
+            ctx.set_option("chunk", chunk)
+            ctx.build_index(d)
+            rows = [z[f"row{h}"].tobytes() for h in range(int(z["nrows"]))]
+            res, m, _ = ctx.parse_batch(rows)
+            for h in range(len(rows)):
+                assert orc.lz_bytes(res[h]) == z[f"lz{h}"].tobytes()
+    ctx.set_option("chunk", 0)
+
+
+def test_parse_low_complexity_fallback(ctx):
+    d = b"A" * 63 + b"C"
+    ctx.set_option("chunk", 64)
+    ctx.build_index(d)
+    _check_rows(ctx, d, [b"A" * 5000, b"C" * 100 + b"A" * 3000])
+    ctx.set_option("chunk", 0)
+
+
+def test_parse_synth_medium(ctx):
+    seed = orc.seed_for(1)
+    d = orc.syn_reference(seed, 2_000_000, repeats=30)
+    rows = orc.syn_rows(seed, d, 0, 6, 1e-3, 1e-4, 1e-4)
+    ctx.build_index(d)
+    sa = _sa = orc.sa_build(d)
+    assert (ctx.index_get("sa").astype(np.int64) == sa).all()
+    _check_rows(ctx, d.tobytes(), [r.tobytes() for r in rows], sa)
+    t = ctx.parse_timings()
+    assert t["launches"] > 0 and t["fix_rounds"] >= 1
+    # several groups through the pipelined host path give identical results
+    ctx.set_option("group_bytes", 3_000_000)
+    _check_rows(ctx, d.tobytes(), [r.tobytes() for r in rows], sa)
+    ctx.set_option("group_bytes", 0)
+
+
+def test_divergent_haplotype(ctx):
+    seed = orc.seed_for(5)
+    d = orc.syn_reference(seed, 300_000)
+    rows = orc.syn_rows(seed, d, 0, 3, 8e-3, 1e-3, 1e-3)
+    rnd = np.random.default_rng(3).choice(list(b"ACGT"), size=50_000).astype(np.uint8)   # unrelated sequence
+    ctx.build_index(d)
+    _check_rows(ctx, d.tobytes(), [r.tobytes() for r in rows] + [rnd.tobytes()])
+
+
+def test_pairs_cap_too_small(ctx):
+    d = orc.syn_reference(orc.seed_for(1), 50_000)
+    rows = orc.syn_rows(orc.seed_for(1), d, 0, 2, 1e-2, 0, 0)
+    ctx.build_index(d)
+    with pytest.raises(D.DrlzError) as e:
+        ctx.parse_batch([r.tobytes() for r in rows], pairs_cap=3)
+    assert e.value.code == -4
+
+
+def test_errors(ctx):
+    with pytest.raises(D.DrlzError) as e:
+        ctx.build_index(b"ACGTNACGT")
+    assert e.value.code == -5
+    c2 = D.Drlz(0)
+    with pytest.raises(D.DrlzError) as e:
+        c2.parse_batch([b"ACGT"])
+    assert e.value.code == -6
+    c2.close()
+
+
+def test_dense_matching_stats(ctx):
+    rng = np.random.default_rng(11)
+    d = orc.syn_reference(orc.seed_for(2), 30_000, repeats=0).tobytes()
+    x = bytearray(d[5000:9000])
+    for p in rng.integers(0, len(x), size=40):
+        x[p] = ord("ACGT"[int(rng.integers(0, 4))])
+    ctx.build_index(d)
+    ms, pos = ctx.matching_stats(bytes(x))
+    sa = orc.sa_build(d)
+    lcp = orc.lcp_build(d, sa)
+    ms_ref, pos_ref = orc.ms_all(d, sa, lcp, bytes(x))
+    assert (ms.astype(np.int64) == ms_ref).all()
+    assert (pos.astype(np.int64) == pos_ref).all()
+
+
+def test_device_resident_rows(ctx):
+    import torch
+    seed = orc.seed_for(1)
+    d = orc.syn_reference(seed, 400_000)
+    rows = orc.syn_rows(seed, d, 0, 5, 1e-3, 1e-4, 1e-4)
+    H, M = rows.shape
+    stride = (M + 15) // 16 * 16 + 16
+    buf = torch.zeros(H * stride, dtype=torch.uint8, device="cuda")
+    for h in range(H):
+        buf[h * stride: h * stride + M] = torch.from_numpy(rows[h]).cuda()
+    torch.cuda.synchronize()
+    ctx.build_index(d)
+    sa = orc.sa_build(d)
+    ptr, npairs, m = ctx.parse_batch_device(buf.data_ptr(), np.arange(H) * stride, np.full(H, M))
+    total = int(npairs.sum())
+    allp = ctx.copy_pairs_to_host(ptr, total)
+    o = 0
+    for h in range(H):
+        a1, _ = orc.encode_literal(d, sa, orc.strip_gaps(rows[h]))
+        assert orc.lz_bytes(allp[o:o + int(npairs[h])]) == orc.lz_bytes(a1)
+        o += int(npairs[h])
+    res, m2, _ = ctx.parse_batch([r.tobytes() for r in rows])
+    assert (m == m2).all()
+    assert [r.shape[0] for r in res] == npairs.tolist()
+    for h in range(H):
+        a1, _ = orc.encode_literal(d, sa, orc.strip_gaps(rows[h]))
+        assert orc.lz_bytes(res[h]) == orc.lz_bytes(a1)
