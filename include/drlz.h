@@ -93,10 +93,11 @@ int drlz_parse_batch_device(drlz_ctx* ctx, const uint8_t* rows_dev, const uint64
 /* Copy bytes from device memory owned by the context (e.g. *pairs_dev) to the host, on the context's stream. */
 int drlz_copy_to_host(drlz_ctx* ctx, void* dst_host, const void* src_dev, uint64_t bytes);
 
-/* Stage timings (ms, CUDA events on the context's stream) of the last parse call:
- * [0] strip+pack, [1] speculative parse, [2] fix-up rounds, [3] pointer jumping + compaction, [4] emission,
- * [5] whole device pipeline, [6] fix-up rounds executed, [7] kernels launched.  */
-int drlz_parse_timings(const drlz_ctx* ctx, double ms[8]);
+/* Per-kernel timings (ms, CUDA events on the context's stream) summed over the groups of the last parse call:
+ * [0] zero-fill of the packed buffer, [1] k_pack_count, [2] tile scans, [3] k_pack_write, [4] k_spec (speculative
+ * parse), [5] k_fix rounds, [6] pointer jumping + compaction scan, [7] k_emit (incl. the host read of the phrase
+ * total), [8] whole device pipeline, [9] fix-up rounds executed, [10] kernels launched, [11] groups. */
+int drlz_parse_timings(const drlz_ctx* ctx, double ms[12]);
 
 /* Dense matching statistics of one gapless, pure-ACGT sequence in host memory: for every position i
  * ms[i] = longest match length of x[i..] in the reference and pos[i] = SA[leftmost index of its interval]

@@ -47,7 +47,7 @@ struct drlz_ctx {
     int device = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
     cudaEvent_t ev_copied[2] = {nullptr, nullptr};
-    cudaEvent_t ev_stage[8] = {};
+    cudaEvent_t ev_stage[10] = {};
     std::string err;
     // options
     int opt_k = 0; uint32_t opt_chunk = 2048; uint64_t opt_group_bytes = 256ull << 20; int opt_lcp = 0;
@@ -61,7 +61,7 @@ struct drlz_ctx {
         jump_b, mark, true_cnt, true_entry, true_off, scan_tmp, hap_pairs, out, ms_a, ms_b;
     HostBuf meta_host, small_host;
     uint64_t exc_cap_hint = 0;
-    double parse_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    double parse_ms[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 };
 
 #define CK(ctx, x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { (ctx)->err = std::string(#x) + ": " + cudaGetErrorString(e_); return e_ == cudaErrorMemoryAllocation ? DRLZ_E_NOMEM : DRLZ_E_CUDA; } } while (0)
@@ -82,7 +82,7 @@ int drlz_create(drlz_ctx** out, int device) {
         cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return DRLZ_E_CUDA; }
     c->stream = c->own_stream;
     for (int i = 0; i < 2; ++i) cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming);
-    for (int i = 0; i < 8; ++i) cudaEventCreate(&c->ev_stage[i]);
+    for (int i = 0; i < 10; ++i) cudaEventCreate(&c->ev_stage[i]);
     *out = c;
     return DRLZ_OK;
 }
@@ -99,7 +99,7 @@ void drlz_destroy(drlz_ctx* c) {
     for (DevBuf* b : bufs) b->release();
     c->meta_host.release(); c->small_host.release();
     for (int i = 0; i < 2; ++i) if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]);
-    for (int i = 0; i < 8; ++i) if (c->ev_stage[i]) cudaEventDestroy(c->ev_stage[i]);
+    for (int i = 0; i < 10; ++i) if (c->ev_stage[i]) cudaEventDestroy(c->ev_stage[i]);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     delete c;
@@ -212,6 +212,7 @@ static int run_device_group(drlz_ctx* c, const uint8_t* rows_dev, const uint64_t
         cudaEventRecord(c->ev_stage[0], s);
         CK(c, cudaMemsetAsync(c->X.p, 0, xwords * 8, s));
         CK(c, cudaMemsetAsync(c->flags.p, 0, 16, s));
+        cudaEventRecord(c->ev_stage[1], s);
         PackJob job;
         job.rows = rows_dev; job.row_off = d_row_off; job.cols = d_cols; job.H = H; job.tiles_per_row = T; job.strip = strip;
         job.tile_cnt = c->tile_cnt.as<uint32_t>(); job.tile_exc = c->tile_exc.as<uint32_t>();
@@ -221,10 +222,9 @@ static int run_device_group(drlz_ctx* c, const uint8_t* rows_dev, const uint64_t
         job.exc_pos = c->excpos.as<uint32_t>(); job.exc_byte = c->excbyte.as<uint8_t>(); job.exc_cap = exc_cap;
         job.flags = c->flags.as<uint32_t>();
         job.gapless = want_gapless ? c->gapless.as<uint8_t>() : nullptr; job.gapless_off = d_goff;
-        launch_pack(job, s);
+        launch_pack(job, s, &c->ev_stage[2]);                            // ev 2,3,4
         launch_make_hapviews(c->haps.as<HapView>(), c->X.as<uint64_t>(), d_xoff, c->mdev.as<uint64_t>(), c->excpos.as<uint32_t>(),
                              c->excbyte.as<uint8_t>(), c->excoff.as<uint64_t>(), H, s);
-        cudaEventRecord(c->ev_stage[1], s);
 
         size_t nn = (size_t)NC * (kAltSlots + 1), na = (size_t)NC * kAltSlots;
         CK(c, c->chunk_hap.ensure((size_t)NC * 4 + 4)); CK(c, c->spec_cnt.ensure((size_t)NC * 4 + 4)); CK(c, c->spec_exit.ensure((size_t)NC * 4 + 4));
@@ -249,7 +249,7 @@ static int run_device_group(drlz_ctx* c, const uint8_t* rows_dev, const uint64_t
         pb.scan_tmp = c->scan_tmp.as<uint64_t>(); pb.hap_pairs = c->hap_pairs.as<uint64_t>();
         pb.host_counters = sh_counters; pb.host_total = sh_total;
         int rounds = 0;
-        int prc = parse_stage_count(pb, s, &rounds, &c->ev_stage[2]);   // ev 2,3,4,5
+        int prc = parse_stage_count(pb, s, &rounds, &c->ev_stage[5]);   // ev 5,6,7,8
         CK(c, cudaGetLastError());
         if (prc == 2) {
             if (single_chunk) { c->err = "parse fix-up did not converge"; return DRLZ_E_INTERNAL; }
@@ -259,7 +259,7 @@ static int run_device_group(drlz_ctx* c, const uint8_t* rows_dev, const uint64_t
         uint64_t total = *sh_total;
         CK(c, c->out.ensure(total * 16 + 16));
         parse_stage_emit(pb, c->out.as<int64_t>(), s);
-        cudaEventRecord(c->ev_stage[6], s);
+        cudaEventRecord(c->ev_stage[9], s);
         CK(c, cudaMemcpyAsync(sh_m, c->mdev.p, (size_t)H * 8, cudaMemcpyDeviceToHost, s));
         CK(c, cudaMemcpyAsync(sh_pairs, c->hap_pairs.p, ((size_t)H + 1) * 8, cudaMemcpyDeviceToHost, s));
         CK(c, cudaMemcpyAsync(sh_excoff, c->excoff.as<uint64_t>() + H, 8, cudaMemcpyDeviceToHost, s));
@@ -277,13 +277,9 @@ static int run_device_group(drlz_ctx* c, const uint8_t* rows_dev, const uint64_t
         // timings
         float t;
         double* pm = c->parse_ms;
-        cudaEventElapsedTime(&t, c->ev_stage[0], c->ev_stage[1]); pm[0] += t;
-        cudaEventElapsedTime(&t, c->ev_stage[2], c->ev_stage[3]); pm[1] += t;
-        cudaEventElapsedTime(&t, c->ev_stage[3], c->ev_stage[4]); pm[2] += t;
-        cudaEventElapsedTime(&t, c->ev_stage[4], c->ev_stage[5]); pm[3] += t;
-        cudaEventElapsedTime(&t, c->ev_stage[5], c->ev_stage[6]); pm[4] += t;
-        cudaEventElapsedTime(&t, c->ev_stage[0], c->ev_stage[6]); pm[5] += t;
-        pm[6] += rounds; pm[7] += (double)(g_launches - launches0);
+        static const int iv[9][2] = {{0, 1}, {1, 2}, {2, 3}, {3, 4}, {5, 6}, {6, 7}, {7, 8}, {8, 9}, {0, 9}};
+        for (int i = 0; i < 9; ++i) { cudaEventElapsedTime(&t, c->ev_stage[iv[i][0]], c->ev_stage[iv[i][1]]); pm[i] += t; }
+        pm[9] += rounds; pm[10] += (double)(g_launches - launches0); pm[11] += 1;
         return DRLZ_OK;
     }
     c->err = "exception list kept overflowing";
@@ -344,7 +340,7 @@ int drlz_build_index(drlz_ctx* c, const uint8_t* ref, uint64_t n) {
         job.m_out = c->mdev.as<uint64_t>(); job.exc_off = c->excoff.as<uint64_t>();
         job.exc_pos = c->excpos.as<uint32_t>(); job.exc_byte = c->excbyte.as<uint8_t>(); job.exc_cap = 64;
         job.flags = c->flags.as<uint32_t>(); job.gapless = nullptr; job.gapless_off = dm + 3;
-        launch_pack(job, s);
+        launch_pack(job, s, nullptr);
         uint64_t* sh = c->small_host.as<uint64_t>();
         CK(c, cudaMemcpyAsync(sh, c->excoff.as<uint64_t>() + 1, 8, cudaMemcpyDeviceToHost, s));
         CK(c, cudaStreamSynchronize(s));
@@ -451,7 +447,7 @@ int drlz_parse_batch_device(drlz_ctx* c, const uint8_t* rows_dev, const uint64_t
     if (!c || (H && (!rows_dev || !row_off || !cols))) return DRLZ_E_ARG;
     if (!c->have_index) { c->err = "index not built"; return DRLZ_E_STATE; }
     CK(c, cudaSetDevice(c->device));
-    for (int i = 0; i < 8; ++i) c->parse_ms[i] = 0;
+    for (int i = 0; i < 12; ++i) c->parse_ms[i] = 0;
     uint64_t total = 0;
     int rc = run_device_group(c, rows_dev, row_off, cols, H, strip_gaps, false, m_out, n_pairs, &total, nullptr);
     if (rc != DRLZ_OK) return rc;
@@ -464,7 +460,7 @@ int drlz_parse_batch(drlz_ctx* c, const uint8_t* const* rows, const uint64_t* co
     if (!c || (H && (!rows || !cols || !n_pairs))) return DRLZ_E_ARG;
     if (!c->have_index) { c->err = "index not built"; return DRLZ_E_STATE; }
     CK(c, cudaSetDevice(c->device));
-    for (int i = 0; i < 8; ++i) c->parse_ms[i] = 0;
+    for (int i = 0; i < 12; ++i) c->parse_ms[i] = 0;
     // trimmed column counts (Spark's text reader drops the line terminator)
     std::vector<uint64_t> tc(H);
     for (uint32_t h = 0; h < H; ++h) {
@@ -547,9 +543,9 @@ int drlz_copy_to_host(drlz_ctx* c, void* dst_host, const void* src_dev, uint64_t
     return DRLZ_OK;
 }
 
-int drlz_parse_timings(const drlz_ctx* c, double ms[8]) {
+int drlz_parse_timings(const drlz_ctx* c, double ms[12]) {
     if (!c || !ms) return DRLZ_E_ARG;
-    for (int i = 0; i < 8; ++i) ms[i] = c->parse_ms[i];
+    for (int i = 0; i < 12; ++i) ms[i] = c->parse_ms[i];
     return DRLZ_OK;
 }
 

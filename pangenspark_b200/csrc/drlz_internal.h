@@ -35,7 +35,8 @@ struct PackJob {
     uint8_t* gapless;             // optional gapless bytes out (device) or null
     const uint64_t* gapless_off;  // [H] byte offsets into gapless
 };
-void launch_pack(const PackJob& job, cudaStream_t s);
+// ev (nullable): 3 events recorded after the count kernel, after the scans, after the write kernel
+void launch_pack(const PackJob& job, cudaStream_t s, cudaEvent_t* ev);
 
 // ---- suffix array + k-mer table (sa_build.cu) ---------------------------------------------------
 struct SaWorkspace;   // opaque

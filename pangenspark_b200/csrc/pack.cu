@@ -167,12 +167,13 @@ __global__ void __launch_bounds__(256) k_pack_write(PackJob job) {
     }
 }
 
-void launch_pack(const PackJob& job, cudaStream_t s) {
-    if (job.H == 0 || job.tiles_per_row == 0) return;
+void launch_pack(const PackJob& job, cudaStream_t s, cudaEvent_t* ev) {
+    if (job.H == 0 || job.tiles_per_row == 0) { if (ev) for (int i = 0; i < 3; ++i) cudaEventRecord(ev[i], s); return; }
     dim3 grid(job.tiles_per_row, job.H);
     uint64_t nt = (uint64_t)job.H * job.tiles_per_row;
     g_launches += 3;
     k_pack_count<<<grid, 256, 0, s>>>(job);
+    if (ev) cudaEventRecord(ev[0], s);
     uint64_t* tmp1 = job.scan_tmp;
     uint64_t* tmp2 = job.scan_tmp + scan_tmp_elems(nt);
     device_scan<uint64_t, LoadArr<uint32_t, uint64_t>, StoreArr<uint64_t>, OpSum, false>(
@@ -181,7 +182,9 @@ void launch_pack(const PackJob& job, cudaStream_t s) {
         LoadArr<uint32_t, uint64_t>{job.tile_exc}, StoreArr<uint64_t>{job.tile_excoff}, nt, tmp2, OpSum(), 0ull, s);
     uint64_t ntiles_scan = (nt + kScanTile - 1) / kScanTile;
     k_pack_rows<<<(job.H + 1 + 127) / 128, 128, 0, s>>>(job, tmp1 + ntiles_scan, tmp2 + ntiles_scan);
+    if (ev) cudaEventRecord(ev[1], s);
     k_pack_write<<<grid, 256, 0, s>>>(job);
+    if (ev) cudaEventRecord(ev[2], s);
 }
 
 __global__ void k_make_hapviews(HapView* haps, const uint64_t* X, const uint64_t* xoff, const uint64_t* m,

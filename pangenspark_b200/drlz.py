@@ -237,9 +237,10 @@ class Drlz:
         return out
 
     def parse_timings(self):
-        a = (C.c_double * 8)()
+        a = (C.c_double * 12)()
         self._ck(self._lib.drlz_parse_timings(self._h, a))
-        keys = ["pack_ms", "spec_ms", "fix_ms", "jump_ms", "emit_ms", "device_ms", "fix_rounds", "launches"]
+        keys = ["memset_ms", "pack_count_ms", "pack_scan_ms", "pack_write_ms", "spec_ms", "fix_ms", "jump_ms", "emit_ms",
+                "device_ms", "fix_rounds", "launches", "groups"]
         return dict(zip(keys, list(a)))
 
     def matching_stats(self, x):
