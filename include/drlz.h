@@ -41,7 +41,9 @@ const char* drlz_last_error(const drlz_ctx* ctx);
  * stream, so that caller-side CUDA events bracket them.  NULL restores the context's own stream. */
 int drlz_set_stream(drlz_ctx* ctx, void* cuda_stream);
 /* options: "kmer" (jump-table k, 0 = auto), "chunk" (bases per parse chunk, 0 = default 2048),
- *          "group_bytes" (host-path pipeline granularity), "lcp" (1 = also build the LCP array) */
+ *          "group_bytes" (host-path pipeline granularity), "lcp" (1 = also build the LCP array),
+ *          "min_cap" (lower bound of the per-lookup compare cap, default 64), "foreign_cap" (longest off-chain
+ *          diagonal compare a single thread may do before the exact sequential fallback is taken) */
 int drlz_set_option(drlz_ctx* ctx, const char* key, int64_t value);
 
 /* pinned host memory for the streaming path (cudaHostAlloc); plain malloc memory also works, slower */
@@ -96,7 +98,8 @@ int drlz_copy_to_host(drlz_ctx* ctx, void* dst_host, const void* src_dev, uint64
 /* Per-kernel timings (ms, CUDA events on the context's stream) summed over the groups of the last parse call:
  * [0] zero-fill of the packed buffer, [1] k_pack_count, [2] tile scans, [3] k_pack_write, [4] k_spec (speculative
  * parse), [5] k_fix rounds, [6] pointer jumping + compaction scan, [7] k_emit (incl. the host read of the phrase
- * total), [8] whole device pipeline, [9] fix-up rounds executed, [10] kernels launched, [11] groups. */
+ * total), [8] whole device pipeline, [9] stage A (k_first + k_link + list ranking), [10] fix-up rounds executed,
+ * [11] kernels launched. */
 int drlz_parse_timings(const drlz_ctx* ctx, double ms[12]);
 
 /* Dense matching statistics of one gapless, pure-ACGT sequence in host memory: for every position i

@@ -47,17 +47,17 @@ struct drlz_ctx {
     int device = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
     cudaEvent_t ev_copied[2] = {nullptr, nullptr};
-    cudaEvent_t ev_stage[10] = {};
+    cudaEvent_t ev_stage[11] = {};
     std::string err;
     // options
-    int opt_k = 0; uint32_t opt_chunk = 2048; uint64_t opt_group_bytes = 256ull << 20; int opt_lcp = 0;
+    int opt_k = 0; uint32_t opt_chunk = 2048; uint32_t opt_min_cap = 64; uint32_t opt_foreign_cap = 1u << 20; uint64_t opt_group_bytes = 256ull << 20; int opt_lcp = 0;
     // index
     bool have_index = false; uint64_t n = 0; int k = 0; int sa_rounds = 0;
     DevBuf text, sa, tab, isa, lcp;
     double idx_ms[5] = {0, 0, 0, 0, 0};
     // batch scratch (grow-only)
     DevBuf stage[2], meta_dev, tile_cnt, tile_exc, tile_off, tile_excoff, pack_tmp, X, mdev, excoff, excpos, excbyte,
-        flags, haps, gapless, chunk_hap, spec_cnt, spec_exit, alt_entry, alt_cnt, alt_exit, alt_round, counters, jump_a,
+        flags, haps, gapless, chunk_hap, first_pos, first_len, run_a, run_b, link_a, link_b, spec_cnt, spec_exit, alt_entry, alt_cnt, alt_exit, alt_round, counters, jump_a,
         jump_b, mark, true_cnt, true_entry, true_off, scan_tmp, hap_pairs, out, ms_a, ms_b;
     HostBuf meta_host, small_host;
     uint64_t exc_cap_hint = 0;
@@ -82,7 +82,7 @@ int drlz_create(drlz_ctx** out, int device) {
         cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return DRLZ_E_CUDA; }
     c->stream = c->own_stream;
     for (int i = 0; i < 2; ++i) cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming);
-    for (int i = 0; i < 10; ++i) cudaEventCreate(&c->ev_stage[i]);
+    for (int i = 0; i < 11; ++i) cudaEventCreate(&c->ev_stage[i]);
     *out = c;
     return DRLZ_OK;
 }
@@ -93,13 +93,13 @@ void drlz_destroy(drlz_ctx* c) {
     cudaDeviceSynchronize();
     DevBuf* bufs[] = {&c->text, &c->sa, &c->tab, &c->isa, &c->lcp, &c->stage[0], &c->stage[1], &c->meta_dev, &c->tile_cnt,
                       &c->tile_exc, &c->tile_off, &c->tile_excoff, &c->pack_tmp, &c->X, &c->mdev, &c->excoff, &c->excpos,
-                      &c->excbyte, &c->flags, &c->haps, &c->gapless, &c->chunk_hap, &c->spec_cnt, &c->spec_exit,
+                      &c->excbyte, &c->flags, &c->haps, &c->gapless, &c->chunk_hap, &c->first_pos, &c->first_len, &c->run_a, &c->run_b, &c->link_a, &c->link_b, &c->spec_cnt, &c->spec_exit,
                       &c->alt_entry, &c->alt_cnt, &c->alt_exit, &c->alt_round, &c->counters, &c->jump_a, &c->jump_b,
                       &c->mark, &c->true_cnt, &c->true_entry, &c->true_off, &c->scan_tmp, &c->hap_pairs, &c->out, &c->ms_a, &c->ms_b};
     for (DevBuf* b : bufs) b->release();
     c->meta_host.release(); c->small_host.release();
     for (int i = 0; i < 2; ++i) if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]);
-    for (int i = 0; i < 10; ++i) if (c->ev_stage[i]) cudaEventDestroy(c->ev_stage[i]);
+    for (int i = 0; i < 11; ++i) if (c->ev_stage[i]) cudaEventDestroy(c->ev_stage[i]);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     delete c;
@@ -119,6 +119,8 @@ int drlz_set_option(drlz_ctx* c, const char* key, int64_t v) {
     else if (!strcmp(key, "chunk")) { if (v < 0 || v > 0x7FFFFFFF) return DRLZ_E_ARG; c->opt_chunk = v ? (uint32_t)v : 2048; }
     else if (!strcmp(key, "group_bytes")) { if (v < 0) return DRLZ_E_ARG; c->opt_group_bytes = v ? (uint64_t)v : (256ull << 20); }
     else if (!strcmp(key, "lcp")) c->opt_lcp = v != 0;
+    else if (!strcmp(key, "min_cap")) { if (v < 0 || v > 0x7FFFFFFF) return DRLZ_E_ARG; c->opt_min_cap = v ? (uint32_t)v : 64; }
+    else if (!strcmp(key, "foreign_cap")) { if (v < 0 || v > 0x7FFFFFFF) return DRLZ_E_ARG; c->opt_foreign_cap = v ? (uint32_t)v : (1u << 20); }
     else return DRLZ_E_ARG;
     return DRLZ_OK;
 }
@@ -227,6 +229,9 @@ static int run_device_group(drlz_ctx* c, const uint8_t* rows_dev, const uint64_t
                              c->excbyte.as<uint8_t>(), c->excoff.as<uint64_t>(), H, s);
 
         size_t nn = (size_t)NC * (kAltSlots + 1), na = (size_t)NC * kAltSlots;
+        CK(c, c->first_pos.ensure((size_t)NC * 4 + 4)); CK(c, c->first_len.ensure((size_t)NC * 4 + 4));
+        CK(c, c->run_a.ensure((size_t)NC * 4 + 4)); CK(c, c->run_b.ensure((size_t)NC * 4 + 4));
+        CK(c, c->link_a.ensure((size_t)NC * 4 + 4)); CK(c, c->link_b.ensure((size_t)NC * 4 + 4));
         CK(c, c->chunk_hap.ensure((size_t)NC * 4 + 4)); CK(c, c->spec_cnt.ensure((size_t)NC * 4 + 4)); CK(c, c->spec_exit.ensure((size_t)NC * 4 + 4));
         CK(c, c->alt_entry.ensure(na * 4 + 4)); CK(c, c->alt_cnt.ensure(na * 4 + 4)); CK(c, c->alt_exit.ensure(na * 4 + 4));
         CK(c, c->alt_round.ensure(na * 4 + 4)); CK(c, c->counters.ensure(sizeof(uint32_t) * (2 + kMaxRounds)));
@@ -239,6 +244,10 @@ static int run_device_group(drlz_ctx* c, const uint8_t* rows_dev, const uint64_t
         pb.pv.ix = IndexView{c->text.as<uint64_t>(), c->sa.as<uint32_t>(), c->tab.as<uint32_t>(), c->n, c->k};
         pb.pv.haps = c->haps.as<HapView>(); pb.pv.chunk_hap = c->chunk_hap.as<uint32_t>(); pb.pv.hap_chunk_base = d_base;
         pb.pv.chunk_bases = Ceff; pb.pv.n_chunks = NC;
+        pb.pv.min_cap = single_chunk ? 0xFFFFFFFFu : c->opt_min_cap; pb.pv.foreign_cap = c->opt_foreign_cap;
+        pb.pv.first_pos = c->first_pos.as<uint32_t>(); pb.pv.first_len = c->first_len.as<uint32_t>();
+        pb.pv.run_len = c->run_a.as<uint32_t>(); pb.pv.link = c->link_a.as<uint32_t>();
+        pb.link_b = c->link_b.as<uint32_t>(); pb.run_b = c->run_b.as<uint32_t>();
         pb.pv.spec_cnt = c->spec_cnt.as<uint32_t>(); pb.pv.spec_exit = c->spec_exit.as<uint32_t>();
         pb.pv.alt_entry = c->alt_entry.as<uint32_t>(); pb.pv.alt_cnt = c->alt_cnt.as<uint32_t>();
         pb.pv.alt_exit = c->alt_exit.as<uint32_t>(); pb.pv.alt_round = c->alt_round.as<uint32_t>();
@@ -249,7 +258,7 @@ static int run_device_group(drlz_ctx* c, const uint8_t* rows_dev, const uint64_t
         pb.scan_tmp = c->scan_tmp.as<uint64_t>(); pb.hap_pairs = c->hap_pairs.as<uint64_t>();
         pb.host_counters = sh_counters; pb.host_total = sh_total;
         int rounds = 0;
-        int prc = parse_stage_count(pb, s, &rounds, &c->ev_stage[5]);   // ev 5,6,7,8
+        int prc = parse_stage_count(pb, s, &rounds, &c->ev_stage[5]);   // ev 5,6,7,8 and 9 (after stage A)
         CK(c, cudaGetLastError());
         if (prc == 2) {
             if (single_chunk) { c->err = "parse fix-up did not converge"; return DRLZ_E_INTERNAL; }
@@ -259,7 +268,7 @@ static int run_device_group(drlz_ctx* c, const uint8_t* rows_dev, const uint64_t
         uint64_t total = *sh_total;
         CK(c, c->out.ensure(total * 16 + 16));
         parse_stage_emit(pb, c->out.as<int64_t>(), s);
-        cudaEventRecord(c->ev_stage[9], s);
+        cudaEventRecord(c->ev_stage[10], s);
         CK(c, cudaMemcpyAsync(sh_m, c->mdev.p, (size_t)H * 8, cudaMemcpyDeviceToHost, s));
         CK(c, cudaMemcpyAsync(sh_pairs, c->hap_pairs.p, ((size_t)H + 1) * 8, cudaMemcpyDeviceToHost, s));
         CK(c, cudaMemcpyAsync(sh_excoff, c->excoff.as<uint64_t>() + H, 8, cudaMemcpyDeviceToHost, s));
@@ -277,9 +286,9 @@ static int run_device_group(drlz_ctx* c, const uint8_t* rows_dev, const uint64_t
         // timings
         float t;
         double* pm = c->parse_ms;
-        static const int iv[9][2] = {{0, 1}, {1, 2}, {2, 3}, {3, 4}, {5, 6}, {6, 7}, {7, 8}, {8, 9}, {0, 9}};
-        for (int i = 0; i < 9; ++i) { cudaEventElapsedTime(&t, c->ev_stage[iv[i][0]], c->ev_stage[iv[i][1]]); pm[i] += t; }
-        pm[9] += rounds; pm[10] += (double)(g_launches - launches0); pm[11] += 1;
+        static const int iv[10][2] = {{0, 1}, {1, 2}, {2, 3}, {3, 4}, {9, 6}, {6, 7}, {7, 8}, {8, 10}, {0, 10}, {5, 9}};
+        for (int i = 0; i < 10; ++i) { cudaEventElapsedTime(&t, c->ev_stage[iv[i][0]], c->ev_stage[iv[i][1]]); pm[i] += t; }
+        pm[10] += rounds; pm[11] += (double)(g_launches - launches0);
         return DRLZ_OK;
     }
     c->err = "exception list kept overflowing";

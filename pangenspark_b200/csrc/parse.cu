@@ -13,6 +13,22 @@
 
 namespace drlz {
 
+__global__ void __launch_bounds__(128) k_first(ParseView pv) {
+    uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < pv.n_chunks) first_phrase_chunk(pv, g);
+}
+
+__global__ void __launch_bounds__(128) k_link(ParseView pv) {
+    uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < pv.n_chunks) link_chunk(pv, g);
+}
+
+__global__ void k_rank(const uint32_t* __restrict__ link_in, const uint32_t* __restrict__ run_in, uint32_t* link_out,
+                       uint32_t* run_out, uint32_t nc) {
+    uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < nc) rank_round(link_in, run_in, link_out, run_out, g);
+}
+
 __global__ void __launch_bounds__(128) k_spec(ParseView pv) {
     uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g < pv.n_chunks) spec_parse_chunk(pv, g);
@@ -71,7 +87,7 @@ int parse_stage_count(ParseBuffers& pb, cudaStream_t s, int* rounds_out, cudaEve
     *pb.host_total = 0;
     if (rounds_out) *rounds_out = 0;
     if (NC == 0) {
-        if (ev) for (int i = 0; i < 4; ++i) cudaEventRecord(ev[i], s);
+        if (ev) for (int i = 0; i < 5; ++i) cudaEventRecord(ev[i], s);
         cudaMemsetAsync(pb.hap_pairs, 0, sizeof(uint64_t) * (pb.H + 1), s);
         cudaStreamSynchronize(s);
         return 0;
@@ -79,6 +95,20 @@ int parse_stage_count(ParseBuffers& pb, cudaStream_t s, int* rounds_out, cudaEve
     cudaMemsetAsync(pv.alt_entry, 0xFF, sizeof(uint32_t) * (size_t)NC * kAltSlots, s);
     cudaMemsetAsync(pv.counters, 0, sizeof(uint32_t) * (2 + kMaxRounds), s);
     if (ev) cudaEventRecord(ev[0], s);
+    // stage A: first phrase of every chunk, diagonal-run links, list ranking
+    g_launches += 2;
+    k_first<<<(NC + 127) / 128, 128, 0, s>>>(pv);
+    k_link<<<(NC + 127) / 128, 128, 0, s>>>(pv);
+    {
+        uint32_t *li = pv.link, *ri = pv.run_len, *lo = pb.link_b, *ro = pb.run_b;
+        for (uint64_t span = 1; span < pb.max_chunks_per_hap; span *= 2) {
+            g_launches += 1;
+            k_rank<<<(NC + 255) / 256, 256, 0, s>>>(li, ri, lo, ro, NC);
+            uint32_t* t = li; li = lo; lo = t; t = ri; ri = ro; ro = t;
+        }
+        pv.link = li; pv.run_len = ri;
+    }
+    if (ev) cudaEventRecord(ev[4], s);
     g_launches += 1;
     k_spec<<<(NC + 127) / 128, 128, 0, s>>>(pv);
     if (ev) cudaEventRecord(ev[1], s);

@@ -13,7 +13,7 @@
 //   text / haplotypes : 2 bits per base (A,C,G,T -> 0..3), 32 bases per 64-bit word, first base in the
 //                       most significant bits, so integer order of words == lexicographic order of bases;
 //                       arrays carry >= 2 zero pad words.
-//   SA                : uint32 suffix array of the reference (n < 2^32 - 64)
+//   SA                : uint32 suffix array of the reference (n < 2^32 - 1024)
 //   tab               : 4^k + 1 entries; tab[K] = #suffixes whose zero-padded k-mer key is < K
 //                       (a jump table replacing the top ~2k levels of the SA binary search)
 //   exceptions        : sorted positions (+ bytes) of haplotype bytes outside {A,C,G,T}; such a byte can
@@ -29,9 +29,9 @@
 
 namespace drlz {
 
-typedef uint32_t pos_t;                   // positions in reference / haplotype
 static const uint32_t kEmpty = 0xFFFFFFFFu;
 static const int kAltSlots = 3;           // alternative entry records per chunk (see parse pipeline)
+static const int kMaxRounds = 30;
 
 DRLZ_HD int clz64(uint64_t v) {
 #if defined(__CUDA_ARCH__)
@@ -103,53 +103,73 @@ DRLZ_HD uint32_t cmp_suffix(const uint64_t* __restrict__ X, uint64_t i, const ui
 }
 
 // Longest match of x[i..i+maxlen) in d with the reference's tie-break.  maxlen >= 1.
-DRLZ_HD Match lookup(const IndexView& ix, const uint64_t* __restrict__ X, uint64_t i, uint32_t maxlen) {
+// cap (>= 1) bounds the compared length: if the pattern's first min(cap, maxlen) bases occur in d, cap < maxlen
+// and exactly ONE suffix carries them, the call stops there and reports *open = true with len = cap -- the
+// match continues along that unique alignment and its full length is the diagonal run resolved by the caller.
+// If several suffixes share the capped prefix the search is redone uncapped (exact, slower; long exact repeats).
+DRLZ_HD Match lookup(const IndexView& ix, const uint64_t* __restrict__ X, uint64_t i, uint32_t maxlen,
+                     uint32_t cap, bool* open) {
     const int k = ix.k;
     const uint64_t n = ix.n;
+    *open = false;
     uint64_t xw = get64(X, i);
-    uint32_t kk = maxlen < (uint32_t)k ? maxlen : (uint32_t)k;
     uint64_t kmer = xw >> (64 - 2 * k);
-    uint64_t lowmask = (1ull << (2 * (k - (int)kk))) - 1;
-    uint64_t lokey = kmer & ~lowmask, hikey = kmer | lowmask;
-    uint32_t lo = ix.tab[lokey], hi = ix.tab[hikey + 1];
-    // r = #suffixes < pattern lies in [lo, hi]
-    uint32_t l = lo, h = hi;
-    uint32_t lcp_left = 0, lcp_right = 0;
-    bool have_left = false, have_right = false;
-    while (l < h) {
-        uint32_t mid = l + ((h - l) >> 1);
-        bool less;
-        uint32_t c = cmp_suffix(X, i, ix.text, ix.sa[mid], n, maxlen, &less);
-        if (less) { l = mid + 1; lcp_left = c; have_left = true; }
-        else { h = mid; lcp_right = c; have_right = true; }
-    }
-    uint32_t r = l;
-    bool dummy;
-    uint32_t l1 = 0, l2 = 0;
-    if (r > 0) l1 = have_left ? lcp_left : cmp_suffix(X, i, ix.text, ix.sa[r - 1], n, maxlen, &dummy);
-    uint32_t sar = 0;
-    if ((uint64_t)r < n) {
-        sar = ix.sa[r];
-        l2 = have_right ? lcp_right : cmp_suffix(X, i, ix.text, sar, n, maxlen, &dummy);
-    }
     Match mt;
-    if (l2 > l1) { mt.len = l2; mt.pos = sar; return mt; }
-    if (l1 == 0) { mt.len = 0; mt.pos = 0; return mt; }
-    // leftmost index whose suffix shares >= L bases with the pattern; it lies in [tab[key(L)], r-1]
-    uint32_t L = l1;
-    uint32_t Lk = L < (uint32_t)k ? L : (uint32_t)k;
-    uint32_t a = lo;
-    if (Lk != kk) {
-        uint64_t m2 = (1ull << (2 * (k - (int)Lk))) - 1;
-        a = ix.tab[kmer & ~m2];
+    uint32_t plen = cap < maxlen ? cap : maxlen;
+    for (int pass = 0; pass < 2; ++pass) {
+        uint32_t kk = plen < (uint32_t)k ? plen : (uint32_t)k;
+        uint64_t lowmask = (1ull << (2 * (k - (int)kk))) - 1;
+        uint64_t lokey = kmer & ~lowmask, hikey = kmer | lowmask;
+        uint32_t lo = ix.tab[lokey], hi = ix.tab[hikey + 1];
+        // r = #suffixes < pattern lies in [lo, hi]
+        uint32_t l = lo, h = hi;
+        uint32_t lcp_left = 0, lcp_right = 0;
+        bool have_left = false, have_right = false;
+        while (l < h) {
+            uint32_t mid = l + ((h - l) >> 1);
+            bool less;
+            uint32_t c = cmp_suffix(X, i, ix.text, ix.sa[mid], n, plen, &less);
+            if (less) { l = mid + 1; lcp_left = c; have_left = true; }
+            else { h = mid; lcp_right = c; have_right = true; }
+        }
+        uint32_t r = l;
+        bool dummy;
+        uint32_t l1 = 0, l2 = 0;
+        if (r > 0) l1 = have_left ? lcp_left : cmp_suffix(X, i, ix.text, ix.sa[r - 1], n, plen, &dummy);
+        uint32_t sar = 0;
+        if ((uint64_t)r < n) {
+            sar = ix.sa[r];
+            l2 = have_right ? lcp_right : cmp_suffix(X, i, ix.text, sar, n, plen, &dummy);
+        }
+        if (l2 > l1) {
+            if (l2 == plen && plen < maxlen) {
+                // capped: is SA[r] the only suffix carrying the capped pattern?
+                bool multi = false;
+                if ((uint64_t)r + 1 < n) multi = cmp_suffix(X, i, ix.text, ix.sa[r + 1], n, plen, &dummy) >= plen;
+                if (multi) { plen = maxlen; continue; }
+                *open = true;
+            }
+            mt.len = l2; mt.pos = sar; return mt;
+        }
+        if (l1 == 0) { mt.len = 0; mt.pos = 0; return mt; }
+        // leftmost index whose suffix shares >= L bases with the pattern; it lies in [tab[key(L)], r-1]
+        uint32_t L = l1;
+        uint32_t Lk = L < (uint32_t)k ? L : (uint32_t)k;
+        uint32_t a = lo;
+        if (Lk != kk) {
+            uint64_t m2 = (1ull << (2 * (k - (int)Lk))) - 1;
+            a = ix.tab[kmer & ~m2];
+        }
+        uint32_t b = r - 1;
+        while (a < b) {
+            uint32_t mid = a + ((b - a) >> 1);
+            uint32_t c = cmp_suffix(X, i, ix.text, ix.sa[mid], n, L, &dummy);
+            if (c >= L) b = mid; else a = mid + 1;
+        }
+        mt.len = L; mt.pos = ix.sa[a];
+        return mt;
     }
-    uint32_t b = r - 1;
-    while (a < b) {
-        uint32_t mid = a + ((b - a) >> 1);
-        uint32_t c = cmp_suffix(X, i, ix.text, ix.sa[mid], n, L, &dummy);
-        if (c >= L) b = mid; else a = mid + 1;
-    }
-    mt.len = L; mt.pos = ix.sa[a];
+    mt.len = 0; mt.pos = 0;      // not reached
     return mt;
 }
 
@@ -163,28 +183,17 @@ DRLZ_HD uint32_t exc_lower_bound(const HapView& hv, uint64_t i) {
     return a;
 }
 
-// One greedy step at position i.  *cursor = index of the first exception >= i (kept monotone by the caller
-// through this function).  Literals carry their byte in .pos.
-DRLZ_HD Match phrase_at(const IndexView& ix, const HapView& hv, uint64_t i, uint32_t* cursor) {
-    uint64_t stop = hv.m;
-    if (hv.n_exc) {
-        uint32_t c = *cursor;
-        while (c < hv.n_exc && (uint64_t)hv.exc_pos[c] < i) ++c;
-        *cursor = c;
-        if (c < hv.n_exc) stop = hv.exc_pos[c];
-        if (stop == i) { Match mt; mt.len = 0; mt.pos = hv.exc_byte[c]; return mt; }
-    }
-    uint32_t maxlen = (uint32_t)(stop - i);
-    Match mt = lookup(ix, hv.x, i, maxlen);
-    if (mt.len == 0) mt.pos = (uint32_t)("ACGT"[base_at(hv.x, i)]);
-    return mt;
-}
-
 // ---------------------------------------------------------------------------------------------
 // Chunk-parallel exact greedy parse.
 //
 // The greedy parse is a deterministic function of its start position, so two parses that ever share
 // a phrase start coincide from there on.  Each haplotype is cut into chunks of C bases:
+//   A   every chunk looks up the phrase at its first base, comparing no further than the chunk end.
+//       A match that reaches the chunk end is "open": it continues along its alignment (diagonal
+//       pos - i).  Chunks whose successor starts on the same diagonal are linked; list ranking by
+//       pointer jumping turns the links into exact run lengths (run_len) -- so no thread ever compares
+//       more than ~one chunk of bases, however long the match (a haplotype identical to the reference is
+//       one 48 Mbp phrase).
 //   P1  every chunk parses speculatively from its first base            -> spec_cnt, spec_exit
 //   R   every exit position e is registered as an "alternative entry" of the chunk containing e
 //   F   every new alternative entry is parsed in tandem with the chunk's speculative parse until the
@@ -203,6 +212,14 @@ struct ParseView {
     const uint32_t* hap_chunk_base; // [H+1]
     uint32_t chunk_bases;           // C
     uint32_t n_chunks;              // NC
+    uint32_t min_cap;               // lower bound of the compare cap (64; 0xFFFFFFFF disables capping)
+    uint32_t foreign_cap;           // bound of an off-chain diagonal compare before the exact fallback is taken
+    // stage A
+    uint32_t* first_pos;            // [NC] phrase at the chunk's first base: position (or literal byte)
+    uint32_t* first_len;            // [NC] its verified length (0 = literal); >= chunk end when open
+    uint32_t* run_len;              // [NC] its exact total length (after list ranking)
+    uint32_t* link;                 // [NC] next chunk of the diagonal run, kEmpty = end
+    // stages P1 / R / F
     uint32_t* spec_cnt;             // [NC]
     uint32_t* spec_exit;            // [NC]
     uint32_t* alt_entry;            // [NC*kAltSlots], kEmpty when unused
@@ -227,7 +244,106 @@ DRLZ_HD void atomic_inc_u32(uint32_t* p) {
 #endif
 }
 
-static const int kMaxRounds = 30;
+// first position past i where the running phrase must stop (next exception or end of the haplotype)
+DRLZ_HD uint64_t stop_after(const HapView& hv, uint64_t i, uint32_t* cursor) {
+    uint64_t stop = hv.m;
+    if (hv.n_exc) {
+        uint32_t c = *cursor;
+        while (c < hv.n_exc && (uint64_t)hv.exc_pos[c] < i) ++c;
+        *cursor = c;
+        if (c < hv.n_exc) stop = hv.exc_pos[c];
+    }
+    return stop;
+}
+
+// capped phrase lookup at position i (chunk-end cap); literals carry their byte in .pos
+DRLZ_HD Match phrase_capped(const ParseView& pv, const HapView& hv, uint64_t i, uint32_t* cursor, bool* open) {
+    *open = false;
+    uint64_t stop = stop_after(hv, i, cursor);
+    if (stop == i) { Match mt; mt.len = 0; mt.pos = hv.exc_byte[*cursor]; return mt; }
+    uint32_t maxlen = (uint32_t)(stop - i);
+    uint64_t C = pv.chunk_bases;
+    uint64_t to_end = (i / C + 1) * C - i;
+    uint32_t cap = to_end > (uint64_t)pv.min_cap ? (to_end > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)to_end) : pv.min_cap;
+    Match mt = lookup(pv.ix, hv.x, i, maxlen, cap, open);
+    if (mt.len == 0) mt.pos = (uint32_t)("ACGT"[base_at(hv.x, i)]);
+    return mt;
+}
+
+// Where an open match (start i, verified len, position pos) continues: the last chunk start j <= i+len.
+// Returns the global chunk id; *j_out = its first base; *same = that chunk's own first phrase lies on the
+// same diagonal (then the remaining length is that chunk's run).
+DRLZ_HD uint32_t open_target(const ParseView& pv, uint32_t h, uint64_t i, const Match& mt, uint64_t* j_out, bool* same) {
+    uint64_t C = pv.chunk_bases;
+    uint64_t cc = (i + mt.len) / C;
+    uint64_t j = cc * C;
+    uint32_t g2 = pv.hap_chunk_base[h] + (uint32_t)cc;
+    *j_out = j;
+    *same = pv.first_len[g2] > 0 && (int64_t)pv.first_pos[g2] - (int64_t)j == (int64_t)mt.pos - (int64_t)i;
+    return g2;
+}
+
+// off-chain continuation: compare along the diagonal from j; flags the exact fallback if it runs too long
+DRLZ_HD uint32_t foreign_run(const ParseView& pv, const HapView& hv, uint64_t i, const Match& mt, uint64_t j) {
+    uint32_t cur = hv.n_exc ? exc_lower_bound(hv, j) : 0;
+    uint64_t stop = stop_after(hv, j, &cur);
+    uint32_t maxlen = (uint32_t)(stop - j);
+    uint32_t cap = maxlen < pv.foreign_cap ? maxlen : pv.foreign_cap;
+    bool less;
+    uint64_t p = (uint64_t)mt.pos + (j - i);
+    uint32_t l = cap ? cmp_suffix(hv.x, j, pv.ix.text, p, pv.ix.n, cap, &less) : 0;
+    if (l == cap && cap < maxlen) pv.counters[0] = 3;        // too long for one thread: take the exact fallback
+    return l;
+}
+
+// exact phrase at position i (uses run_len of the chunk starts; valid after stage A)
+DRLZ_HD Match phrase_at(const ParseView& pv, uint32_t h, const HapView& hv, uint64_t i, uint32_t* cursor) {
+    bool open;
+    Match mt = phrase_capped(pv, hv, i, cursor, &open);
+    if (open) {
+        uint64_t j; bool same;
+        uint32_t g2 = open_target(pv, h, i, mt, &j, &same);
+        uint32_t rest = same ? pv.run_len[g2] : foreign_run(pv, hv, i, mt, j);
+        mt.len = (uint32_t)(j - i) + rest;
+    }
+    return mt;
+}
+
+// A1: phrase at the first base of chunk g, compared no further than the chunk end
+DRLZ_HD void first_phrase_chunk(const ParseView& pv, uint32_t g) {
+    uint32_t h = pv.chunk_hap[g];
+    const HapView& hv = pv.haps[h];
+    uint64_t s = (uint64_t)(g - pv.hap_chunk_base[h]) * pv.chunk_bases;
+    pv.link[g] = kEmpty;
+    if (s >= hv.m) { pv.first_pos[g] = 0; pv.first_len[g] = 0; pv.run_len[g] = 0; return; }
+    uint32_t cur = hv.n_exc ? exc_lower_bound(hv, s) : 0;
+    bool open;
+    Match mt = phrase_capped(pv, hv, s, &cur, &open);
+    pv.first_pos[g] = mt.pos;
+    pv.first_len[g] = mt.len;
+    pv.run_len[g] = open ? kEmpty : mt.len;                   // kEmpty = still open, see link_chunk
+}
+
+// A2: link open chunks to the chunk their match continues in, or finish them by a direct compare
+DRLZ_HD void link_chunk(const ParseView& pv, uint32_t g) {
+    if (pv.run_len[g] != kEmpty) return;
+    uint32_t h = pv.chunk_hap[g];
+    const HapView& hv = pv.haps[h];
+    uint64_t s = (uint64_t)(g - pv.hap_chunk_base[h]) * pv.chunk_bases;
+    Match mt; mt.pos = pv.first_pos[g]; mt.len = pv.first_len[g];
+    uint64_t j; bool same;
+    uint32_t g2 = open_target(pv, h, s, mt, &j, &same);
+    if (same) { pv.link[g] = g2; pv.run_len[g] = (uint32_t)(j - s); }          // partial sum; rest follows the link
+    else pv.run_len[g] = (uint32_t)(j - s) + foreign_run(pv, hv, s, mt, j);
+}
+
+// A3: one pointer-jumping round of the list ranking (double buffered by the caller)
+DRLZ_HD void rank_round(const uint32_t* link_in, const uint32_t* run_in, uint32_t* link_out, uint32_t* run_out, uint32_t g) {
+    uint32_t l = link_in[g];
+    if (l == kEmpty) { link_out[g] = kEmpty; run_out[g] = run_in[g]; return; }
+    run_out[g] = run_in[g] + run_in[l];
+    link_out[g] = link_in[l];
+}
 
 // R: register exit position x of haplotype h as an entry; new records are scheduled for `next_round`.
 DRLZ_HD void register_exit(const ParseView& pv, uint32_t h, uint64_t x, uint32_t next_round) {
@@ -248,6 +364,12 @@ DRLZ_HD void register_exit(const ParseView& pv, uint32_t h, uint64_t x, uint32_t
     pv.counters[0] = 1;                                      // more distinct entries than slots
 }
 
+// one greedy step of the parse of chunk g at position i (i == chunk start reuses stage A's result)
+DRLZ_HD Match chunk_step(const ParseView& pv, uint32_t g, uint32_t h, const HapView& hv, uint64_t s, uint64_t i, uint32_t* cursor) {
+    if (i == s) { Match mt; mt.pos = pv.first_pos[g]; mt.len = pv.run_len[g]; return mt; }
+    return phrase_at(pv, h, hv, i, cursor);
+}
+
 // P1 for global chunk g
 DRLZ_HD void spec_parse_chunk(const ParseView& pv, uint32_t g) {
     uint32_t h = pv.chunk_hap[g];
@@ -257,7 +379,7 @@ DRLZ_HD void spec_parse_chunk(const ParseView& pv, uint32_t g) {
     uint64_t i = s; uint32_t cnt = 0;
     uint32_t cur = hv.n_exc ? exc_lower_bound(hv, i) : 0;
     while (i < e) {
-        Match mt = phrase_at(pv.ix, hv, i, &cur);
+        Match mt = chunk_step(pv, g, h, hv, s, i, &cur);
         ++cnt;
         i += mt.len ? mt.len : 1;
     }
@@ -281,12 +403,12 @@ DRLZ_HD void fix_parse_record(const ParseView& pv, uint32_t g, int slot, uint32_
     bool merged = false;
     while (iB < e) {
         while (iA < iB) {
-            Match mt = phrase_at(pv.ix, hv, iA, &curA);
+            Match mt = chunk_step(pv, g, h, hv, s, iA, &curA);
             ++cntA;
             iA += mt.len ? mt.len : 1;
         }
         if (iA == iB) { merged = true; break; }
-        Match mt = phrase_at(pv.ix, hv, iB, &curB);
+        Match mt = phrase_at(pv, h, hv, iB, &curB);
         ++cntB;
         iB += mt.len ? mt.len : 1;
     }
@@ -340,10 +462,11 @@ DRLZ_HD uint32_t chunk_true_record(const ParseView& pv, const uint8_t* mark, uin
 DRLZ_HD void emit_chunk(const ParseView& pv, uint32_t g, uint32_t entry, uint32_t cnt, int64_t* out) {
     uint32_t h = pv.chunk_hap[g];
     const HapView& hv = pv.haps[h];
+    uint64_t s = (uint64_t)(g - pv.hap_chunk_base[h]) * pv.chunk_bases;
     uint64_t i = entry;
     uint32_t cur = hv.n_exc ? exc_lower_bound(hv, i) : 0;
     for (uint32_t t = 0; t < cnt; ++t) {
-        Match mt = phrase_at(pv.ix, hv, i, &cur);
+        Match mt = chunk_step(pv, g, h, hv, s, i, &cur);
         out[2 * (uint64_t)t] = (int64_t)mt.pos;
         out[2 * (uint64_t)t + 1] = (int64_t)mt.len;
         i += mt.len ? mt.len : 1;

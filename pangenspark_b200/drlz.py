@@ -240,7 +240,7 @@ class Drlz:
         a = (C.c_double * 12)()
         self._ck(self._lib.drlz_parse_timings(self._h, a))
         keys = ["memset_ms", "pack_count_ms", "pack_scan_ms", "pack_write_ms", "spec_ms", "fix_ms", "jump_ms", "emit_ms",
-                "device_ms", "fix_rounds", "launches", "groups"]
+                "device_ms", "first_ms", "fix_rounds", "launches"]
         return dict(zip(keys, list(a)))
 
     def matching_stats(self, x):

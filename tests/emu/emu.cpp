@@ -39,7 +39,7 @@ extern "C" {
 void emu_free(void* p) { free(p); }
 
 // returns 0 ok, 1 reference not ACGT, 2 overflow/unresolved
-int emu_parse(const uint8_t* ref, uint64_t n, const int64_t* sa64, int k, uint32_t chunk, int H,
+int emu_parse(const uint8_t* ref, uint64_t n, const int64_t* sa64, int k, uint32_t chunk, uint32_t min_cap, uint32_t foreign_cap, int H,
               const uint8_t* const* rows, const uint64_t* cols, int64_t** pairs_out, uint64_t* npairs,
               uint64_t* m_out, int* rounds_out) {
     for (uint64_t i = 0; i < n; ++i) if (code_of(ref[i]) < 0) return 1;
@@ -66,11 +66,26 @@ int emu_parse(const uint8_t* ref, uint64_t n, const int64_t* sa64, int k, uint32
     uint32_t NC = base[H];
     std::vector<uint32_t> chunk_hap(NC);
     for (int h = 0; h < H; ++h) for (uint32_t g = base[h]; g < base[h + 1]; ++g) chunk_hap[g] = h;
+    std::vector<uint32_t> first_pos(NC), first_len(NC), run_a(NC), run_b(NC), link_a(NC), link_b(NC);
     std::vector<uint32_t> spec_cnt(NC), spec_exit(NC), alt_entry((size_t)NC * kAltSlots, kEmpty),
         alt_cnt((size_t)NC * kAltSlots, 0), alt_exit((size_t)NC * kAltSlots, 0), alt_round((size_t)NC * kAltSlots, 0),
         counters(2 + kMaxRounds, 0);
-    ParseView pv{ix, haps.data(), chunk_hap.data(), base.data(), chunk, NC, spec_cnt.data(), spec_exit.data(),
+    ParseView pv{ix, haps.data(), chunk_hap.data(), base.data(), chunk, NC, min_cap, foreign_cap,
+                 first_pos.data(), first_len.data(), run_a.data(), link_a.data(), spec_cnt.data(), spec_exit.data(),
                  alt_entry.data(), alt_cnt.data(), alt_exit.data(), alt_round.data(), counters.data()};
+    uint32_t maxc0 = 1;
+    for (int h = 0; h < H; ++h) if (base[h + 1] - base[h] > maxc0) maxc0 = base[h + 1] - base[h];
+    for (uint32_t g = 0; g < NC; ++g) first_phrase_chunk(pv, g);
+    for (uint32_t g = 0; g < NC; ++g) link_chunk(pv, g);
+    if (counters[0]) return 2;
+    {
+        uint32_t *li = link_a.data(), *ri = run_a.data(), *lo = link_b.data(), *ro = run_b.data();
+        for (uint32_t span = 1; span < maxc0; span *= 2) {
+            for (uint32_t g = 0; g < NC; ++g) rank_round(li, ri, lo, ro, g);
+            std::swap(li, lo); std::swap(ri, ro);
+        }
+        pv.run_len = ri; pv.link = li;
+    }
     for (uint32_t g = 0; g < NC; ++g) spec_parse_chunk(pv, g);
     int round = 1;
     while (counters[1 + round] > 0 && round < kMaxRounds) {

@@ -8,9 +8,9 @@ from tests.emu import emu
 from tests.util import random_case
 
 
-def check(d, rows, k, chunk):
+def check(d, rows, k, chunk, min_cap=64, foreign_cap=1 << 20):
     sa = orc.sa_build(d)
-    rc, res, m, rounds = emu.parse(d, sa, rows, k, chunk)
+    rc, res, m, rounds = emu.parse(d, sa, rows, k, chunk, min_cap, foreign_cap)
     assert rc == 0, (rc, rounds)
     for h, r in enumerate(rows):
         x = orc.strip_gaps(r).tobytes()
@@ -32,7 +32,8 @@ def test_random_small(seed):
             x = bytes(xb)
         k = int(rng.integers(1, 6))
         chunk = int(rng.choice([1, 2, 3, 5, 8, 16, 64]))
-        check(d, [x, x[::-1], b""], k, chunk)
+        min_cap = int(rng.choice([1, 2, 4, 64]))
+        check(d, [x, x[::-1], b"", d, d[3:]], k, chunk, min_cap)
 
 
 def test_low_complexity_never_merging():
@@ -47,6 +48,18 @@ def test_low_complexity_never_merging():
         assert res[0].tolist() == a1.tolist()
     else:
         assert rc == 2
+
+
+def test_long_matches_are_chained():
+    # haplotype == reference (one phrase), long shared stretches, an exact long repeat in the reference
+    rng = np.random.default_rng(3)
+    d = bytes(rng.choice(list(b"ACGT"), size=5000).astype(np.uint8))
+    d = d + d[1000:3000] + bytes(rng.choice(list(b"ACGT"), size=500).astype(np.uint8))      # exact 2 kb repeat
+    rows = [d, d[:2500] + b"T" + d[2500:], d[1000:3000] * 2, d[4000:] + d[:4000], b"N" + d[10:4000] + b"N" + d[4000:]]
+    for chunk, min_cap in ((16, 1), (16, 8), (64, 64), (256, 64), (2048, 64)):
+        check(d, rows, 5, chunk, min_cap)
+    # homopolymers: every suffix ties, the diagonal is still consistent
+    check(b"A" * 700 + b"C", [b"A" * 300, b"A" * 700, b"A" * 699 + b"CA"], 3, 32, 4)
 
 
 def test_synth_medium():

@@ -132,10 +132,12 @@ def test_parse_random_small(ctx, seed):
                 xb.insert(int(rng.integers(0, len(xb) + 1)), int(rng.choice(list(b"N-n-"))))
         ctx.set_option("kmer", int(rng.integers(1, 6)))
         ctx.set_option("chunk", int(rng.choice([1, 2, 3, 7, 16, 64, 2048])))
+        ctx.set_option("min_cap", int(rng.choice([1, 3, 64])))
         ctx.build_index(d)
         _check_rows(ctx, d, [bytes(xb), bytes(xb)[::-1], b"", b"----", bytes(xb) + b"\n"])
     ctx.set_option("kmer", 0)
     ctx.set_option("chunk", 0)
+    ctx.set_option("min_cap", 0)
 
 
 def test_parse_golden(ctx):
@@ -152,6 +154,22 @@ def test_parse_golden(ctx):
             for h in range(len(rows)):
                 assert orc.lz_bytes(res[h]) == z[f"lz{h}"].tobytes()
     ctx.set_option("chunk", 0)
+
+
+def test_long_matches(ctx):
+    rng = np.random.default_rng(3)
+    d = bytes(rng.choice(list(b"ACGT"), size=50000).astype(np.uint8))
+    d = d + d[10000:30000] + bytes(rng.choice(list(b"ACGT"), size=5000).astype(np.uint8))      # exact 20 kb repeat
+    rows = [d, d[:25000] + b"T" + d[25000:], d[10000:30000] * 2, d[40000:] + d[:40000], b"N" + d[10:40000] + b"N" + d[40000:]]
+    for chunk, min_cap, fcap in ((16, 1, 0), (64, 8, 0), (2048, 64, 0), (2048, 64, 100), (256, 64, 3000)):
+        ctx.set_option("chunk", chunk); ctx.set_option("min_cap", min_cap); ctx.set_option("foreign_cap", fcap)
+        ctx.build_index(d)
+        _check_rows(ctx, d, rows)
+    d2 = b"A" * 7000 + b"C"
+    ctx.set_option("chunk", 512)
+    ctx.build_index(d2)
+    _check_rows(ctx, d2, [b"A" * 3000, b"A" * 7000, b"A" * 6999 + b"CA"])
+    ctx.set_option("chunk", 0); ctx.set_option("min_cap", 0); ctx.set_option("foreign_cap", 0)
 
 
 def test_parse_low_complexity_fallback(ctx):
