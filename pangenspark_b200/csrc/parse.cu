@@ -176,7 +176,8 @@ void launch_fill_chunk_hap(uint32_t* chunk_hap, const uint32_t* hap_chunk_base, 
 __global__ void __launch_bounds__(128) k_ms_dense(IndexView ix, const uint64_t* __restrict__ X, uint64_t m, uint32_t* ms, uint32_t* pos) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= m) return;
-    Match mt = lookup(ix, X, i, (uint32_t)(m - i));
+    bool open;
+    Match mt = lookup(ix, X, i, (uint32_t)(m - i), (uint32_t)(m - i), &open);
     if (mt.len == 0) mt.pos = (uint32_t)("ACGT"[base_at(X, i)]);
     ms[i] = mt.len; pos[i] = mt.pos;
 }
