@@ -1,0 +1,108 @@
+"""Host-side logic of the drop-in stage (file naming, ordering, sharding, record layout) on CPU.
+The parser is replaced by the oracle here -- these tests check plumbing, not the CUDA path."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+from oracle import oracle as orc
+from pangenspark_b200 import distributed_rlz as drz
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def oracle_parser(ref, rows):
+    sa = orc.sa_build(ref)
+    pairs, gapless = [], []
+    for r in rows:
+        x = orc.strip_gaps(r).tobytes()
+        pairs.append(orc.encode_literal(ref, sa, x)[0])
+        gapless.append(x)
+    return pairs, gapless
+
+
+def make_dataset(tmp, H=7, n=3000):
+    seed = orc.seed_for(1)
+    d = orc.syn_reference(seed, n)
+    rows = orc.syn_rows(seed, d, 0, H, 1e-2, 2e-3, 2e-3)
+    os.makedirs(os.path.join(tmp, "msa"))
+    with open(os.path.join(tmp, "ref.txt"), "wb") as f:
+        f.write(d.tobytes())
+    for h in range(H):
+        with open(os.path.join(tmp, "msa", "H%05d.01" % h), "wb") as f:
+            f.write(rows[h].tobytes() + b"\n")
+    return d, rows
+
+
+def check_outputs(tmp, d, rows, out="drlz", gap="gapless"):
+    sa = orc.sa_build(d)
+    parts = sorted(f for f in os.listdir(os.path.join(tmp, gap)) if f.startswith("part-"))
+    assert len(parts) == rows.shape[0] and os.path.exists(os.path.join(tmp, gap, "_SUCCESS"))
+    fasta = b"".join(open(os.path.join(tmp, gap, p), "rb").read() for p in parts)
+    expect = b""
+    for h in range(rows.shape[0]):
+        x = orc.strip_gaps(rows[h]).tobytes()
+        lz = open(os.path.join(tmp, out, "H%05d.01.lz" % h), "rb").read()
+        assert lz == orc.lz_bytes(orc.encode_literal(d, sa, x)[0])
+        assert len(lz) % 16 == 0
+        expect += b">H%05d.01\n" % h + x + b"\n"
+    assert fasta == expect            # getmerge order == sorted basenames (index_chr.sh:16,20)
+
+
+def test_single_rank_layout(tmp_path):
+    tmp = str(tmp_path)
+    d, rows = make_dataset(tmp)
+    rc = drz.main([tmp + "/radix", tmp + "/ref.txt", tmp + "/msa/*.01", "file:///", tmp + "/drlz", tmp + "/gapless"],
+                  parser=oracle_parser, rank=0, world=1, batch_bytes=5000)
+    assert rc == 0
+    check_outputs(tmp, d, rows)
+
+
+def test_shards_cover_everything():
+    for n in range(0, 40):
+        for w in (1, 2, 3, 8):
+            got = sum((drz.shard(list(range(n)), r, w) for r in range(w)), [])
+            assert got == list(range(n))
+
+
+def test_multiline_row_rejected(tmp_path):
+    p = tmp_path / "x.01"
+    p.write_bytes(b"ACGT\nACGT\n")
+    try:
+        drz.read_row(str(p))
+        assert False
+    except ValueError:
+        pass
+    assert drz.read_reference(str(p)) == b"ACGTACGT"
+
+
+WORKER = r'''
+import os, sys
+sys.path.insert(0, {root!r})
+import torch.distributed as dist
+from pangenspark_b200 import distributed_rlz as drz
+from tests.test_host_logic import oracle_parser
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=int(sys.argv[1]), world_size=2)
+tmp = {tmp!r}
+rc = drz.main([tmp + "/radix", tmp + "/ref.txt", tmp + "/msa/*.01", "", tmp + "/drlz", tmp + "/gapless"],
+              parser=oracle_parser, rank=dist.get_rank(), world=dist.get_world_size())
+dist.barrier()
+dist.destroy_process_group()
+sys.exit(rc)
+'''
+
+
+def test_world_size_2_gloo(tmp_path):
+    """Two ranks (gloo, CPU) shard the haplotypes; the union of their outputs equals the single-rank result."""
+    tmp = str(tmp_path)
+    d, rows = make_dataset(tmp, H=9)
+    script = os.path.join(tmp, "worker.py")
+    import random
+    port = 29500 + random.randint(0, 2000)
+    with open(script, "w") as f:
+        f.write(WORKER.format(root=ROOT, port=port, tmp=tmp))
+    procs = [subprocess.Popen([sys.executable, script, str(r)]) for r in range(2)]
+    for p in procs:
+        assert p.wait(timeout=300) == 0
+    check_outputs(tmp, d, rows)
