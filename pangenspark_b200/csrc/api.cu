@@ -57,7 +57,7 @@ struct drlz_ctx {
     double idx_ms[5] = {0, 0, 0, 0, 0};
     // batch scratch (grow-only)
     DevBuf stage[2], meta_dev, tile_cnt, tile_exc, tile_off, tile_excoff, pack_tmp, X, mdev, excoff, excpos, excbyte,
-        flags, haps, gapless, chunk_hap, first_pos, first_len, run_a, run_b, link_a, link_b, spec_cnt, spec_exit, alt_entry, alt_cnt, alt_exit, alt_round, counters, jump_a,
+        flags, haps, gapless, chunk_hap, first_pos, first_len, run_a, run_b, link_a, link_b, spec_cnt, spec_exit, alt_entry, alt_cnt, alt_exit, alt_round, alt_own, alt_merge, spec_ph, alt_ph, true_slot, counters, jump_a,
         jump_b, mark, true_cnt, true_entry, true_off, scan_tmp, hap_pairs, out, ms_a, ms_b;
     HostBuf meta_host, small_host;
     uint64_t exc_cap_hint = 0;
@@ -94,7 +94,7 @@ void drlz_destroy(drlz_ctx* c) {
     DevBuf* bufs[] = {&c->text, &c->sa, &c->tab, &c->isa, &c->lcp, &c->stage[0], &c->stage[1], &c->meta_dev, &c->tile_cnt,
                       &c->tile_exc, &c->tile_off, &c->tile_excoff, &c->pack_tmp, &c->X, &c->mdev, &c->excoff, &c->excpos,
                       &c->excbyte, &c->flags, &c->haps, &c->gapless, &c->chunk_hap, &c->first_pos, &c->first_len, &c->run_a, &c->run_b, &c->link_a, &c->link_b, &c->spec_cnt, &c->spec_exit,
-                      &c->alt_entry, &c->alt_cnt, &c->alt_exit, &c->alt_round, &c->counters, &c->jump_a, &c->jump_b,
+                      &c->alt_entry, &c->alt_cnt, &c->alt_exit, &c->alt_round, &c->alt_own, &c->alt_merge, &c->spec_ph, &c->alt_ph, &c->true_slot, &c->counters, &c->jump_a, &c->jump_b,
                       &c->mark, &c->true_cnt, &c->true_entry, &c->true_off, &c->scan_tmp, &c->hap_pairs, &c->out, &c->ms_a, &c->ms_b};
     for (DevBuf* b : bufs) b->release();
     c->meta_host.release(); c->small_host.release();
@@ -234,6 +234,9 @@ static int run_device_group(drlz_ctx* c, const uint8_t* rows_dev, const uint64_t
         CK(c, c->link_a.ensure((size_t)NC * 4 + 4)); CK(c, c->link_b.ensure((size_t)NC * 4 + 4));
         CK(c, c->chunk_hap.ensure((size_t)NC * 4 + 4)); CK(c, c->spec_cnt.ensure((size_t)NC * 4 + 4)); CK(c, c->spec_exit.ensure((size_t)NC * 4 + 4));
         CK(c, c->alt_entry.ensure(na * 4 + 4)); CK(c, c->alt_cnt.ensure(na * 4 + 4)); CK(c, c->alt_exit.ensure(na * 4 + 4));
+        CK(c, c->alt_own.ensure(na * 4 + 4)); CK(c, c->alt_merge.ensure(na * 4 + 4));
+        CK(c, c->spec_ph.ensure((size_t)NC * kSpecStore * 8 + 8)); CK(c, c->alt_ph.ensure(na * kAltStore * 8 + 8));
+        CK(c, c->true_slot.ensure((size_t)NC * 4 + 4));
         CK(c, c->alt_round.ensure(na * 4 + 4)); CK(c, c->counters.ensure(sizeof(uint32_t) * (2 + kMaxRounds)));
         CK(c, c->jump_a.ensure(nn * 4 + 4)); CK(c, c->jump_b.ensure(nn * 4 + 4)); CK(c, c->mark.ensure(nn + 4));
         CK(c, c->true_cnt.ensure((size_t)NC * 4 + 4)); CK(c, c->true_entry.ensure((size_t)NC * 4 + 4)); CK(c, c->true_off.ensure((size_t)NC * 8 + 8));
@@ -251,6 +254,9 @@ static int run_device_group(drlz_ctx* c, const uint8_t* rows_dev, const uint64_t
         pb.pv.spec_cnt = c->spec_cnt.as<uint32_t>(); pb.pv.spec_exit = c->spec_exit.as<uint32_t>();
         pb.pv.alt_entry = c->alt_entry.as<uint32_t>(); pb.pv.alt_cnt = c->alt_cnt.as<uint32_t>();
         pb.pv.alt_exit = c->alt_exit.as<uint32_t>(); pb.pv.alt_round = c->alt_round.as<uint32_t>();
+        pb.pv.alt_own = c->alt_own.as<uint32_t>(); pb.pv.alt_merge = c->alt_merge.as<uint32_t>();
+        pb.pv.spec_ph = c->spec_ph.as<uint2>(); pb.pv.alt_ph = c->alt_ph.as<uint2>();
+        pb.true_slot = c->true_slot.as<uint32_t>();
         pb.pv.counters = c->counters.as<uint32_t>();
         pb.H = H; pb.max_chunks_per_hap = maxc ? maxc : 1;
         pb.jump_a = c->jump_a.as<uint32_t>(); pb.jump_b = c->jump_b.as<uint32_t>(); pb.mark = c->mark.as<uint8_t>();

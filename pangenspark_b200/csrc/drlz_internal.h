@@ -61,6 +61,7 @@ struct ParseBuffers {
     uint8_t* mark;                // [NC*(kAltSlots+1)]
     uint32_t* true_cnt;           // [NC]
     uint32_t* true_entry;         // [NC]
+    uint32_t* true_slot;          // [NC] 0 = speculative record, 1+s = alternative record s
     uint64_t* true_off;           // [NC]
     uint64_t* scan_tmp;           // scan_tmp_elems(NC)
     uint64_t* hap_pairs;          // [H+1]: [h] phrases of haplotype h's start offset, [H] = total

@@ -27,11 +27,18 @@
 #define DRLZ_HD inline
 #endif
 
+#if !defined(__CUDACC__)
+struct uint2 { uint32_t x, y; };
+static inline uint2 make_uint2(uint32_t x, uint32_t y) { uint2 r; r.x = x; r.y = y; return r; }
+#endif
+
 namespace drlz {
 
 static const uint32_t kEmpty = 0xFFFFFFFFu;
 static const int kAltSlots = 3;           // alternative entry records per chunk (see parse pipeline)
 static const int kMaxRounds = 30;
+static const int kSpecStore = 16;         // phrases of a chunk's speculative parse kept for emission
+static const int kAltStore = 4;           // own phrases of an alternative record kept for emission
 
 DRLZ_HD int clz64(uint64_t v) {
 #if defined(__CUDA_ARCH__)
@@ -226,6 +233,10 @@ struct ParseView {
     uint32_t* alt_cnt;              // [NC*kAltSlots]
     uint32_t* alt_exit;             // [NC*kAltSlots]
     uint32_t* alt_round;            // [NC*kAltSlots] round in which the record must be fix-parsed
+    uint32_t* alt_own;              // [NC*kAltSlots] phrases before the merge point
+    uint32_t* alt_merge;            // [NC*kAltSlots] index into the speculative phrase list where the tail starts, kEmpty = no merge
+    uint2* spec_ph;                 // [NC*kSpecStore] (pos, len) of the first phrases of the speculative parse
+    uint2* alt_ph;                  // [NC*kAltSlots*kAltStore] own phrases of the alternative records
     uint32_t* counters;             // [0] overflow flag, [1 + r] records created for round r
 };
 
@@ -380,6 +391,7 @@ DRLZ_HD void spec_parse_chunk(const ParseView& pv, uint32_t g) {
     uint32_t cur = hv.n_exc ? exc_lower_bound(hv, i) : 0;
     while (i < e) {
         Match mt = chunk_step(pv, g, h, hv, s, i, &cur);
+        if (cnt < (uint32_t)kSpecStore) pv.spec_ph[(size_t)g * kSpecStore + cnt] = make_uint2(mt.pos, mt.len);
         ++cnt;
         i += mt.len ? mt.len : 1;
     }
@@ -409,9 +421,12 @@ DRLZ_HD void fix_parse_record(const ParseView& pv, uint32_t g, int slot, uint32_
         }
         if (iA == iB) { merged = true; break; }
         Match mt = phrase_at(pv, h, hv, iB, &curB);
+        if (cntB < (uint32_t)kAltStore) pv.alt_ph[(size_t)rid * kAltStore + cntB] = make_uint2(mt.pos, mt.len);
         ++cntB;
         iB += mt.len ? mt.len : 1;
     }
+    pv.alt_own[rid] = cntB;
+    pv.alt_merge[rid] = merged ? cntA : kEmpty;
     if (merged) {
         pv.alt_cnt[rid] = cntB + (pv.spec_cnt[g] - cntA);
         pv.alt_exit[rid] = pv.spec_exit[g];                  // already registered by P1
@@ -445,20 +460,45 @@ DRLZ_HD uint32_t node_succ(const ParseView& pv, uint32_t node) {
 }
 
 // E: after marking, pick the chunk's true record: returns phrase count, *entry = true entry position
-DRLZ_HD uint32_t chunk_true_record(const ParseView& pv, const uint8_t* mark, uint32_t g, uint32_t* entry) {
+// *slot = 0 for the speculative record, 1 + s for alternative record s
+DRLZ_HD uint32_t chunk_true_record(const ParseView& pv, const uint8_t* mark, uint32_t g, uint32_t* entry, uint32_t* slot) {
     uint32_t base = g * (kAltSlots + 1);
+    *slot = 0;
     if (mark[base]) {
         uint32_t h = pv.chunk_hap[g];
         *entry = (g - pv.hap_chunk_base[h]) * pv.chunk_bases;
         return pv.spec_cnt[g];
     }
     for (int s = 0; s < kAltSlots; ++s)
-        if (mark[base + 1 + s]) { *entry = pv.alt_entry[g * kAltSlots + s]; return pv.alt_cnt[g * kAltSlots + s]; }
+        if (mark[base + 1 + s]) { *entry = pv.alt_entry[g * kAltSlots + s]; *slot = 1 + s; return pv.alt_cnt[g * kAltSlots + s]; }
     *entry = 0;
     return 0;
 }
 
-// E: write `cnt` phrases of chunk g starting at `entry` as (int64 pos, int64 len) records
+DRLZ_HD void put_record(int64_t* out, uint32_t t, uint2 ph) {
+    out[2 * (uint64_t)t] = (int64_t)ph.x;
+    out[2 * (uint64_t)t + 1] = (int64_t)ph.y;
+}
+
+// E (fast path): copy the stored phrases of the true record; returns false if some were not stored
+DRLZ_HD bool emit_stored(const ParseView& pv, uint32_t g, uint32_t slot, uint32_t cnt, int64_t* out) {
+    const uint2* sp = pv.spec_ph + (size_t)g * kSpecStore;
+    if (slot == 0) {
+        if (cnt > (uint32_t)kSpecStore) return false;
+        for (uint32_t t = 0; t < cnt; ++t) put_record(out, t, sp[t]);
+        return true;
+    }
+    uint32_t rid = g * kAltSlots + slot - 1;
+    uint32_t own = pv.alt_own[rid], mg = pv.alt_merge[rid];
+    if (own > (uint32_t)kAltStore) return false;
+    if (mg != kEmpty && pv.spec_cnt[g] > (uint32_t)kSpecStore) return false;
+    const uint2* ap = pv.alt_ph + (size_t)rid * kAltStore;
+    for (uint32_t t = 0; t < own; ++t) put_record(out, t, ap[t]);
+    if (mg != kEmpty) for (uint32_t t = mg; t < pv.spec_cnt[g]; ++t) put_record(out, own + t - mg, sp[t]);
+    return true;
+}
+
+// E (slow path): write `cnt` phrases of chunk g starting at `entry` as (int64 pos, int64 len) records
 DRLZ_HD void emit_chunk(const ParseView& pv, uint32_t g, uint32_t entry, uint32_t cnt, int64_t* out) {
     uint32_t h = pv.chunk_hap[g];
     const HapView& hv = pv.haps[h];

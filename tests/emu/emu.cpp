@@ -69,10 +69,12 @@ int emu_parse(const uint8_t* ref, uint64_t n, const int64_t* sa64, int k, uint32
     std::vector<uint32_t> first_pos(NC), first_len(NC), run_a(NC), run_b(NC), link_a(NC), link_b(NC);
     std::vector<uint32_t> spec_cnt(NC), spec_exit(NC), alt_entry((size_t)NC * kAltSlots, kEmpty),
         alt_cnt((size_t)NC * kAltSlots, 0), alt_exit((size_t)NC * kAltSlots, 0), alt_round((size_t)NC * kAltSlots, 0),
-        counters(2 + kMaxRounds, 0);
+        counters(2 + kMaxRounds, 0), alt_own((size_t)NC * kAltSlots, 0), alt_merge((size_t)NC * kAltSlots, kEmpty);
+    std::vector<uint2> spec_ph((size_t)NC * kSpecStore), alt_ph((size_t)NC * kAltSlots * kAltStore);
     ParseView pv{ix, haps.data(), chunk_hap.data(), base.data(), chunk, NC, min_cap, foreign_cap,
                  first_pos.data(), first_len.data(), run_a.data(), link_a.data(), spec_cnt.data(), spec_exit.data(),
-                 alt_entry.data(), alt_cnt.data(), alt_exit.data(), alt_round.data(), counters.data()};
+                 alt_entry.data(), alt_cnt.data(), alt_exit.data(), alt_round.data(), alt_own.data(), alt_merge.data(),
+                 spec_ph.data(), alt_ph.data(), counters.data()};
     uint32_t maxc0 = 1;
     for (int h = 0; h < H; ++h) if (base[h + 1] - base[h] > maxc0) maxc0 = base[h + 1] - base[h];
     for (uint32_t g = 0; g < NC; ++g) first_phrase_chunk(pv, g);
@@ -106,10 +108,11 @@ int emu_parse(const uint8_t* ref, uint64_t n, const int64_t* sa64, int k, uint32
         jump.swap(jump2);
     }
     std::vector<uint64_t> off(NC + 1, 0);
-    std::vector<uint32_t> ent(NC), cnt(NC);
-    for (uint32_t g = 0; g < NC; ++g) { cnt[g] = chunk_true_record(pv, mark.data(), g, &ent[g]); off[g + 1] = off[g] + cnt[g]; }
+    std::vector<uint32_t> ent(NC), cnt(NC), slot(NC);
+    for (uint32_t g = 0; g < NC; ++g) { cnt[g] = chunk_true_record(pv, mark.data(), g, &ent[g], &slot[g]); off[g + 1] = off[g] + cnt[g]; }
     std::vector<int64_t> out(2 * off[NC] + 2);
-    for (uint32_t g = 0; g < NC; ++g) if (cnt[g]) emit_chunk(pv, g, ent[g], cnt[g], out.data() + 2 * off[g]);
+    for (uint32_t g = 0; g < NC; ++g)
+        if (cnt[g] && !emit_stored(pv, g, slot[g], cnt[g], out.data() + 2 * off[g])) emit_chunk(pv, g, ent[g], cnt[g], out.data() + 2 * off[g]);
     for (int h = 0; h < H; ++h) {
         uint64_t a = off[base[h]], b = off[base[h + 1]];
         npairs[h] = b - a;
