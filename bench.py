@@ -302,8 +302,7 @@ def run_ours(args):
     steps = args.steps
     Mtot, mtot = float(H) * M, float(bases)
     per_launch = {   # name: (avg ms per launch, algorithmic bytes per launch)
-        "k_pack_count": (kt["pack_count_ms"] / steps, Mtot),
-        "k_pack_write": (kt["pack_write_ms"] / steps, Mtot + mtot / 4),
+        "k_pack": (kt["pack_write_ms"] / steps, Mtot + mtot / 4),
         "k_first+k_link": (kt["first_ms"] / steps, 0.0),
         "k_spec": (kt["spec_ms"] / steps, mtot / 4),
         "k_fix": (kt["fix_ms"] / max(1.0, kt["fix_rounds"] - steps) if kt["fix_rounds"] > steps else 0.0, 0.0),

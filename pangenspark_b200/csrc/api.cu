@@ -50,23 +50,58 @@ struct drlz_ctx {
     cudaEvent_t ev_stage[11] = {};
     std::string err;
     // options
-    int opt_k = 0; uint32_t opt_chunk = 2048; uint32_t opt_min_cap = 64; uint32_t opt_foreign_cap = 1u << 20; uint64_t opt_group_bytes = 256ull << 20; int opt_lcp = 0;
+    int opt_k = 0; uint32_t opt_chunk = 2048; uint32_t opt_min_cap = 64; uint32_t opt_foreign_cap = 1u << 20; int opt_machine = 0; uint64_t opt_group_bytes = 256ull << 20; int opt_lcp = 0;
     // index
     bool have_index = false; uint64_t n = 0; int k = 0; int sa_rounds = 0;
-    DevBuf text, sa, tab, isa, lcp;
+    DevBuf blob, sa, isa, lcp;             // blob = [k-mer table | packed text] (one L2 access-policy window)
+    uint64_t* d_text = nullptr; uint32_t* d_tab = nullptr; size_t blob_bytes = 0;
+    cudaStream_t l2_stream = nullptr; int opt_l2persist = 0; int opt_occ = 16;
     double idx_ms[5] = {0, 0, 0, 0, 0};
     // batch scratch (grow-only)
-    DevBuf stage[2], meta_dev, tile_cnt, tile_exc, tile_off, tile_excoff, pack_tmp, X, mdev, excoff, excpos, excbyte,
+    DevBuf stage[2], meta_dev, desc_cnt, desc_exc, tile_counter, X, mdev, exccnt, excpos, excbyte,
         flags, haps, gapless, chunk_hap, first_pos, first_len, run_a, run_b, link_a, link_b, spec_cnt, spec_exit, alt_entry, alt_cnt, alt_exit, alt_round, alt_own, alt_merge, spec_ph, alt_ph, true_slot, counters, jump_a,
         jump_b, mark, true_cnt, true_entry, true_off, scan_tmp, hap_pairs, out, ms_a, ms_b;
     HostBuf meta_host, small_host;
-    uint64_t exc_cap_hint = 0;
+    uint64_t exc_stride_hint = 0;
     double parse_ms[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 };
 
 #define CK(ctx, x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { (ctx)->err = std::string(#x) + ": " + cudaGetErrorString(e_); return e_ == cudaErrorMemoryAllocation ? DRLZ_E_NOMEM : DRLZ_E_CUDA; } } while (0)
 
 static const uint64_t kMaxLen = 0xFFFFFFFFull - 1024;
+
+static cudaError_t alloc_index_blob(drlz_ctx* c, uint64_t n, int k) {
+    size_t tab_bytes = (((1ull << (2 * k)) + 1) * 4 + 255) & ~(size_t)255;
+    size_t text_bytes = (n / 32 + 3) * 8 + 64;
+    cudaError_t e = c->blob.ensure(tab_bytes + text_bytes);
+    if (e != cudaSuccess) return e;
+    c->d_tab = c->blob.as<uint32_t>();
+    c->d_text = reinterpret_cast<uint64_t*>(c->blob.as<uint8_t>() + tab_bytes);
+    c->blob_bytes = tab_bytes + text_bytes;
+    c->l2_stream = nullptr;
+    return cudaSuccess;
+}
+
+// keep the k-mer table and the packed reference resident in L2 while haplotype data streams through
+static void apply_l2_policy(drlz_ctx* c) {
+    if (!c->opt_l2persist || !c->blob.p || c->l2_stream == c->stream) return;
+    int max_persist = 0, max_window = 0;
+    cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, c->device);
+    cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, c->device);
+    if (max_persist <= 0 || max_window <= 0) return;
+    size_t want = c->blob_bytes < (size_t)max_persist ? c->blob_bytes : (size_t)max_persist;
+    cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+    cudaStreamAttrValue attr;
+    memset(&attr, 0, sizeof attr);
+    size_t win = c->blob_bytes < (size_t)max_window ? c->blob_bytes : (size_t)max_window;
+    attr.accessPolicyWindow.base_ptr = c->blob.p;
+    attr.accessPolicyWindow.num_bytes = win;
+    attr.accessPolicyWindow.hitRatio = win <= want ? 1.0f : (float)((double)want / (double)win);
+    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+    c->l2_stream = c->stream;
+}
 
 extern "C" {
 
@@ -91,8 +126,8 @@ void drlz_destroy(drlz_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
-    DevBuf* bufs[] = {&c->text, &c->sa, &c->tab, &c->isa, &c->lcp, &c->stage[0], &c->stage[1], &c->meta_dev, &c->tile_cnt,
-                      &c->tile_exc, &c->tile_off, &c->tile_excoff, &c->pack_tmp, &c->X, &c->mdev, &c->excoff, &c->excpos,
+    DevBuf* bufs[] = {&c->blob, &c->sa, &c->isa, &c->lcp, &c->stage[0], &c->stage[1], &c->meta_dev, &c->desc_cnt,
+                      &c->desc_exc, &c->tile_counter, &c->X, &c->mdev, &c->exccnt, &c->excpos,
                       &c->excbyte, &c->flags, &c->haps, &c->gapless, &c->chunk_hap, &c->first_pos, &c->first_len, &c->run_a, &c->run_b, &c->link_a, &c->link_b, &c->spec_cnt, &c->spec_exit,
                       &c->alt_entry, &c->alt_cnt, &c->alt_exit, &c->alt_round, &c->alt_own, &c->alt_merge, &c->spec_ph, &c->alt_ph, &c->true_slot, &c->counters, &c->jump_a, &c->jump_b,
                       &c->mark, &c->true_cnt, &c->true_entry, &c->true_off, &c->scan_tmp, &c->hap_pairs, &c->out, &c->ms_a, &c->ms_b};
@@ -119,6 +154,9 @@ int drlz_set_option(drlz_ctx* c, const char* key, int64_t v) {
     else if (!strcmp(key, "chunk")) { if (v < 0 || v > 0x7FFFFFFF) return DRLZ_E_ARG; c->opt_chunk = v ? (uint32_t)v : 2048; }
     else if (!strcmp(key, "group_bytes")) { if (v < 0) return DRLZ_E_ARG; c->opt_group_bytes = v ? (uint64_t)v : (256ull << 20); }
     else if (!strcmp(key, "lcp")) c->opt_lcp = v != 0;
+    else if (!strcmp(key, "machine")) c->opt_machine = v != 0;
+    else if (!strcmp(key, "l2persist")) { c->opt_l2persist = v != 0; c->l2_stream = nullptr; }
+    else if (!strcmp(key, "occ")) c->opt_occ = (int)v;
     else if (!strcmp(key, "min_cap")) { if (v < 0 || v > 0x7FFFFFFF) return DRLZ_E_ARG; c->opt_min_cap = v ? (uint32_t)v : 64; }
     else if (!strcmp(key, "foreign_cap")) { if (v < 0 || v > 0x7FFFFFFF) return DRLZ_E_ARG; c->opt_foreign_cap = v ? (uint32_t)v : (1u << 20); }
     else return DRLZ_E_ARG;
@@ -145,6 +183,7 @@ static int run_device_group(drlz_ctx* c, const uint8_t* rows_dev, const uint64_t
     cudaStream_t s = c->stream;
     *total_pairs = 0;
     if (H == 0) return DRLZ_OK;
+    apply_l2_policy(c);
     if (H > 65535) { c->err = "more than 65535 rows in one device group"; return DRLZ_E_LIMIT; }
     uint64_t maxcols = 0, sumcols = 0;
     for (uint32_t h = 0; h < H; ++h) {
@@ -174,26 +213,24 @@ static int run_device_group(drlz_ctx* c, const uint8_t* rows_dev, const uint64_t
         h_goff[h] = gbytes; gbytes += (cols[h] + 15) & ~15ull;
         if (gapless_off_out) gapless_off_out[h] = h_goff[h];
     }
-    CK(c, c->small_host.ensure(sizeof(uint64_t) * (2 * (size_t)H + 8) + sizeof(uint32_t) * (4 + kMaxRounds)));
+    CK(c, c->small_host.ensure(sizeof(uint64_t) * (3 * (size_t)H + 8) + sizeof(uint32_t) * (4 + kMaxRounds)));
     uint64_t* sh_m = c->small_host.as<uint64_t>();            // [H]
     uint64_t* sh_pairs = sh_m + H;                            // [H+1]
     uint64_t* sh_total = sh_pairs + H + 1;                    // [1]
-    uint64_t* sh_excoff = sh_total + 1;                       // [1] total exceptions
-    uint32_t* sh_flags = reinterpret_cast<uint32_t*>(sh_excoff + 1);   // [1] (+1 pad)
+    uint64_t* sh_exccnt = sh_total + 1;                       // [H] exceptions per row
+    uint32_t* sh_flags = reinterpret_cast<uint32_t*>(sh_exccnt + H);   // [1] (+1 pad)
     uint32_t* sh_counters = sh_flags + 2;                     // [2 + kMaxRounds]
 
-    CK(c, c->tile_cnt.ensure(nt * 4)); CK(c, c->tile_exc.ensure(nt * 4));
-    CK(c, c->tile_off.ensure(nt * 8)); CK(c, c->tile_excoff.ensure(nt * 8));
-    CK(c, c->pack_tmp.ensure(scan_tmp_elems(nt) * 8 * 2));
+    CK(c, c->desc_cnt.ensure(nt * 8)); CK(c, c->desc_exc.ensure(nt * 8)); CK(c, c->tile_counter.ensure(16));
     CK(c, c->X.ensure(xwords * 8));
-    CK(c, c->mdev.ensure((size_t)H * 8)); CK(c, c->excoff.ensure(((size_t)H + 1) * 8));
+    CK(c, c->mdev.ensure((size_t)H * 8)); CK(c, c->exccnt.ensure(((size_t)H + 1) * 8));
     CK(c, c->flags.ensure(16)); CK(c, c->haps.ensure((size_t)H * sizeof(HapView)));
     if (want_gapless) CK(c, c->gapless.ensure(gbytes + 16));
-    if (c->exc_cap_hint < sumcols / 256 + 1024) c->exc_cap_hint = sumcols / 256 + 1024;
+    if (c->exc_stride_hint < maxcols / 256 + 256) c->exc_stride_hint = maxcols / 256 + 256;
 
     for (int attempt = 0; attempt < 4; ++attempt) {
-        uint64_t exc_cap = c->exc_cap_hint;
-        CK(c, c->excpos.ensure(exc_cap * 4)); CK(c, c->excbyte.ensure(exc_cap));
+        uint64_t exc_stride = c->exc_stride_hint;
+        CK(c, c->excpos.ensure(exc_stride * H * 4)); CK(c, c->excbyte.ensure(exc_stride * H));
         // chunk layout (upper bound from cols; chunks past the gapless length stay empty)
         uint64_t NC64 = 0; uint32_t maxc = 0;
         for (uint32_t h = 0; h < H; ++h) {
@@ -217,16 +254,15 @@ static int run_device_group(drlz_ctx* c, const uint8_t* rows_dev, const uint64_t
         cudaEventRecord(c->ev_stage[1], s);
         PackJob job;
         job.rows = rows_dev; job.row_off = d_row_off; job.cols = d_cols; job.H = H; job.tiles_per_row = T; job.strip = strip;
-        job.tile_cnt = c->tile_cnt.as<uint32_t>(); job.tile_exc = c->tile_exc.as<uint32_t>();
-        job.tile_off = c->tile_off.as<uint64_t>(); job.tile_excoff = c->tile_excoff.as<uint64_t>();
-        job.scan_tmp = c->pack_tmp.as<uint64_t>(); job.X = c->X.as<uint64_t>(); job.xoff = d_xoff;
-        job.m_out = c->mdev.as<uint64_t>(); job.exc_off = c->excoff.as<uint64_t>();
-        job.exc_pos = c->excpos.as<uint32_t>(); job.exc_byte = c->excbyte.as<uint8_t>(); job.exc_cap = exc_cap;
+        job.desc_cnt = c->desc_cnt.as<uint64_t>(); job.desc_exc = c->desc_exc.as<uint64_t>();
+        job.tile_counter = c->tile_counter.as<uint32_t>(); job.X = c->X.as<uint64_t>(); job.xoff = d_xoff;
+        job.m_out = c->mdev.as<uint64_t>(); job.exc_cnt = c->exccnt.as<uint64_t>();
+        job.exc_pos = c->excpos.as<uint32_t>(); job.exc_byte = c->excbyte.as<uint8_t>(); job.exc_stride = exc_stride;
         job.flags = c->flags.as<uint32_t>();
         job.gapless = want_gapless ? c->gapless.as<uint8_t>() : nullptr; job.gapless_off = d_goff;
         launch_pack(job, s, &c->ev_stage[2]);                            // ev 2,3,4
         launch_make_hapviews(c->haps.as<HapView>(), c->X.as<uint64_t>(), d_xoff, c->mdev.as<uint64_t>(), c->excpos.as<uint32_t>(),
-                             c->excbyte.as<uint8_t>(), c->excoff.as<uint64_t>(), H, s);
+                             c->excbyte.as<uint8_t>(), c->exccnt.as<uint64_t>(), exc_stride, H, s);
 
         size_t nn = (size_t)NC * (kAltSlots + 1), na = (size_t)NC * kAltSlots;
         CK(c, c->first_pos.ensure((size_t)NC * 4 + 4)); CK(c, c->first_len.ensure((size_t)NC * 4 + 4));
@@ -244,7 +280,7 @@ static int run_device_group(drlz_ctx* c, const uint8_t* rows_dev, const uint64_t
         launch_fill_chunk_hap(c->chunk_hap.as<uint32_t>(), d_base, H, NC, s);
 
         ParseBuffers pb;
-        pb.pv.ix = IndexView{c->text.as<uint64_t>(), c->sa.as<uint32_t>(), c->tab.as<uint32_t>(), c->n, c->k};
+        pb.pv.ix = IndexView{c->d_text, c->sa.as<uint32_t>(), c->d_tab, c->n, c->k};
         pb.pv.haps = c->haps.as<HapView>(); pb.pv.chunk_hap = c->chunk_hap.as<uint32_t>(); pb.pv.hap_chunk_base = d_base;
         pb.pv.chunk_bases = Ceff; pb.pv.n_chunks = NC;
         pb.pv.min_cap = single_chunk ? 0xFFFFFFFFu : c->opt_min_cap; pb.pv.foreign_cap = c->opt_foreign_cap;
@@ -258,7 +294,7 @@ static int run_device_group(drlz_ctx* c, const uint8_t* rows_dev, const uint64_t
         pb.pv.spec_ph = c->spec_ph.as<uint2>(); pb.pv.alt_ph = c->alt_ph.as<uint2>();
         pb.true_slot = c->true_slot.as<uint32_t>();
         pb.pv.counters = c->counters.as<uint32_t>();
-        pb.H = H; pb.max_chunks_per_hap = maxc ? maxc : 1;
+        pb.H = H; pb.max_chunks_per_hap = maxc ? maxc : 1; pb.use_machine = c->opt_machine; pb.occ = c->opt_occ;
         pb.jump_a = c->jump_a.as<uint32_t>(); pb.jump_b = c->jump_b.as<uint32_t>(); pb.mark = c->mark.as<uint8_t>();
         pb.true_cnt = c->true_cnt.as<uint32_t>(); pb.true_entry = c->true_entry.as<uint32_t>(); pb.true_off = c->true_off.as<uint64_t>();
         pb.scan_tmp = c->scan_tmp.as<uint64_t>(); pb.hap_pairs = c->hap_pairs.as<uint64_t>();
@@ -277,11 +313,13 @@ static int run_device_group(drlz_ctx* c, const uint8_t* rows_dev, const uint64_t
         cudaEventRecord(c->ev_stage[10], s);
         CK(c, cudaMemcpyAsync(sh_m, c->mdev.p, (size_t)H * 8, cudaMemcpyDeviceToHost, s));
         CK(c, cudaMemcpyAsync(sh_pairs, c->hap_pairs.p, ((size_t)H + 1) * 8, cudaMemcpyDeviceToHost, s));
-        CK(c, cudaMemcpyAsync(sh_excoff, c->excoff.as<uint64_t>() + H, 8, cudaMemcpyDeviceToHost, s));
+        CK(c, cudaMemcpyAsync(sh_exccnt, c->exccnt.p, (size_t)H * 8, cudaMemcpyDeviceToHost, s));
         CK(c, cudaMemcpyAsync(sh_flags, c->flags.p, 4, cudaMemcpyDeviceToHost, s));
         CK(c, cudaStreamSynchronize(s));
         if (*sh_flags & 1u) {           // exception list overflowed: grow and redo the group
-            c->exc_cap_hint = *sh_excoff + *sh_excoff / 8 + 1024;
+            uint64_t mx = 0;
+            for (uint32_t h = 0; h < H; ++h) if (sh_exccnt[h] > mx) mx = sh_exccnt[h];
+            c->exc_stride_hint = mx + mx / 8 + 1024;
             continue;
         }
         for (uint32_t h = 0; h < H; ++h) {
@@ -308,8 +346,8 @@ extern "C" {
 // ---------------------------------------------------------------------------------------------------
 static int auto_k(uint64_t n) {
     int k = 1;
-    while (k < 13 && (1ull << (2 * (k + 1))) <= n) ++k;    // largest k with 4^k <= n, capped at 13
-    return k;
+    while (k < 14 && (1ull << (2 * k)) < n / 2) ++k;       // smallest k with 4^k >= n/2 (about one suffix per table
+    return k;                                             // slot; measured best on B200), capped at 14 (1 GiB table)
 }
 
 int drlz_build_index(drlz_ctx* c, const uint8_t* ref, uint64_t n) {
@@ -325,7 +363,8 @@ int drlz_build_index(drlz_ctx* c, const uint8_t* ref, uint64_t n) {
     CK(c, c->stage[0].ensure(padded));
     if (n) CK(c, cudaMemcpyAsync(c->stage[0].p, ref, n, cudaMemcpyHostToDevice, s));
     uint64_t words = n / 32 + 3;
-    CK(c, c->text.ensure(words * 8));
+    int k = c->opt_k ? c->opt_k : auto_k(n);
+    CK(c, alloc_index_blob(c, n, k));
     CK(c, c->sa.ensure(n * 4 + 4));
     CK(c, c->isa.ensure(n * 4 + 4));
     cudaEventRecord(e[0], s);
@@ -334,48 +373,43 @@ int drlz_build_index(drlz_ctx* c, const uint8_t* ref, uint64_t n) {
     // pack through the generic group path needs an index view only for parsing; call the pack pieces directly
     {
         uint32_t T = (uint32_t)((n + kPackTileBytes - 1) / kPackTileBytes); if (!T) T = 1;
-        CK(c, c->tile_cnt.ensure((size_t)T * 4)); CK(c, c->tile_exc.ensure((size_t)T * 4));
-        CK(c, c->tile_off.ensure((size_t)T * 8)); CK(c, c->tile_excoff.ensure((size_t)T * 8));
-        CK(c, c->pack_tmp.ensure(scan_tmp_elems(T) * 8 * 2));
-        CK(c, c->mdev.ensure(8)); CK(c, c->excoff.ensure(16)); CK(c, c->flags.ensure(16));
+        CK(c, c->desc_cnt.ensure((size_t)T * 8)); CK(c, c->desc_exc.ensure((size_t)T * 8)); CK(c, c->tile_counter.ensure(16));
+        CK(c, c->mdev.ensure(8)); CK(c, c->exccnt.ensure(16)); CK(c, c->flags.ensure(16));
         CK(c, c->excpos.ensure(64 * 4)); CK(c, c->excbyte.ensure(64));
         CK(c, c->meta_host.ensure(64)); CK(c, c->meta_dev.ensure(64));
         CK(c, c->small_host.ensure(64));
         uint64_t* mh = c->meta_host.as<uint64_t>();
         mh[0] = 0; mh[1] = n; mh[2] = 0; mh[3] = 0;
         CK(c, cudaMemcpyAsync(c->meta_dev.p, mh, 32, cudaMemcpyHostToDevice, s));
-        CK(c, cudaMemsetAsync(c->text.p, 0, words * 8, s));
+        CK(c, cudaMemsetAsync(c->d_text, 0, words * 8, s));
         CK(c, cudaMemsetAsync(c->flags.p, 0, 16, s));
         PackJob job;
         const uint64_t* dm = c->meta_dev.as<uint64_t>();
         job.rows = c->stage[0].as<uint8_t>(); job.row_off = dm; job.cols = dm + 1; job.H = 1; job.tiles_per_row = T; job.strip = 0;
-        job.tile_cnt = c->tile_cnt.as<uint32_t>(); job.tile_exc = c->tile_exc.as<uint32_t>();
-        job.tile_off = c->tile_off.as<uint64_t>(); job.tile_excoff = c->tile_excoff.as<uint64_t>();
-        job.scan_tmp = c->pack_tmp.as<uint64_t>(); job.X = c->text.as<uint64_t>(); job.xoff = dm + 2;
-        job.m_out = c->mdev.as<uint64_t>(); job.exc_off = c->excoff.as<uint64_t>();
-        job.exc_pos = c->excpos.as<uint32_t>(); job.exc_byte = c->excbyte.as<uint8_t>(); job.exc_cap = 64;
+        job.desc_cnt = c->desc_cnt.as<uint64_t>(); job.desc_exc = c->desc_exc.as<uint64_t>();
+        job.tile_counter = c->tile_counter.as<uint32_t>(); job.X = c->d_text; job.xoff = dm + 2;
+        job.m_out = c->mdev.as<uint64_t>(); job.exc_cnt = c->exccnt.as<uint64_t>();
+        job.exc_pos = c->excpos.as<uint32_t>(); job.exc_byte = c->excbyte.as<uint8_t>(); job.exc_stride = 64;
         job.flags = c->flags.as<uint32_t>(); job.gapless = nullptr; job.gapless_off = dm + 3;
         launch_pack(job, s, nullptr);
         uint64_t* sh = c->small_host.as<uint64_t>();
-        CK(c, cudaMemcpyAsync(sh, c->excoff.as<uint64_t>() + 1, 8, cudaMemcpyDeviceToHost, s));
+        CK(c, cudaMemcpyAsync(sh, c->exccnt.p, 8, cudaMemcpyDeviceToHost, s));
         CK(c, cudaStreamSynchronize(s));
         if (sh[0] != 0) { c->err = "reference contains bytes outside {A,C,G,T}"; for (int i = 0; i < 5; ++i) cudaEventDestroy(e[i]); return DRLZ_E_ALPHABET; }
     }
     (void)off0; (void)m; (void)np; (void)tot;
     cudaEventRecord(e[1], s);
     char ebuf[256]; ebuf[0] = 0;
-    int rc = build_suffix_array(c->text.as<uint64_t>(), n, c->sa.as<uint32_t>(), c->isa.as<uint32_t>(), s, &c->sa_rounds, ebuf, sizeof ebuf);
+    int rc = build_suffix_array(c->d_text, n, c->sa.as<uint32_t>(), c->isa.as<uint32_t>(), s, &c->sa_rounds, ebuf, sizeof ebuf);
     if (rc != 0) { c->err = std::string("suffix array: ") + ebuf; for (int i = 0; i < 5; ++i) cudaEventDestroy(e[i]); return rc == (int)cudaErrorMemoryAllocation ? DRLZ_E_NOMEM : DRLZ_E_CUDA; }
     cudaEventRecord(e[2], s);
-    int k = c->opt_k ? c->opt_k : auto_k(n);
-    uint64_t tcnt = (1ull << (2 * k)) + 1;
-    CK(c, c->tab.ensure(tcnt * 4));
-    rc = build_kmer_table(c->text.as<uint64_t>(), n, c->sa.as<uint32_t>(), k, c->tab.as<uint32_t>(), s);
+
+    rc = build_kmer_table(c->d_text, n, c->sa.as<uint32_t>(), k, c->d_tab, s);
     if (rc != 0) { c->err = "k-mer table build failed"; for (int i = 0; i < 5; ++i) cudaEventDestroy(e[i]); return DRLZ_E_CUDA; }
     cudaEventRecord(e[3], s);
     if (c->opt_lcp) {
         CK(c, c->lcp.ensure(n * 4 + 4));
-        rc = build_lcp(c->text.as<uint64_t>(), n, c->sa.as<uint32_t>(), c->isa.as<uint32_t>(), c->lcp.as<uint32_t>(), s);
+        rc = build_lcp(c->d_text, n, c->sa.as<uint32_t>(), c->isa.as<uint32_t>(), c->lcp.as<uint32_t>(), s);
         if (rc != 0) { c->err = "lcp build failed"; for (int i = 0; i < 5; ++i) cudaEventDestroy(e[i]); return DRLZ_E_CUDA; }
     }
     cudaEventRecord(e[4], s);
@@ -401,8 +435,8 @@ int drlz_index_get(drlz_ctx* c, int what, void* host_out, uint64_t bytes) {
         case 0: src = c->sa.p; need = c->n * 4; break;
         case 1: src = c->isa.p; need = c->n * 4; if (!c->isa.p) return DRLZ_E_STATE; break;
         case 2: if (!c->opt_lcp || !c->lcp.p) { c->err = "lcp not built (option lcp=1)"; return DRLZ_E_STATE; } src = c->lcp.p; need = c->n * 4; break;
-        case 3: src = c->tab.p; need = ((1ull << (2 * c->k)) + 1) * 4; break;
-        case 4: src = c->text.p; need = ((c->n + 31) / 32) * 8; break;
+        case 3: src = c->d_tab; need = ((1ull << (2 * c->k)) + 1) * 4; break;
+        case 4: src = c->d_text; need = ((c->n + 31) / 32) * 8; break;
         default: return DRLZ_E_ARG;
     }
     if (bytes < need) { c->err = "host buffer too small"; return DRLZ_E_NOSPACE; }
@@ -429,10 +463,9 @@ int drlz_index_reserve(drlz_ctx* c, uint64_t n, int k) {
     if (n > kMaxLen) return DRLZ_E_LIMIT;
     CK(c, cudaSetDevice(c->device));
     c->have_index = false;
-    CK(c, c->text.ensure((n / 32 + 3) * 8));
+    CK(c, alloc_index_blob(c, n, k));
     CK(c, c->sa.ensure(n * 4 + 4));
-    CK(c, c->tab.ensure(((1ull << (2 * k)) + 1) * 4));
-    CK(c, cudaMemsetAsync(c->text.p, 0, (n / 32 + 3) * 8, c->stream));
+    CK(c, cudaMemsetAsync(c->d_text, 0, (n / 32 + 3) * 8, c->stream));
     CK(c, cudaStreamSynchronize(c->stream));
     c->n = n; c->k = k;
     return DRLZ_OK;
@@ -440,16 +473,16 @@ int drlz_index_reserve(drlz_ctx* c, uint64_t n, int k) {
 
 int drlz_index_buffers(drlz_ctx* c, void* dev_ptrs[3], uint64_t bytes[3]) {
     if (!c || !dev_ptrs || !bytes) return DRLZ_E_ARG;
-    if (!c->text.p || !c->tab.p) { c->err = "no index buffers (build or reserve first)"; return DRLZ_E_STATE; }
-    dev_ptrs[0] = c->text.p; bytes[0] = (c->n / 32 + 3) * 8;
+    if (!c->d_text || !c->d_tab) { c->err = "no index buffers (build or reserve first)"; return DRLZ_E_STATE; }
+    dev_ptrs[0] = c->d_text; bytes[0] = (c->n / 32 + 3) * 8;
     dev_ptrs[1] = c->sa.p; bytes[1] = c->n * 4;
-    dev_ptrs[2] = c->tab.p; bytes[2] = ((1ull << (2 * c->k)) + 1) * 4;
+    dev_ptrs[2] = c->d_tab; bytes[2] = ((1ull << (2 * c->k)) + 1) * 4;
     return DRLZ_OK;
 }
 
 int drlz_index_commit(drlz_ctx* c) {
     if (!c) return DRLZ_E_ARG;
-    if (!c->text.p || !c->tab.p) return DRLZ_E_STATE;
+    if (!c->d_text || !c->d_tab) return DRLZ_E_STATE;
     c->have_index = true;
     return DRLZ_OK;
 }
@@ -580,11 +613,11 @@ int drlz_matching_stats(drlz_ctx* c, const uint8_t* x, uint64_t m, uint32_t* ms_
     int rc = run_device_group(c, c->stage[0].as<uint8_t>(), &off, &m, 1, 0, false, &mm, &np, &total, nullptr);
     if (rc != DRLZ_OK) return rc;
     uint64_t* sh = c->small_host.as<uint64_t>();
-    CK(c, cudaMemcpyAsync(sh, c->excoff.as<uint64_t>() + 1, 8, cudaMemcpyDeviceToHost, s));
+    CK(c, cudaMemcpyAsync(sh, c->exccnt.p, 8, cudaMemcpyDeviceToHost, s));
     CK(c, cudaStreamSynchronize(s));
     if (sh[0] != 0) { c->err = "sequence contains bytes outside {A,C,G,T}"; return DRLZ_E_ALPHABET; }
     CK(c, c->ms_a.ensure(m * 4)); CK(c, c->ms_b.ensure(m * 4));
-    IndexView ix{c->text.as<uint64_t>(), c->sa.as<uint32_t>(), c->tab.as<uint32_t>(), c->n, c->k};
+    IndexView ix{c->d_text, c->sa.as<uint32_t>(), c->d_tab, c->n, c->k};
     launch_ms_dense(ix, c->X.as<uint64_t>(), m, c->ms_a.as<uint32_t>(), c->ms_b.as<uint32_t>(), s);
     CK(c, cudaMemcpyAsync(ms_out, c->ms_a.p, m * 4, cudaMemcpyDeviceToHost, s));
     CK(c, cudaMemcpyAsync(pos_out, c->ms_b.p, m * 4, cudaMemcpyDeviceToHost, s));

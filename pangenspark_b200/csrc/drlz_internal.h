@@ -8,7 +8,7 @@ namespace drlz {
 
 extern unsigned long long g_launches;
 
-static const int kPackTileBytes = 4096;      // MSA bytes per CTA in the strip/pack kernels
+static const int kPackTileBytes = 16384;     // MSA bytes per CTA in the strip/pack kernel (256 threads x 64 B)
 
 // ---- strip + pack (pack.cu) --------------------------------------------------------------------
 struct PackJob {
@@ -19,23 +19,21 @@ struct PackJob {
     uint32_t H;
     uint32_t tiles_per_row;       // ceil(max cols / kPackTileBytes)
     int strip;                    // 1: '-' is a gap column (DistributedRLZ.scala:72,86); 0: keep it (a literal)
-    uint32_t* tile_cnt;           // [H*tiles_per_row] non-gap bytes per tile
-    uint32_t* tile_exc;           // [H*tiles_per_row] non-ACGT non-gap bytes per tile
-    uint64_t* tile_off;           // [H*tiles_per_row] exclusive prefix of tile_cnt over the whole batch
-    uint64_t* tile_excoff;        // same for tile_exc
-    uint64_t* scan_tmp;           // scan_tmp_elems(H*tiles_per_row) * 2
+    uint64_t* desc_cnt;           // [H*tiles_per_row] look-back descriptors: non-gap bytes   (zeroed by launch_pack)
+    uint64_t* desc_exc;           // [H*tiles_per_row] look-back descriptors: exceptions
+    uint32_t* tile_counter;       // [1] dynamic tile ids
     uint64_t* X;                  // packed output, zero-filled by the caller
     const uint64_t* xoff;         // [H] word offset of haplotype h inside X (device)
     uint64_t* m_out;              // [H] gapless lengths (device)
-    uint64_t* exc_off;            // [H+1] exception offsets (device)
-    uint32_t* exc_pos;            // [exc_cap]
-    uint8_t* exc_byte;            // [exc_cap]
-    uint64_t exc_cap;
-    uint32_t* flags;              // bit 0: exception capacity exceeded
+    uint64_t* exc_cnt;            // [H] exceptions per row (device)
+    uint32_t* exc_pos;            // [H*exc_stride] row h owns [h*exc_stride, (h+1)*exc_stride)
+    uint8_t* exc_byte;            // [H*exc_stride]
+    uint64_t exc_stride;
+    uint32_t* flags;              // bit 0: a row has more exceptions than exc_stride
     uint8_t* gapless;             // optional gapless bytes out (device) or null
     const uint64_t* gapless_off;  // [H] byte offsets into gapless
 };
-// ev (nullable): 3 events recorded after the count kernel, after the scans, after the write kernel
+// ev (nullable): 3 events: [0],[1] before the kernel, [2] after it
 void launch_pack(const PackJob& job, cudaStream_t s, cudaEvent_t* ev);
 
 // ---- suffix array + k-mer table (sa_build.cu) ---------------------------------------------------
@@ -54,6 +52,8 @@ struct ParseBuffers {
     ParseView pv;                 // device pointers (see rlz_core.cuh)
     uint32_t H;
     uint32_t max_chunks_per_hap;
+    int occ;                      // 0: default register budget, 16: 32 registers per thread (max occupancy)
+    int use_machine;              // 1: k_chunk_machine kernels, 0: scalar thread-per-chunk kernels
     uint32_t* link_b;             // [NC] second buffers of the list ranking
     uint32_t* run_b;              // [NC]
     uint32_t* jump_a;             // [NC*(kAltSlots+1)]
@@ -76,8 +76,8 @@ int parse_stage_count(ParseBuffers& pb, cudaStream_t s, int* rounds_out, cudaEve
 void parse_stage_emit(ParseBuffers& pb, int64_t* out, cudaStream_t s);
 
 void launch_make_hapviews(HapView* haps, const uint64_t* X, const uint64_t* xoff, const uint64_t* m,
-                          const uint32_t* exc_pos, const uint8_t* exc_byte, const uint64_t* exc_off, uint32_t H,
-                          cudaStream_t s);
+                          const uint32_t* exc_pos, const uint8_t* exc_byte, const uint64_t* exc_cnt, uint64_t exc_stride,
+                          uint32_t H, cudaStream_t s);
 
 }  // namespace drlz
 

@@ -1,17 +1,17 @@
-// pack.cu -- gap strip + 2-bit pack + exception list for MSA rows (DistributedRLZ.scala:72,86).
+// pack.cu -- gap strip + 2-bit pack + exception list for MSA rows (DistributedRLZ.scala:72,86), one pass.
 //
 // A row is a gapped MSA line; every '-' is removed (stream compaction) and the remaining bases are packed
 // 2 bits each, 32 per 64-bit word, first base in the top bits.  Bytes outside {A,C,G,T} are stored as code 0
-// and listed (position, byte) in a sorted exception list -- they become literal phrases.
+// and listed (position, byte) in a sorted per-row exception list -- they become literal phrases.
 //
-//   k_pack_count : one CTA per 4096-byte tile; 16 bytes per thread (one 128-bit load);
-//                  SIMD-in-register validity test handles the all-ACGT case in ~10 integer ops per 4 bytes
-//   device_scan  : tile counts -> output base offsets (whole batch at once)
-//   k_pack_write : same tiling; block scan of per-thread counts, bases assembled in a shared-memory bit
-//                  buffer, then written as aligned 64-bit words (interior words plain stores, the two
-//                  boundary words OR-ed atomically into the zero-filled output)
-// HBM traffic: 2 * M read (count + write pass) + m/4 written; a single-pass chained-scan variant is the
-// obvious next step.
+// k_pack: one CTA per 16 KB tile, 64 bytes per thread (four 128-bit loads).  The tile's output offset (number of
+// non-gap bytes before it in the row) comes from a decoupled look-back over per-tile descriptors
+// {status:2, value:62} in the same kernel (tiles take their ids from an atomic counter, so every predecessor is
+// already running): the MSA bytes are read from HBM exactly once.  ACGT validation and code extraction are
+// SIMD-in-register (~15 integer ops per 4 bytes).  Tiles without gaps or foreign bytes (the common case) assemble
+// their 64-bit output words in registers with one shuffle; other tiles go through a shared-memory bit buffer.
+// The first / last partially covered output word of a tile is OR-ed atomically into the zero-filled output.
+// HBM traffic = M read + m/4 written (+ m/4 zero fill): the algorithmic bytes of SURVEY.md 8(d).
 #include "drlz_internal.h"
 #include "scan.cuh"
 
@@ -64,101 +64,176 @@ __device__ __forceinline__ Seg16 classify16(uint4 v, int nvalid, int strip) {
     return s;
 }
 
-__global__ void __launch_bounds__(256) k_pack_count(PackJob job) {
-    uint32_t h = blockIdx.y, t = blockIdx.x;
-    uint64_t cols = job.cols[h];
-    uint64_t off = (uint64_t)t * kPackTileBytes + (uint64_t)threadIdx.x * 16;
-    uint32_t packed = 0;
-    if (off < cols) {
-        int nvalid = cols - off >= 16 ? 16 : (int)(cols - off);
-        Seg16 s = classify16(load16(job.rows + job.row_off[h] + off), nvalid, job.strip);
-        packed = s.cnt | (s.exc << 16);
+static const uint64_t kDescAgg = 1ull << 62, kDescPrefix = 2ull << 62, kDescMask = (1ull << 62) - 1;
+
+__device__ __forceinline__ uint64_t ld_desc(const uint64_t* p) { return *reinterpret_cast<const volatile uint64_t*>(p); }
+__device__ __forceinline__ void st_desc(uint64_t* p, uint64_t v) { *reinterpret_cast<volatile uint64_t*>(p) = v; }
+
+// decoupled look-back by one warp: exclusive prefix of `agg` over tiles [0, t) of the row; publishes the tile
+__device__ __forceinline__ uint64_t lookback(uint64_t* desc_row, uint32_t t, uint64_t agg) {
+    const int lane = threadIdx.x & 31;
+    if (t == 0) { if (lane == 0) st_desc(&desc_row[0], kDescPrefix | agg); return 0; }
+    if (lane == 0) st_desc(&desc_row[t], kDescAgg | agg);
+    uint64_t excl = 0;
+    int64_t look = (int64_t)t - 1;
+    for (;;) {
+        int64_t idx = look - lane;
+        uint64_t v = idx >= 0 ? ld_desc(&desc_row[idx]) : kDescPrefix;
+        unsigned st = (unsigned)(v >> 62);
+        if (__any_sync(0xffffffffu, st == 0)) continue;          // a predecessor has not published yet
+        unsigned pm = __ballot_sync(0xffffffffu, st == 2);
+        int first = pm ? __ffs(pm) - 1 : 32;
+        uint64_t val = lane <= first ? (v & kDescMask) : 0;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) val += __shfl_xor_sync(0xffffffffu, val, d);
+        excl += val;
+        if (pm) break;
+        look -= 32;
     }
-    __shared__ uint32_t sm[33];
-    uint32_t total;
-    block_exclusive_scan<uint32_t, OpSum>(packed, OpSum(), 0u, &total, sm);
-    if (threadIdx.x == 0) {
-        job.tile_cnt[(uint64_t)h * job.tiles_per_row + t] = total & 0xFFFFu;
-        job.tile_exc[(uint64_t)h * job.tiles_per_row + t] = total >> 16;
-    }
+    if (lane == 0) st_desc(&desc_row[t], kDescPrefix | (excl + agg));
+    return excl;
 }
 
-// per-row totals from the scanned tile offsets
-__global__ void k_pack_rows(PackJob job, const uint64_t* total_cnt, const uint64_t* total_exc) {
-    uint32_t h = blockIdx.x * blockDim.x + threadIdx.x;
-    if (h > job.H) return;
-    uint64_t T = job.tiles_per_row;
-    uint64_t nt = (uint64_t)job.H * T;
-    uint64_t eo = h < job.H ? job.tile_excoff[h * T] : *total_exc;
-    job.exc_off[h] = eo;
-    if (h < job.H) {
-        uint64_t a = job.tile_off[h * T];
-        uint64_t b = (uint64_t)(h + 1) * T < nt ? job.tile_off[(uint64_t)(h + 1) * T] : *total_cnt;
-        job.m_out[h] = b - a;
-    } else if (eo > job.exc_cap) atomicOr(job.flags, 1u);
-}
-
-__global__ void __launch_bounds__(256) k_pack_write(PackJob job) {
+__global__ void __launch_bounds__(256) k_pack(PackJob job) {
     __shared__ uint32_t sbits[kPackTileBytes / 16 + 8];
     __shared__ uint32_t sm[33];
-    uint32_t h = blockIdx.y, t = blockIdx.x;
-    uint64_t cols = job.cols[h];
-    uint64_t tile_start = (uint64_t)t * kPackTileBytes;
-    if (tile_start >= cols) return;
-    for (int i = threadIdx.x; i < kPackTileBytes / 16 + 8; i += 256) sbits[i] = 0;
-    uint64_t off = tile_start + (uint64_t)threadIdx.x * 16;
-    Seg16 s; s.cnt = 0; s.exc = 0; s.codes = 0;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    int nvalid = 0;
-    if (off < cols) {
-        nvalid = cols - off >= 16 ? 16 : (int)(cols - off);
-        v = load16(job.rows + job.row_off[h] + off);
-        s = classify16(v, nvalid, job.strip);
+    __shared__ uint64_t s_bcast[4];
+    __shared__ uint64_t s_wlast[8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_bcast[0] = atomicAdd(job.tile_counter, 1u);
+    __syncthreads();
+    const uint32_t id = (uint32_t)s_bcast[0];
+    // rows interleaved: consecutive ids are the same tile index of consecutive rows, so each row has only a few
+    // tiles in flight and its look-back resolves within one 32-descriptor window
+    const uint32_t h = id % job.H, t = id / job.H;
+    const uint64_t cols = job.cols[h];
+    const uint64_t tile_start = (uint64_t)t * kPackTileBytes;
+    uint64_t* dcnt = job.desc_cnt + (uint64_t)h * job.tiles_per_row;
+    uint64_t* dexc = job.desc_exc + (uint64_t)h * job.tiles_per_row;
+    const bool last_tile = t + 1 == job.tiles_per_row;
+
+    // ---- load and classify 64 bytes per thread -------------------------------------------------------------
+    const uint64_t off = tile_start + (uint64_t)tid * 64;
+    Seg16 sg[4];
+    uint32_t cnt = 0, exc = 0;
+    const uint8_t* rowp = job.rows + job.row_off[h];
+    {
+        uint4 v[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            uint64_t o = off + 16u * q;
+            v[q] = make_uint4(0, 0, 0, 0);
+            if (o < cols) v[q] = load16(rowp + o);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            uint64_t o = off + 16u * q;
+            sg[q].cnt = 0; sg[q].exc = 0; sg[q].codes = 0;
+            if (o < cols) {
+                int nvalid = cols - o >= 16 ? 16 : (int)(cols - o);
+                sg[q] = classify16(v[q], nvalid, job.strip);
+            }
+            cnt += sg[q].cnt; exc += sg[q].exc;
+        }
     }
     uint32_t total;
-    uint32_t ex = block_exclusive_scan<uint32_t, OpSum>(s.cnt | (s.exc << 16), OpSum(), 0u, &total, sm);
-    uint32_t lo = ex & 0xFFFFu, elo = ex >> 16;     // local base offset, local exception offset
-    uint32_t T = total & 0xFFFFu;
-    if (s.cnt) {
-        uint32_t wi = lo >> 4, sh = (lo & 15u) * 2;
-        atomicOr(&sbits[wi], s.codes >> sh);
-        if (sh && s.cnt > 16 - (lo & 15u)) atomicOr(&sbits[wi + 1], s.codes << (32 - sh));
+    uint32_t ex = block_exclusive_scan<uint32_t, OpSum>(cnt | (exc << 16), OpSum(), 0u, &total, sm);
+    const uint32_t lo = ex & 0xFFFFu, elo = ex >> 16;     // local base offset, local exception offset
+    const uint32_t T = total & 0xFFFFu, TE = total >> 16;
+
+    // ---- tile offset inside the row: decoupled look-back -----------------------------------------------------
+    if (warp == 0) {
+        uint64_t o = lookback(dcnt, t, T);
+        uint64_t eo = 0;
+        if (TE || last_tile) eo = lookback(dexc, t, TE);
+        else if (lane == 0) st_desc(&dexc[t], (t == 0 ? kDescPrefix : kDescAgg) | 0ull);
+        if (lane == 0) {
+            s_bcast[1] = o; s_bcast[2] = eo;
+            if (last_tile) {
+                job.m_out[h] = o + T;
+                uint64_t ne = eo + TE;
+                job.exc_cnt[h] = ne;
+                if (ne > job.exc_stride) atomicOr(job.flags, 1u);
+            }
+        }
     }
-    uint64_t gidx = (uint64_t)h * job.tiles_per_row + t;
-    uint64_t rowbase = job.tile_off[(uint64_t)h * job.tiles_per_row];
-    uint64_t o = job.tile_off[gidx] - rowbase;      // first output base of this tile within the haplotype
-    // exceptions and optional gapless bytes (rare / optional paths: plain byte loops)
-    if (s.exc || job.gapless) {
-        uint32_t w[4] = {v.x, v.y, v.z, v.w};
-        uint64_t e = job.tile_excoff[gidx] + elo;
+    const bool fast = T == kPackTileBytes && TE == 0;        // no gap, no foreign byte, full tile
+    if (!fast) for (int i = tid; i < kPackTileBytes / 16 + 8; i += 256) sbits[i] = 0;
+    __syncthreads();
+    const uint64_t o = s_bcast[1];
+    if (T == 0) return;
+    uint64_t* X = job.X + job.xoff[h];
+    const uint32_t lead = (uint32_t)(o & 31);
+    const uint64_t W0 = o >> 5;
+
+    if (job.gapless || exc) {          // optional gapless bytes / rare exceptions: plain byte loops
+        uint64_t e = s_bcast[2] + elo;
         uint64_t p = o + lo;
         uint8_t* gl = job.gapless ? job.gapless + job.gapless_off[h] : nullptr;
-        for (int b = 0; b < nvalid; ++b) {
-            uint32_t byte = (w[b >> 2] >> (8 * (b & 3))) & 255u;
-            if (job.strip && byte == '-') continue;
-            bool valid = byte == 'A' || byte == 'C' || byte == 'G' || byte == 'T';
-            if (!valid) {
-                if (e < job.exc_cap) { job.exc_pos[e] = (uint32_t)p; job.exc_byte[e] = (uint8_t)byte; }
-                ++e;
+        uint32_t* ep = job.exc_pos + (uint64_t)h * job.exc_stride;
+        uint8_t* eb = job.exc_byte + (uint64_t)h * job.exc_stride;
+        for (int q = 0; q < 4; ++q) {
+            uint64_t ob = off + 16u * q;
+            int nvalid = ob >= cols ? 0 : (cols - ob >= 16 ? 16 : (int)(cols - ob));
+            for (int b = 0; b < nvalid; ++b) {
+                uint32_t byte = rowp[ob + b];              // rare path: re-read (L1/L2 hit)
+                if (job.strip && byte == '-') continue;
+                bool valid = byte == 'A' || byte == 'C' || byte == 'G' || byte == 'T';
+                if (!valid) {
+                    if (e < job.exc_stride) { ep[e] = (uint32_t)p; eb[e] = (uint8_t)byte; }
+                    ++e;
+                }
+                if (gl) gl[p] = (uint8_t)byte;
+                ++p;
             }
-            if (gl) gl[p] = (uint8_t)byte;
-            ++p;
+        }
+    }
+
+    if (fast) {
+        // thread owns local 64-bit words 2*tid, 2*tid+1; global word j = (local[j-1] << 2(32-lead)) | (local[j] >> 2 lead)
+        uint64_t w0 = ((uint64_t)sg[0].codes << 32) | sg[1].codes;
+        uint64_t w1 = ((uint64_t)sg[2].codes << 32) | sg[3].codes;
+        if (lane == 31) s_wlast[warp] = w1;
+        uint64_t prev = __shfl_up_sync(0xffffffffu, w1, 1);
+        __syncthreads();
+        if (lane == 0) prev = warp ? s_wlast[warp - 1] : 0ull;
+        uint64_t g0, g1;
+        if (lead == 0) { g0 = w0; g1 = w1; }
+        else {
+            unsigned sh = 2 * lead;
+            g0 = (prev << (64 - sh)) | (w0 >> sh);
+            g1 = (w0 << (64 - sh)) | (w1 >> sh);
+        }
+        uint64_t* dst = X + W0 + 2 * (uint64_t)tid;
+        if (tid == 0 && lead != 0) atomicOr(reinterpret_cast<unsigned long long*>(dst), (unsigned long long)g0);
+        else dst[0] = g0;
+        dst[1] = g1;
+        if (tid == 255 && lead != 0)
+            atomicOr(reinterpret_cast<unsigned long long*>(dst + 2), (unsigned long long)(w1 << (64 - 2 * lead)));
+        return;
+    }
+
+    // ---- general path: bases assembled in a shared-memory bit buffer -------------------------------------------
+    {
+        uint32_t l = lo;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (sg[q].cnt) {
+                uint32_t wi = l >> 4, sh = (l & 15u) * 2;
+                atomicOr(&sbits[wi], sg[q].codes >> sh);
+                if (sh && sg[q].cnt > 16 - (l & 15u)) atomicOr(&sbits[wi + 1], sg[q].codes << (32 - sh));
+                l += sg[q].cnt;
+            }
         }
     }
     __syncthreads();
-    if (T == 0) return;
-    // assemble aligned 64-bit output words
-    uint32_t lead = (uint32_t)(o & 31);
-    uint64_t W0 = o >> 5;
     uint32_t nwords = (lead + T + 31) >> 5;
-    uint64_t* X = job.X + job.xoff[h];
-    for (uint32_t j = threadIdx.x; j < nwords; j += 256) {
+    for (uint32_t j = tid; j < nwords; j += 256) {
         int64_t lb = (int64_t)j * 32 - (int64_t)lead;      // local base index of the word's first base
-        uint64_t val;
         uint32_t b0 = lb < 0 ? 0u : (uint32_t)lb;
         uint32_t wi = b0 >> 4, sh = (b0 & 15u) * 2;
         uint64_t hi = ((uint64_t)sbits[wi] << 32) | sbits[wi + 1];
-        val = sh ? (hi << sh) | ((uint64_t)sbits[wi + 2] >> (32 - sh)) : hi;
+        uint64_t val = sh ? (hi << sh) | ((uint64_t)sbits[wi + 2] >> (32 - sh)) : hi;
         if (lb < 0) val >>= 2 * lead;
         bool first_partial = j == 0 && lead != 0;
         bool last_partial = j == nwords - 1 && ((lead + T) & 31u) != 0;
@@ -169,43 +244,37 @@ __global__ void __launch_bounds__(256) k_pack_write(PackJob job) {
 
 void launch_pack(const PackJob& job, cudaStream_t s, cudaEvent_t* ev) {
     if (job.H == 0 || job.tiles_per_row == 0) { if (ev) for (int i = 0; i < 3; ++i) cudaEventRecord(ev[i], s); return; }
-    dim3 grid(job.tiles_per_row, job.H);
     uint64_t nt = (uint64_t)job.H * job.tiles_per_row;
-    g_launches += 3;
-    k_pack_count<<<grid, 256, 0, s>>>(job);
-    if (ev) cudaEventRecord(ev[0], s);
-    uint64_t* tmp1 = job.scan_tmp;
-    uint64_t* tmp2 = job.scan_tmp + scan_tmp_elems(nt);
-    device_scan<uint64_t, LoadArr<uint32_t, uint64_t>, StoreArr<uint64_t>, OpSum, false>(
-        LoadArr<uint32_t, uint64_t>{job.tile_cnt}, StoreArr<uint64_t>{job.tile_off}, nt, tmp1, OpSum(), 0ull, s);
-    device_scan<uint64_t, LoadArr<uint32_t, uint64_t>, StoreArr<uint64_t>, OpSum, false>(
-        LoadArr<uint32_t, uint64_t>{job.tile_exc}, StoreArr<uint64_t>{job.tile_excoff}, nt, tmp2, OpSum(), 0ull, s);
-    uint64_t ntiles_scan = (nt + kScanTile - 1) / kScanTile;
-    k_pack_rows<<<(job.H + 1 + 127) / 128, 128, 0, s>>>(job, tmp1 + ntiles_scan, tmp2 + ntiles_scan);
-    if (ev) cudaEventRecord(ev[1], s);
-    k_pack_write<<<grid, 256, 0, s>>>(job);
+    cudaMemsetAsync(job.desc_cnt, 0, nt * 8, s);
+    cudaMemsetAsync(job.desc_exc, 0, nt * 8, s);
+    cudaMemsetAsync(job.tile_counter, 0, 4, s);
+    if (ev) { cudaEventRecord(ev[0], s); cudaEventRecord(ev[1], s); }
+    g_launches += 1;
+    k_pack<<<(unsigned)nt, 256, 0, s>>>(job);
     if (ev) cudaEventRecord(ev[2], s);
 }
 
 __global__ void k_make_hapviews(HapView* haps, const uint64_t* X, const uint64_t* xoff, const uint64_t* m,
-                                const uint32_t* exc_pos, const uint8_t* exc_byte, const uint64_t* exc_off, uint32_t H) {
+                                const uint32_t* exc_pos, const uint8_t* exc_byte, const uint64_t* exc_cnt,
+                                uint64_t exc_stride, uint32_t H) {
     uint32_t h = blockIdx.x * blockDim.x + threadIdx.x;
     if (h >= H) return;
     HapView hv;
     hv.x = X + xoff[h];
     hv.m = m[h];
-    hv.exc_pos = exc_pos + exc_off[h];
-    hv.exc_byte = exc_byte + exc_off[h];
-    hv.n_exc = (uint32_t)(exc_off[h + 1] - exc_off[h]);
+    hv.exc_pos = exc_pos + (uint64_t)h * exc_stride;
+    hv.exc_byte = exc_byte + (uint64_t)h * exc_stride;
+    uint64_t ne = exc_cnt[h];
+    hv.n_exc = (uint32_t)(ne < exc_stride ? ne : exc_stride);
     haps[h] = hv;
 }
 
 void launch_make_hapviews(HapView* haps, const uint64_t* X, const uint64_t* xoff, const uint64_t* m,
-                          const uint32_t* exc_pos, const uint8_t* exc_byte, const uint64_t* exc_off, uint32_t H,
-                          cudaStream_t s) {
+                          const uint32_t* exc_pos, const uint8_t* exc_byte, const uint64_t* exc_cnt, uint64_t exc_stride,
+                          uint32_t H, cudaStream_t s) {
     if (H == 0) return;
     g_launches += 1;
-    k_make_hapviews<<<(H + 127) / 128, 128, 0, s>>>(haps, X, xoff, m, exc_pos, exc_byte, exc_off, H);
+    k_make_hapviews<<<(H + 127) / 128, 128, 0, s>>>(haps, X, xoff, m, exc_pos, exc_byte, exc_cnt, exc_stride, H);
 }
 
 }  // namespace drlz

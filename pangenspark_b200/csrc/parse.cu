@@ -240,16 +240,18 @@ __global__ void k_rank(const uint32_t* __restrict__ link_in, const uint32_t* __r
 }
 
 // scalar versions (used by the exact sequential fallback, where one chunk = one haplotype)
-__global__ void __launch_bounds__(128) k_first(ParseView pv) {
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) k_first(ParseView pv) {
     uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g < pv.n_chunks) first_phrase_chunk(pv, g);
 }
-__global__ void __launch_bounds__(128) k_spec(ParseView pv) {
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) k_spec(ParseView pv) {
     uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g < pv.n_chunks) spec_parse_chunk(pv, g);
 }
-
-__global__ void __launch_bounds__(128) k_fix(ParseView pv, uint32_t round) {
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) k_fix(ParseView pv, uint32_t round) {
     uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r < pv.n_chunks * kAltSlots) fix_parse_record(pv, r / kAltSlots, (int)(r % kAltSlots), round);
 }
@@ -310,13 +312,14 @@ int parse_stage_count(ParseBuffers& pb, cudaStream_t s, int* rounds_out, cudaEve
         cudaStreamSynchronize(s);
         return 0;
     }
-    bool scalar = pv.min_cap == 0xFFFFFFFFu;          // exact sequential fallback
+    bool scalar = pv.min_cap == 0xFFFFFFFFu || !pb.use_machine;   // exact sequential fallback, or scalar kernels by choice
     cudaMemsetAsync(pv.alt_entry, 0xFF, sizeof(uint32_t) * (size_t)NC * kAltSlots, s);
     cudaMemsetAsync(pv.counters, 0, sizeof(uint32_t) * (2 + kMaxRounds), s);
     if (ev) cudaEventRecord(ev[0], s);
     // stage A: first phrase of every chunk, diagonal-run links, list ranking
     g_launches += 2;
-    if (scalar) k_first<<<(NC + 127) / 128, 128, 0, s>>>(pv);
+    if (scalar && pb.occ >= 16) k_first<16><<<(NC + 127) / 128, 128, 0, s>>>(pv);
+    else if (scalar) k_first<1><<<(NC + 127) / 128, 128, 0, s>>>(pv);
     else k_chunk_machine<true><<<(NC + 127) / 128, 128, 0, s>>>(pv);
     k_link<<<(NC + 127) / 128, 128, 0, s>>>(pv);
     {
@@ -330,7 +333,8 @@ int parse_stage_count(ParseBuffers& pb, cudaStream_t s, int* rounds_out, cudaEve
     }
     if (ev) cudaEventRecord(ev[4], s);
     g_launches += 1;
-    if (scalar) k_spec<<<(NC + 127) / 128, 128, 0, s>>>(pv);
+    if (scalar && pb.occ >= 16) k_spec<16><<<(NC + 127) / 128, 128, 0, s>>>(pv);
+    else if (scalar) k_spec<1><<<(NC + 127) / 128, 128, 0, s>>>(pv);
     else k_chunk_machine<false><<<(NC + 127) / 128, 128, 0, s>>>(pv);
     if (ev) cudaEventRecord(ev[1], s);
     int round = 1;
@@ -342,7 +346,8 @@ int parse_stage_count(ParseBuffers& pb, cudaStream_t s, int* rounds_out, cudaEve
         if (pb.host_counters[1 + round] == 0) break;
         uint32_t nr = NC * kAltSlots;
         g_launches += 1;
-        k_fix<<<(nr + 127) / 128, 128, 0, s>>>(pv, (uint32_t)round);
+        if (pb.occ >= 16) k_fix<16><<<(nr + 127) / 128, 128, 0, s>>>(pv, (uint32_t)round);
+        else k_fix<1><<<(nr + 127) / 128, 128, 0, s>>>(pv, (uint32_t)round);
         ++round;
     }
     if (rounds_out) *rounds_out = round;
