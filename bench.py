@@ -28,6 +28,14 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+# torchrun exports OMP_NUM_THREADS=1; the host-side input generator and the CPU baseline are OpenMP code
+_world = int(os.environ.get("WORLD_SIZE", "1"))
+_cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+if "--impl" in sys.argv and "reference" in sys.argv:
+    os.environ["OMP_NUM_THREADS"] = str(_cores)
+elif _world > 1:
+    os.environ["OMP_NUM_THREADS"] = str(max(1, _cores // _world))
+
 METRIC = "rlz_parse_throughput"
 UNIT = "Gbp/s"
 
@@ -134,7 +142,7 @@ def run_reference(args):
         return 0
     from oracle import oracle as orc
     wl = workload(0)
-    threads = orc.max_threads()
+    threads = _cores
     d = orc.syn_reference(orc.seed_for(wl["cfg"]), wl["n"])
     sample = min(wl["H"], int(os.environ.get("DRLZ_BENCH_REF_ROWS", 16)))
     rows_arr, M, stride = gen_rows(orc, wl, d, rows=sample)
@@ -330,7 +338,7 @@ def run_ours(args):
     cpu = None
     parity_rows = 0
     if rank == 0 and world == 1 and not os.environ.get("DRLZ_BENCH_SKIP_CPU"):
-        threads = orc.max_threads()
+        threads = _cores
         sample = min(H, int(os.environ.get("DRLZ_BENCH_REF_ROWS", 16)))
         sa_gpu = ctx.index_get("sa").astype(np.int64)
         cb = cpu_baseline(orc, wl, d, rows_arr, M, sample, threads)
