@@ -50,7 +50,7 @@ struct drlz_ctx {
     cudaEvent_t ev_stage[11] = {};
     std::string err;
     // options
-    int opt_k = 0; uint32_t opt_chunk = 2048; uint32_t opt_min_cap = 64; uint32_t opt_foreign_cap = 1u << 20; int opt_machine = 0; uint64_t opt_group_bytes = 256ull << 20; int opt_lcp = 0;
+    int opt_k = 0; uint32_t opt_chunk = 2048; uint32_t opt_min_cap = 64; uint32_t opt_foreign_cap = 1u << 20; uint64_t opt_group_bytes = 256ull << 20; int opt_lcp = 0;
     // index
     bool have_index = false; uint64_t n = 0; int k = 0; int sa_rounds = 0;
     DevBuf blob, sa, isa, lcp;             // blob = [k-mer table | packed text] (one L2 access-policy window)
@@ -59,7 +59,7 @@ struct drlz_ctx {
     double idx_ms[5] = {0, 0, 0, 0, 0};
     // batch scratch (grow-only)
     DevBuf stage[2], meta_dev, desc_cnt, desc_exc, tile_counter, X, mdev, exccnt, excpos, excbyte,
-        flags, haps, gapless, chunk_hap, first_pos, first_len, run_a, run_b, link_a, link_b, spec_cnt, spec_exit, alt_entry, alt_cnt, alt_exit, alt_round, alt_own, alt_merge, spec_ph, alt_ph, true_slot, counters, jump_a,
+        flags, haps, gapless, chunk_hap, first_pos, first_len, run_a, run_b, link_a, link_b, open_i, open_pos, open_len, spec_cnt, spec_exit, alt_entry, alt_cnt, alt_exit, alt_round, alt_own, alt_merge, spec_ph, alt_ph, true_slot, counters, jump_a,
         jump_b, mark, true_cnt, true_entry, true_off, scan_tmp, hap_pairs, out, ms_a, ms_b;
     HostBuf meta_host, small_host;
     uint64_t exc_stride_hint = 0;
@@ -128,7 +128,7 @@ void drlz_destroy(drlz_ctx* c) {
     cudaDeviceSynchronize();
     DevBuf* bufs[] = {&c->blob, &c->sa, &c->isa, &c->lcp, &c->stage[0], &c->stage[1], &c->meta_dev, &c->desc_cnt,
                       &c->desc_exc, &c->tile_counter, &c->X, &c->mdev, &c->exccnt, &c->excpos,
-                      &c->excbyte, &c->flags, &c->haps, &c->gapless, &c->chunk_hap, &c->first_pos, &c->first_len, &c->run_a, &c->run_b, &c->link_a, &c->link_b, &c->spec_cnt, &c->spec_exit,
+                      &c->excbyte, &c->flags, &c->haps, &c->gapless, &c->chunk_hap, &c->first_pos, &c->first_len, &c->run_a, &c->run_b, &c->link_a, &c->link_b, &c->open_i, &c->open_pos, &c->open_len, &c->spec_cnt, &c->spec_exit,
                       &c->alt_entry, &c->alt_cnt, &c->alt_exit, &c->alt_round, &c->alt_own, &c->alt_merge, &c->spec_ph, &c->alt_ph, &c->true_slot, &c->counters, &c->jump_a, &c->jump_b,
                       &c->mark, &c->true_cnt, &c->true_entry, &c->true_off, &c->scan_tmp, &c->hap_pairs, &c->out, &c->ms_a, &c->ms_b};
     for (DevBuf* b : bufs) b->release();
@@ -154,7 +154,6 @@ int drlz_set_option(drlz_ctx* c, const char* key, int64_t v) {
     else if (!strcmp(key, "chunk")) { if (v < 0 || v > 0x7FFFFFFF) return DRLZ_E_ARG; c->opt_chunk = v ? (uint32_t)v : 2048; }
     else if (!strcmp(key, "group_bytes")) { if (v < 0) return DRLZ_E_ARG; c->opt_group_bytes = v ? (uint64_t)v : (256ull << 20); }
     else if (!strcmp(key, "lcp")) c->opt_lcp = v != 0;
-    else if (!strcmp(key, "machine")) c->opt_machine = v != 0;
     else if (!strcmp(key, "l2persist")) { c->opt_l2persist = v != 0; c->l2_stream = nullptr; }
     else if (!strcmp(key, "occ")) c->opt_occ = (int)v;
     else if (!strcmp(key, "min_cap")) { if (v < 0 || v > 0x7FFFFFFF) return DRLZ_E_ARG; c->opt_min_cap = v ? (uint32_t)v : 64; }
@@ -268,6 +267,7 @@ static int run_device_group(drlz_ctx* c, const uint8_t* rows_dev, const uint64_t
         CK(c, c->first_pos.ensure((size_t)NC * 4 + 4)); CK(c, c->first_len.ensure((size_t)NC * 4 + 4));
         CK(c, c->run_a.ensure((size_t)NC * 4 + 4)); CK(c, c->run_b.ensure((size_t)NC * 4 + 4));
         CK(c, c->link_a.ensure((size_t)NC * 4 + 4)); CK(c, c->link_b.ensure((size_t)NC * 4 + 4));
+        CK(c, c->open_i.ensure((size_t)NC * 4 + 4)); CK(c, c->open_pos.ensure((size_t)NC * 4 + 4)); CK(c, c->open_len.ensure((size_t)NC * 4 + 4));
         CK(c, c->chunk_hap.ensure((size_t)NC * 4 + 4)); CK(c, c->spec_cnt.ensure((size_t)NC * 4 + 4)); CK(c, c->spec_exit.ensure((size_t)NC * 4 + 4));
         CK(c, c->alt_entry.ensure(na * 4 + 4)); CK(c, c->alt_cnt.ensure(na * 4 + 4)); CK(c, c->alt_exit.ensure(na * 4 + 4));
         CK(c, c->alt_own.ensure(na * 4 + 4)); CK(c, c->alt_merge.ensure(na * 4 + 4));
@@ -287,6 +287,7 @@ static int run_device_group(drlz_ctx* c, const uint8_t* rows_dev, const uint64_t
         pb.pv.first_pos = c->first_pos.as<uint32_t>(); pb.pv.first_len = c->first_len.as<uint32_t>();
         pb.pv.run_len = c->run_a.as<uint32_t>(); pb.pv.link = c->link_a.as<uint32_t>();
         pb.link_b = c->link_b.as<uint32_t>(); pb.run_b = c->run_b.as<uint32_t>();
+        pb.pv.open_i = c->open_i.as<uint32_t>(); pb.pv.open_pos = c->open_pos.as<uint32_t>(); pb.pv.open_len = c->open_len.as<uint32_t>();
         pb.pv.spec_cnt = c->spec_cnt.as<uint32_t>(); pb.pv.spec_exit = c->spec_exit.as<uint32_t>();
         pb.pv.alt_entry = c->alt_entry.as<uint32_t>(); pb.pv.alt_cnt = c->alt_cnt.as<uint32_t>();
         pb.pv.alt_exit = c->alt_exit.as<uint32_t>(); pb.pv.alt_round = c->alt_round.as<uint32_t>();
@@ -294,7 +295,7 @@ static int run_device_group(drlz_ctx* c, const uint8_t* rows_dev, const uint64_t
         pb.pv.spec_ph = c->spec_ph.as<uint2>(); pb.pv.alt_ph = c->alt_ph.as<uint2>();
         pb.true_slot = c->true_slot.as<uint32_t>();
         pb.pv.counters = c->counters.as<uint32_t>();
-        pb.H = H; pb.max_chunks_per_hap = maxc ? maxc : 1; pb.use_machine = c->opt_machine; pb.occ = c->opt_occ;
+        pb.H = H; pb.max_chunks_per_hap = maxc ? maxc : 1; pb.occ = c->opt_occ;
         pb.jump_a = c->jump_a.as<uint32_t>(); pb.jump_b = c->jump_b.as<uint32_t>(); pb.mark = c->mark.as<uint8_t>();
         pb.true_cnt = c->true_cnt.as<uint32_t>(); pb.true_entry = c->true_entry.as<uint32_t>(); pb.true_off = c->true_off.as<uint64_t>();
         pb.scan_tmp = c->scan_tmp.as<uint64_t>(); pb.hap_pairs = c->hap_pairs.as<uint64_t>();
@@ -330,7 +331,7 @@ static int run_device_group(drlz_ctx* c, const uint8_t* rows_dev, const uint64_t
         // timings
         float t;
         double* pm = c->parse_ms;
-        static const int iv[10][2] = {{0, 1}, {1, 2}, {2, 3}, {3, 4}, {9, 6}, {6, 7}, {7, 8}, {8, 10}, {0, 10}, {5, 9}};
+        static const int iv[10][2] = {{0, 1}, {1, 2}, {2, 3}, {3, 4}, {5, 6}, {9, 7}, {7, 8}, {8, 10}, {0, 10}, {6, 9}};
         for (int i = 0; i < 10; ++i) { cudaEventElapsedTime(&t, c->ev_stage[iv[i][0]], c->ev_stage[iv[i][1]]); pm[i] += t; }
         pm[10] += rounds; pm[11] += (double)(g_launches - launches0);
         return DRLZ_OK;

@@ -53,7 +53,6 @@ struct ParseBuffers {
     uint32_t H;
     uint32_t max_chunks_per_hap;
     int occ;                      // 0: default register budget, 16: 32 registers per thread (max occupancy)
-    int use_machine;              // 1: k_chunk_machine kernels, 0: scalar thread-per-chunk kernels
     uint32_t* link_b;             // [NC] second buffers of the list ranking
     uint32_t* run_b;              // [NC]
     uint32_t* jump_a;             // [NC*(kAltSlots+1)]
@@ -70,7 +69,7 @@ struct ParseBuffers {
 };
 // Stage A: speculative parse, fix-up rounds, pointer jumping, per-chunk counts and offsets.
 // Synchronises the stream (reads round counters and the phrase total).  Returns 0, or 2 on overflow.
-// ev (nullable): 5 events: [0] start, [4] after stage A, [1] after P1, [2] after the fix-up rounds, [3] after compaction.
+// ev (nullable): 5 events: [0] start, [1] after P1, [4] after stage A, [2] after the fix-up rounds, [3] after compaction.
 int parse_stage_count(ParseBuffers& pb, cudaStream_t s, int* rounds_out, cudaEvent_t* ev);
 // Stage B: emission into `out` (device, >= 2*total int64).
 void parse_stage_emit(ParseBuffers& pb, int64_t* out, cudaStream_t s);

@@ -226,6 +226,9 @@ struct ParseView {
     uint32_t* first_len;            // [NC] its verified length (0 = literal); >= chunk end when open
     uint32_t* run_len;              // [NC] its exact total length (after list ranking)
     uint32_t* link;                 // [NC] next chunk of the diagonal run, kEmpty = end
+    uint32_t* open_i;               // [NC] start of the chunk's last phrase if it is still open (kEmpty otherwise)
+    uint32_t* open_pos;             // [NC] its reference position
+    uint32_t* open_len;             // [NC] its verified length
     // stages P1 / R / F
     uint32_t* spec_cnt;             // [NC]
     uint32_t* spec_exit;            // [NC]
@@ -320,21 +323,6 @@ DRLZ_HD Match phrase_at(const ParseView& pv, uint32_t h, const HapView& hv, uint
     return mt;
 }
 
-// A1: phrase at the first base of chunk g, compared no further than the chunk end
-DRLZ_HD void first_phrase_chunk(const ParseView& pv, uint32_t g) {
-    uint32_t h = pv.chunk_hap[g];
-    const HapView& hv = pv.haps[h];
-    uint64_t s = (uint64_t)(g - pv.hap_chunk_base[h]) * pv.chunk_bases;
-    pv.link[g] = kEmpty;
-    if (s >= hv.m) { pv.first_pos[g] = 0; pv.first_len[g] = 0; pv.run_len[g] = 0; return; }
-    uint32_t cur = hv.n_exc ? exc_lower_bound(hv, s) : 0;
-    bool open;
-    Match mt = phrase_capped(pv, hv, s, &cur, &open);
-    pv.first_pos[g] = mt.pos;
-    pv.first_len[g] = mt.len;
-    pv.run_len[g] = open ? kEmpty : mt.len;                   // kEmpty = still open, see link_chunk
-}
-
 // A2: link open chunks to the chunk their match continues in, or finish them by a direct compare
 DRLZ_HD void link_chunk(const ParseView& pv, uint32_t g) {
     if (pv.run_len[g] != kEmpty) return;
@@ -381,23 +369,59 @@ DRLZ_HD Match chunk_step(const ParseView& pv, uint32_t g, uint32_t h, const HapV
     return phrase_at(pv, h, hv, i, cursor);
 }
 
-// P1 for global chunk g
+// P1 for global chunk g: speculative greedy parse from the chunk's first base with chunk-capped lookups.  Only
+// the last phrase of a chunk can be open (it reaches the chunk end); its total length -- hence the exit of the
+// chunk -- is filled in by resolve_chunk() once the diagonal runs are ranked.  The first phrase doubles as
+// stage A's "phrase at the chunk start" (first_pos / first_len / run_len).
 DRLZ_HD void spec_parse_chunk(const ParseView& pv, uint32_t g) {
     uint32_t h = pv.chunk_hap[g];
     const HapView& hv = pv.haps[h];
     uint64_t s = (uint64_t)(g - pv.hap_chunk_base[h]) * pv.chunk_bases;
     uint64_t e = s + pv.chunk_bases; if (e > hv.m) e = hv.m;
+    pv.link[g] = kEmpty;
+    pv.open_i[g] = kEmpty;
+    if (s >= hv.m) {
+        pv.first_pos[g] = 0; pv.first_len[g] = 0; pv.run_len[g] = 0;
+        pv.spec_cnt[g] = 0; pv.spec_exit[g] = (uint32_t)(s > 0xFFFFFFFEull ? 0xFFFFFFFEull : s);
+        return;
+    }
     uint64_t i = s; uint32_t cnt = 0;
     uint32_t cur = hv.n_exc ? exc_lower_bound(hv, i) : 0;
+    bool open = false;
     while (i < e) {
-        Match mt = chunk_step(pv, g, h, hv, s, i, &cur);
+        Match mt = phrase_capped(pv, hv, i, &cur, &open);
+        if (i == s) { pv.first_pos[g] = mt.pos; pv.first_len[g] = mt.len; pv.run_len[g] = open ? kEmpty : mt.len; }
         if (cnt < (uint32_t)kSpecStore) pv.spec_ph[(size_t)g * kSpecStore + cnt] = make_uint2(mt.pos, mt.len);
         ++cnt;
+        if (open) { pv.open_i[g] = (uint32_t)i; pv.open_pos[g] = mt.pos; pv.open_len[g] = mt.len; break; }
         i += mt.len ? mt.len : 1;
     }
     pv.spec_cnt[g] = cnt;
-    pv.spec_exit[g] = (uint32_t)i;
-    register_exit(pv, h, i, 1);
+    if (open) pv.spec_exit[g] = kEmpty;                       // resolved later
+    else { pv.spec_exit[g] = (uint32_t)i; register_exit(pv, h, i, 1); }
+}
+
+// after link_chunk + list ranking: total length of the chunk's open last phrase, exit of the chunk
+DRLZ_HD void resolve_chunk(const ParseView& pv, uint32_t g) {
+    uint32_t oi = pv.open_i[g];
+    if (oi == kEmpty) return;
+    uint32_t h = pv.chunk_hap[g];
+    const HapView& hv = pv.haps[h];
+    uint64_t s = (uint64_t)(g - pv.hap_chunk_base[h]) * pv.chunk_bases;
+    uint64_t i = oi;
+    uint32_t total;
+    if (i == s) total = pv.run_len[g];
+    else {
+        Match mt; mt.pos = pv.open_pos[g]; mt.len = pv.open_len[g];
+        uint64_t j; bool same;
+        uint32_t g2 = open_target(pv, h, i, mt, &j, &same);
+        total = (uint32_t)(j - i) + (same ? pv.run_len[g2] : foreign_run(pv, hv, i, mt, j));
+    }
+    uint32_t cnt = pv.spec_cnt[g];
+    if (cnt - 1 < (uint32_t)kSpecStore) pv.spec_ph[(size_t)g * kSpecStore + cnt - 1].y = total;
+    uint64_t x = i + total;
+    pv.spec_exit[g] = (uint32_t)x;
+    register_exit(pv, h, x, 1);
 }
 
 // F for alternative record (g, slot) scheduled for `round`
@@ -415,9 +439,11 @@ DRLZ_HD void fix_parse_record(const ParseView& pv, uint32_t g, int slot, uint32_
     bool merged = false;
     while (iB < e) {
         while (iA < iB) {
-            Match mt = chunk_step(pv, g, h, hv, s, iA, &curA);
+            uint32_t lenA;
+            if (cntA < (uint32_t)kSpecStore && cntA < pv.spec_cnt[g]) lenA = pv.spec_ph[(size_t)g * kSpecStore + cntA].y;
+            else lenA = chunk_step(pv, g, h, hv, s, iA, &curA).len;
             ++cntA;
-            iA += mt.len ? mt.len : 1;
+            iA += lenA ? lenA : 1;
         }
         if (iA == iB) { merged = true; break; }
         Match mt = phrase_at(pv, h, hv, iB, &curB);

@@ -66,18 +66,18 @@ int emu_parse(const uint8_t* ref, uint64_t n, const int64_t* sa64, int k, uint32
     uint32_t NC = base[H];
     std::vector<uint32_t> chunk_hap(NC);
     for (int h = 0; h < H; ++h) for (uint32_t g = base[h]; g < base[h + 1]; ++g) chunk_hap[g] = h;
-    std::vector<uint32_t> first_pos(NC), first_len(NC), run_a(NC), run_b(NC), link_a(NC), link_b(NC);
+    std::vector<uint32_t> first_pos(NC), first_len(NC), run_a(NC), run_b(NC), link_a(NC), link_b(NC), open_i(NC), open_pos(NC), open_len(NC);
     std::vector<uint32_t> spec_cnt(NC), spec_exit(NC), alt_entry((size_t)NC * kAltSlots, kEmpty),
         alt_cnt((size_t)NC * kAltSlots, 0), alt_exit((size_t)NC * kAltSlots, 0), alt_round((size_t)NC * kAltSlots, 0),
         counters(2 + kMaxRounds, 0), alt_own((size_t)NC * kAltSlots, 0), alt_merge((size_t)NC * kAltSlots, kEmpty);
     std::vector<uint2> spec_ph((size_t)NC * kSpecStore), alt_ph((size_t)NC * kAltSlots * kAltStore);
     ParseView pv{ix, haps.data(), chunk_hap.data(), base.data(), chunk, NC, min_cap, foreign_cap,
-                 first_pos.data(), first_len.data(), run_a.data(), link_a.data(), spec_cnt.data(), spec_exit.data(),
+                 first_pos.data(), first_len.data(), run_a.data(), link_a.data(), open_i.data(), open_pos.data(), open_len.data(), spec_cnt.data(), spec_exit.data(),
                  alt_entry.data(), alt_cnt.data(), alt_exit.data(), alt_round.data(), alt_own.data(), alt_merge.data(),
                  spec_ph.data(), alt_ph.data(), counters.data()};
     uint32_t maxc0 = 1;
     for (int h = 0; h < H; ++h) if (base[h + 1] - base[h] > maxc0) maxc0 = base[h + 1] - base[h];
-    for (uint32_t g = 0; g < NC; ++g) first_phrase_chunk(pv, g);
+    for (uint32_t g = 0; g < NC; ++g) spec_parse_chunk(pv, g);
     for (uint32_t g = 0; g < NC; ++g) link_chunk(pv, g);
     if (counters[0]) return 2;
     {
@@ -88,7 +88,8 @@ int emu_parse(const uint8_t* ref, uint64_t n, const int64_t* sa64, int k, uint32
         }
         pv.run_len = ri; pv.link = li;
     }
-    for (uint32_t g = 0; g < NC; ++g) spec_parse_chunk(pv, g);
+    for (uint32_t g = 0; g < NC; ++g) resolve_chunk(pv, g);
+    if (counters[0]) return 2;
     int round = 1;
     while (counters[1 + round] > 0 && round < kMaxRounds) {
         for (uint32_t g = 0; g < NC; ++g) for (int s = 0; s < kAltSlots; ++s) fix_parse_record(pv, g, s, round);
