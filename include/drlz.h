@@ -9,8 +9,9 @@
  * Each entry point names the reference code it replaces.
  *
  * Conventions: plain pointers and sizes; the caller owns every buffer; 0 = success, negative = DRLZ_E_*;
- * no exceptions or exit() cross this boundary; one context per GPU (one process per GPU).  A context may be
- * used from one thread at a time.  There is no CPU fallback: without a CUDA device drlz_create fails.
+ * no exceptions or exit() cross this boundary; one context per GPU (one process per GPU).  A context may be shared
+ * by several threads (Spark runs several tasks per executor JVM): calls are serialised on the device by a mutex.
+ * There is no CPU fallback: without a CUDA device drlz_create fails.
  */
 #ifndef DRLZ_H
 #define DRLZ_H
@@ -83,6 +84,14 @@ int drlz_parse(drlz_ctx* ctx, const uint8_t* msa_row, uint64_t cols, int strip_g
 int drlz_parse_batch(drlz_ctx* ctx, const uint8_t* const* rows, const uint64_t* cols, uint32_t H, int strip_gaps,
                      uint8_t* const* gapless_out, uint64_t* m_out, int64_t* pairs_out, uint64_t pairs_cap,
                      uint64_t* n_pairs);
+
+/* Asynchronous form of drlz_parse_batch for streaming producers: the call returns at once with a
+ * ticket; one worker thread per context runs the submitted batches in FIFO order.  Every buffer (including the
+ * rows/cols arrays) must stay valid and untouched until drlz_wait(ticket) returns that batch's status code. */
+int drlz_submit(drlz_ctx* ctx, const uint8_t* const* rows, const uint64_t* cols, uint32_t H, int strip_gaps,
+                uint8_t* const* gapless_out, uint64_t* m_out, int64_t* pairs_out, uint64_t pairs_cap, uint64_t* n_pairs,
+                uint64_t* ticket);
+int drlz_wait(drlz_ctx* ctx, uint64_t ticket);
 
 /* Same with the rows already resident in device memory: row h = rows_dev + row_off[h]; every row_off is a
  * multiple of 16 and the buffer is readable up to the next multiple of 16 past each row's end; cols excludes

@@ -2,7 +2,11 @@
 #include <math.h>
 #include <stdio.h>
 #include <string.h>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 #include "../../include/drlz.h"
 #include "drlz_internal.h"
@@ -63,6 +67,14 @@ struct drlz_ctx {
         jump_b, mark, true_cnt, true_entry, true_off, scan_tmp, hap_pairs, out, ms_a, ms_b;
     HostBuf meta_host, small_host;
     uint64_t exc_stride_hint = 0;
+    // thread safety: every entry point takes `mu` (calls from several threads are serialised on the device)
+    std::recursive_mutex mu;
+    // async form (drlz_submit / drlz_wait): one worker thread per context, FIFO
+    struct Job { uint64_t ticket; const uint8_t* const* rows; const uint64_t* cols; uint32_t H; int strip; uint8_t* const* gapless;
+                 uint64_t* m_out; int64_t* pairs; uint64_t cap; uint64_t* n_pairs; };
+    std::mutex qmu; std::condition_variable qcv, done_cv;
+    std::deque<Job> queue; std::vector<std::pair<uint64_t, int>> done;
+    std::thread worker; bool worker_started = false, stopping = false; uint64_t next_ticket = 1;
     double parse_ms[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 };
 
@@ -82,23 +94,28 @@ static cudaError_t alloc_index_blob(drlz_ctx* c, uint64_t n, int k) {
     return cudaSuccess;
 }
 
-// keep the k-mer table and the packed reference resident in L2 while haplotype data streams through
+// keep the packed reference (the target of every candidate probe) resident in L2 while haplotype data, table and
+// suffix-array probes stream through
 static void apply_l2_policy(drlz_ctx* c) {
-    if (!c->opt_l2persist || !c->blob.p || c->l2_stream == c->stream) return;
-    int max_persist = 0, max_window = 0;
-    cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, c->device);
-    cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, c->device);
-    if (max_persist <= 0 || max_window <= 0) return;
-    size_t want = c->blob_bytes < (size_t)max_persist ? c->blob_bytes : (size_t)max_persist;
-    cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+    if (!c->blob.p || c->l2_stream == c->stream) return;
     cudaStreamAttrValue attr;
     memset(&attr, 0, sizeof attr);
-    size_t win = c->blob_bytes < (size_t)max_window ? c->blob_bytes : (size_t)max_window;
-    attr.accessPolicyWindow.base_ptr = c->blob.p;
-    attr.accessPolicyWindow.num_bytes = win;
-    attr.accessPolicyWindow.hitRatio = win <= want ? 1.0f : (float)((double)want / (double)win);
-    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    if (c->opt_l2persist) {
+        int max_persist = 0, max_window = 0;
+        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, c->device);
+        cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, c->device);
+        size_t text_bytes = c->blob_bytes - (size_t)((uint8_t*)c->d_text - c->blob.as<uint8_t>());
+        if (max_persist > 0 && max_window > 0) {
+            size_t want = text_bytes < (size_t)max_persist ? text_bytes : (size_t)max_persist;
+            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+            size_t win = text_bytes < (size_t)max_window ? text_bytes : (size_t)max_window;
+            attr.accessPolicyWindow.base_ptr = c->d_text;
+            attr.accessPolicyWindow.num_bytes = win;
+            attr.accessPolicyWindow.hitRatio = win <= want ? 1.0f : (float)((double)want / (double)win);
+            attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            attr.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+        }
+    }
     cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
     c->l2_stream = c->stream;
 }
@@ -124,6 +141,11 @@ int drlz_create(drlz_ctx** out, int device) {
 
 void drlz_destroy(drlz_ctx* c) {
     if (!c) return;
+    if (c->worker_started) {
+        { std::lock_guard<std::mutex> lk(c->qmu); c->stopping = true; }
+        c->qcv.notify_all();
+        c->worker.join();
+    }
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     DevBuf* bufs[] = {&c->blob, &c->sa, &c->isa, &c->lcp, &c->stage[0], &c->stage[1], &c->meta_dev, &c->desc_cnt,
@@ -144,12 +166,14 @@ const char* drlz_last_error(const drlz_ctx* c) { return c ? c->err.c_str() : "nu
 
 int drlz_set_stream(drlz_ctx* c, void* s) {
     if (!c) return DRLZ_E_ARG;
+    std::lock_guard<std::recursive_mutex> lk_(c->mu);
     c->stream = s ? (cudaStream_t)s : c->own_stream;
     return DRLZ_OK;
 }
 
 int drlz_set_option(drlz_ctx* c, const char* key, int64_t v) {
     if (!c || !key) return DRLZ_E_ARG;
+    std::lock_guard<std::recursive_mutex> lk_(c->mu);
     if (!strcmp(key, "kmer")) { if (v < 0 || v > 15) return DRLZ_E_ARG; c->opt_k = (int)v; }
     else if (!strcmp(key, "chunk")) { if (v < 0 || v > 0x7FFFFFFF) return DRLZ_E_ARG; c->opt_chunk = v ? (uint32_t)v : 2048; }
     else if (!strcmp(key, "group_bytes")) { if (v < 0) return DRLZ_E_ARG; c->opt_group_bytes = v ? (uint64_t)v : (256ull << 20); }
@@ -353,6 +377,7 @@ static int auto_k(uint64_t n) {
 
 int drlz_build_index(drlz_ctx* c, const uint8_t* ref, uint64_t n) {
     if (!c || (!ref && n)) return DRLZ_E_ARG;
+    std::lock_guard<std::recursive_mutex> lk_(c->mu);
     if (n > kMaxLen) { c->err = "reference longer than 2^32-1024"; return DRLZ_E_LIMIT; }
     CK(c, cudaSetDevice(c->device));
     cudaStream_t s = c->stream;
@@ -429,6 +454,7 @@ int drlz_build_index(drlz_ctx* c, const uint8_t* ref, uint64_t n) {
 
 int drlz_index_get(drlz_ctx* c, int what, void* host_out, uint64_t bytes) {
     if (!c || !host_out) return DRLZ_E_ARG;
+    std::lock_guard<std::recursive_mutex> lk_(c->mu);
     if (!c->have_index) { c->err = "index not built"; return DRLZ_E_STATE; }
     CK(c, cudaSetDevice(c->device));
     const void* src = nullptr; uint64_t need = 0;
@@ -461,6 +487,7 @@ int drlz_index_timings(const drlz_ctx* c, double ms[5]) {
 
 int drlz_index_reserve(drlz_ctx* c, uint64_t n, int k) {
     if (!c || k < 1 || k > 15) return DRLZ_E_ARG;
+    std::lock_guard<std::recursive_mutex> lk_(c->mu);
     if (n > kMaxLen) return DRLZ_E_LIMIT;
     CK(c, cudaSetDevice(c->device));
     c->have_index = false;
@@ -474,6 +501,7 @@ int drlz_index_reserve(drlz_ctx* c, uint64_t n, int k) {
 
 int drlz_index_buffers(drlz_ctx* c, void* dev_ptrs[3], uint64_t bytes[3]) {
     if (!c || !dev_ptrs || !bytes) return DRLZ_E_ARG;
+    std::lock_guard<std::recursive_mutex> lk_(c->mu);
     if (!c->d_text || !c->d_tab) { c->err = "no index buffers (build or reserve first)"; return DRLZ_E_STATE; }
     dev_ptrs[0] = c->d_text; bytes[0] = (c->n / 32 + 3) * 8;
     dev_ptrs[1] = c->sa.p; bytes[1] = c->n * 4;
@@ -483,6 +511,7 @@ int drlz_index_buffers(drlz_ctx* c, void* dev_ptrs[3], uint64_t bytes[3]) {
 
 int drlz_index_commit(drlz_ctx* c) {
     if (!c) return DRLZ_E_ARG;
+    std::lock_guard<std::recursive_mutex> lk_(c->mu);
     if (!c->d_text || !c->d_tab) return DRLZ_E_STATE;
     c->have_index = true;
     return DRLZ_OK;
@@ -494,6 +523,7 @@ int drlz_index_commit(drlz_ctx* c) {
 int drlz_parse_batch_device(drlz_ctx* c, const uint8_t* rows_dev, const uint64_t* row_off, const uint64_t* cols, uint32_t H,
                             int strip_gaps, uint64_t* m_out, const int64_t** pairs_dev, uint64_t* n_pairs) {
     if (!c || (H && (!rows_dev || !row_off || !cols))) return DRLZ_E_ARG;
+    std::lock_guard<std::recursive_mutex> lk_(c->mu);
     if (!c->have_index) { c->err = "index not built"; return DRLZ_E_STATE; }
     CK(c, cudaSetDevice(c->device));
     for (int i = 0; i < 12; ++i) c->parse_ms[i] = 0;
@@ -507,6 +537,7 @@ int drlz_parse_batch_device(drlz_ctx* c, const uint8_t* rows_dev, const uint64_t
 int drlz_parse_batch(drlz_ctx* c, const uint8_t* const* rows, const uint64_t* cols, uint32_t H, int strip_gaps,
                      uint8_t* const* gapless_out, uint64_t* m_out, int64_t* pairs_out, uint64_t pairs_cap, uint64_t* n_pairs) {
     if (!c || (H && (!rows || !cols || !n_pairs))) return DRLZ_E_ARG;
+    std::lock_guard<std::recursive_mutex> lk_(c->mu);
     if (!c->have_index) { c->err = "index not built"; return DRLZ_E_STATE; }
     CK(c, cudaSetDevice(c->device));
     for (int i = 0; i < 12; ++i) c->parse_ms[i] = 0;
@@ -584,8 +615,49 @@ int drlz_parse(drlz_ctx* c, const uint8_t* msa_row, uint64_t cols, int strip_gap
     return drlz_parse_batch(c, rows, &cols, 1, strip_gaps, gapless_out ? gl : nullptr, m_out, pairs_out, pairs_cap, n_pairs);
 }
 
+// ---- async form: FIFO worker thread per context -----------------------------------------------------------
+static void drlz_worker(drlz_ctx* c) {
+    for (;;) {
+        drlz_ctx::Job j;
+        {
+            std::unique_lock<std::mutex> lk(c->qmu);
+            c->qcv.wait(lk, [&] { return c->stopping || !c->queue.empty(); });
+            if (c->queue.empty()) return;
+            j = c->queue.front(); c->queue.pop_front();
+        }
+        int rc = drlz_parse_batch(c, j.rows, j.cols, j.H, j.strip, j.gapless, j.m_out, j.pairs, j.cap, j.n_pairs);
+        { std::lock_guard<std::mutex> lk(c->qmu); c->done.push_back(std::make_pair(j.ticket, rc)); }
+        c->done_cv.notify_all();
+    }
+}
+
+int drlz_submit(drlz_ctx* c, const uint8_t* const* rows, const uint64_t* cols, uint32_t H, int strip_gaps,
+                uint8_t* const* gapless_out, uint64_t* m_out, int64_t* pairs_out, uint64_t pairs_cap, uint64_t* n_pairs,
+                uint64_t* ticket) {
+    if (!c || !ticket || (H && (!rows || !cols || !n_pairs))) return DRLZ_E_ARG;
+    std::lock_guard<std::mutex> lk(c->qmu);
+    if (!c->worker_started) { c->worker = std::thread(drlz_worker, c); c->worker_started = true; }
+    drlz_ctx::Job j{c->next_ticket++, rows, cols, H, strip_gaps, gapless_out, m_out, pairs_out, pairs_cap, n_pairs};
+    *ticket = j.ticket;
+    c->queue.push_back(j);
+    c->qcv.notify_one();
+    return DRLZ_OK;
+}
+
+int drlz_wait(drlz_ctx* c, uint64_t ticket) {
+    if (!c || ticket == 0) return DRLZ_E_ARG;
+    std::unique_lock<std::mutex> lk(c->qmu);
+    if (ticket >= c->next_ticket) return DRLZ_E_ARG;
+    for (;;) {
+        for (size_t i = 0; i < c->done.size(); ++i)
+            if (c->done[i].first == ticket) { int rc = c->done[i].second; c->done.erase(c->done.begin() + i); return rc; }
+        c->done_cv.wait(lk);
+    }
+}
+
 int drlz_copy_to_host(drlz_ctx* c, void* dst_host, const void* src_dev, uint64_t bytes) {
     if (!c || (bytes && (!dst_host || !src_dev))) return DRLZ_E_ARG;
+    std::lock_guard<std::recursive_mutex> lk_(c->mu);
     CK(c, cudaSetDevice(c->device));
     if (bytes) CK(c, cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, c->stream));
     CK(c, cudaStreamSynchronize(c->stream));
@@ -600,6 +672,7 @@ int drlz_parse_timings(const drlz_ctx* c, double ms[12]) {
 
 int drlz_matching_stats(drlz_ctx* c, const uint8_t* x, uint64_t m, uint32_t* ms_out, uint32_t* pos_out) {
     if (!c || (m && (!x || !ms_out || !pos_out))) return DRLZ_E_ARG;
+    std::lock_guard<std::recursive_mutex> lk_(c->mu);
     if (!c->have_index) { c->err = "index not built"; return DRLZ_E_STATE; }
     if (m > kMaxLen) return DRLZ_E_LIMIT;
     if (m == 0) return DRLZ_OK;

@@ -108,6 +108,9 @@ int parse_stage_count(ParseBuffers& pb, cudaStream_t s, int* rounds_out, cudaEve
     if (ev) cudaEventRecord(ev[0], s);
     g_launches += 1;
     if (pb.occ >= 16) k_spec<16><<<(NC + 127) / 128, 128, 0, s>>>(pv);
+    else if (pb.occ >= 12) k_spec<12><<<(NC + 127) / 128, 128, 0, s>>>(pv);
+    else if (pb.occ >= 10) k_spec<10><<<(NC + 127) / 128, 128, 0, s>>>(pv);
+    else if (pb.occ >= 8) k_spec<8><<<(NC + 127) / 128, 128, 0, s>>>(pv);
     else k_spec<1><<<(NC + 127) / 128, 128, 0, s>>>(pv);
     if (ev) cudaEventRecord(ev[1], s);
     // stage A: diagonal-run links, list ranking, exits of the chunks whose last phrase is open
@@ -134,6 +137,7 @@ int parse_stage_count(ParseBuffers& pb, cudaStream_t s, int* rounds_out, cudaEve
         uint32_t nr = NC * kAltSlots;
         g_launches += 1;
         if (pb.occ >= 16) k_fix<16><<<(nr + 127) / 128, 128, 0, s>>>(pv, (uint32_t)round);
+        else if (pb.occ >= 10) k_fix<10><<<(nr + 127) / 128, 128, 0, s>>>(pv, (uint32_t)round);
         else k_fix<1><<<(nr + 127) / 128, 128, 0, s>>>(pv, (uint32_t)round);
         ++round;
     }

@@ -22,7 +22,7 @@ SYMBOLS = [
     "drlz_create", "drlz_destroy", "drlz_last_error", "drlz_set_stream", "drlz_set_option", "drlz_host_alloc",
     "drlz_host_free", "drlz_build_index", "drlz_index_get", "drlz_index_info", "drlz_index_timings",
     "drlz_index_reserve", "drlz_index_buffers", "drlz_index_commit", "drlz_parse", "drlz_parse_batch",
-    "drlz_parse_batch_device", "drlz_parse_timings", "drlz_matching_stats", "drlz_copy_to_host",
+    "drlz_parse_batch_device", "drlz_parse_timings", "drlz_matching_stats", "drlz_copy_to_host", "drlz_submit", "drlz_wait",
 ]
 
 
@@ -72,6 +72,8 @@ def load_library() -> C.CDLL:
         L.drlz_parse_batch_device.restype = i32
         L.drlz_parse_timings.argtypes = [vp, vp]; L.drlz_parse_timings.restype = i32
         L.drlz_copy_to_host.argtypes = [vp, vp, vp, u64]; L.drlz_copy_to_host.restype = i32
+        L.drlz_submit.argtypes = [vp, vp, vp, C.c_uint32, i32, vp, vp, vp, u64, vp, vp]; L.drlz_submit.restype = i32
+        L.drlz_wait.argtypes = [vp, u64]; L.drlz_wait.restype = i32
         L.drlz_matching_stats.argtypes = [vp, vp, u64, vp, vp]; L.drlz_matching_stats.restype = i32
         _LIB = L
     return _LIB
@@ -212,6 +214,31 @@ class Drlz:
         if gl is not None:
             gl = [g[: int(m[h])] for h, g in enumerate(gl)]
         return res, m, gl
+
+    def submit(self, rows, pairs_cap: int, strip_gaps: bool = True):
+        """Async form: returns a handle; call .wait() for (pairs list, m).  Buffers are kept alive by the handle."""
+        rows = [_u8(r) for r in rows]
+        H = len(rows)
+        st = {"rows": rows, "ptrs": (C.c_void_p * max(1, H))(*[r.ctypes.data if r.size else None for r in rows]),
+              "cols": np.array([r.size for r in rows], dtype=np.uint64), "m": np.zeros(max(1, H), dtype=np.uint64),
+              "np": np.zeros(max(1, H), dtype=np.uint64), "buf": np.empty(2 * pairs_cap, dtype=np.int64), "H": H}
+        t = C.c_uint64(0)
+        self._ck(self._lib.drlz_submit(self._h, st["ptrs"], st["cols"].ctypes.data_as(C.c_void_p), H, int(strip_gaps), None,
+                                       st["m"].ctypes.data_as(C.c_void_p), st["buf"].ctypes.data_as(C.c_void_p), pairs_cap,
+                                       st["np"].ctypes.data_as(C.c_void_p), C.byref(t)))
+        st["ticket"] = t.value
+        ctx = self
+
+        class Handle:
+            def wait(self_inner):
+                ctx._ck(ctx._lib.drlz_wait(ctx._h, st["ticket"]))
+                res, o = [], 0
+                for h in range(st["H"]):
+                    c = int(st["np"][h])
+                    res.append(st["buf"][2 * o: 2 * (o + c)].reshape(-1, 2))
+                    o += c
+                return res, st["m"][: st["H"]].astype(np.int64)
+        return Handle()
 
     def parse(self, row, strip_gaps: bool = True):
         res, m, _ = self.parse_batch([row], strip_gaps)

@@ -214,6 +214,30 @@ def test_pairs_cap_too_small(ctx):
     assert e.value.code == -4
 
 
+def test_submit_wait_and_threads(ctx):
+    import threading
+    seed = orc.seed_for(1)
+    d = orc.syn_reference(seed, 300_000)
+    rows = orc.syn_rows(seed, d, 0, 6, 1e-3, 1e-4, 1e-4)
+    ctx.build_index(d)
+    sa = orc.sa_build(d)
+    expect = [orc.lz_bytes(orc.encode_literal(d, sa, orc.strip_gaps(r))[0]) for r in rows]
+    handles = [ctx.submit([rows[h].tobytes(), rows[(h + 1) % 6].tobytes()], pairs_cap=20000) for h in range(6)]
+    for h, hd in reversed(list(enumerate(handles))):
+        res, m = hd.wait()
+        assert orc.lz_bytes(res[0]) == expect[h] and orc.lz_bytes(res[1]) == expect[(h + 1) % 6]
+    # concurrent callers on one context are serialised, results stay correct
+    out = {}
+
+    def work(h):
+        out[h] = ctx.parse_batch([rows[h].tobytes()])[0][0]
+    ths = [threading.Thread(target=work, args=(h,)) for h in range(6)]
+    [t.start() for t in ths]
+    [t.join() for t in ths]
+    for h in range(6):
+        assert orc.lz_bytes(out[h]) == expect[h]
+
+
 def test_errors(ctx):
     with pytest.raises(D.DrlzError) as e:
         ctx.build_index(b"ACGTNACGT")
