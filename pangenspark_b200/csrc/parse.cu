@@ -3,12 +3,12 @@
 //   k_spec      P1: one thread per chunk, speculative greedy parse from the chunk's first base with chunk-capped
 //                   lookups; phrases stored; the first phrase doubles as stage A's phrase at the chunk start
 //   k_link      A : open first phrases linked to the chunk their match continues in
-//   k_rank      A : list ranking (pointer jumping) -> exact lengths of arbitrarily long matches
+//   scan/k_rank A : list ranking of the diagonal runs (a right-to-left segmented sum; pointer jumping when chunks
+//                   are smaller than min_cap) -> exact lengths of arbitrarily long matches
 //   k_resolve   A : total length of each chunk's open last phrase -> exit of the chunk
 //   k_fix       F : one thread per (chunk, alternative entry) created in the previous round
-//   k_succ      J : successor of every record; roots marked
-//   k_jump      J : pointer jumping (mark[jump[v]] |= mark[v]; jump = jump o jump), log2(chunks) rounds
-//   k_true      E : per chunk the marked record's phrase count, entry and slot
+//   k_mark_*    J : records form a functional graph; the true chain is marked in two levels (shared-memory pointer
+//                   jumping per block of 1024 chunks + one hop per block), then each chunk's true record is picked
 //   device_scan E : exclusive prefix of the counts = output slot of every chunk (stream compaction)
 //   k_emit      E : gather the stored phrases of the true records into (int64 pos, int64 len) records
 //                   (DistributedRLZ.scala:263-284 record layout); re-parses only what was not stored
@@ -47,33 +47,111 @@ __global__ void __launch_bounds__(128, MINB) k_fix(ParseView pv, uint32_t round)
     if (r < pv.n_chunks * kAltSlots) fix_parse_record(pv, r / kAltSlots, (int)(r % kAltSlots), round);
 }
 
-__global__ void k_succ(ParseView pv, uint32_t* jump, uint8_t* mark) {
-    uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t nn = pv.n_chunks * (kAltSlots + 1);
-    if (v >= nn) return;
-    jump[v] = node_succ(pv, v);
-    uint32_t g = v / (kAltSlots + 1);
-    uint32_t h = pv.chunk_hap[g];
-    // root: speculative record of the first chunk of a non-empty haplotype
-    mark[v] = (v % (kAltSlots + 1) == 0 && g == pv.hap_chunk_base[h] && pv.haps[h].m > 0) ? 1 : 0;
+// ---- J: marking the true chain, two levels ------------------------------------------------------------------
+// A record's successor always lies in a later chunk, so inside a block of kMarkChunks consecutive chunks every
+// chain is resolved by pointer jumping in shared memory (k_mark_local: record -> last record of the block on its
+// chain).  One thread per haplotype then hops from block to block (k_mark_walk), marking the record through which
+// the true chain enters each block, and k_mark_spread propagates those marks inside the blocks (again in shared
+// memory) and picks each chunk's true record.  3 launches instead of 2 + log2(chunks) global passes.
+static const int kMarkChunks = 1024;
+static const int kMarkNodes = kMarkChunks * (kAltSlots + 1);
+
+__device__ __forceinline__ void mark_load_links(const ParseView& pv, const uint32_t* succ_in, uint32_t* succ_out, uint32_t base,
+                                                uint32_t nn, uint16_t* ja) {
+    for (uint32_t l = threadIdx.x; l < (uint32_t)kMarkNodes; l += blockDim.x) {
+        uint32_t v = base + l;
+        uint16_t loc = (uint16_t)l;
+        if (v < nn) {
+            uint32_t sv = succ_in ? succ_in[v] : node_succ(pv, v);
+            if (succ_out) succ_out[v] = sv;
+            if (sv != v && sv >= base && sv - base < (uint32_t)kMarkNodes) loc = (uint16_t)(sv - base);
+        }
+        ja[l] = loc;
+    }
 }
 
-__global__ void k_jump(const uint32_t* __restrict__ jump, uint32_t* __restrict__ jump2, uint8_t* mark, uint32_t nn) {
-    uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= nn) return;
-    uint32_t j = jump[v];
-    if (mark[v]) mark[j] = 1;
-    jump2[v] = jump[j];
+__global__ void __launch_bounds__(256) k_mark_local(ParseView pv, uint32_t* succ_glob, uint32_t* block_last) {
+    __shared__ uint16_t ja[kMarkNodes], jb[kMarkNodes];
+    const uint32_t nn = pv.n_chunks * (kAltSlots + 1);
+    const uint32_t base = blockIdx.x * kMarkNodes;
+    mark_load_links(pv, nullptr, succ_glob, base, nn, ja);
+    __syncthreads();
+    uint16_t *a = ja, *b = jb;
+    for (int span = 1; span < kMarkChunks; span *= 2) {
+        for (uint32_t l = threadIdx.x; l < (uint32_t)kMarkNodes; l += blockDim.x) b[l] = a[a[l]];
+        __syncthreads();
+        uint16_t* t = a; a = b; b = t;
+    }
+    for (uint32_t l = threadIdx.x; l < (uint32_t)kMarkNodes; l += blockDim.x)
+        if (base + l < nn) block_last[base + l] = base + a[l];
 }
 
-__global__ void k_true(ParseView pv, const uint8_t* mark, uint32_t* true_cnt, uint32_t* true_entry, uint32_t* true_slot) {
-    uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= pv.n_chunks) return;
-    uint32_t e, sl;
-    true_cnt[g] = chunk_true_record(pv, mark, g, &e, &sl);
-    true_entry[g] = e;
-    true_slot[g] = sl;
+__global__ void k_mark_walk(ParseView pv, uint32_t H, const uint32_t* __restrict__ succ_glob,
+                            const uint32_t* __restrict__ block_last, uint8_t* mark) {
+    uint32_t h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= H) return;
+    if (pv.haps[h].m == 0 || pv.hap_chunk_base[h] >= pv.hap_chunk_base[h + 1]) return;
+    uint32_t cur = pv.hap_chunk_base[h] * (kAltSlots + 1);       // root: speculative record of the first chunk
+    for (;;) {
+        mark[cur] = 1;
+        uint32_t ex = block_last[cur];
+        uint32_t nx = succ_glob[ex];
+        if (nx == ex) break;                                     // parse finished
+        cur = nx;
+    }
 }
+
+__global__ void __launch_bounds__(256) k_mark_spread(ParseView pv, const uint32_t* __restrict__ succ_glob,
+                                                      const uint8_t* __restrict__ mark_in, uint32_t* true_cnt,
+                                                      uint32_t* true_entry, uint32_t* true_slot) {
+    __shared__ uint16_t ja[kMarkNodes], jb[kMarkNodes];
+    __shared__ uint8_t mk[kMarkNodes];
+    const uint32_t nn = pv.n_chunks * (kAltSlots + 1);
+    const uint32_t base = blockIdx.x * kMarkNodes;
+    mark_load_links(pv, succ_glob, nullptr, base, nn, ja);
+    for (uint32_t l = threadIdx.x; l < (uint32_t)kMarkNodes; l += blockDim.x) mk[l] = base + l < nn ? mark_in[base + l] : 0;
+    __syncthreads();
+    uint16_t *a = ja, *b = jb;
+    for (int span = 1; span < kMarkChunks; span *= 2) {
+        for (uint32_t l = threadIdx.x; l < (uint32_t)kMarkNodes; l += blockDim.x) {
+            uint16_t j = a[l];
+            if (mk[l]) mk[j] = 1;           // marks only ever travel along the chain: racing writes are benign
+            b[l] = a[j];
+        }
+        __syncthreads();
+        uint16_t* t = a; a = b; b = t;
+    }
+    for (uint32_t c = threadIdx.x; c < (uint32_t)kMarkChunks; c += blockDim.x) {
+        uint32_t g = blockIdx.x * kMarkChunks + c;
+        if (g >= pv.n_chunks) continue;
+        uint32_t e, sl;
+        true_cnt[g] = chunk_true_record(pv, mk + c * (kAltSlots + 1), g, &e, &sl);
+        true_entry[g] = e;
+        true_slot[g] = sl;
+    }
+}
+
+// ---- A: run lengths of open first phrases as a right-to-left segmented sum ---------------------------------------
+// With min_cap <= chunk size an open first phrase is verified exactly to its chunk end, so link[g] == g + 1 and the
+// list ranking is a segmented suffix sum over consecutive chunks: one 3-launch scan instead of log2(chunks) rounds.
+struct OpSegSum {
+    __device__ __forceinline__ uint64_t operator()(uint64_t a, uint64_t b) const {
+        const uint64_t F = 1ull << 63, M = F - 1;
+        uint64_t sum = ((b & F) ? 0ull : (a & M)) + (b & M);
+        return ((a | b) & F) | (sum & M);
+    }
+};
+struct LoadRunRev {
+    const uint32_t* run; const uint32_t* link; uint64_t nc;
+    __device__ __forceinline__ uint64_t operator()(uint64_t e) const {
+        uint64_t g = nc - 1 - e;
+        return (uint64_t)run[g] | (link[g] == kEmpty ? (1ull << 63) : 0ull);
+    }
+};
+struct StoreRunRev {
+    uint32_t* out; uint64_t nc;
+    __device__ __forceinline__ void operator()(uint64_t e, uint64_t v) const { out[nc - 1 - e] = (uint32_t)v; }
+};
 
 __global__ void k_hap_pairs(ParseView pv, uint32_t H, const uint64_t* true_off, const uint64_t* total, uint64_t* hap_pairs) {
     uint32_t h = blockIdx.x * blockDim.x + threadIdx.x;
@@ -116,7 +194,11 @@ int parse_stage_count(ParseBuffers& pb, cudaStream_t s, int* rounds_out, cudaEve
     // stage A: diagonal-run links, list ranking, exits of the chunks whose last phrase is open
     g_launches += 2;
     k_link<<<(NC + 127) / 128, 128, 0, s>>>(pv);
-    {
+    if (pv.min_cap <= pv.chunk_bases) {
+        device_scan<uint64_t, LoadRunRev, StoreRunRev, OpSegSum, true>(LoadRunRev{pv.run_len, pv.link, NC}, StoreRunRev{pb.run_b, NC},
+                                                                        NC, pb.scan_tmp, OpSegSum(), 0ull, s);
+        pv.run_len = pb.run_b;
+    } else {
         uint32_t *li = pv.link, *ri = pv.run_len, *lo = pb.link_b, *ro = pb.run_b;
         for (uint64_t span = 1; span < pb.max_chunks_per_hap; span *= 2) {
             g_launches += 1;
@@ -144,15 +226,12 @@ int parse_stage_count(ParseBuffers& pb, cudaStream_t s, int* rounds_out, cudaEve
     if (rounds_out) *rounds_out = round;
     if (ev) cudaEventRecord(ev[2], s);
     uint32_t nn = NC * (kAltSlots + 1);
-    g_launches += 3;
-    k_succ<<<(nn + 255) / 256, 256, 0, s>>>(pv, pb.jump_a, pb.mark);
-    uint32_t* ja = pb.jump_a; uint32_t* jb = pb.jump_b;
-    for (uint64_t span = 1; span < 2ull * pb.max_chunks_per_hap; span *= 2) {
-        g_launches += 1;
-        k_jump<<<(nn + 255) / 256, 256, 0, s>>>(ja, jb, pb.mark, nn);
-        uint32_t* t = ja; ja = jb; jb = t;
-    }
-    k_true<<<(NC + 255) / 256, 256, 0, s>>>(pv, pb.mark, pb.true_cnt, pb.true_entry, pb.true_slot);
+    uint32_t nmb = (nn + kMarkNodes - 1) / kMarkNodes;
+    g_launches += 4;
+    cudaMemsetAsync(pb.mark, 0, nn, s);
+    k_mark_local<<<nmb, 256, 0, s>>>(pv, pb.jump_a, pb.jump_b);
+    k_mark_walk<<<(pb.H + 127) / 128, 128, 0, s>>>(pv, pb.H, pb.jump_a, pb.jump_b, pb.mark);
+    k_mark_spread<<<nmb, 256, 0, s>>>(pv, pb.jump_a, pb.mark, pb.true_cnt, pb.true_entry, pb.true_slot);
     device_scan<uint64_t, LoadArr<uint32_t, uint64_t>, StoreArr<uint64_t>, OpSum, false>(
         LoadArr<uint32_t, uint64_t>{pb.true_cnt}, StoreArr<uint64_t>{pb.true_off}, NC, pb.scan_tmp, OpSum(), 0ull, s);
     uint64_t nt = ((uint64_t)NC + kScanTile - 1) / kScanTile;

@@ -509,17 +509,16 @@ DRLZ_HD uint32_t node_succ(const ParseView& pv, uint32_t node) {
 }
 
 // E: after marking, pick the chunk's true record: returns phrase count, *entry = true entry position
-// *slot = 0 for the speculative record, 1 + s for alternative record s
-DRLZ_HD uint32_t chunk_true_record(const ParseView& pv, const uint8_t* mark, uint32_t g, uint32_t* entry, uint32_t* slot) {
-    uint32_t base = g * (kAltSlots + 1);
+// *slot = 0 for the speculative record, 1 + s for alternative record s.  m4 = the chunk's kAltSlots+1 mark bytes.
+DRLZ_HD uint32_t chunk_true_record(const ParseView& pv, const uint8_t* m4, uint32_t g, uint32_t* entry, uint32_t* slot) {
     *slot = 0;
-    if (mark[base]) {
+    if (m4[0]) {
         uint32_t h = pv.chunk_hap[g];
         *entry = (g - pv.hap_chunk_base[h]) * pv.chunk_bases;
         return pv.spec_cnt[g];
     }
     for (int s = 0; s < kAltSlots; ++s)
-        if (mark[base + 1 + s]) { *entry = pv.alt_entry[g * kAltSlots + s]; *slot = 1 + s; return pv.alt_cnt[g * kAltSlots + s]; }
+        if (m4[1 + s]) { *entry = pv.alt_entry[g * kAltSlots + s]; *slot = 1 + s; return pv.alt_cnt[g * kAltSlots + s]; }
     *entry = 0;
     return 0;
 }

@@ -110,7 +110,7 @@ int emu_parse(const uint8_t* ref, uint64_t n, const int64_t* sa64, int k, uint32
     }
     std::vector<uint64_t> off(NC + 1, 0);
     std::vector<uint32_t> ent(NC), cnt(NC), slot(NC);
-    for (uint32_t g = 0; g < NC; ++g) { cnt[g] = chunk_true_record(pv, mark.data(), g, &ent[g], &slot[g]); off[g + 1] = off[g] + cnt[g]; }
+    for (uint32_t g = 0; g < NC; ++g) { cnt[g] = chunk_true_record(pv, mark.data() + (size_t)g * (kAltSlots + 1), g, &ent[g], &slot[g]); off[g + 1] = off[g] + cnt[g]; }
     std::vector<int64_t> out(2 * off[NC] + 2);
     for (uint32_t g = 0; g < NC; ++g)
         if (cnt[g] && !emit_stored(pv, g, slot[g], cnt[g], out.data() + 2 * off[g])) emit_chunk(pv, g, ent[g], cnt[g], out.data() + 2 * off[g]);
