@@ -59,7 +59,7 @@ struct drlz_ctx {
     bool have_index = false; uint64_t n = 0; int k = 0; int sa_rounds = 0;
     DevBuf blob, sa, isa, lcp;             // blob = [k-mer table | packed text] (one L2 access-policy window)
     uint64_t* d_text = nullptr; uint32_t* d_tab = nullptr; size_t blob_bytes = 0;
-    cudaStream_t l2_stream = nullptr; int opt_l2persist = 0; int opt_occ = 16;
+    cudaStream_t l2_stream = nullptr; int opt_l2persist = 0; int opt_occ = 10;
     double idx_ms[5] = {0, 0, 0, 0, 0};
     // batch scratch (grow-only)
     DevBuf stage[2], meta_dev, desc_cnt, desc_exc, tile_counter, X, mdev, exccnt, excpos, excbyte,

@@ -94,15 +94,12 @@ __device__ __forceinline__ uint64_t lookback(uint64_t* desc_row, uint32_t t, uin
     return excl;
 }
 
-__global__ void __launch_bounds__(256) k_pack(PackJob job) {
-    __shared__ uint32_t sbits[kPackTileBytes / 16 + 8];
-    __shared__ uint32_t sm[33];
-    __shared__ uint64_t s_bcast[4];
-    __shared__ uint64_t s_wlast[8];
+static const int kTilesPerCta = 1;            // tiles per atomic ticket (4 was measured 18x slower: a tile is published only after
+                                              // its CTA finished the earlier ones, which serialises every row's look-back chain)
+
+__device__ __forceinline__ void pack_tile(const PackJob& job, uint32_t id, uint32_t* sbits, uint32_t* sm, uint64_t* s_bcast,
+                                          uint64_t* s_wlast) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_bcast[0] = atomicAdd(job.tile_counter, 1u);
-    __syncthreads();
-    const uint32_t id = (uint32_t)s_bcast[0];
     // rows interleaved: consecutive ids are the same tile index of consecutive rows, so each row has only a few
     // tiles in flight and its look-back resolves within one 32-descriptor window
     const uint32_t h = id % job.H, t = id / job.H;
@@ -242,6 +239,23 @@ __global__ void __launch_bounds__(256) k_pack(PackJob job) {
     }
 }
 
+__global__ void __launch_bounds__(256) k_pack(PackJob job, uint32_t n_tiles) {
+    __shared__ uint32_t sbits[kPackTileBytes / 16 + 8];
+    __shared__ uint32_t sm[33];
+    __shared__ uint64_t s_bcast[4];
+    __shared__ uint64_t s_wlast[8];
+    __shared__ uint32_t s_ticket;
+    if (threadIdx.x == 0) s_ticket = atomicAdd(job.tile_counter, (uint32_t)kTilesPerCta);
+    __syncthreads();
+    const uint32_t first = s_ticket;
+    for (int q = 0; q < kTilesPerCta; ++q) {
+        uint32_t id = first + (uint32_t)q;
+        if (id >= n_tiles) break;
+        pack_tile(job, id, sbits, sm, s_bcast, s_wlast);
+        __syncthreads();                                   // shared buffers are reused by the next tile
+    }
+}
+
 void launch_pack(const PackJob& job, cudaStream_t s, cudaEvent_t* ev) {
     if (job.H == 0 || job.tiles_per_row == 0) { if (ev) for (int i = 0; i < 3; ++i) cudaEventRecord(ev[i], s); return; }
     uint64_t nt = (uint64_t)job.H * job.tiles_per_row;
@@ -250,7 +264,7 @@ void launch_pack(const PackJob& job, cudaStream_t s, cudaEvent_t* ev) {
     cudaMemsetAsync(job.tile_counter, 0, 4, s);
     if (ev) { cudaEventRecord(ev[0], s); cudaEventRecord(ev[1], s); }
     g_launches += 1;
-    k_pack<<<(unsigned)nt, 256, 0, s>>>(job);
+    k_pack<<<(unsigned)((nt + kTilesPerCta - 1) / kTilesPerCta), 256, 0, s>>>(job, (uint32_t)nt);
     if (ev) cudaEventRecord(ev[2], s);
 }
 
