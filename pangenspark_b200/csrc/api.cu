@@ -59,7 +59,7 @@ struct drlz_ctx {
     bool have_index = false; uint64_t n = 0; int k = 0; int sa_rounds = 0;
     DevBuf blob, sa, isa, lcp;             // blob = [k-mer table | packed text] (one L2 access-policy window)
     uint64_t* d_text = nullptr; uint32_t* d_tab = nullptr; size_t blob_bytes = 0;
-    cudaStream_t l2_stream = nullptr; int opt_l2persist = 0; int opt_occ = 10;
+    cudaStream_t l2_stream = nullptr; int opt_l2persist = 0; int opt_occ = 10; int opt_tickets = 1;
     double idx_ms[5] = {0, 0, 0, 0, 0};
     // batch scratch (grow-only)
     DevBuf stage[2], meta_dev, desc_cnt, desc_exc, tile_counter, X, mdev, exccnt, excpos, excbyte,
@@ -180,6 +180,7 @@ int drlz_set_option(drlz_ctx* c, const char* key, int64_t v) {
     else if (!strcmp(key, "lcp")) c->opt_lcp = v != 0;
     else if (!strcmp(key, "l2persist")) { c->opt_l2persist = v != 0; c->l2_stream = nullptr; }
     else if (!strcmp(key, "occ")) c->opt_occ = (int)v;
+    else if (!strcmp(key, "tickets")) c->opt_tickets = v != 0;
     else if (!strcmp(key, "min_cap")) { if (v < 0 || v > 0x7FFFFFFF) return DRLZ_E_ARG; c->opt_min_cap = v ? (uint32_t)v : 64; }
     else if (!strcmp(key, "foreign_cap")) { if (v < 0 || v > 0x7FFFFFFF) return DRLZ_E_ARG; c->opt_foreign_cap = v ? (uint32_t)v : (1u << 20); }
     else return DRLZ_E_ARG;
@@ -279,6 +280,7 @@ static int run_device_group(drlz_ctx* c, const uint8_t* rows_dev, const uint64_t
         job.rows = rows_dev; job.row_off = d_row_off; job.cols = d_cols; job.H = H; job.tiles_per_row = T; job.strip = strip;
         job.desc_cnt = c->desc_cnt.as<uint64_t>(); job.desc_exc = c->desc_exc.as<uint64_t>();
         job.tile_counter = c->tile_counter.as<uint32_t>(); job.X = c->X.as<uint64_t>(); job.xoff = d_xoff;
+        job.use_tickets = c->opt_tickets;
         job.m_out = c->mdev.as<uint64_t>(); job.exc_cnt = c->exccnt.as<uint64_t>();
         job.exc_pos = c->excpos.as<uint32_t>(); job.exc_byte = c->excbyte.as<uint8_t>(); job.exc_stride = exc_stride;
         job.flags = c->flags.as<uint32_t>();
@@ -341,6 +343,10 @@ static int run_device_group(drlz_ctx* c, const uint8_t* rows_dev, const uint64_t
         CK(c, cudaMemcpyAsync(sh_exccnt, c->exccnt.p, (size_t)H * 8, cudaMemcpyDeviceToHost, s));
         CK(c, cudaMemcpyAsync(sh_flags, c->flags.p, 4, cudaMemcpyDeviceToHost, s));
         CK(c, cudaStreamSynchronize(s));
+        if (*sh_flags & 2u) {           // look-back timed out (CTAs not dispatched in index order): redo with tickets
+            c->opt_tickets = 1;
+            continue;
+        }
         if (*sh_flags & 1u) {           // exception list overflowed: grow and redo the group
             uint64_t mx = 0;
             for (uint32_t h = 0; h < H; ++h) if (sh_exccnt[h] > mx) mx = sh_exccnt[h];
@@ -414,6 +420,7 @@ int drlz_build_index(drlz_ctx* c, const uint8_t* ref, uint64_t n) {
         job.rows = c->stage[0].as<uint8_t>(); job.row_off = dm; job.cols = dm + 1; job.H = 1; job.tiles_per_row = T; job.strip = 0;
         job.desc_cnt = c->desc_cnt.as<uint64_t>(); job.desc_exc = c->desc_exc.as<uint64_t>();
         job.tile_counter = c->tile_counter.as<uint32_t>(); job.X = c->d_text; job.xoff = dm + 2;
+        job.use_tickets = 1;
         job.m_out = c->mdev.as<uint64_t>(); job.exc_cnt = c->exccnt.as<uint64_t>();
         job.exc_pos = c->excpos.as<uint32_t>(); job.exc_byte = c->excbyte.as<uint8_t>(); job.exc_stride = 64;
         job.flags = c->flags.as<uint32_t>(); job.gapless = nullptr; job.gapless_off = dm + 3;

@@ -8,7 +8,7 @@ namespace drlz {
 
 extern unsigned long long g_launches;
 
-static const int kPackTileBytes = 16384;     // MSA bytes per CTA in the strip/pack kernel (256 threads x 64 B)
+static const int kPackTileBytes = 16384;     // MSA bytes per CTA in the strip/pack kernel (256 threads x 64 B; 8 KB and 32 KB measured slower)
 
 // ---- strip + pack (pack.cu) --------------------------------------------------------------------
 struct PackJob {
@@ -22,6 +22,7 @@ struct PackJob {
     uint64_t* desc_cnt;           // [H*tiles_per_row] look-back descriptors: non-gap bytes   (zeroed by launch_pack)
     uint64_t* desc_exc;           // [H*tiles_per_row] look-back descriptors: exceptions
     uint32_t* tile_counter;       // [1] dynamic tile ids
+    int use_tickets;              // 1: tile ids from the atomic counter; 0: from blockIdx (dispatch order), guarded by a timeout
     uint64_t* X;                  // packed output, zero-filled by the caller
     const uint64_t* xoff;         // [H] word offset of haplotype h inside X (device)
     uint64_t* m_out;              // [H] gapless lengths (device)
@@ -29,7 +30,7 @@ struct PackJob {
     uint32_t* exc_pos;            // [H*exc_stride] row h owns [h*exc_stride, (h+1)*exc_stride)
     uint8_t* exc_byte;            // [H*exc_stride]
     uint64_t exc_stride;
-    uint32_t* flags;              // bit 0: a row has more exceptions than exc_stride
+    uint32_t* flags;              // bit 0: a row has more exceptions than exc_stride; bit 1: look-back timed out
     uint8_t* gapless;             // optional gapless bytes out (device) or null
     const uint64_t* gapless_off;  // [H] byte offsets into gapless
 };

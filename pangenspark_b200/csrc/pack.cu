@@ -70,8 +70,12 @@ __device__ __forceinline__ uint64_t ld_desc(const uint64_t* p) { return *reinter
 __device__ __forceinline__ void st_desc(uint64_t* p, uint64_t v) { *reinterpret_cast<volatile uint64_t*>(p) = v; }
 
 // decoupled look-back by one warp: exclusive prefix of `agg` over tiles [0, t) of the row; publishes the tile
-__device__ __forceinline__ uint64_t lookback(uint64_t* desc_row, uint32_t t, uint64_t agg) {
+// `flags` bit 1 is raised (and the wait abandoned) if a predecessor does not publish within ~0.2 s: with ids taken
+// from blockIdx the kernel relies on the hardware dispatching CTAs in index order; the host then redoes the batch
+// with atomic tickets.
+__device__ __forceinline__ uint64_t lookback(uint64_t* desc_row, uint32_t t, uint64_t agg, uint32_t* flags) {
     const int lane = threadIdx.x & 31;
+    long long t0 = 0; bool timing = false;
     if (t == 0) { if (lane == 0) st_desc(&desc_row[0], kDescPrefix | agg); return 0; }
     if (lane == 0) st_desc(&desc_row[t], kDescAgg | agg);
     uint64_t excl = 0;
@@ -80,7 +84,11 @@ __device__ __forceinline__ uint64_t lookback(uint64_t* desc_row, uint32_t t, uin
         int64_t idx = look - lane;
         uint64_t v = idx >= 0 ? ld_desc(&desc_row[idx]) : kDescPrefix;
         unsigned st = (unsigned)(v >> 62);
-        if (__any_sync(0xffffffffu, st == 0)) continue;          // a predecessor has not published yet
+        if (__any_sync(0xffffffffu, st == 0)) {                  // a predecessor has not published yet
+            if (!timing) { t0 = clock64(); timing = true; }
+            else if (clock64() - t0 > 400000000ll) { if (lane == 0) atomicOr(flags, 2u); break; }
+            continue;
+        }
         unsigned pm = __ballot_sync(0xffffffffu, st == 2);
         int first = pm ? __ffs(pm) - 1 : 32;
         uint64_t val = lane <= first ? (v & kDescMask) : 0;
@@ -96,6 +104,8 @@ __device__ __forceinline__ uint64_t lookback(uint64_t* desc_row, uint32_t t, uin
 
 static const int kTilesPerCta = 1;            // tiles per atomic ticket (4 was measured 18x slower: a tile is published only after
                                               // its CTA finished the earlier ones, which serialises every row's look-back chain)
+
+static const int kPackThreads = kPackTileBytes / 64;
 
 __device__ __forceinline__ void pack_tile(const PackJob& job, uint32_t id, uint32_t* sbits, uint32_t* sm, uint64_t* s_bcast,
                                           uint64_t* s_wlast) {
@@ -140,9 +150,9 @@ __device__ __forceinline__ void pack_tile(const PackJob& job, uint32_t id, uint3
 
     // ---- tile offset inside the row: decoupled look-back -----------------------------------------------------
     if (warp == 0) {
-        uint64_t o = lookback(dcnt, t, T);
+        uint64_t o = lookback(dcnt, t, T, job.flags);
         uint64_t eo = 0;
-        if (TE || last_tile) eo = lookback(dexc, t, TE);
+        if (TE || last_tile) eo = lookback(dexc, t, TE, job.flags);
         else if (lane == 0) st_desc(&dexc[t], (t == 0 ? kDescPrefix : kDescAgg) | 0ull);
         if (lane == 0) {
             s_bcast[1] = o; s_bcast[2] = eo;
@@ -155,7 +165,7 @@ __device__ __forceinline__ void pack_tile(const PackJob& job, uint32_t id, uint3
         }
     }
     const bool fast = T == kPackTileBytes && TE == 0;        // no gap, no foreign byte, full tile
-    if (!fast) for (int i = tid; i < kPackTileBytes / 16 + 8; i += 256) sbits[i] = 0;
+    if (!fast) for (int i = tid; i < kPackTileBytes / 16 + 8; i += kPackThreads) sbits[i] = 0;
     __syncthreads();
     const uint64_t o = s_bcast[1];
     if (T == 0) return;
@@ -205,7 +215,7 @@ __device__ __forceinline__ void pack_tile(const PackJob& job, uint32_t id, uint3
         if (tid == 0 && lead != 0) atomicOr(reinterpret_cast<unsigned long long*>(dst), (unsigned long long)g0);
         else dst[0] = g0;
         dst[1] = g1;
-        if (tid == 255 && lead != 0)
+        if (tid == kPackThreads - 1 && lead != 0)
             atomicOr(reinterpret_cast<unsigned long long*>(dst + 2), (unsigned long long)(w1 << (64 - 2 * lead)));
         return;
     }
@@ -225,7 +235,7 @@ __device__ __forceinline__ void pack_tile(const PackJob& job, uint32_t id, uint3
     }
     __syncthreads();
     uint32_t nwords = (lead + T + 31) >> 5;
-    for (uint32_t j = tid; j < nwords; j += 256) {
+    for (uint32_t j = tid; j < nwords; j += kPackThreads) {
         int64_t lb = (int64_t)j * 32 - (int64_t)lead;      // local base index of the word's first base
         uint32_t b0 = lb < 0 ? 0u : (uint32_t)lb;
         uint32_t wi = b0 >> 4, sh = (b0 & 15u) * 2;
@@ -239,15 +249,18 @@ __device__ __forceinline__ void pack_tile(const PackJob& job, uint32_t id, uint3
     }
 }
 
-__global__ void __launch_bounds__(256) k_pack(PackJob job, uint32_t n_tiles) {
+__global__ void __launch_bounds__(kPackThreads) k_pack(PackJob job, uint32_t n_tiles) {
     __shared__ uint32_t sbits[kPackTileBytes / 16 + 8];
     __shared__ uint32_t sm[33];
     __shared__ uint64_t s_bcast[4];
-    __shared__ uint64_t s_wlast[8];
+    __shared__ uint64_t s_wlast[kPackThreads / 32];
     __shared__ uint32_t s_ticket;
-    if (threadIdx.x == 0) s_ticket = atomicAdd(job.tile_counter, (uint32_t)kTilesPerCta);
-    __syncthreads();
-    const uint32_t first = s_ticket;
+    uint32_t first;
+    if (job.use_tickets) {
+        if (threadIdx.x == 0) s_ticket = atomicAdd(job.tile_counter, (uint32_t)kTilesPerCta);
+        __syncthreads();
+        first = s_ticket;
+    } else first = blockIdx.x * (uint32_t)kTilesPerCta;
     for (int q = 0; q < kTilesPerCta; ++q) {
         uint32_t id = first + (uint32_t)q;
         if (id >= n_tiles) break;
@@ -264,7 +277,7 @@ void launch_pack(const PackJob& job, cudaStream_t s, cudaEvent_t* ev) {
     cudaMemsetAsync(job.tile_counter, 0, 4, s);
     if (ev) { cudaEventRecord(ev[0], s); cudaEventRecord(ev[1], s); }
     g_launches += 1;
-    k_pack<<<(unsigned)((nt + kTilesPerCta - 1) / kTilesPerCta), 256, 0, s>>>(job, (uint32_t)nt);
+    k_pack<<<(unsigned)((nt + kTilesPerCta - 1) / kTilesPerCta), kPackThreads, 0, s>>>(job, (uint32_t)nt);
     if (ev) cudaEventRecord(ev[2], s);
 }
 
