@@ -169,8 +169,27 @@ def run_reference(args):
            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample_txt},
            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
-    print(json.dumps(out))
+    _emit(json.dumps(out))
     return 0
+
+
+def bind_to_gpu_numa(local_rank: int):
+    """Pin this rank to the CPUs next to its GPU (NVML affinity) BEFORE pinned host memory is allocated, so the
+    staging buffers live on the NUMA node that feeds the GPU's PCIe root port."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = [64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1]
+        allowed = set(os.sched_getaffinity(0))
+        cpus = [c for c in cpus if c in allowed]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:
+        return 0
 
 
 class _Raw:
@@ -188,6 +207,7 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
+    ncpu_bound = bind_to_gpu_numa(local) if world > 1 else 0
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     wl = workload(rank)
@@ -359,7 +379,7 @@ def run_ours(args):
                "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
                "data": "synthetic",
                "config": {"workload": wl["name"], "l2": "inputs (%.2f GB of MSA rows per GPU) exceed the 126 MB L2; no explicit flush" % (H * M / 1e9),
-                          "bases_per_step": total_bases, "phrases_per_step_rank0": phrases, "kmer": info["k"],
+                          "bases_per_step": total_bases, "cpus_bound_per_rank": ncpu_bound, "phrases_per_step_rank0": phrases, "kmer": info["k"],
                           "index": "built once outside the step" + (", NCCL broadcast from rank 0" if world > 1 else "")},
                "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(H * M), "d2h_bytes_per_step": int(16 * phrases),
                        "ms_per_step": ms_e2e, "wall_ms_per_step": wall_e2e},
@@ -370,14 +390,27 @@ def run_ours(args):
                                "algorithmic_bytes": 9 * info["n"], "bcast_ms": bcast_ms,
                                "ref_mbp_per_s": info["n"] / max(idx_t["total_ms"], 1e-9) / 1e3},
                "parity_checked_rows": parity_rows, "fix_rounds_per_step": kt["fix_rounds"] / steps}
-        print(json.dumps(out))
+        _emit(json.dumps(out))
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
     return 0
 
 
+def _emit(line: str):
+    """The driver parses stdout: exactly one JSON line goes to the real stdout (libraries such as NCCL print
+    banners to fd 1, so fd 1 is pointed at stderr for the whole run, see main)."""
+    os.write(_REAL_STDOUT, (line + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
