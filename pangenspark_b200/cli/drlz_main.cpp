@@ -13,7 +13,8 @@
 //   gaplessOut  directory of part-NNNNN files, each ">basename\n<gapless>\n", plus _SUCCESS   (:66-80)
 // Extra arguments (the stray "2" that drlz.sh:15 passes) are ignored.
 // Environment: DRLZ_DEVICE (default 0), DRLZ_GPUS (default 1; haplotypes are dealt round-robin to the devices,
-// each device builds its own index), DRLZ_BATCH_BYTES (default 1 GiB of MSA bytes per batch).
+// each device builds its own index), DRLZ_BATCH_BYTES (default 1 GiB of MSA bytes per batch), DRLZ_MERGED_LZ /
+// DRLZ_MERGED_FA (also write the merged chrNN.lz / chrNN.fa that index_chr.sh:16,20 builds with getmerge).
 #include <glob.h>
 #include <libgen.h>
 #include <sys/stat.h>
@@ -205,6 +206,25 @@ int main(int argc, char** argv) {
     for (auto c : ctxs) drlz_destroy(c);
     if (failed) return 1;
     write_file_atomic(local_gap + "/_SUCCESS", "", 0);
+    // the two `hdfs dfs -getmerge` steps of components/index/index_chr.sh:16,20 done here --
+    // concatenation in sorted-basename order -- when DRLZ_MERGED_LZ / DRLZ_MERGED_FA name the target files.
+    for (int which = 0; which < 2; ++which) {
+        const char* target = getenv(which == 0 ? "DRLZ_MERGED_LZ" : "DRLZ_MERGED_FA");
+        if (!target || !*target) continue;
+        std::string tmp = std::string(target) + ".tmp";
+        FILE* out = fopen(tmp.c_str(), "wb");
+        if (!out) { fprintf(stderr, "drlz: cannot write %s\n", target); return 1; }
+        std::vector<uint8_t> buf;
+        for (size_t j = 0; j < jobs.size(); ++j) {
+            char part[64]; snprintf(part, sizeof part, "/part-%05zu", jobs[j].index);
+            std::string src = which == 0 ? local_out + "/" + jobs[j].name + ".lz" : local_gap + part;
+            if (!read_file(src, buf) || (buf.size() && fwrite(buf.data(), 1, buf.size(), out) != buf.size())) {
+                fprintf(stderr, "drlz: merge failed at %s\n", src.c_str()); fclose(out); return 1;
+            }
+        }
+        fclose(out);
+        rename(tmp.c_str(), target);
+    }
     printf("encoded %zu haplotypes, %llu bases, %llu phrases\n", jobs.size(), (unsigned long long)tot_bases, (unsigned long long)tot_pairs);
     if (hdfs) {
         std::string cmd = "hdfs dfs -mkdir -p '" + out_dir + "' '" + gapless_dir + "' && hdfs dfs -put -f " + local_out + "/* '" + out_dir +

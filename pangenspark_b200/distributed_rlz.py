@@ -114,7 +114,29 @@ def main(argv, parser=None, rank: int | None = None, world: int | None = None, b
         ctx.close()
     if rank == 0:
         write_atomic(os.path.join(gapless_dir, "_SUCCESS"), [])
+    if world == 1:
+        merge_outputs(out_dir, gapless_dir, [os.path.basename(f) for f in files])
     return 0
+
+
+def merge_outputs(out_dir: str, gapless_dir: str, names):
+    """what `hdfs dfs -getmerge <outDir>/*.NN.lz chrNN.lz` and `-getmerge <gapless>/*NN* chrNN.fa`
+    do in components/index/index_chr.sh:16,20 -- concatenation in sorted-basename order -- written directly when
+    DRLZ_MERGED_LZ / DRLZ_MERGED_FA name the target files (call after every rank has finished)."""
+    lz, fa = os.environ.get("DRLZ_MERGED_LZ"), os.environ.get("DRLZ_MERGED_FA")
+    if lz:
+        with open(lz + ".tmp", "wb") as out:
+            for n in sorted(names):
+                with open(os.path.join(out_dir, n + ".lz"), "rb") as f:
+                    out.write(f.read())
+        os.replace(lz + ".tmp", lz)
+    if fa:
+        parts = sorted(p for p in os.listdir(gapless_dir) if p.startswith("part-"))
+        with open(fa + ".tmp", "wb") as out:
+            for p in parts:
+                with open(os.path.join(gapless_dir, p), "rb") as f:
+                    out.write(f.read())
+        os.replace(fa + ".tmp", fa)
 
 
 if __name__ == "__main__":

@@ -16,12 +16,16 @@ def test_native_cli(tmp_path):
     tmp = str(tmp_path)
     d, rows = make_dataset(tmp, H=6, n=200_000)
     exe = os.path.join(ROOT, "pangenspark_b200", "bin", "drlz")
-    env = dict(os.environ, DRLZ_EMIT_RADIX="1", DRLZ_BATCH_BYTES="500000")
+    env = dict(os.environ, DRLZ_EMIT_RADIX="1", DRLZ_BATCH_BYTES="500000", DRLZ_MERGED_LZ=tmp + "/chr01.lz",
+               DRLZ_MERGED_FA=tmp + "/chr01.fa")
     r = subprocess.run([exe, tmp + "/radix", tmp + "/ref.txt", tmp + "/msa/*.01", "file:///", tmp + "/drlz", tmp + "/gapless", "2"],
                        capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 0, r.stderr
     assert "started encoding" in r.stdout
     check_outputs(tmp, d, rows)
+    lz = b"".join(open(tmp + "/drlz/H%05d.01.lz" % h, "rb").read() for h in range(6))
+    assert open(tmp + "/chr01.lz", "rb").read() == lz
+    assert open(tmp + "/chr01.fa", "rb").read().count(b">") == 6
     from oracle import oracle as orc
     sa = [int(x) for x in open(tmp + "/radix").read().split()]
     assert sa == orc.sa_build(d).tolist()

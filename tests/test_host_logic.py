@@ -59,6 +59,20 @@ def test_single_rank_layout(tmp_path):
     check_outputs(tmp, d, rows)
 
 
+def test_merged_outputs(tmp_path, monkeypatch):
+    tmp = str(tmp_path)
+    d, rows = make_dataset(tmp, H=4)
+    monkeypatch.setenv("DRLZ_MERGED_LZ", tmp + "/chr01.lz")
+    monkeypatch.setenv("DRLZ_MERGED_FA", tmp + "/chr01.fa")
+    rc = drz.main([tmp + "/radix", tmp + "/ref.txt", tmp + "/msa/*.01", "", tmp + "/drlz", tmp + "/gapless"],
+                  parser=oracle_parser, rank=0, world=1)
+    assert rc == 0
+    lz = b"".join(open(tmp + "/drlz/H%05d.01.lz" % h, "rb").read() for h in range(4))
+    assert open(tmp + "/chr01.lz", "rb").read() == lz
+    fa = open(tmp + "/chr01.fa", "rb").read()
+    assert fa.count(b">") == 4 and fa.startswith(b">H00000.01\n")
+
+
 def test_shards_cover_everything():
     for n in range(0, 40):
         for w in (1, 2, 3, 8):
