@@ -219,7 +219,9 @@ static int run_device_group(drlz_ctx* c, const uint8_t* rows_dev, const uint64_t
     uint32_t T = (uint32_t)((maxcols + kPackTileBytes - 1) / kPackTileBytes);
     if (T == 0) T = 1;
     uint64_t nt = (uint64_t)H * T;
-    uint32_t C = c->opt_chunk;
+    uint32_t chunk_shift = 0;
+    while ((2u << chunk_shift) <= c->opt_chunk && chunk_shift < 30) ++chunk_shift;    // chunk size: power of two
+    uint32_t C = 1u << chunk_shift;
     bool single_chunk = false;
     unsigned long long launches0 = g_launches;
 
@@ -308,7 +310,7 @@ static int run_device_group(drlz_ctx* c, const uint8_t* rows_dev, const uint64_t
         ParseBuffers pb;
         pb.pv.ix = IndexView{c->d_text, c->sa.as<uint32_t>(), c->d_tab, c->n, c->k};
         pb.pv.haps = c->haps.as<HapView>(); pb.pv.chunk_hap = c->chunk_hap.as<uint32_t>(); pb.pv.hap_chunk_base = d_base;
-        pb.pv.chunk_bases = Ceff; pb.pv.n_chunks = NC;
+        pb.pv.chunk_bases = Ceff; pb.pv.chunk_shift = single_chunk ? 32u : chunk_shift; pb.pv.n_chunks = NC;
         pb.pv.min_cap = single_chunk ? 0xFFFFFFFFu : c->opt_min_cap; pb.pv.foreign_cap = c->opt_foreign_cap;
         pb.pv.first_pos = c->first_pos.as<uint32_t>(); pb.pv.first_len = c->first_len.as<uint32_t>();
         pb.pv.run_len = c->run_a.as<uint32_t>(); pb.pv.link = c->link_a.as<uint32_t>();

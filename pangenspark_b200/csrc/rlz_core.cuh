@@ -85,23 +85,32 @@ struct Match {
 // shifted word: bases [pos, pos+32) from two consecutive packed words a (holding pos) and b
 DRLZ_HD uint64_t funnel64(uint64_t a, uint64_t b, unsigned sh) { return sh ? (a << sh) | (b >> (64 - sh)) : a; }
 
-// lcp(x[i..i+maxlen), d[p..n)) and whether the suffix d[p..] sorts before the pattern.
+// get64 with a 32-bit position (n, m < 2^32: half the integer work of the 64-bit form)
+DRLZ_HD uint64_t get64u(const uint64_t* __restrict__ w, uint32_t pos) {
+    uint32_t wi = pos >> 5;
+    unsigned sh = (pos & 31u) * 2;
+    uint64_t a = w[wi];
+    if (sh == 0) return a;
+    return (a << sh) | (w[wi + 1] >> (64 - sh));
+}
+
+// lcp(x[i..i+maxlen), d[p..n)) and whether the suffix d[p..] sorts before the pattern; xw0 = get64u(X, i).
 // The first 32 bases are compared alone (most probes differ there); longer matches stream 128 bases per
 // iteration: 4 new words per stream with a carry word, 8 independent loads in flight, one OR-reduced test.
-DRLZ_HD uint32_t cmp_suffix(const uint64_t* __restrict__ X, uint64_t i, const uint64_t* __restrict__ D,
-                            uint64_t p, uint64_t n, uint32_t maxlen, bool* less) {
-    uint64_t rem = n - p;
-    uint32_t lim = rem < (uint64_t)maxlen ? (uint32_t)rem : maxlen;
+DRLZ_HD uint32_t cmp_suffix_w(uint64_t xw0, const uint64_t* __restrict__ X, uint32_t i, const uint64_t* __restrict__ D,
+                              uint32_t p, uint32_t n, uint32_t maxlen, bool* less) {
+    uint32_t rem = n - p;
+    uint32_t lim = rem < maxlen ? rem : maxlen;
     uint32_t l = 0;
     bool diff_less = false, found = false;
     if (lim > 0) {
-        uint64_t a = get64(X, i), b = get64(D, p);
-        uint64_t xr = a ^ b;
-        if (xr) { l = (uint32_t)(clz64(xr) >> 1); diff_less = b < a; found = true; }
+        uint64_t b = get64u(D, p);
+        uint64_t xr = xw0 ^ b;
+        if (xr) { l = (uint32_t)(clz64(xr) >> 1); diff_less = b < xw0; found = true; }
         else l = 32;
     }
     if (!found && l + 128 <= lim) {
-        const unsigned shx = (unsigned)((i + l) & 31) * 2, shd = (unsigned)((p + l) & 31) * 2;
+        const unsigned shx = ((i + l) & 31u) * 2, shd = ((p + l) & 31u) * 2;
         const uint64_t* xp = X + ((i + l) >> 5);
         const uint64_t* dp = D + ((p + l) >> 5);
         uint64_t cx = xp[0], cd = dp[0];
@@ -117,7 +126,7 @@ DRLZ_HD uint32_t cmp_suffix(const uint64_t* __restrict__ X, uint64_t i, const ui
         }
     }
     while (!found && l < lim) {
-        uint64_t a = get64(X, i + l), b = get64(D, p + l);
+        uint64_t a = get64u(X, i + l), b = get64u(D, p + l);
         uint64_t xr = a ^ b;
         if (xr) { l += (uint32_t)(clz64(xr) >> 1); diff_less = b < a; found = true; }
         else l += 32;
@@ -132,18 +141,26 @@ DRLZ_HD uint32_t cmp_suffix(const uint64_t* __restrict__ X, uint64_t i, const ui
     return l;
 }
 
+DRLZ_HD uint32_t cmp_suffix(const uint64_t* __restrict__ X, uint64_t i, const uint64_t* __restrict__ D,
+                            uint64_t p, uint64_t n, uint32_t maxlen, bool* less) {
+    return cmp_suffix_w(get64u(X, (uint32_t)i), X, (uint32_t)i, D, (uint32_t)p, (uint32_t)n, maxlen, less);
+}
+
 // Longest match of x[i..i+maxlen) in d with the reference's tie-break.  maxlen >= 1.
 // cap (>= 1) bounds the compared length: if the pattern's first min(cap, maxlen) bases occur in d, cap < maxlen
 // and exactly ONE suffix carries them, the call stops there and reports *open = true with len = cap -- the
 // match continues along that unique alignment and its full length is the diagonal run resolved by the caller.
 // If several suffixes share the capped prefix the search is redone uncapped (exact, slower; long exact repeats).
-DRLZ_HD Match lookup(const IndexView& ix, const uint64_t* __restrict__ X, uint64_t i, uint32_t maxlen,
+DRLZ_HD Match lookup(const IndexView& ix, const uint64_t* __restrict__ X, uint64_t i64, uint32_t maxlen,
                      uint32_t cap, bool* open) {
     const int k = ix.k;
-    const uint64_t n = ix.n;
+    const uint32_t n = (uint32_t)ix.n;
+    const uint32_t i = (uint32_t)i64;
+    const uint64_t* __restrict__ D = ix.text;
+    const uint32_t* __restrict__ SA = ix.sa;
     *open = false;
-    uint64_t xw = get64(X, i);
-    uint64_t kmer = xw >> (64 - 2 * k);
+    const uint64_t xw = get64u(X, i);
+    const uint64_t kmer = xw >> (64 - 2 * k);
     Match mt;
     uint32_t plen = cap < maxlen ? cap : maxlen;
     for (int pass = 0; pass < 2; ++pass) {
@@ -153,29 +170,29 @@ DRLZ_HD Match lookup(const IndexView& ix, const uint64_t* __restrict__ X, uint64
         uint32_t lo = ix.tab[lokey], hi = ix.tab[hikey + 1];
         // r = #suffixes < pattern lies in [lo, hi]
         uint32_t l = lo, h = hi;
-        uint32_t lcp_left = 0, lcp_right = 0;
+        uint32_t lcp_left = 0, lcp_right = 0, sar = 0;
         bool have_left = false, have_right = false;
         while (l < h) {
             uint32_t mid = l + ((h - l) >> 1);
             bool less;
-            uint32_t c = cmp_suffix(X, i, ix.text, ix.sa[mid], n, plen, &less);
+            uint32_t pm = SA[mid];
+            uint32_t c = cmp_suffix_w(xw, X, i, D, pm, n, plen, &less);
             if (less) { l = mid + 1; lcp_left = c; have_left = true; }
-            else { h = mid; lcp_right = c; have_right = true; }
+            else { h = mid; lcp_right = c; have_right = true; sar = pm; }
         }
         uint32_t r = l;
         bool dummy;
         uint32_t l1 = 0, l2 = 0;
-        if (r > 0) l1 = have_left ? lcp_left : cmp_suffix(X, i, ix.text, ix.sa[r - 1], n, plen, &dummy);
-        uint32_t sar = 0;
-        if ((uint64_t)r < n) {
-            sar = ix.sa[r];
-            l2 = have_right ? lcp_right : cmp_suffix(X, i, ix.text, sar, n, plen, &dummy);
+        if (r > 0) l1 = have_left ? lcp_left : cmp_suffix_w(xw, X, i, D, SA[r - 1], n, plen, &dummy);
+        if (r < n) {
+            if (!have_right) { sar = SA[r]; lcp_right = cmp_suffix_w(xw, X, i, D, sar, n, plen, &dummy); }
+            l2 = lcp_right;
         }
         if (l2 > l1) {
             if (l2 == plen && plen < maxlen) {
                 // capped: is SA[r] the only suffix carrying the capped pattern?
                 bool multi = false;
-                if ((uint64_t)r + 1 < n) multi = cmp_suffix(X, i, ix.text, ix.sa[r + 1], n, plen, &dummy) >= plen;
+                if (r + 1 < n) multi = cmp_suffix_w(xw, X, i, D, SA[r + 1], n, plen, &dummy) >= plen;
                 if (multi) { plen = maxlen; continue; }
                 *open = true;
             }
@@ -193,10 +210,10 @@ DRLZ_HD Match lookup(const IndexView& ix, const uint64_t* __restrict__ X, uint64
         uint32_t b = r - 1;
         while (a < b) {
             uint32_t mid = a + ((b - a) >> 1);
-            uint32_t c = cmp_suffix(X, i, ix.text, ix.sa[mid], n, L, &dummy);
+            uint32_t c = cmp_suffix_w(xw, X, i, D, SA[mid], n, L, &dummy);
             if (c >= L) b = mid; else a = mid + 1;
         }
-        mt.len = L; mt.pos = ix.sa[a];
+        mt.len = L; mt.pos = SA[a];
         return mt;
     }
     mt.len = 0; mt.pos = 0;      // not reached
@@ -240,7 +257,8 @@ struct ParseView {
     const HapView* haps;            // [H]
     const uint32_t* chunk_hap;      // [NC] haplotype of global chunk g
     const uint32_t* hap_chunk_base; // [H+1]
-    uint32_t chunk_bases;           // C
+    uint32_t chunk_bases;           // C = 2^chunk_shift (0xFFFFFFFF when chunk_shift == 32: one chunk per haplotype)
+    uint32_t chunk_shift;           // chunk index of position x = x >> chunk_shift (no divisions in the kernels)
     uint32_t n_chunks;              // NC
     uint32_t min_cap;               // lower bound of the compare cap (64; 0xFFFFFFFF disables capping)
     uint32_t foreign_cap;           // bound of an off-chain diagonal compare before the exact fallback is taken
@@ -299,8 +317,7 @@ DRLZ_HD Match phrase_capped(const ParseView& pv, const HapView& hv, uint64_t i, 
     uint64_t stop = stop_after(hv, i, cursor);
     if (stop == i) { Match mt; mt.len = 0; mt.pos = hv.exc_byte[*cursor]; return mt; }
     uint32_t maxlen = (uint32_t)(stop - i);
-    uint64_t C = pv.chunk_bases;
-    uint64_t to_end = (i / C + 1) * C - i;
+    uint64_t to_end = (((i >> pv.chunk_shift) + 1) << pv.chunk_shift) - i;
     uint32_t cap = to_end > (uint64_t)pv.min_cap ? (to_end > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)to_end) : pv.min_cap;
     Match mt = lookup(pv.ix, hv.x, i, maxlen, cap, open);
     if (mt.len == 0) mt.pos = (uint32_t)("ACGT"[base_at(hv.x, i)]);
@@ -311,9 +328,8 @@ DRLZ_HD Match phrase_capped(const ParseView& pv, const HapView& hv, uint64_t i, 
 // Returns the global chunk id; *j_out = its first base; *same = that chunk's own first phrase lies on the
 // same diagonal (then the remaining length is that chunk's run).
 DRLZ_HD uint32_t open_target(const ParseView& pv, uint32_t h, uint64_t i, const Match& mt, uint64_t* j_out, bool* same) {
-    uint64_t C = pv.chunk_bases;
-    uint64_t cc = (i + mt.len) / C;
-    uint64_t j = cc * C;
+    uint64_t cc = (i + mt.len) >> pv.chunk_shift;
+    uint64_t j = cc << pv.chunk_shift;
     uint32_t g2 = pv.hap_chunk_base[h] + (uint32_t)cc;
     *j_out = j;
     *same = pv.first_len[g2] > 0 && (int64_t)pv.first_pos[g2] - (int64_t)j == (int64_t)mt.pos - (int64_t)i;
@@ -351,7 +367,7 @@ DRLZ_HD void link_chunk(const ParseView& pv, uint32_t g) {
     if (pv.run_len[g] != kEmpty) return;
     uint32_t h = pv.chunk_hap[g];
     const HapView& hv = pv.haps[h];
-    uint64_t s = (uint64_t)(g - pv.hap_chunk_base[h]) * pv.chunk_bases;
+    uint64_t s = (uint64_t)(g - pv.hap_chunk_base[h]) << pv.chunk_shift;
     Match mt; mt.pos = pv.first_pos[g]; mt.len = pv.first_len[g];
     uint64_t j; bool same;
     uint32_t g2 = open_target(pv, h, s, mt, &j, &same);
@@ -371,9 +387,8 @@ DRLZ_HD void rank_round(const uint32_t* link_in, const uint32_t* run_in, uint32_
 DRLZ_HD void register_exit(const ParseView& pv, uint32_t h, uint64_t x, uint32_t next_round) {
     const HapView& hv = pv.haps[h];
     if (x >= hv.m) return;                                   // parse finished
-    uint32_t C = pv.chunk_bases;
-    if (x % C == 0) return;                                  // that is the chunk's speculative record
-    uint32_t g = pv.hap_chunk_base[h] + (uint32_t)(x / C);
+    if ((x & ((1ull << pv.chunk_shift) - 1)) == 0) return;   // that is the chunk's speculative record
+    uint32_t g = pv.hap_chunk_base[h] + (uint32_t)(x >> pv.chunk_shift);
     for (int s = 0; s < kAltSlots; ++s) {
         uint32_t old = atomic_cas_u32(&pv.alt_entry[g * kAltSlots + s], kEmpty, (uint32_t)x);
         if (old == kEmpty) {
@@ -399,8 +414,8 @@ DRLZ_HD Match chunk_step(const ParseView& pv, uint32_t g, uint32_t h, const HapV
 DRLZ_HD void spec_parse_chunk(const ParseView& pv, uint32_t g) {
     uint32_t h = pv.chunk_hap[g];
     const HapView& hv = pv.haps[h];
-    uint64_t s = (uint64_t)(g - pv.hap_chunk_base[h]) * pv.chunk_bases;
-    uint64_t e = s + pv.chunk_bases; if (e > hv.m) e = hv.m;
+    uint64_t s = (uint64_t)(g - pv.hap_chunk_base[h]) << pv.chunk_shift;
+    uint64_t e = s + (1ull << pv.chunk_shift); if (e > hv.m) e = hv.m;
     pv.link[g] = kEmpty;
     pv.open_i[g] = kEmpty;
     if (s >= hv.m) {
@@ -430,7 +445,7 @@ DRLZ_HD void resolve_chunk(const ParseView& pv, uint32_t g) {
     if (oi == kEmpty) return;
     uint32_t h = pv.chunk_hap[g];
     const HapView& hv = pv.haps[h];
-    uint64_t s = (uint64_t)(g - pv.hap_chunk_base[h]) * pv.chunk_bases;
+    uint64_t s = (uint64_t)(g - pv.hap_chunk_base[h]) << pv.chunk_shift;
     uint64_t i = oi;
     uint32_t total;
     if (i == s) total = pv.run_len[g];
@@ -453,8 +468,8 @@ DRLZ_HD void fix_parse_record(const ParseView& pv, uint32_t g, int slot, uint32_
     if (pv.alt_entry[rid] == kEmpty || pv.alt_round[rid] != round) return;
     uint32_t h = pv.chunk_hap[g];
     const HapView& hv = pv.haps[h];
-    uint64_t s = (uint64_t)(g - pv.hap_chunk_base[h]) * pv.chunk_bases;
-    uint64_t e = s + pv.chunk_bases; if (e > hv.m) e = hv.m;
+    uint64_t s = (uint64_t)(g - pv.hap_chunk_base[h]) << pv.chunk_shift;
+    uint64_t e = s + (1ull << pv.chunk_shift); if (e > hv.m) e = hv.m;
     uint64_t iA = s, iB = pv.alt_entry[rid];
     uint32_t cntA = 0, cntB = 0;
     uint32_t curA = hv.n_exc ? exc_lower_bound(hv, iA) : 0;
@@ -499,9 +514,8 @@ DRLZ_HD uint32_t node_succ(const ParseView& pv, uint32_t node) {
         x = pv.alt_exit[g * kAltSlots + r - 1];
     }
     if (x >= hv.m) return node;                              // terminal: self loop
-    uint32_t C = pv.chunk_bases;
-    uint32_t g2 = pv.hap_chunk_base[h] + (uint32_t)(x / C);
-    if (x % C == 0) return g2 * (kAltSlots + 1);
+    uint32_t g2 = pv.hap_chunk_base[h] + (uint32_t)(x >> pv.chunk_shift);
+    if ((x & ((1ull << pv.chunk_shift) - 1)) == 0) return g2 * (kAltSlots + 1);
     for (int s = 0; s < kAltSlots; ++s)
         if (pv.alt_entry[g2 * kAltSlots + s] == (uint32_t)x) return g2 * (kAltSlots + 1) + 1 + s;
     pv.counters[0] = 2;                                      // unresolved link (cannot happen after convergence)
@@ -514,7 +528,7 @@ DRLZ_HD uint32_t chunk_true_record(const ParseView& pv, const uint8_t* m4, uint3
     *slot = 0;
     if (m4[0]) {
         uint32_t h = pv.chunk_hap[g];
-        *entry = (g - pv.hap_chunk_base[h]) * pv.chunk_bases;
+        *entry = (uint32_t)((uint64_t)(g - pv.hap_chunk_base[h]) << pv.chunk_shift);
         return pv.spec_cnt[g];
     }
     for (int s = 0; s < kAltSlots; ++s)
@@ -550,7 +564,7 @@ DRLZ_HD bool emit_stored(const ParseView& pv, uint32_t g, uint32_t slot, uint32_
 DRLZ_HD void emit_chunk(const ParseView& pv, uint32_t g, uint32_t entry, uint32_t cnt, int64_t* out) {
     uint32_t h = pv.chunk_hap[g];
     const HapView& hv = pv.haps[h];
-    uint64_t s = (uint64_t)(g - pv.hap_chunk_base[h]) * pv.chunk_bases;
+    uint64_t s = (uint64_t)(g - pv.hap_chunk_base[h]) << pv.chunk_shift;
     uint64_t i = entry;
     uint32_t cur = hv.n_exc ? exc_lower_bound(hv, i) : 0;
     for (uint32_t t = 0; t < cnt; ++t) {

@@ -43,6 +43,9 @@ int emu_parse(const uint8_t* ref, uint64_t n, const int64_t* sa64, int k, uint32
               const uint8_t* const* rows, const uint64_t* cols, int64_t** pairs_out, uint64_t* npairs,
               uint64_t* m_out, int* rounds_out) {
     for (uint64_t i = 0; i < n; ++i) if (code_of(ref[i]) < 0) return 1;
+    uint32_t chunk_shift = 0;
+    while ((2u << chunk_shift) <= chunk && chunk_shift < 31) ++chunk_shift;     // round down to a power of two
+    chunk = 1u << chunk_shift;
     std::vector<uint64_t> text; pack_seq(ref, n, text, nullptr, nullptr);
     std::vector<uint32_t> sa(n); for (uint64_t i = 0; i < n; ++i) sa[i] = (uint32_t)sa64[i];
     std::vector<uint32_t> tab; build_tab(text, n, sa, k, tab);
@@ -71,7 +74,7 @@ int emu_parse(const uint8_t* ref, uint64_t n, const int64_t* sa64, int k, uint32
         alt_cnt((size_t)NC * kAltSlots, 0), alt_exit((size_t)NC * kAltSlots, 0), alt_round((size_t)NC * kAltSlots, 0),
         counters(2 + kMaxRounds, 0), alt_own((size_t)NC * kAltSlots, 0), alt_merge((size_t)NC * kAltSlots, kEmpty);
     std::vector<uint2> spec_ph((size_t)NC * kSpecStore), alt_ph((size_t)NC * kAltSlots * kAltStore);
-    ParseView pv{ix, haps.data(), chunk_hap.data(), base.data(), chunk, NC, min_cap, foreign_cap,
+    ParseView pv{ix, haps.data(), chunk_hap.data(), base.data(), chunk, chunk_shift, NC, min_cap, foreign_cap,
                  first_pos.data(), first_len.data(), run_a.data(), link_a.data(), open_i.data(), open_pos.data(), open_len.data(), spec_cnt.data(), spec_exit.data(),
                  alt_entry.data(), alt_cnt.data(), alt_exit.data(), alt_round.data(), alt_own.data(), alt_merge.data(),
                  spec_ph.data(), alt_ph.data(), counters.data()};
