@@ -58,7 +58,8 @@ struct drlz_ctx {
     // index
     bool have_index = false; uint64_t n = 0; int k = 0; int sa_rounds = 0;
     DevBuf blob, sa, isa, lcp;             // blob = [k-mer table | packed text] (one L2 access-policy window)
-    uint64_t* d_text = nullptr; uint32_t* d_tab = nullptr; size_t blob_bytes = 0;
+    uint64_t* d_text = nullptr; uint32_t* d_tab = nullptr; uint16_t* d_uniq = nullptr; size_t blob_bytes = 0, text_bytes = 0, uniq_bytes = 0;
+    int opt_predict = 1;
     cudaStream_t l2_stream = nullptr; int opt_l2persist = 0; int opt_occ = 10; int opt_tickets = 1;
     double idx_ms[5] = {0, 0, 0, 0, 0};
     // batch scratch (grow-only)
@@ -84,12 +85,15 @@ static const uint64_t kMaxLen = 0xFFFFFFFFull - 1024;
 
 static cudaError_t alloc_index_blob(drlz_ctx* c, uint64_t n, int k) {
     size_t tab_bytes = (((1ull << (2 * k)) + 1) * 4 + 255) & ~(size_t)255;
-    size_t text_bytes = (n / 32 + 3) * 8 + 64;
-    cudaError_t e = c->blob.ensure(tab_bytes + text_bytes);
+    size_t text_bytes = ((n / 32 + 3) * 8 + 64 + 255) & ~(size_t)255;
+    size_t uniq_bytes = ((n + 1) * 2 + 255) & ~(size_t)255;
+    cudaError_t e = c->blob.ensure(tab_bytes + text_bytes + uniq_bytes);
     if (e != cudaSuccess) return e;
     c->d_tab = c->blob.as<uint32_t>();
     c->d_text = reinterpret_cast<uint64_t*>(c->blob.as<uint8_t>() + tab_bytes);
-    c->blob_bytes = tab_bytes + text_bytes;
+    c->d_uniq = reinterpret_cast<uint16_t*>(c->blob.as<uint8_t>() + tab_bytes + text_bytes);
+    c->text_bytes = text_bytes; c->uniq_bytes = uniq_bytes;
+    c->blob_bytes = tab_bytes + text_bytes + uniq_bytes;
     c->l2_stream = nullptr;
     return cudaSuccess;
 }
@@ -181,6 +185,7 @@ int drlz_set_option(drlz_ctx* c, const char* key, int64_t v) {
     else if (!strcmp(key, "l2persist")) { c->opt_l2persist = v != 0; c->l2_stream = nullptr; }
     else if (!strcmp(key, "occ")) c->opt_occ = (int)v;
     else if (!strcmp(key, "tickets")) c->opt_tickets = v != 0;
+    else if (!strcmp(key, "predict")) c->opt_predict = v != 0;
     else if (!strcmp(key, "min_cap")) { if (v < 0 || v > 0x7FFFFFFF) return DRLZ_E_ARG; c->opt_min_cap = v ? (uint32_t)v : 64; }
     else if (!strcmp(key, "foreign_cap")) { if (v < 0 || v > 0x7FFFFFFF) return DRLZ_E_ARG; c->opt_foreign_cap = v ? (uint32_t)v : (1u << 20); }
     else return DRLZ_E_ARG;
@@ -308,7 +313,7 @@ static int run_device_group(drlz_ctx* c, const uint8_t* rows_dev, const uint64_t
         launch_fill_chunk_hap(c->chunk_hap.as<uint32_t>(), d_base, H, NC, s);
 
         ParseBuffers pb;
-        pb.pv.ix = IndexView{c->d_text, c->sa.as<uint32_t>(), c->d_tab, c->n, c->k};
+        pb.pv.ix = IndexView{c->d_text, c->sa.as<uint32_t>(), c->d_tab, c->n, c->k, c->opt_predict ? c->d_uniq : nullptr};
         pb.pv.haps = c->haps.as<HapView>(); pb.pv.chunk_hap = c->chunk_hap.as<uint32_t>(); pb.pv.hap_chunk_base = d_base;
         pb.pv.chunk_bases = Ceff; pb.pv.chunk_shift = single_chunk ? 32u : chunk_shift; pb.pv.n_chunks = NC;
         pb.pv.min_cap = single_chunk ? 0xFFFFFFFFu : c->opt_min_cap; pb.pv.foreign_cap = c->opt_foreign_cap;
@@ -442,10 +447,11 @@ int drlz_build_index(drlz_ctx* c, const uint8_t* ref, uint64_t n) {
     rc = build_kmer_table(c->d_text, n, c->sa.as<uint32_t>(), k, c->d_tab, s);
     if (rc != 0) { c->err = "k-mer table build failed"; for (int i = 0; i < 5; ++i) cudaEventDestroy(e[i]); return DRLZ_E_CUDA; }
     cudaEventRecord(e[3], s);
-    if (c->opt_lcp) {
-        CK(c, c->lcp.ensure(n * 4 + 4));
+    {   // LCP (kept only on request) and the uniqueness array derived from it
+        CK(c, c->lcp.ensure(n * 4 + 8));
         rc = build_lcp(c->d_text, n, c->sa.as<uint32_t>(), c->isa.as<uint32_t>(), c->lcp.as<uint32_t>(), s);
-        if (rc != 0) { c->err = "lcp build failed"; for (int i = 0; i < 5; ++i) cudaEventDestroy(e[i]); return DRLZ_E_CUDA; }
+        if (rc == 0) rc = build_uniq(n, c->isa.as<uint32_t>(), c->lcp.as<uint32_t>(), c->d_uniq, s);
+        if (rc != 0) { c->err = "lcp / uniqueness build failed"; for (int i = 0; i < 5; ++i) cudaEventDestroy(e[i]); return DRLZ_E_CUDA; }
     }
     cudaEventRecord(e[4], s);
     CK(c, cudaStreamSynchronize(s));
@@ -502,7 +508,7 @@ int drlz_index_reserve(drlz_ctx* c, uint64_t n, int k) {
     c->have_index = false;
     CK(c, alloc_index_blob(c, n, k));
     CK(c, c->sa.ensure(n * 4 + 4));
-    CK(c, cudaMemsetAsync(c->d_text, 0, (n / 32 + 3) * 8, c->stream));
+    CK(c, cudaMemsetAsync(c->d_text, 0, c->text_bytes, c->stream));
     CK(c, cudaStreamSynchronize(c->stream));
     c->n = n; c->k = k;
     return DRLZ_OK;
@@ -512,7 +518,7 @@ int drlz_index_buffers(drlz_ctx* c, void* dev_ptrs[3], uint64_t bytes[3]) {
     if (!c || !dev_ptrs || !bytes) return DRLZ_E_ARG;
     std::lock_guard<std::recursive_mutex> lk_(c->mu);
     if (!c->d_text || !c->d_tab) { c->err = "no index buffers (build or reserve first)"; return DRLZ_E_STATE; }
-    dev_ptrs[0] = c->d_text; bytes[0] = (c->n / 32 + 3) * 8;
+    dev_ptrs[0] = c->d_text; bytes[0] = c->text_bytes + c->uniq_bytes;      // packed text followed by the uniqueness array
     dev_ptrs[1] = c->sa.p; bytes[1] = c->n * 4;
     dev_ptrs[2] = c->d_tab; bytes[2] = ((1ull << (2 * c->k)) + 1) * 4;
     return DRLZ_OK;
@@ -700,7 +706,7 @@ int drlz_matching_stats(drlz_ctx* c, const uint8_t* x, uint64_t m, uint32_t* ms_
     CK(c, cudaStreamSynchronize(s));
     if (sh[0] != 0) { c->err = "sequence contains bytes outside {A,C,G,T}"; return DRLZ_E_ALPHABET; }
     CK(c, c->ms_a.ensure(m * 4)); CK(c, c->ms_b.ensure(m * 4));
-    IndexView ix{c->d_text, c->sa.as<uint32_t>(), c->d_tab, c->n, c->k};
+    IndexView ix{c->d_text, c->sa.as<uint32_t>(), c->d_tab, c->n, c->k, nullptr};
     launch_ms_dense(ix, c->X.as<uint64_t>(), m, c->ms_a.as<uint32_t>(), c->ms_b.as<uint32_t>(), s);
     CK(c, cudaMemcpyAsync(ms_out, c->ms_a.p, m * 4, cudaMemcpyDeviceToHost, s));
     CK(c, cudaMemcpyAsync(pos_out, c->ms_b.p, m * 4, cudaMemcpyDeviceToHost, s));

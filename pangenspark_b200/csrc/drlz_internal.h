@@ -47,6 +47,8 @@ int build_kmer_table(const uint64_t* text, uint64_t n, const uint32_t* sa, int k
 // LCP[j] = lcp(suffix SA[j-1], suffix SA[j]), LCP[0] = 0
 int build_lcp(const uint64_t* text, uint64_t n, const uint32_t* sa, const uint32_t* isa, uint32_t* lcp,
               cudaStream_t s);
+// uniq[p] = min(65535, max(LCP[ISA[p]], LCP[ISA[p]+1]))
+int build_uniq(uint64_t n, const uint32_t* isa, const uint32_t* lcp, uint16_t* uniq, cudaStream_t s);
 
 // ---- parse pipeline (parse.cu) -----------------------------------------------------------------
 struct ParseBuffers {

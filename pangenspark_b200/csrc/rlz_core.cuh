@@ -67,6 +67,7 @@ struct IndexView {
     const uint32_t* tab;    // 4^k + 1
     uint64_t n;
     int k;
+    const uint16_t* uniq;   // [n] min(65535, longest repeat starting at p) = max(LCP[ISA[p]], LCP[ISA[p]+1]); may be null
 };
 
 struct HapView {
@@ -312,15 +313,44 @@ DRLZ_HD uint64_t stop_after(const HapView& hv, uint64_t i, uint32_t* cursor) {
 }
 
 // capped phrase lookup at position i (chunk-end cap); literals carry their byte in .pos
-DRLZ_HD Match phrase_capped(const ParseView& pv, const HapView& hv, uint64_t i, uint32_t* cursor, bool* open) {
+static const int64_t kNoDiag = INT64_MIN;
+static const uint32_t kDiagMinLen = 32;   // phrases at least this long update the predicted diagonal
+
+// capped phrase lookup at position i (chunk-end cap); literals carry their byte in .pos.
+// *diag (in/out, kNoDiag = none): the alignment pos - i of the last long phrase.  The next long phrase nearly always
+// continues on it (a SNP costs one short phrase in between), so the candidate p = i + *diag is tried first: if the
+// match along that alignment is longer than uniq[p] -- the longest repeat starting at p anywhere else in the
+// reference -- then every other suffix shares fewer bases with the pattern, i.e. p is the unique longest match and
+// the SA interval is a singleton: exactly what lookup() would return, for one 2-byte read instead of the
+// table -> SA -> text probe chain.  Anything else falls through to lookup().
+DRLZ_HD Match phrase_capped(const ParseView& pv, const HapView& hv, uint64_t i, uint32_t* cursor, bool* open, int64_t* diag) {
     *open = false;
     uint64_t stop = stop_after(hv, i, cursor);
     if (stop == i) { Match mt; mt.len = 0; mt.pos = hv.exc_byte[*cursor]; return mt; }
     uint32_t maxlen = (uint32_t)(stop - i);
     uint64_t to_end = (((i >> pv.chunk_shift) + 1) << pv.chunk_shift) - i;
     uint32_t cap = to_end > (uint64_t)pv.min_cap ? (to_end > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)to_end) : pv.min_cap;
-    Match mt = lookup(pv.ix, hv.x, i, maxlen, cap, open);
+    Match mt;
+    if (pv.ix.uniq && *diag != kNoDiag) {
+        int64_t p64 = (int64_t)i + *diag;
+        if (p64 >= 0 && (uint64_t)p64 < pv.ix.n) {
+            uint32_t p = (uint32_t)p64;
+            uint32_t plen = cap < maxlen ? cap : maxlen;
+            bool less;
+            uint32_t c = cmp_suffix_w(get64u(hv.x, (uint32_t)i), hv.x, (uint32_t)i, pv.ix.text, p, (uint32_t)pv.ix.n, plen, &less);
+            if (c > 0) {
+                uint32_t u = pv.ix.uniq[p];
+                if (u != 0xFFFFu && c > u) {
+                    mt.len = c; mt.pos = p;
+                    *open = (c == plen && plen < maxlen);
+                    return mt;
+                }
+            }
+        }
+    }
+    mt = lookup(pv.ix, hv.x, i, maxlen, cap, open);
     if (mt.len == 0) mt.pos = (uint32_t)("ACGT"[base_at(hv.x, i)]);
+    else if (mt.len >= kDiagMinLen) *diag = (int64_t)mt.pos - (int64_t)i;
     return mt;
 }
 
@@ -350,9 +380,9 @@ DRLZ_HD uint32_t foreign_run(const ParseView& pv, const HapView& hv, uint64_t i,
 }
 
 // exact phrase at position i (uses run_len of the chunk starts; valid after stage A)
-DRLZ_HD Match phrase_at(const ParseView& pv, uint32_t h, const HapView& hv, uint64_t i, uint32_t* cursor) {
+DRLZ_HD Match phrase_at(const ParseView& pv, uint32_t h, const HapView& hv, uint64_t i, uint32_t* cursor, int64_t* diag) {
     bool open;
-    Match mt = phrase_capped(pv, hv, i, cursor, &open);
+    Match mt = phrase_capped(pv, hv, i, cursor, &open, diag);
     if (open) {
         uint64_t j; bool same;
         uint32_t g2 = open_target(pv, h, i, mt, &j, &same);
@@ -402,9 +432,14 @@ DRLZ_HD void register_exit(const ParseView& pv, uint32_t h, uint64_t x, uint32_t
 }
 
 // one greedy step of the parse of chunk g at position i (i == chunk start reuses stage A's result)
-DRLZ_HD Match chunk_step(const ParseView& pv, uint32_t g, uint32_t h, const HapView& hv, uint64_t s, uint64_t i, uint32_t* cursor) {
-    if (i == s) { Match mt; mt.pos = pv.first_pos[g]; mt.len = pv.run_len[g]; return mt; }
-    return phrase_at(pv, h, hv, i, cursor);
+DRLZ_HD Match chunk_step(const ParseView& pv, uint32_t g, uint32_t h, const HapView& hv, uint64_t s, uint64_t i, uint32_t* cursor,
+                         int64_t* diag) {
+    if (i == s) {
+        Match mt; mt.pos = pv.first_pos[g]; mt.len = pv.run_len[g];
+        if (mt.len >= kDiagMinLen) *diag = (int64_t)mt.pos - (int64_t)i;
+        return mt;
+    }
+    return phrase_at(pv, h, hv, i, cursor, diag);
 }
 
 // P1 for global chunk g: speculative greedy parse from the chunk's first base with chunk-capped lookups.  Only
@@ -426,8 +461,9 @@ DRLZ_HD void spec_parse_chunk(const ParseView& pv, uint32_t g) {
     uint64_t i = s; uint32_t cnt = 0;
     uint32_t cur = hv.n_exc ? exc_lower_bound(hv, i) : 0;
     bool open = false;
+    int64_t diag = kNoDiag;
     while (i < e) {
-        Match mt = phrase_capped(pv, hv, i, &cur, &open);
+        Match mt = phrase_capped(pv, hv, i, &cur, &open, &diag);
         if (i == s) { pv.first_pos[g] = mt.pos; pv.first_len[g] = mt.len; pv.run_len[g] = open ? kEmpty : mt.len; }
         if (cnt < (uint32_t)kSpecStore) pv.spec_ph[(size_t)g * kSpecStore + cnt] = make_uint2(mt.pos, mt.len);
         ++cnt;
@@ -475,16 +511,17 @@ DRLZ_HD void fix_parse_record(const ParseView& pv, uint32_t g, int slot, uint32_
     uint32_t curA = hv.n_exc ? exc_lower_bound(hv, iA) : 0;
     uint32_t curB = hv.n_exc ? exc_lower_bound(hv, iB) : 0;
     bool merged = false;
+    int64_t diagA = kNoDiag, diagB = kNoDiag;
     while (iB < e) {
         while (iA < iB) {
             uint32_t lenA;
             if (cntA < (uint32_t)kSpecStore && cntA < pv.spec_cnt[g]) lenA = pv.spec_ph[(size_t)g * kSpecStore + cntA].y;
-            else lenA = chunk_step(pv, g, h, hv, s, iA, &curA).len;
+            else lenA = chunk_step(pv, g, h, hv, s, iA, &curA, &diagA).len;
             ++cntA;
             iA += lenA ? lenA : 1;
         }
         if (iA == iB) { merged = true; break; }
-        Match mt = phrase_at(pv, h, hv, iB, &curB);
+        Match mt = phrase_at(pv, h, hv, iB, &curB, &diagB);
         if (cntB < (uint32_t)kAltStore) pv.alt_ph[(size_t)rid * kAltStore + cntB] = make_uint2(mt.pos, mt.len);
         ++cntB;
         iB += mt.len ? mt.len : 1;
@@ -567,8 +604,9 @@ DRLZ_HD void emit_chunk(const ParseView& pv, uint32_t g, uint32_t entry, uint32_
     uint64_t s = (uint64_t)(g - pv.hap_chunk_base[h]) << pv.chunk_shift;
     uint64_t i = entry;
     uint32_t cur = hv.n_exc ? exc_lower_bound(hv, i) : 0;
+    int64_t diag = kNoDiag;
     for (uint32_t t = 0; t < cnt; ++t) {
-        Match mt = chunk_step(pv, g, h, hv, s, i, &cur);
+        Match mt = chunk_step(pv, g, h, hv, s, i, &cur, &diag);
         out[2 * (uint64_t)t] = (int64_t)mt.pos;
         out[2 * (uint64_t)t + 1] = (int64_t)mt.len;
         i += mt.len ? mt.len : 1;

@@ -234,6 +234,29 @@ int build_lcp(const uint64_t* text, uint64_t n, const uint32_t* sa, const uint32
 
 }  // namespace drlz
 
+namespace drlz {
+// ---- uniqueness array: longest repeat starting at each text position --------------------------------------------
+// uniq[p] = min(65535, max(LCP[ISA[p]], LCP[ISA[p]+1])): a match of more than uniq[p] bases that starts at reference
+// position p cannot be matched as long anywhere else (used by the predicted-diagonal path of the parse).
+__global__ void k_uniq(uint64_t n, const uint32_t* __restrict__ isa, const uint32_t* __restrict__ lcp, uint16_t* __restrict__ uniq) {
+    uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    uint32_t r = isa[p];
+    uint32_t a = lcp[r];
+    uint32_t b = (uint64_t)r + 1 < n ? lcp[r + 1] : 0u;
+    uint32_t u = a > b ? a : b;
+    uniq[p] = (uint16_t)(u > 65535u ? 65535u : u);
+}
+
+int build_uniq(uint64_t n, const uint32_t* isa, const uint32_t* lcp, uint16_t* uniq, cudaStream_t s) {
+    if (n == 0) return 0;
+    g_launches += 1;
+    k_uniq<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(n, isa, lcp, uniq);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace drlz
+
 // ---- debug/test entry points (not part of include/drlz.h): exercise the primitives in isolation ----
 extern "C" int drlz_debug_sort_pairs(uint64_t* keys_host, uint32_t* vals_host, uint64_t n, int begin_bit, int end_bit) {
     using namespace drlz;

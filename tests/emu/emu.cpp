@@ -39,7 +39,7 @@ extern "C" {
 void emu_free(void* p) { free(p); }
 
 // returns 0 ok, 1 reference not ACGT, 2 overflow/unresolved
-int emu_parse(const uint8_t* ref, uint64_t n, const int64_t* sa64, int k, uint32_t chunk, uint32_t min_cap, uint32_t foreign_cap, int H,
+int emu_parse(const uint8_t* ref, uint64_t n, const int64_t* sa64, int k, uint32_t chunk, uint32_t min_cap, uint32_t foreign_cap, int use_uniq, int H,
               const uint8_t* const* rows, const uint64_t* cols, int64_t** pairs_out, uint64_t* npairs,
               uint64_t* m_out, int* rounds_out) {
     for (uint64_t i = 0; i < n; ++i) if (code_of(ref[i]) < 0) return 1;
@@ -49,7 +49,27 @@ int emu_parse(const uint8_t* ref, uint64_t n, const int64_t* sa64, int k, uint32
     std::vector<uint64_t> text; pack_seq(ref, n, text, nullptr, nullptr);
     std::vector<uint32_t> sa(n); for (uint64_t i = 0; i < n; ++i) sa[i] = (uint32_t)sa64[i];
     std::vector<uint32_t> tab; build_tab(text, n, sa, k, tab);
-    IndexView ix{text.data(), sa.data(), tab.data(), n, k};
+    // uniqueness array: longest repeat starting at p (Kasai LCP on the host; test harness only)
+    std::vector<uint16_t> uniq(n + 1, 0);
+    {
+        std::vector<uint32_t> isa(n), lcp(n + 1, 0);
+        for (uint64_t j = 0; j < n; ++j) isa[sa[j]] = (uint32_t)j;
+        uint64_t hh = 0;
+        for (uint64_t p = 0; p < n; ++p) {
+            uint32_t r = isa[p];
+            if (r == 0) { hh = 0; continue; }
+            uint64_t q = sa[r - 1];
+            while (p + hh < n && q + hh < n && ref[p + hh] == ref[q + hh]) ++hh;
+            lcp[r] = (uint32_t)hh;
+            if (hh) --hh;
+        }
+        for (uint64_t p = 0; p < n; ++p) {
+            uint32_t r = isa[p];
+            uint32_t u = lcp[r] > lcp[r + 1] ? lcp[r] : lcp[r + 1];
+            uniq[p] = (uint16_t)(u > 65535u ? 65535u : u);
+        }
+    }
+    IndexView ix{text.data(), sa.data(), tab.data(), n, k, use_uniq ? uniq.data() : nullptr};
 
     std::vector<std::vector<uint64_t>> xs(H);
     std::vector<std::vector<uint32_t>> eps(H);

@@ -24,7 +24,7 @@ def lib():
     return _LIB
 
 
-def parse(ref: bytes, sa: np.ndarray, rows, k: int, chunk: int, min_cap: int = 64, foreign_cap: int = 1 << 20):
+def parse(ref: bytes, sa: np.ndarray, rows, k: int, chunk: int, min_cap: int = 64, foreign_cap: int = 1 << 20, use_uniq: int = 1):
     L = lib()
     d = np.frombuffer(bytes(ref), dtype=np.uint8)
     sa = np.ascontiguousarray(sa, dtype=np.int64)
@@ -37,7 +37,7 @@ def parse(ref: bytes, sa: np.ndarray, rows, k: int, chunk: int, min_cap: int = 6
     m = np.zeros(H, dtype=np.uint64)
     rounds = C.c_int(0)
     rc = L.emu_parse(d.ctypes.data_as(C.c_void_p), C.c_uint64(d.size), sa.ctypes.data_as(C.c_void_p), C.c_int(k),
-                     C.c_uint32(chunk), C.c_uint32(min_cap), C.c_uint32(foreign_cap), C.c_int(H), ptrs, cols.ctypes.data_as(C.c_void_p), outp,
+                     C.c_uint32(chunk), C.c_uint32(min_cap), C.c_uint32(foreign_cap), C.c_int(use_uniq), C.c_int(H), ptrs, cols.ctypes.data_as(C.c_void_p), outp,
                      npairs.ctypes.data_as(C.c_void_p), m.ctypes.data_as(C.c_void_p), C.byref(rounds))
     if rc != 0:
         return rc, None, None, rounds.value

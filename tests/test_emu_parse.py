@@ -8,9 +8,9 @@ from tests.emu import emu
 from tests.util import random_case
 
 
-def check(d, rows, k, chunk, min_cap=64, foreign_cap=1 << 20):
+def check(d, rows, k, chunk, min_cap=64, foreign_cap=1 << 20, use_uniq=1):
     sa = orc.sa_build(d)
-    rc, res, m, rounds = emu.parse(d, sa, rows, k, chunk, min_cap, foreign_cap)
+    rc, res, m, rounds = emu.parse(d, sa, rows, k, chunk, min_cap, foreign_cap, use_uniq)
     assert rc == 0, (rc, rounds)
     for h, r in enumerate(rows):
         x = orc.strip_gaps(r).tobytes()
@@ -33,7 +33,7 @@ def test_random_small(seed):
         k = int(rng.integers(1, 6))
         chunk = int(rng.choice([1, 2, 3, 5, 8, 16, 64]))
         min_cap = int(rng.choice([1, 2, 4, 64]))
-        check(d, [x, x[::-1], b"", d, d[3:]], k, chunk, min_cap)
+        check(d, [x, x[::-1], b"", d, d[3:]], k, chunk, min_cap, use_uniq=int(rng.integers(0, 2)))
 
 
 def test_low_complexity_never_merging():
