@@ -55,7 +55,9 @@ struct ParseBuffers {
     ParseView pv;                 // device pointers (see rlz_core.cuh)
     uint32_t H;
     uint32_t max_chunks_per_hap;
-    int occ;                      // 0: default register budget, 16: 32 registers per thread (max occupancy)
+    int occ;                      // min CTAs per SM of k_spec (0 = compiler default; 8 / 10 / 12 / 16)
+    int occ_fix;                  // same for k_fix
+    int64_t* hint;                // [ceil(NC / kHintGroup)] diagonal hints (null = no hint pass)
     uint32_t* link_b;             // [NC] second buffers of the list ranking
     uint32_t* run_b;              // [NC]
     uint32_t* jump_a;             // [NC*(kAltSlots+1)]

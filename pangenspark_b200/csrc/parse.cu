@@ -1,5 +1,6 @@
 // parse.cu -- kernels of the chunk-parallel exact greedy RLZ parse (per-thread logic in rlz_core.cuh).
 //
+//   k_hint      H : one 64-base lookup per 32 chunks seeds the predicted diagonal of the group
 //   k_spec      P1: one thread per chunk, speculative greedy parse from the chunk's first base with chunk-capped
 //                   lookups; phrases stored; the first phrase doubles as stage A's phrase at the chunk start
 //   k_link      A : open first phrases linked to the chunk their match continues in
@@ -30,6 +31,11 @@ __global__ void k_rank(const uint32_t* __restrict__ link_in, const uint32_t* __r
                        uint32_t* run_out, uint32_t nc) {
     uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g < nc) rank_round(link_in, run_in, link_out, run_out, g);
+}
+
+__global__ void __launch_bounds__(128) k_hint(ParseView pv, int64_t* hint, uint32_t nq) {
+    uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < nq) hint_group(pv, hint, q);
 }
 
 __global__ void __launch_bounds__(128) k_resolve(ParseView pv) {
@@ -184,6 +190,12 @@ int parse_stage_count(ParseBuffers& pb, cudaStream_t s, int* rounds_out, cudaEve
     cudaMemsetAsync(pv.alt_entry, 0xFF, sizeof(uint32_t) * (size_t)NC * kAltSlots, s);
     cudaMemsetAsync(pv.counters, 0, sizeof(uint32_t) * (2 + kMaxRounds), s);
     if (ev) cudaEventRecord(ev[0], s);
+    if (pv.ix.uniq && pb.hint) {            // H: one 64-base lookup per group of chunks seeds the predicted diagonals
+        uint32_t nq = (NC + kHintGroup - 1) / kHintGroup;
+        g_launches += 1;
+        k_hint<<<(nq + 127) / 128, 128, 0, s>>>(pv, pb.hint, nq);
+        pv.hint = pb.hint;
+    } else pv.hint = nullptr;
     g_launches += 1;
     if (pb.occ >= 16) k_spec<16><<<(NC + 127) / 128, 128, 0, s>>>(pv);
     else if (pb.occ >= 12) k_spec<12><<<(NC + 127) / 128, 128, 0, s>>>(pv);
@@ -218,8 +230,8 @@ int parse_stage_count(ParseBuffers& pb, cudaStream_t s, int* rounds_out, cudaEve
         if (pb.host_counters[1 + round] == 0) break;
         uint32_t nr = NC * kAltSlots;
         g_launches += 1;
-        if (pb.occ >= 16) k_fix<16><<<(nr + 127) / 128, 128, 0, s>>>(pv, (uint32_t)round);
-        else if (pb.occ >= 10) k_fix<10><<<(nr + 127) / 128, 128, 0, s>>>(pv, (uint32_t)round);
+        if (pb.occ_fix >= 16) k_fix<16><<<(nr + 127) / 128, 128, 0, s>>>(pv, (uint32_t)round);
+        else if (pb.occ_fix >= 10) k_fix<10><<<(nr + 127) / 128, 128, 0, s>>>(pv, (uint32_t)round);
         else k_fix<1><<<(nr + 127) / 128, 128, 0, s>>>(pv, (uint32_t)round);
         ++round;
     }

@@ -37,7 +37,7 @@ namespace drlz {
 static const uint32_t kEmpty = 0xFFFFFFFFu;
 static const int kAltSlots = 3;           // alternative entry records per chunk (see parse pipeline)
 static const int kMaxRounds = 30;
-static const int kSpecStore = 16;         // phrases of a chunk's speculative parse kept for emission
+static const int kHintGroup = 32;         // chunks per diagonal hint (one full lookup seeds the prediction of the group)
 static const int kAltStore = 4;           // own phrases of an alternative record kept for emission
 
 DRLZ_HD int clz64(uint64_t v) {
@@ -280,7 +280,9 @@ struct ParseView {
     uint32_t* alt_round;            // [NC*kAltSlots] round in which the record must be fix-parsed
     uint32_t* alt_own;              // [NC*kAltSlots] phrases before the merge point
     uint32_t* alt_merge;            // [NC*kAltSlots] index into the speculative phrase list where the tail starts, kEmpty = no merge
-    uint2* spec_ph;                 // [NC*kSpecStore] (pos, len) of the first phrases of the speculative parse
+    uint2* spec_ph;                 // [NC*spec_store] (pos, len) of the first phrases of the speculative parse
+    uint32_t spec_store;            // phrases of a chunk's speculative parse kept for emission
+    const int64_t* hint;            // [ceil(NC / kHintGroup)] predicted diagonal of each chunk group (kNoDiag = none); may be null
     uint2* alt_ph;                  // [NC*kAltSlots*kAltStore] own phrases of the alternative records
     uint32_t* counters;             // [0] overflow flag, [1 + r] records created for round r
 };
@@ -442,6 +444,23 @@ DRLZ_HD Match chunk_step(const ParseView& pv, uint32_t g, uint32_t h, const HapV
     return phrase_at(pv, h, hv, i, cursor, diag);
 }
 
+// H: diagonal hint of chunk group q = alignment of the phrase at the first base of its first chunk (64-base probe)
+DRLZ_HD void hint_group(const ParseView& pv, int64_t* hint, uint32_t q) {
+    uint32_t g = q * kHintGroup;
+    hint[q] = kNoDiag;
+    if (g >= pv.n_chunks) return;
+    uint32_t h = pv.chunk_hap[g];
+    const HapView& hv = pv.haps[h];
+    uint64_t s = (uint64_t)(g - pv.hap_chunk_base[h]) << pv.chunk_shift;
+    if (s >= hv.m) return;
+    uint32_t cur = hv.n_exc ? exc_lower_bound(hv, s) : 0;
+    uint64_t stop = stop_after(hv, s, &cur);
+    if (stop == s) return;
+    bool open;
+    Match mt = lookup(pv.ix, hv.x, s, (uint32_t)(stop - s), 64u, &open);
+    if (mt.len >= kDiagMinLen) hint[q] = (int64_t)mt.pos - (int64_t)s;
+}
+
 // P1 for global chunk g: speculative greedy parse from the chunk's first base with chunk-capped lookups.  Only
 // the last phrase of a chunk can be open (it reaches the chunk end); its total length -- hence the exit of the
 // chunk -- is filled in by resolve_chunk() once the diagonal runs are ranked.  The first phrase doubles as
@@ -461,11 +480,11 @@ DRLZ_HD void spec_parse_chunk(const ParseView& pv, uint32_t g) {
     uint64_t i = s; uint32_t cnt = 0;
     uint32_t cur = hv.n_exc ? exc_lower_bound(hv, i) : 0;
     bool open = false;
-    int64_t diag = kNoDiag;
+    int64_t diag = pv.hint ? pv.hint[g / kHintGroup] : kNoDiag;
     while (i < e) {
         Match mt = phrase_capped(pv, hv, i, &cur, &open, &diag);
         if (i == s) { pv.first_pos[g] = mt.pos; pv.first_len[g] = mt.len; pv.run_len[g] = open ? kEmpty : mt.len; }
-        if (cnt < (uint32_t)kSpecStore) pv.spec_ph[(size_t)g * kSpecStore + cnt] = make_uint2(mt.pos, mt.len);
+        if (cnt < pv.spec_store) pv.spec_ph[(size_t)g * pv.spec_store + cnt] = make_uint2(mt.pos, mt.len);
         ++cnt;
         if (open) { pv.open_i[g] = (uint32_t)i; pv.open_pos[g] = mt.pos; pv.open_len[g] = mt.len; break; }
         i += mt.len ? mt.len : 1;
@@ -492,7 +511,7 @@ DRLZ_HD void resolve_chunk(const ParseView& pv, uint32_t g) {
         total = (uint32_t)(j - i) + (same ? pv.run_len[g2] : foreign_run(pv, hv, i, mt, j));
     }
     uint32_t cnt = pv.spec_cnt[g];
-    if (cnt - 1 < (uint32_t)kSpecStore) pv.spec_ph[(size_t)g * kSpecStore + cnt - 1].y = total;
+    if (cnt - 1 < pv.spec_store) pv.spec_ph[(size_t)g * pv.spec_store + cnt - 1].y = total;
     uint64_t x = i + total;
     pv.spec_exit[g] = (uint32_t)x;
     register_exit(pv, h, x, 1);
@@ -512,10 +531,11 @@ DRLZ_HD void fix_parse_record(const ParseView& pv, uint32_t g, int slot, uint32_
     uint32_t curB = hv.n_exc ? exc_lower_bound(hv, iB) : 0;
     bool merged = false;
     int64_t diagA = kNoDiag, diagB = kNoDiag;
+    if (pv.first_len[g] >= kDiagMinLen) diagA = diagB = (int64_t)pv.first_pos[g] - (int64_t)s;
     while (iB < e) {
         while (iA < iB) {
             uint32_t lenA;
-            if (cntA < (uint32_t)kSpecStore && cntA < pv.spec_cnt[g]) lenA = pv.spec_ph[(size_t)g * kSpecStore + cntA].y;
+            if (cntA < pv.spec_store && cntA < pv.spec_cnt[g]) lenA = pv.spec_ph[(size_t)g * pv.spec_store + cntA].y;
             else lenA = chunk_step(pv, g, h, hv, s, iA, &curA, &diagA).len;
             ++cntA;
             iA += lenA ? lenA : 1;
@@ -581,16 +601,16 @@ DRLZ_HD void put_record(int64_t* out, uint32_t t, uint2 ph) {
 
 // E (fast path): copy the stored phrases of the true record; returns false if some were not stored
 DRLZ_HD bool emit_stored(const ParseView& pv, uint32_t g, uint32_t slot, uint32_t cnt, int64_t* out) {
-    const uint2* sp = pv.spec_ph + (size_t)g * kSpecStore;
+    const uint2* sp = pv.spec_ph + (size_t)g * pv.spec_store;
     if (slot == 0) {
-        if (cnt > (uint32_t)kSpecStore) return false;
+        if (cnt > pv.spec_store) return false;
         for (uint32_t t = 0; t < cnt; ++t) put_record(out, t, sp[t]);
         return true;
     }
     uint32_t rid = g * kAltSlots + slot - 1;
     uint32_t own = pv.alt_own[rid], mg = pv.alt_merge[rid];
     if (own > (uint32_t)kAltStore) return false;
-    if (mg != kEmpty && pv.spec_cnt[g] > (uint32_t)kSpecStore) return false;
+    if (mg != kEmpty && pv.spec_cnt[g] > pv.spec_store) return false;
     const uint2* ap = pv.alt_ph + (size_t)rid * kAltStore;
     for (uint32_t t = 0; t < own; ++t) put_record(out, t, ap[t]);
     if (mg != kEmpty) for (uint32_t t = mg; t < pv.spec_cnt[g]; ++t) put_record(out, own + t - mg, sp[t]);
