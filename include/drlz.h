@@ -41,7 +41,7 @@ const char* drlz_last_error(const drlz_ctx* ctx);
 /* Run all kernels of this context on the caller's CUDA stream (cudaStream_t as void*), e.g. torch's current
  * stream, so that caller-side CUDA events bracket them.  NULL restores the context's own stream. */
 int drlz_set_stream(drlz_ctx* ctx, void* cuda_stream);
-/* options: "kmer" (jump-table k, 0 = auto), "chunk" (bases per parse chunk, 0 = default 2048),
+/* options: "kmer" (jump-table k, 0 = auto), "chunk" (bases per parse chunk, rounded down to a power of two, 0 = default 4096),
  *          "group_bytes" (host-path pipeline granularity), "lcp" (1 = also build the LCP array),
  *          "min_cap" (lower bound of the per-lookup compare cap, default 64), "foreign_cap" (longest off-chain
  *          diagonal compare a single thread may do before the exact sequential fallback is taken) */
