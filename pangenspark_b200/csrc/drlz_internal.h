@@ -58,6 +58,7 @@ struct ParseBuffers {
     int occ;                      // min CTAs per SM of k_spec (0 = compiler default; 8 / 10 / 12 / 16)
     int occ_fix;                  // same for k_fix
     int64_t* hint;                // [ceil(NC / kHintGroup)] diagonal hints (null = no hint pass)
+    uint16_t* mm;                 // [NC*kMmStride] mismatch lists (null = no diagonal pre-scan)
     uint32_t* link_b;             // [NC] second buffers of the list ranking
     uint32_t* run_b;              // [NC]
     uint32_t* jump_a;             // [NC*(kAltSlots+1)]

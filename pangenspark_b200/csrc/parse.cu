@@ -1,6 +1,7 @@
 // parse.cu -- kernels of the chunk-parallel exact greedy RLZ parse (per-thread logic in rlz_core.cuh).
 //
-//   k_hint      H : one 64-base lookup per 32 chunks seeds the predicted diagonal of the group
+//   k_hint      H : a 64-base lookup at every chunk start gives the chunk's predicted diagonal
+//   k_diag      D : mismatch offsets of every chunk along that diagonal (the streaming compare, done once, up front)
 //   k_spec      P1: one thread per chunk, speculative greedy parse from the chunk's first base with chunk-capped
 //                   lookups; phrases stored; the first phrase doubles as stage A's phrase at the chunk start
 //   k_link      A : open first phrases linked to the chunk their match continues in
@@ -36,6 +37,11 @@ __global__ void k_rank(const uint32_t* __restrict__ link_in, const uint32_t* __r
 __global__ void __launch_bounds__(128) k_hint(ParseView pv, int64_t* hint, uint32_t nq) {
     uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q < nq) hint_group(pv, hint, q);
+}
+
+__global__ void __launch_bounds__(128) k_diag(ParseView pv) {
+    uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < pv.n_chunks) diag_scan_chunk(pv, g);
 }
 
 __global__ void __launch_bounds__(128) k_resolve(ParseView pv) {
@@ -195,7 +201,12 @@ int parse_stage_count(ParseBuffers& pb, cudaStream_t s, int* rounds_out, cudaEve
         g_launches += 1;
         k_hint<<<(nq + 127) / 128, 128, 0, s>>>(pv, pb.hint, nq);
         pv.hint = pb.hint;
-    } else pv.hint = nullptr;
+        if (pb.mm && pv.chunk_shift >= 5 && pv.chunk_shift <= 15) {   // D: mismatch lists along the hinted diagonals
+            pv.mm = pb.mm;
+            g_launches += 1;
+            k_diag<<<(NC + 127) / 128, 128, 0, s>>>(pv);
+        } else pv.mm = nullptr;
+    } else { pv.hint = nullptr; pv.mm = nullptr; }
     g_launches += 1;
     if (pb.occ >= 16) k_spec<16><<<(NC + 127) / 128, 128, 0, s>>>(pv);
     else if (pb.occ >= 12) k_spec<12><<<(NC + 127) / 128, 128, 0, s>>>(pv);

@@ -37,7 +37,9 @@ namespace drlz {
 static const uint32_t kEmpty = 0xFFFFFFFFu;
 static const int kAltSlots = 3;           // alternative entry records per chunk (see parse pipeline)
 static const int kMaxRounds = 30;
-static const int kHintGroup = 32;         // chunks per diagonal hint (one full lookup seeds the prediction of the group)
+static const int kHintGroup = 1;          // chunks per diagonal hint (a 64-base lookup at the chunk start)
+static const int kMmMax = 14;             // mismatch offsets kept per chunk by the diagonal pre-scan
+static const int kMmStride = 16;          // uint16 per chunk: [count, valid_until, offsets...]
 static const int kAltStore = 4;           // own phrases of an alternative record kept for emission
 
 DRLZ_HD int clz64(uint64_t v) {
@@ -283,6 +285,7 @@ struct ParseView {
     uint2* spec_ph;                 // [NC*spec_store] (pos, len) of the first phrases of the speculative parse
     uint32_t spec_store;            // phrases of a chunk's speculative parse kept for emission
     const int64_t* hint;            // [ceil(NC / kHintGroup)] predicted diagonal of each chunk group (kNoDiag = none); may be null
+    uint16_t* mm;                   // [NC*kMmStride] mismatch offsets of each chunk along its hinted diagonal; may be null
     uint2* alt_ph;                  // [NC*kAltSlots*kAltStore] own phrases of the alternative records
     uint32_t* counters;             // [0] overflow flag, [1 + r] records created for round r
 };
@@ -325,7 +328,26 @@ static const uint32_t kDiagMinLen = 32;   // phrases at least this long update t
 // reference -- then every other suffix shares fewer bases with the pattern, i.e. p is the unique longest match and
 // the SA interval is a singleton: exactly what lookup() would return, for one 2-byte read instead of the
 // table -> SA -> text probe chain.  Anything else falls through to lookup().
-DRLZ_HD Match phrase_capped(const ParseView& pv, const HapView& hv, uint64_t i, uint32_t* cursor, bool* open, int64_t* diag) {
+// verified length of the match of x[i..i+plen) along the chunk's hinted diagonal, from the pre-scanned mismatch list;
+// returns false if the list cannot answer (position past the classified range, or plen reaches beyond the chunk)
+DRLZ_HD bool list_extent(const ParseView& pv, uint32_t g, uint64_t s, uint64_t i, uint32_t plen, uint32_t* c_out) {
+    const uint16_t* mm = pv.mm + (size_t)g * kMmStride;
+    uint32_t cnt = mm[0], V = mm[1];
+    uint32_t off = (uint32_t)(i - s);
+    if (off >= V) return false;
+    uint32_t c = V - off;
+    bool closed = false;
+    for (uint32_t t = 0; t < cnt; ++t) {
+        uint32_t mo = mm[2 + t];
+        if (mo >= off) { c = mo - off; closed = true; break; }
+    }
+    if (c >= plen) { *c_out = plen; return true; }
+    if (closed) { *c_out = c; return true; }
+    return false;                                            // classified range ends before the pattern does
+}
+
+DRLZ_HD Match phrase_capped(const ParseView& pv, const HapView& hv, uint64_t i, uint32_t* cursor, bool* open, int64_t* diag,
+                            uint32_t g, uint64_t s) {
     *open = false;
     uint64_t stop = stop_after(hv, i, cursor);
     if (stop == i) { Match mt; mt.len = 0; mt.pos = hv.exc_byte[*cursor]; return mt; }
@@ -338,8 +360,10 @@ DRLZ_HD Match phrase_capped(const ParseView& pv, const HapView& hv, uint64_t i, 
         if (p64 >= 0 && (uint64_t)p64 < pv.ix.n) {
             uint32_t p = (uint32_t)p64;
             uint32_t plen = cap < maxlen ? cap : maxlen;
+            uint32_t c;
             bool less;
-            uint32_t c = cmp_suffix_w(get64u(hv.x, (uint32_t)i), hv.x, (uint32_t)i, pv.ix.text, p, (uint32_t)pv.ix.n, plen, &less);
+            if (!(pv.mm && g != kEmpty && pv.hint[g / kHintGroup] == *diag && list_extent(pv, g, s, i, plen, &c)))
+                c = cmp_suffix_w(get64u(hv.x, (uint32_t)i), hv.x, (uint32_t)i, pv.ix.text, p, (uint32_t)pv.ix.n, plen, &less);
             if (c > 0) {
                 uint32_t u = pv.ix.uniq[p];
                 if (u != 0xFFFFu && c > u) {
@@ -382,9 +406,10 @@ DRLZ_HD uint32_t foreign_run(const ParseView& pv, const HapView& hv, uint64_t i,
 }
 
 // exact phrase at position i (uses run_len of the chunk starts; valid after stage A)
-DRLZ_HD Match phrase_at(const ParseView& pv, uint32_t h, const HapView& hv, uint64_t i, uint32_t* cursor, int64_t* diag) {
+DRLZ_HD Match phrase_at(const ParseView& pv, uint32_t h, const HapView& hv, uint64_t i, uint32_t* cursor, int64_t* diag,
+                        uint32_t g, uint64_t s) {
     bool open;
-    Match mt = phrase_capped(pv, hv, i, cursor, &open, diag);
+    Match mt = phrase_capped(pv, hv, i, cursor, &open, diag, g, s);
     if (open) {
         uint64_t j; bool same;
         uint32_t g2 = open_target(pv, h, i, mt, &j, &same);
@@ -441,7 +466,7 @@ DRLZ_HD Match chunk_step(const ParseView& pv, uint32_t g, uint32_t h, const HapV
         if (mt.len >= kDiagMinLen) *diag = (int64_t)mt.pos - (int64_t)i;
         return mt;
     }
-    return phrase_at(pv, h, hv, i, cursor, diag);
+    return phrase_at(pv, h, hv, i, cursor, diag, g, s);
 }
 
 // H: diagonal hint of chunk group q = alignment of the phrase at the first base of its first chunk (64-base probe)
@@ -459,6 +484,43 @@ DRLZ_HD void hint_group(const ParseView& pv, int64_t* hint, uint32_t q) {
     bool open;
     Match mt = lookup(pv.ix, hv.x, s, (uint32_t)(stop - s), 64u, &open);
     if (mt.len >= kDiagMinLen) hint[q] = (int64_t)mt.pos - (int64_t)s;
+}
+
+// D: mismatch offsets of chunk g along its hinted diagonal (scalar form; the kernel k_diag_w does the same with one
+// warp per chunk and coalesced loads).  mm = [count, valid_until, offsets...]: every position below valid_until is
+// classified (mismatch iff listed); a reference that ends inside the chunk counts as a mismatch there.
+DRLZ_HD void diag_scan_chunk(const ParseView& pv, uint32_t g) {
+    uint16_t* mm = pv.mm + (size_t)g * kMmStride;
+    mm[0] = 0; mm[1] = 0;
+    int64_t dg = pv.hint[g / kHintGroup];
+    if (dg == kNoDiag) return;
+    uint32_t h = pv.chunk_hap[g];
+    const HapView& hv = pv.haps[h];
+    uint64_t s = (uint64_t)(g - pv.hap_chunk_base[h]) << pv.chunk_shift;
+    if (s >= hv.m) return;
+    uint64_t e = s + (1ull << pv.chunk_shift); if (e > hv.m) e = hv.m;
+    int64_t p0 = (int64_t)s + dg;
+    if (p0 < 0 || (uint64_t)p0 >= pv.ix.n) return;
+    uint32_t p = (uint32_t)p0, len = (uint32_t)(e - s);
+    uint32_t avail = (uint32_t)pv.ix.n - p;
+    uint32_t cmplen = len < avail ? len : avail;
+    uint32_t cnt = 0, V = len;
+    bool full = false;
+    for (uint32_t o = 0; o < cmplen && !full; o += 32) {
+        uint64_t xr = get64u(hv.x, (uint32_t)s + o) ^ get64u(pv.ix.text, p + o);
+        uint32_t nb = cmplen - o < 32u ? cmplen - o : 32u;
+        if (nb < 32) xr &= ~0ull << (64 - 2 * nb);
+        while (xr) {
+            uint32_t b = (uint32_t)(clz64(xr) >> 1);
+            if (cnt == (uint32_t)kMmMax) { V = o + b; full = true; break; }
+            mm[2 + cnt++] = (uint16_t)(o + b);
+            xr &= ~(3ull << (62 - 2 * b));
+        }
+    }
+    if (!full && cmplen < len) {
+        if (cnt == (uint32_t)kMmMax) V = cmplen; else mm[2 + cnt++] = (uint16_t)cmplen;
+    }
+    mm[0] = (uint16_t)cnt; mm[1] = (uint16_t)V;
 }
 
 // P1 for global chunk g: speculative greedy parse from the chunk's first base with chunk-capped lookups.  Only
@@ -482,7 +544,7 @@ DRLZ_HD void spec_parse_chunk(const ParseView& pv, uint32_t g) {
     bool open = false;
     int64_t diag = pv.hint ? pv.hint[g / kHintGroup] : kNoDiag;
     while (i < e) {
-        Match mt = phrase_capped(pv, hv, i, &cur, &open, &diag);
+        Match mt = phrase_capped(pv, hv, i, &cur, &open, &diag, g, s);
         if (i == s) { pv.first_pos[g] = mt.pos; pv.first_len[g] = mt.len; pv.run_len[g] = open ? kEmpty : mt.len; }
         if (cnt < pv.spec_store) pv.spec_ph[(size_t)g * pv.spec_store + cnt] = make_uint2(mt.pos, mt.len);
         ++cnt;
@@ -541,7 +603,7 @@ DRLZ_HD void fix_parse_record(const ParseView& pv, uint32_t g, int slot, uint32_
             iA += lenA ? lenA : 1;
         }
         if (iA == iB) { merged = true; break; }
-        Match mt = phrase_at(pv, h, hv, iB, &curB, &diagB);
+        Match mt = phrase_at(pv, h, hv, iB, &curB, &diagB, g, s);
         if (cntB < (uint32_t)kAltStore) pv.alt_ph[(size_t)rid * kAltStore + cntB] = make_uint2(mt.pos, mt.len);
         ++cntB;
         iB += mt.len ? mt.len : 1;

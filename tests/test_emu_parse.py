@@ -62,6 +62,23 @@ def test_long_matches_are_chained():
     check(b"A" * 700 + b"C", [b"A" * 300, b"A" * 700, b"A" * 699 + b"CA"], 3, 32, 4)
 
 
+@pytest.mark.parametrize("chunk", [32, 64, 128, 1024])
+def test_diag_scan_paths(chunk):
+    # chunk sizes >= 32 enable the hinted-diagonal pre-scan; dense edits overflow its 14-entry lists,
+    # repeats make the uniqueness test fail, N's cut phrases: every fall-through path must stay exact
+    seed = orc.seed_for(2)
+    d = orc.syn_reference(seed, 60_000, repeats=12)
+    rows = orc.syn_rows(seed, d, 0, 4, 1.5e-2, 2e-3, 2e-3)
+    extra = bytearray(rows[1].tobytes())
+    for p in range(500, len(extra), 7000):
+        extra[p] = ord("N")
+    dense = bytearray(rows[2].tobytes())
+    rng = np.random.default_rng(chunk)
+    for p in rng.integers(3000, 6000, size=400):
+        dense[p] = ord("ACGT"[int(rng.integers(0, 4))])
+    check(d.tobytes(), [r.tobytes() for r in rows] + [bytes(extra), bytes(dense), d.tobytes()[100:30000]], 7, chunk)
+
+
 def test_synth_medium():
     seed = orc.seed_for(1)
     d = orc.syn_reference(seed, 200_000, repeats=20)
