@@ -1,7 +1,7 @@
 // parse.cu -- kernels of the chunk-parallel exact greedy RLZ parse (per-thread logic in rlz_core.cuh).
 //
 //   k_hint      H : a 64-base lookup at every chunk start gives the chunk's predicted diagonal
-//   k_diag      D : mismatch offsets of every chunk along that diagonal (the streaming compare, done once, up front)
+//   k_diag_w    D : mismatch offsets of every chunk along that diagonal (the streaming compare, done once, up front)
 //   k_spec      P1: one thread per chunk, speculative greedy parse from the chunk's first base with chunk-capped
 //                   lookups; phrases stored; the first phrase doubles as stage A's phrase at the chunk start
 //   k_link      A : open first phrases linked to the chunk their match continues in
@@ -39,9 +39,60 @@ __global__ void __launch_bounds__(128) k_hint(ParseView pv, int64_t* hint, uint3
     if (q < nq) hint_group(pv, hint, q);
 }
 
-__global__ void __launch_bounds__(128) k_diag(ParseView pv) {
-    uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g < pv.n_chunks) diag_scan_chunk(pv, g);
+// D: one warp per chunk; lane l compares packed word l of each 1024-base slab (the haplotype side is word aligned
+// because chunks start at multiples of 32 bases), so both streams are read with coalesced 256-byte requests at
+// 32 active lanes -- this is the whole streaming compare of the parse, done once.  Mismatching words are decoded
+// in lane order (ballot), which keeps the offsets sorted.  Same result as diag_scan_chunk().
+__global__ void __launch_bounds__(128) k_diag_w(ParseView pv) {
+    const uint32_t g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (g >= pv.n_chunks) return;
+    uint16_t* mm = pv.mm + (size_t)g * kMmStride;
+    const int64_t dg = pv.hint[g / kHintGroup];
+    const uint32_t h = pv.chunk_hap[g];
+    const HapView& hv = pv.haps[h];
+    const uint64_t s = (uint64_t)(g - pv.hap_chunk_base[h]) << pv.chunk_shift;
+    const int64_t p0 = (int64_t)s + dg;
+    if (dg == kNoDiag || s >= hv.m || p0 < 0 || (uint64_t)p0 >= pv.ix.n) {
+        if (lane == 0) { mm[0] = 0; mm[1] = 0; }
+        return;
+    }
+    uint64_t e = s + (1ull << pv.chunk_shift); if (e > hv.m) e = hv.m;
+    const uint32_t p = (uint32_t)p0, len = (uint32_t)(e - s);
+    const uint32_t avail = (uint32_t)pv.ix.n - p;
+    const uint32_t cmplen = len < avail ? len : avail;
+    const uint64_t* __restrict__ xw = hv.x + (s >> 5);
+    const uint64_t* __restrict__ D = pv.ix.text;
+    uint32_t cnt = 0, V = len;
+    bool full = false;
+    for (uint32_t o0 = 0; o0 < cmplen && !full; o0 += 1024) {
+        const uint32_t o = o0 + 32u * (uint32_t)lane;
+        uint64_t xr = 0;
+        if (o < cmplen) {
+            xr = xw[o >> 5] ^ get64u(D, p + o);
+            uint32_t nb = cmplen - o < 32u ? cmplen - o : 32u;
+            if (nb < 32) xr &= ~0ull << (64 - 2 * nb);
+        }
+        unsigned bal = __ballot_sync(0xffffffffu, xr != 0);
+        while (bal && !full) {
+            const int src = __ffs(bal) - 1;
+            bal &= bal - 1;
+            uint64_t w = __shfl_sync(0xffffffffu, xr, src);
+            const uint32_t ob = o0 + 32u * (uint32_t)src;
+            while (w) {
+                uint32_t b = (uint32_t)(clz64(w) >> 1);
+                if (cnt == (uint32_t)kMmMax) { V = ob + b; full = true; break; }
+                if (lane == 0) mm[2 + cnt] = (uint16_t)(ob + b);
+                ++cnt;
+                w &= ~(3ull << (62 - 2 * b));
+            }
+        }
+    }
+    if (!full && cmplen < len) {
+        if (cnt == (uint32_t)kMmMax) V = cmplen;
+        else { if (lane == 0) mm[2 + cnt] = (uint16_t)cmplen; ++cnt; }
+    }
+    if (lane == 0) { mm[0] = (uint16_t)cnt; mm[1] = (uint16_t)V; }
 }
 
 __global__ void __launch_bounds__(128) k_resolve(ParseView pv) {
@@ -204,7 +255,7 @@ int parse_stage_count(ParseBuffers& pb, cudaStream_t s, int* rounds_out, cudaEve
         if (pb.mm && pv.chunk_shift >= 5 && pv.chunk_shift <= 15) {   // D: mismatch lists along the hinted diagonals
             pv.mm = pb.mm;
             g_launches += 1;
-            k_diag<<<(NC + 127) / 128, 128, 0, s>>>(pv);
+            k_diag_w<<<(unsigned)(((uint64_t)NC * 32 + 127) / 128), 128, 0, s>>>(pv);
         } else pv.mm = nullptr;
     } else { pv.hint = nullptr; pv.mm = nullptr; }
     g_launches += 1;
