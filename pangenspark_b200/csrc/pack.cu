@@ -102,17 +102,14 @@ __device__ __forceinline__ uint64_t lookback(uint64_t* desc_row, uint32_t t, uin
     return excl;
 }
 
-static const int kTilesPerCta = 1;            // tiles per atomic ticket (4 was measured 18x slower: a tile is published only after
+static const int kTilesPerCta = 1;            // (kept for the record, see below)            // tiles per atomic ticket (4 was measured 18x slower: a tile is published only after
                                               // its CTA finished the earlier ones, which serialises every row's look-back chain)
 
 static const int kPackThreads = kPackTileBytes / 64;
 
-__device__ __forceinline__ void pack_tile(const PackJob& job, uint32_t id, uint32_t* sbits, uint32_t* sm, uint64_t* s_bcast,
-                                          uint64_t* s_wlast) {
+__device__ __forceinline__ void pack_tile(const PackJob& job, uint32_t h, uint32_t t, uint32_t* sbits, uint32_t* sm,
+                                          uint64_t* s_bcast, uint64_t* s_wlast) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // rows interleaved: consecutive ids are the same tile index of consecutive rows, so each row has only a few
-    // tiles in flight and its look-back resolves within one 32-descriptor window
-    const uint32_t h = id % job.H, t = id / job.H;
     const uint64_t cols = job.cols[h];
     const uint64_t tile_start = (uint64_t)t * kPackTileBytes;
     uint64_t* dcnt = job.desc_cnt + (uint64_t)h * job.tiles_per_row;
@@ -124,7 +121,14 @@ __device__ __forceinline__ void pack_tile(const PackJob& job, uint32_t id, uint3
     Seg16 sg[4];
     uint32_t cnt = 0, exc = 0;
     const uint8_t* rowp = job.rows + job.row_off[h];
-    {
+    if (tile_start + kPackTileBytes <= cols) {            // interior tile (block-uniform): no bounds logic at all
+        const uint4* src = reinterpret_cast<const uint4*>(rowp + off);
+        uint4 v0 = src[0], v1 = src[1], v2 = src[2], v3 = src[3];
+        sg[0] = classify16(v0, 16, job.strip); sg[1] = classify16(v1, 16, job.strip);
+        sg[2] = classify16(v2, 16, job.strip); sg[3] = classify16(v3, 16, job.strip);
+        cnt = sg[0].cnt + sg[1].cnt + sg[2].cnt + sg[3].cnt;
+        exc = sg[0].exc + sg[1].exc + sg[2].exc + sg[3].exc;
+    } else {
         uint4 v[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -254,19 +258,17 @@ __global__ void __launch_bounds__(kPackThreads) k_pack(PackJob job, uint32_t n_t
     __shared__ uint32_t sm[33];
     __shared__ uint64_t s_bcast[4];
     __shared__ uint64_t s_wlast[kPackThreads / 32];
-    __shared__ uint32_t s_ticket;
-    uint32_t first;
-    if (job.use_tickets) {
-        if (threadIdx.x == 0) s_ticket = atomicAdd(job.tile_counter, (uint32_t)kTilesPerCta);
-        __syncthreads();
-        first = s_ticket;
-    } else first = blockIdx.x * (uint32_t)kTilesPerCta;
-    for (int q = 0; q < kTilesPerCta; ++q) {
-        uint32_t id = first + (uint32_t)q;
-        if (id >= n_tiles) break;
-        pack_tile(job, id, sbits, sm, s_bcast, s_wlast);
-        __syncthreads();                                   // shared buffers are reused by the next tile
+    __shared__ uint32_t s_ticket[3];
+    // rows interleaved: consecutive ids are the same tile index of consecutive rows, so each row has only a few
+    // tiles in flight and its look-back resolves within one 32-descriptor window.  Thread 0 takes the ticket and
+    // does the one integer division of the CTA.
+    if (threadIdx.x == 0) {
+        uint32_t id = job.use_tickets ? atomicAdd(job.tile_counter, 1u) : blockIdx.x;
+        s_ticket[0] = id; s_ticket[1] = id % job.H; s_ticket[2] = id / job.H;
     }
+    __syncthreads();
+    if (s_ticket[0] >= n_tiles) return;
+    pack_tile(job, s_ticket[1], s_ticket[2], sbits, sm, s_bcast, s_wlast);
 }
 
 void launch_pack(const PackJob& job, cudaStream_t s, cudaEvent_t* ev) {

@@ -65,26 +65,34 @@ __global__ void __launch_bounds__(128) k_diag_w(ParseView pv) {
     const uint64_t* __restrict__ D = pv.ix.text;
     uint32_t cnt = 0, V = len;
     bool full = false;
-    for (uint32_t o0 = 0; o0 < cmplen && !full; o0 += 1024) {
-        const uint32_t o = o0 + 32u * (uint32_t)lane;
-        uint64_t xr = 0;
-        if (o < cmplen) {
-            xr = xw[o >> 5] ^ get64u(D, p + o);
-            uint32_t nb = cmplen - o < 32u ? cmplen - o : 32u;
-            if (nb < 32) xr &= ~0ull << (64 - 2 * nb);
+    for (uint32_t o0 = 0; o0 < cmplen && !full; o0 += 4096) {        // 4 slabs of 1024 bases per iteration
+        uint64_t xr[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {                                // all 8 loads of the lane are independent
+            const uint32_t o = o0 + 1024u * r + 32u * (uint32_t)lane;
+            xr[r] = 0;
+            if (o < cmplen) {
+                xr[r] = xw[o >> 5] ^ get64u(D, p + o);
+                uint32_t nb = cmplen - o < 32u ? cmplen - o : 32u;
+                if (nb < 32) xr[r] &= ~0ull << (64 - 2 * nb);
+            }
         }
-        unsigned bal = __ballot_sync(0xffffffffu, xr != 0);
-        while (bal && !full) {
-            const int src = __ffs(bal) - 1;
-            bal &= bal - 1;
-            uint64_t w = __shfl_sync(0xffffffffu, xr, src);
-            const uint32_t ob = o0 + 32u * (uint32_t)src;
-            while (w) {
-                uint32_t b = (uint32_t)(clz64(w) >> 1);
-                if (cnt == (uint32_t)kMmMax) { V = ob + b; full = true; break; }
-                if (lane == 0) mm[2 + cnt] = (uint16_t)(ob + b);
-                ++cnt;
-                w &= ~(3ull << (62 - 2 * b));
+        if (!__any_sync(0xffffffffu, (xr[0] | xr[1] | xr[2] | xr[3]) != 0)) continue;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            unsigned bal = __ballot_sync(0xffffffffu, xr[r] != 0);
+            while (bal && !full) {
+                const int src = __ffs(bal) - 1;
+                bal &= bal - 1;
+                uint64_t w = __shfl_sync(0xffffffffu, xr[r], src);
+                const uint32_t ob = o0 + 1024u * r + 32u * (uint32_t)src;
+                while (w) {
+                    uint32_t b = (uint32_t)(clz64(w) >> 1);
+                    if (cnt == (uint32_t)kMmMax) { V = ob + b; full = true; break; }
+                    if (lane == 0) mm[2 + cnt] = (uint16_t)(ob + b);
+                    ++cnt;
+                    w &= ~(3ull << (62 - 2 * b));
+                }
             }
         }
     }
