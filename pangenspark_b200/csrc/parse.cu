@@ -2,6 +2,7 @@
 //
 //   k_hint      H : a 64-base lookup at every chunk start gives the chunk's predicted diagonal
 //   k_diag_w    D : mismatch offsets of every chunk along that diagonal (the streaming compare, done once, up front)
+//   k_snp       S : the phrase at every listed mismatch position (the short phrase after a SNP), one thread each
 //   k_spec      P1: one thread per chunk, speculative greedy parse from the chunk's first base with chunk-capped
 //                   lookups; phrases stored; the first phrase doubles as stage A's phrase at the chunk start
 //   k_link      A : open first phrases linked to the chunk their match continues in
@@ -101,6 +102,13 @@ __global__ void __launch_bounds__(128) k_diag_w(ParseView pv) {
         else { if (lane == 0) mm[2 + cnt] = (uint16_t)cmplen; ++cnt; }
     }
     if (lane == 0) { mm[0] = (uint16_t)cnt; mm[1] = (uint16_t)V; }
+}
+
+// S: one thread per listed mismatch position
+__global__ void __launch_bounds__(128, 8) k_snp(ParseView pv) {
+    uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t g = (uint32_t)(idx / kMmMax), t = (uint32_t)(idx % kMmMax);
+    if (g < pv.n_chunks) snp_lookup(pv, g, t);
 }
 
 __global__ void __launch_bounds__(128) k_resolve(ParseView pv) {
@@ -264,8 +272,13 @@ int parse_stage_count(ParseBuffers& pb, cudaStream_t s, int* rounds_out, cudaEve
             pv.mm = pb.mm;
             g_launches += 1;
             k_diag_w<<<(unsigned)(((uint64_t)NC * 32 + 127) / 128), 128, 0, s>>>(pv);
-        } else pv.mm = nullptr;
-    } else { pv.hint = nullptr; pv.mm = nullptr; }
+            if (pb.ml) {                    // S: the short phrase after every listed mismatch, looked up convergently
+                pv.ml = pb.ml;
+                g_launches += 1;
+                k_snp<<<(unsigned)(((uint64_t)NC * kMmMax + 127) / 128), 128, 0, s>>>(pv);
+            } else pv.ml = nullptr;
+        } else { pv.mm = nullptr; pv.ml = nullptr; }
+    } else { pv.hint = nullptr; pv.mm = nullptr; pv.ml = nullptr; }
     g_launches += 1;
     if (pb.occ >= 16) k_spec<16><<<(NC + 127) / 128, 128, 0, s>>>(pv);
     else if (pb.occ >= 12) k_spec<12><<<(NC + 127) / 128, 128, 0, s>>>(pv);
