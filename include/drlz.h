@@ -41,10 +41,14 @@ const char* drlz_last_error(const drlz_ctx* ctx);
 /* Run all kernels of this context on the caller's CUDA stream (cudaStream_t as void*), e.g. torch's current
  * stream, so that caller-side CUDA events bracket them.  NULL restores the context's own stream. */
 int drlz_set_stream(drlz_ctx* ctx, void* cuda_stream);
-/* options: "kmer" (jump-table k, 0 = auto), "chunk" (bases per parse chunk, rounded down to a power of two, 0 = default 4096),
+/* options: "kmer" (jump-table k, 0 = auto), "chunk" (bases per parse chunk, rounded down to a power of two, 0 = default 8192),
  *          "group_bytes" (host-path pipeline granularity), "lcp" (1 = also build the LCP array),
  *          "min_cap" (lower bound of the per-lookup compare cap, default 64), "foreign_cap" (longest off-chain
- *          diagonal compare a single thread may do before the exact sequential fallback is taken) */
+ *          diagonal compare a single thread may do before the exact sequential fallback is taken),
+ *          tuning / A-B switches: "occ", "occ_fix" (min CTAs per SM of k_spec / k_fix), "predict" (uniqueness-array
+ *          prediction), "hint" + "diag" (per-chunk diagonal hint and mismatch pre-scan), "snp" (lookups at listed
+ *          mismatches in their own kernel; measured slower, default 0), "tickets" (1 = atomic tile tickets in k_pack),
+ *          "spec_store", "l2persist".  None of them changes results. */
 int drlz_set_option(drlz_ctx* ctx, const char* key, int64_t value);
 
 /* pinned host memory for the streaming path (cudaHostAlloc); plain malloc memory also works, slower */

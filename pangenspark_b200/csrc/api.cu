@@ -54,13 +54,13 @@ struct drlz_ctx {
     cudaEvent_t ev_stage[11] = {};
     std::string err;
     // options
-    int opt_k = 0; uint32_t opt_chunk = 4096; uint32_t opt_min_cap = 64; uint32_t opt_foreign_cap = 1u << 20; uint64_t opt_group_bytes = 256ull << 20; int opt_lcp = 0;
+    int opt_k = 0; uint32_t opt_chunk = 8192; uint32_t opt_min_cap = 64; uint32_t opt_foreign_cap = 1u << 20; uint64_t opt_group_bytes = 256ull << 20; int opt_lcp = 0;
     // index
     bool have_index = false; uint64_t n = 0; int k = 0; int sa_rounds = 0;
     DevBuf blob, sa, isa, lcp;             // blob = [k-mer table | packed text] (one L2 access-policy window)
     uint64_t* d_text = nullptr; uint32_t* d_tab = nullptr; uint16_t* d_uniq = nullptr; size_t blob_bytes = 0, text_bytes = 0, uniq_bytes = 0;
     int opt_predict = 1;
-    cudaStream_t l2_stream = nullptr; int opt_l2persist = 0; int opt_occ = 8; int opt_occ_fix = 10; int opt_tickets = 1; int opt_hint = 1; int opt_diag = 1; int opt_snp = 1; uint32_t opt_spec_store = 0;
+    cudaStream_t l2_stream = nullptr; int opt_l2persist = 0; int opt_occ = 8; int opt_occ_fix = 10; int opt_tickets = 1; int opt_hint = 1; int opt_diag = 1; int opt_snp = 0; uint32_t opt_spec_store = 0;
     double idx_ms[5] = {0, 0, 0, 0, 0};
     // batch scratch (grow-only)
     DevBuf stage[2], meta_dev, desc_cnt, desc_exc, tile_counter, X, mdev, exccnt, excpos, excbyte,
@@ -179,7 +179,7 @@ int drlz_set_option(drlz_ctx* c, const char* key, int64_t v) {
     if (!c || !key) return DRLZ_E_ARG;
     std::lock_guard<std::recursive_mutex> lk_(c->mu);
     if (!strcmp(key, "kmer")) { if (v < 0 || v > 15) return DRLZ_E_ARG; c->opt_k = (int)v; }
-    else if (!strcmp(key, "chunk")) { if (v < 0 || v > 0x7FFFFFFF) return DRLZ_E_ARG; c->opt_chunk = v ? (uint32_t)v : 4096; }
+    else if (!strcmp(key, "chunk")) { if (v < 0 || v > 0x7FFFFFFF) return DRLZ_E_ARG; c->opt_chunk = v ? (uint32_t)v : 8192; }
     else if (!strcmp(key, "group_bytes")) { if (v < 0) return DRLZ_E_ARG; c->opt_group_bytes = v ? (uint64_t)v : (256ull << 20); }
     else if (!strcmp(key, "lcp")) c->opt_lcp = v != 0;
     else if (!strcmp(key, "l2persist")) { c->opt_l2persist = v != 0; c->l2_stream = nullptr; }
