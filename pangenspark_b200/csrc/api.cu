@@ -309,7 +309,7 @@ static int run_device_group(drlz_ctx* c, const uint8_t* rows_dev, const uint64_t
         CK(c, c->chunk_hap.ensure((size_t)NC * 4 + 4)); CK(c, c->spec_cnt.ensure((size_t)NC * 4 + 4)); CK(c, c->spec_exit.ensure((size_t)NC * 4 + 4));
         CK(c, c->alt_entry.ensure(na * 4 + 4)); CK(c, c->alt_cnt.ensure(na * 4 + 4)); CK(c, c->alt_exit.ensure(na * 4 + 4));
         CK(c, c->alt_own.ensure(na * 4 + 4)); CK(c, c->alt_merge.ensure(na * 4 + 4));
-        uint32_t spec_store = c->opt_spec_store ? c->opt_spec_store : (C / 128 > 16 ? C / 128 : 16);
+        uint32_t spec_store = c->opt_spec_store ? c->opt_spec_store : (C / 32 > 16 ? C / 32 : 16);   // 2 phrases per SNP: covers ~1.5 % divergence
         if (single_chunk) spec_store = 1;
         CK(c, c->spec_ph.ensure((size_t)NC * spec_store * 8 + 8)); CK(c, c->alt_ph.ensure(na * kAltStore * 8 + 8));
         CK(c, c->hint.ensure(((size_t)NC / kHintGroup + 2) * 8)); CK(c, c->mm.ensure(((size_t)NC + 1) * kMmStride * 2)); CK(c, c->ml.ensure(((size_t)NC + 1) * kMmMax * 8));
