@@ -331,6 +331,7 @@ def run_ours(args):
     Mtot, mtot = float(H) * M, float(bases)
     per_launch = {   # name: (avg ms per launch, algorithmic bytes per launch)
         "k_pack": (kt["pack_write_ms"] / steps, Mtot + mtot / 4),
+        "k_hint+k_diag_w": (kt["prescan_ms"] / steps, mtot / 4),
         "k_spec": (kt["spec_ms"] / steps, mtot / 4),
         "k_fix": (kt["fix_ms"] / max(1.0, kt["fix_rounds"] - steps) if kt["fix_rounds"] > steps else 0.0, 0.0),
         "k_emit": (kt["emit_ms"] / steps, mtot / 4 + 16.0 * phrases),

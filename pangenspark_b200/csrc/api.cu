@@ -51,7 +51,7 @@ struct drlz_ctx {
     int device = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
     cudaEvent_t ev_copied[2] = {nullptr, nullptr};
-    cudaEvent_t ev_stage[11] = {};
+    cudaEvent_t ev_stage[12] = {};
     std::string err;
     // options
     int opt_k = 0; uint32_t opt_chunk = 8192; uint32_t opt_min_cap = 64; uint32_t opt_foreign_cap = 1u << 20; uint64_t opt_group_bytes = 256ull << 20; int opt_lcp = 0;
@@ -138,7 +138,7 @@ int drlz_create(drlz_ctx** out, int device) {
         cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return DRLZ_E_CUDA; }
     c->stream = c->own_stream;
     for (int i = 0; i < 2; ++i) cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming);
-    for (int i = 0; i < 11; ++i) cudaEventCreate(&c->ev_stage[i]);
+    for (int i = 0; i < 12; ++i) cudaEventCreate(&c->ev_stage[i]);
     *out = c;
     return DRLZ_OK;
 }
@@ -160,7 +160,7 @@ void drlz_destroy(drlz_ctx* c) {
     for (DevBuf* b : bufs) b->release();
     c->meta_host.release(); c->small_host.release();
     for (int i = 0; i < 2; ++i) if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]);
-    for (int i = 0; i < 11; ++i) if (c->ev_stage[i]) cudaEventDestroy(c->ev_stage[i]);
+    for (int i = 0; i < 12; ++i) if (c->ev_stage[i]) cudaEventDestroy(c->ev_stage[i]);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     delete c;
@@ -356,7 +356,7 @@ static int run_device_group(drlz_ctx* c, const uint8_t* rows_dev, const uint64_t
         uint64_t total = *sh_total;
         CK(c, c->out.ensure(total * 16 + 16));
         parse_stage_emit(pb, c->out.as<int64_t>(), s);
-        cudaEventRecord(c->ev_stage[10], s);
+        cudaEventRecord(c->ev_stage[11], s);
         CK(c, cudaMemcpyAsync(sh_m, c->mdev.p, (size_t)H * 8, cudaMemcpyDeviceToHost, s));
         CK(c, cudaMemcpyAsync(sh_pairs, c->hap_pairs.p, ((size_t)H + 1) * 8, cudaMemcpyDeviceToHost, s));
         CK(c, cudaMemcpyAsync(sh_exccnt, c->exccnt.p, (size_t)H * 8, cudaMemcpyDeviceToHost, s));
@@ -380,7 +380,7 @@ static int run_device_group(drlz_ctx* c, const uint8_t* rows_dev, const uint64_t
         // timings
         float t;
         double* pm = c->parse_ms;
-        static const int iv[10][2] = {{0, 1}, {1, 2}, {2, 3}, {3, 4}, {5, 6}, {9, 7}, {7, 8}, {8, 10}, {0, 10}, {6, 9}};
+        static const int iv[10][2] = {{0, 1}, {5, 10}, {2, 3}, {3, 4}, {10, 6}, {9, 7}, {7, 8}, {8, 11}, {0, 11}, {6, 9}};
         for (int i = 0; i < 10; ++i) { cudaEventElapsedTime(&t, c->ev_stage[iv[i][0]], c->ev_stage[iv[i][1]]); pm[i] += t; }
         pm[10] += rounds; pm[11] += (double)(g_launches - launches0);
         return DRLZ_OK;

@@ -76,7 +76,8 @@ struct ParseBuffers {
 };
 // Stage A: speculative parse, fix-up rounds, pointer jumping, per-chunk counts and offsets.
 // Synchronises the stream (reads round counters and the phrase total).  Returns 0, or 2 on overflow.
-// ev (nullable): 5 events: [0] start, [1] after P1, [4] after stage A, [2] after the fix-up rounds, [3] after compaction.
+// ev (nullable): 6 events: [0] start, [5] after the pre-scan (k_hint, k_diag_w), [1] after P1, [4] after stage A,
+// [2] after the fix-up rounds, [3] after compaction.
 int parse_stage_count(ParseBuffers& pb, cudaStream_t s, int* rounds_out, cudaEvent_t* ev);
 // Stage B: emission into `out` (device, >= 2*total int64).
 void parse_stage_emit(ParseBuffers& pb, int64_t* out, cudaStream_t s);

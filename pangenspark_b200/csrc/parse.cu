@@ -255,7 +255,7 @@ int parse_stage_count(ParseBuffers& pb, cudaStream_t s, int* rounds_out, cudaEve
     *pb.host_total = 0;
     if (rounds_out) *rounds_out = 0;
     if (NC == 0) {
-        if (ev) for (int i = 0; i < 5; ++i) cudaEventRecord(ev[i], s);
+        if (ev) for (int i = 0; i < 6; ++i) cudaEventRecord(ev[i], s);
         cudaMemsetAsync(pb.hap_pairs, 0, sizeof(uint64_t) * (pb.H + 1), s);
         cudaStreamSynchronize(s);
         return 0;
@@ -279,6 +279,7 @@ int parse_stage_count(ParseBuffers& pb, cudaStream_t s, int* rounds_out, cudaEve
             } else pv.ml = nullptr;
         } else { pv.mm = nullptr; pv.ml = nullptr; }
     } else { pv.hint = nullptr; pv.mm = nullptr; pv.ml = nullptr; }
+    if (ev) cudaEventRecord(ev[5], s);
     g_launches += 1;
     if (pb.occ >= 16) k_spec<16><<<(NC + 127) / 128, 128, 0, s>>>(pv);
     else if (pb.occ >= 12) k_spec<12><<<(NC + 127) / 128, 128, 0, s>>>(pv);
