@@ -237,7 +237,7 @@ def run_ours(args):
     if world > 1:
         meta = torch.zeros(2, dtype=torch.int64, device="cuda")
         if rank == 0:
-            meta[0], meta[1] = info["n"], info["k"]
+            meta[0], meta[1] = info["n"], info["kinfo"]
         dist.broadcast(meta, 0)
         if rank != 0:
             ctx.index_reserve(int(meta[0]), int(meta[1]))

@@ -27,7 +27,7 @@ extern "C" {
 #define DRLZ_E_CUDA (-2)       /* CUDA runtime error (see drlz_last_error) */
 #define DRLZ_E_NOMEM (-3)
 #define DRLZ_E_NOSPACE (-4)    /* pairs_cap too small; required count returned */
-#define DRLZ_E_ALPHABET (-5)   /* reference contains bytes outside {A,C,G,T} (2-bit path) */
+#define DRLZ_E_ALPHABET (-5)   /* reference uses all 256 byte values (one code is reserved) */
 #define DRLZ_E_STATE (-6)      /* index not built / wrong call order */
 #define DRLZ_E_LIMIT (-7)      /* n or m >= 2^32 - 1024, or more than 65535 rows in one batch */
 #define DRLZ_E_INTERNAL (-8)
@@ -56,20 +56,27 @@ void* drlz_host_alloc(size_t bytes);
 void drlz_host_free(void* p);
 
 /* ---- index: replaces `./radixSA localref localradix` + the SA text load + both broadcasts -------------
- * (DistributedRLZ.scala:45,52,55,58,61,63).  ref = exactly n sequence bytes (no header, no newline). */
+ * (DistributedRLZ.scala:45,52,55,58,61,63).  ref = exactly n sequence bytes (no header, no newline).
+ * Any byte alphabet works, like the reference's byte-wise binary search: a pure {A,C,G,T} reference is packed at
+ * 2 bits per base (the measured fast path); otherwise the distinct bytes of the reference get dense, order-
+ * preserving codes at 4 bits (<= 16 symbols, e.g. ACGTN + lower case) or 8 bits per symbol.  Haplotype bytes
+ * that do not occur in the reference become literal phrases, as in the reference. */
 int drlz_build_index(drlz_ctx* ctx, const uint8_t* ref, uint64_t n);
 /* copy index arrays to the host.  what: 0 = SA (uint32[n]), 1 = inverse SA (uint32[n]), 2 = LCP (uint32[n],
- * needs option lcp=1), 3 = k-mer table (uint32[4^k+1]), 4 = packed text (uint64[(n+31)/32]).  */
+ * needs option lcp=1), 3 = k-mer table (uint32[sigma^k+1]), 4 = packed text (uint64[ceil(n * bits / 64)]).  */
 int drlz_index_get(drlz_ctx* ctx, int what, void* host_out, uint64_t bytes);
-/* info[0]=n, [1]=k, [2]=prefix-doubling rounds, [3]=index bytes on device */
+/* info[0]=n, [1]=k | log2(bits per symbol) << 8 | alphabet size sigma << 16, [2]=prefix-doubling rounds,
+ * [3]=index bytes on device */
 int drlz_index_info(const drlz_ctx* ctx, uint64_t info[4]);
 /* time of the last drlz_build_index in ms: [0] total, [1] pack, [2] suffix array, [3] k-mer table, [4] lcp */
 int drlz_index_timings(const drlz_ctx* ctx, double ms[5]);
 
-/* Multi-GPU: rank 0 builds, the others call drlz_index_reserve(n, k) and receive the three buffers by an
- * NCCL broadcast (done by the caller, e.g. torch.distributed) into the device pointers returned by
- * drlz_index_buffers, then call drlz_index_commit.  bufs: [0] packed text, [1] SA, [2] k-mer table. */
-int drlz_index_reserve(drlz_ctx* ctx, uint64_t n, int k);
+/* Multi-GPU: rank 0 builds, the others call drlz_index_reserve(n, info[1] of rank 0) and receive the three
+ * buffers by an NCCL broadcast (done by the caller, e.g. torch.distributed) into the device pointers returned by
+ * drlz_index_buffers, then call drlz_index_commit.  bufs: [0] packed text + uniqueness array + byte<->code
+ * tables, [1] SA, [2] k-mer table.  kinfo = k | log2(bits per symbol) << 8 | alphabet size << 16, exactly
+ * drlz_index_info's info[1]; a plain k (upper bits 0) means the 2-bit {A,C,G,T} layout. */
+int drlz_index_reserve(drlz_ctx* ctx, uint64_t n, int kinfo);
 int drlz_index_buffers(drlz_ctx* ctx, void* dev_ptrs[3], uint64_t bytes[3]);
 int drlz_index_commit(drlz_ctx* ctx);
 

@@ -128,8 +128,9 @@ int main(int argc, char** argv) {
     {
         double ms[5]; uint64_t info[4];
         drlz_index_timings(ctxs[0], ms); drlz_index_info(ctxs[0], info);
-        printf("Load suffix\nbroadcasting\nindex: n=%llu k=%llu rounds=%llu build=%.1f ms on %d device(s)\n",
-               (unsigned long long)info[0], (unsigned long long)info[1], (unsigned long long)info[2], ms[0], ngpu);
+        printf("Load suffix\nbroadcasting\nindex: n=%llu k=%llu sigma=%llu bits=%d rounds=%llu build=%.1f ms on %d device(s)\n",
+               (unsigned long long)info[0], (unsigned long long)(info[1] & 0xFF), (unsigned long long)(info[1] >> 16),
+               1 << ((info[1] >> 8) & 0xFF), (unsigned long long)info[2], ms[0], ngpu);
     }
     if (getenv("DRLZ_EMIT_RADIX") && atoi(getenv("DRLZ_EMIT_RADIX"))) {
         std::vector<uint32_t> sa(ref.size());

@@ -58,13 +58,15 @@ struct drlz_ctx {
     // index
     bool have_index = false; uint64_t n = 0; int k = 0; int sa_rounds = 0;
     DevBuf blob, sa, isa, lcp;             // blob = [k-mer table | packed text] (one L2 access-policy window)
-    uint64_t* d_text = nullptr; uint32_t* d_tab = nullptr; uint16_t* d_uniq = nullptr; size_t blob_bytes = 0, text_bytes = 0, uniq_bytes = 0;
+    uint64_t* d_text = nullptr; uint32_t* d_tab = nullptr; uint16_t* d_uniq = nullptr; uint8_t* d_lut = nullptr;   // lut = b2c[256], c2b[256]
+    size_t blob_bytes = 0, text_bytes = 0, uniq_bytes = 0, tab_bytes = 0;
+    uint32_t bl = 1, sigma = 4;        // symbol width (log2 bits) and alphabet size of the index
     int opt_predict = 1;
     cudaStream_t l2_stream = nullptr; int opt_l2persist = 0; int opt_occ = 8; int opt_occ_fix = 10; int opt_tickets = 1; int opt_hint = 1; int opt_diag = 1; int opt_snp = 0; uint32_t opt_spec_store = 0;
     double idx_ms[5] = {0, 0, 0, 0, 0};
     // batch scratch (grow-only)
     DevBuf stage[2], meta_dev, desc_cnt, desc_exc, tile_counter, X, mdev, exccnt, excpos, excbyte,
-        flags, haps, gapless, chunk_hap, first_pos, first_len, run_a, run_b, link_a, link_b, open_i, open_pos, open_len, spec_cnt, spec_exit, alt_entry, alt_cnt, alt_exit, alt_round, alt_own, alt_merge, spec_ph, alt_ph, hint, mm, ml, true_slot, counters, jump_a,
+        flags, haps, gapless, gtile_cnt, gtile_exc, gtile_off, gtile_excoff, gscan_tmp, chunk_hap, first_pos, first_len, run_a, run_b, link_a, link_b, open_i, open_pos, open_len, spec_cnt, spec_exit, alt_entry, alt_cnt, alt_exit, alt_round, alt_own, alt_merge, spec_ph, alt_ph, hint, mm, ml, true_slot, counters, jump_a,
         jump_b, mark, true_cnt, true_entry, true_off, scan_tmp, hap_pairs, out, ms_a, ms_b;
     HostBuf meta_host, small_host;
     uint64_t exc_stride_hint = 0;
@@ -83,17 +85,26 @@ struct drlz_ctx {
 
 static const uint64_t kMaxLen = 0xFFFFFFFFull - 1024;
 
-static cudaError_t alloc_index_blob(drlz_ctx* c, uint64_t n, int k) {
-    size_t tab_bytes = (((1ull << (2 * k)) + 1) * 4 + 255) & ~(size_t)255;
-    size_t text_bytes = ((n / 32 + 3) * 8 + 64 + 255) & ~(size_t)255;
+static uint64_t table_entries(uint32_t sigma, int k) {
+    uint64_t e = 1;
+    for (int t = 0; t < k; ++t) e *= sigma;
+    return e + 1;
+}
+
+// blob = [k-mer table | packed text | uniqueness array | byte<->code tables]
+static cudaError_t alloc_index_blob(drlz_ctx* c, uint64_t n, int k, uint32_t sigma, uint32_t bl) {
+    size_t tab_bytes = (table_entries(sigma, k) * 4 + 255) & ~(size_t)255;
+    size_t text_bytes = (((n >> (6 - bl)) + 8) * 8 + 64 + 255) & ~(size_t)255;
     size_t uniq_bytes = ((n + 1) * 2 + 255) & ~(size_t)255;
-    cudaError_t e = c->blob.ensure(tab_bytes + text_bytes + uniq_bytes);
+    cudaError_t e = c->blob.ensure(tab_bytes + text_bytes + uniq_bytes + 512);
     if (e != cudaSuccess) return e;
     c->d_tab = c->blob.as<uint32_t>();
     c->d_text = reinterpret_cast<uint64_t*>(c->blob.as<uint8_t>() + tab_bytes);
     c->d_uniq = reinterpret_cast<uint16_t*>(c->blob.as<uint8_t>() + tab_bytes + text_bytes);
-    c->text_bytes = text_bytes; c->uniq_bytes = uniq_bytes;
-    c->blob_bytes = tab_bytes + text_bytes + uniq_bytes;
+    c->d_lut = c->blob.as<uint8_t>() + tab_bytes + text_bytes + uniq_bytes;
+    c->tab_bytes = tab_bytes; c->text_bytes = text_bytes; c->uniq_bytes = uniq_bytes;
+    c->blob_bytes = tab_bytes + text_bytes + uniq_bytes + 512;
+    c->bl = bl; c->sigma = sigma;
     c->l2_stream = nullptr;
     return cudaSuccess;
 }
@@ -108,7 +119,7 @@ static void apply_l2_policy(drlz_ctx* c) {
         int max_persist = 0, max_window = 0;
         cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, c->device);
         cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, c->device);
-        size_t text_bytes = c->blob_bytes - (size_t)((uint8_t*)c->d_text - c->blob.as<uint8_t>());
+        size_t text_bytes = c->text_bytes;
         if (max_persist > 0 && max_window > 0) {
             size_t want = text_bytes < (size_t)max_persist ? text_bytes : (size_t)max_persist;
             cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
@@ -154,7 +165,7 @@ void drlz_destroy(drlz_ctx* c) {
     cudaDeviceSynchronize();
     DevBuf* bufs[] = {&c->blob, &c->sa, &c->isa, &c->lcp, &c->stage[0], &c->stage[1], &c->meta_dev, &c->desc_cnt,
                       &c->desc_exc, &c->tile_counter, &c->X, &c->mdev, &c->exccnt, &c->excpos,
-                      &c->excbyte, &c->flags, &c->haps, &c->gapless, &c->chunk_hap, &c->first_pos, &c->first_len, &c->run_a, &c->run_b, &c->link_a, &c->link_b, &c->open_i, &c->open_pos, &c->open_len, &c->spec_cnt, &c->spec_exit,
+                      &c->excbyte, &c->flags, &c->haps, &c->gapless, &c->gtile_cnt, &c->gtile_exc, &c->gtile_off, &c->gtile_excoff, &c->gscan_tmp, &c->chunk_hap, &c->first_pos, &c->first_len, &c->run_a, &c->run_b, &c->link_a, &c->link_b, &c->open_i, &c->open_pos, &c->open_len, &c->spec_cnt, &c->spec_exit,
                       &c->alt_entry, &c->alt_cnt, &c->alt_exit, &c->alt_round, &c->alt_own, &c->alt_merge, &c->spec_ph, &c->alt_ph, &c->hint, &c->mm, &c->ml, &c->true_slot, &c->counters, &c->jump_a, &c->jump_b,
                       &c->mark, &c->true_cnt, &c->true_entry, &c->true_off, &c->scan_tmp, &c->hap_pairs, &c->out, &c->ms_a, &c->ms_b};
     for (DevBuf* b : bufs) b->release();
@@ -178,7 +189,7 @@ int drlz_set_stream(drlz_ctx* c, void* s) {
 int drlz_set_option(drlz_ctx* c, const char* key, int64_t v) {
     if (!c || !key) return DRLZ_E_ARG;
     std::lock_guard<std::recursive_mutex> lk_(c->mu);
-    if (!strcmp(key, "kmer")) { if (v < 0 || v > 15) return DRLZ_E_ARG; c->opt_k = (int)v; }
+    if (!strcmp(key, "kmer")) { if (v < 0 || v > 32) return DRLZ_E_ARG; c->opt_k = (int)v; }
     else if (!strcmp(key, "chunk")) { if (v < 0 || v > 0x7FFFFFFF) return DRLZ_E_ARG; c->opt_chunk = v ? (uint32_t)v : 8192; }
     else if (!strcmp(key, "group_bytes")) { if (v < 0) return DRLZ_E_ARG; c->opt_group_bytes = v ? (uint64_t)v : (256ull << 20); }
     else if (!strcmp(key, "lcp")) c->opt_lcp = v != 0;
@@ -245,7 +256,7 @@ static int run_device_group(drlz_ctx* c, const uint8_t* rows_dev, const uint64_t
     uint64_t xwords = 0, gbytes = 0;
     for (uint32_t h = 0; h < H; ++h) {
         h_row_off[h] = row_off[h]; h_cols[h] = cols[h];
-        h_xoff[h] = xwords; xwords += cols[h] / 32 + 3;
+        h_xoff[h] = xwords; xwords += (cols[h] >> (6 - c->bl)) + 8;
         h_goff[h] = gbytes; gbytes += (cols[h] + 15) & ~15ull;
         if (gapless_off_out) gapless_off_out[h] = h_goff[h];
     }
@@ -258,7 +269,14 @@ static int run_device_group(drlz_ctx* c, const uint8_t* rows_dev, const uint64_t
     uint32_t* sh_counters = sh_flags + 2;                     // [2 + kMaxRounds]
 
     CK(c, c->desc_cnt.ensure(nt * 8)); CK(c, c->desc_exc.ensure(nt * 8)); CK(c, c->tile_counter.ensure(16));
-    CK(c, c->X.ensure(xwords * 8));
+    CK(c, c->X.ensure(xwords * 8 + 256));
+    uint32_t GT = (uint32_t)((maxcols + kPackGTileBytes - 1) / kPackGTileBytes); if (GT == 0) GT = 1;
+    if (c->bl != 1) {
+        uint64_t gnt = (uint64_t)H * GT;
+        CK(c, c->gtile_cnt.ensure(gnt * 4)); CK(c, c->gtile_exc.ensure(gnt * 4));
+        CK(c, c->gtile_off.ensure(gnt * 8)); CK(c, c->gtile_excoff.ensure(gnt * 8));
+        CK(c, c->gscan_tmp.ensure(scan_tmp_elems(gnt) * 8 * 2));
+    }
     CK(c, c->mdev.ensure((size_t)H * 8)); CK(c, c->exccnt.ensure(((size_t)H + 1) * 8));
     CK(c, c->flags.ensure(16)); CK(c, c->haps.ensure((size_t)H * sizeof(HapView)));
     if (want_gapless) CK(c, c->gapless.ensure(gbytes + 16));
@@ -297,6 +315,10 @@ static int run_device_group(drlz_ctx* c, const uint8_t* rows_dev, const uint64_t
         job.exc_pos = c->excpos.as<uint32_t>(); job.exc_byte = c->excbyte.as<uint8_t>(); job.exc_stride = exc_stride;
         job.flags = c->flags.as<uint32_t>();
         job.gapless = want_gapless ? c->gapless.as<uint8_t>() : nullptr; job.gapless_off = d_goff;
+        job.bl = c->bl; job.b2c = c->d_lut; job.gtiles_per_row = GT;
+        job.gtile_cnt = c->gtile_cnt.as<uint32_t>(); job.gtile_exc = c->gtile_exc.as<uint32_t>();
+        job.gtile_off = c->gtile_off.as<uint64_t>(); job.gtile_excoff = c->gtile_excoff.as<uint64_t>();
+        job.gscan_tmp = c->gscan_tmp.as<uint64_t>();
         launch_pack(job, s, &c->ev_stage[2]);                            // ev 2,3,4
         launch_make_hapviews(c->haps.as<HapView>(), c->X.as<uint64_t>(), d_xoff, c->mdev.as<uint64_t>(), c->excpos.as<uint32_t>(),
                              c->excbyte.as<uint8_t>(), c->exccnt.as<uint64_t>(), exc_stride, H, s);
@@ -321,7 +343,8 @@ static int run_device_group(drlz_ctx* c, const uint8_t* rows_dev, const uint64_t
         launch_fill_chunk_hap(c->chunk_hap.as<uint32_t>(), d_base, H, NC, s);
 
         ParseBuffers pb;
-        pb.pv.ix = IndexView{c->d_text, c->sa.as<uint32_t>(), c->d_tab, c->n, c->k, c->opt_predict ? c->d_uniq : nullptr};
+        pb.pv.ix = IndexView{c->d_text, c->sa.as<uint32_t>(), c->d_tab, c->n, c->k, c->opt_predict ? c->d_uniq : nullptr,
+                             c->bl, c->sigma, c->d_lut + 256};
         pb.pv.haps = c->haps.as<HapView>(); pb.pv.chunk_hap = c->chunk_hap.as<uint32_t>(); pb.pv.hap_chunk_base = d_base;
         pb.pv.chunk_bases = Ceff; pb.pv.chunk_shift = single_chunk ? 32u : chunk_shift; pb.pv.n_chunks = NC;
         pb.pv.min_cap = single_chunk ? 0xFFFFFFFFu : c->opt_min_cap; pb.pv.foreign_cap = c->opt_foreign_cap;
@@ -394,10 +417,15 @@ extern "C" {
 // ---------------------------------------------------------------------------------------------------
 // index
 // ---------------------------------------------------------------------------------------------------
-static int auto_k(uint64_t n) {
+// smallest k with sigma^k >= n/2 (about one suffix per table slot; measured best on B200), bounded by the symbols
+// of one packed word and by a 1 GiB table
+static int auto_k(uint64_t n, uint32_t sigma, uint32_t bl) {
+    int kmax = (int)(64u >> bl);
+    if (kmax > 15) kmax = 15;
     int k = 1;
-    while (k < 14 && (1ull << (2 * k)) < n / 2) ++k;       // smallest k with 4^k >= n/2 (about one suffix per table
-    return k;                                             // slot; measured best on B200), capped at 14 (1 GiB table)
+    double e = sigma;
+    while (k < kmax && e < (double)n / 2 && e * sigma <= 268435456.0) { ++k; e *= sigma; }
+    return k;
 }
 
 int drlz_build_index(drlz_ctx* c, const uint8_t* ref, uint64_t n) {
@@ -413,9 +441,30 @@ int drlz_build_index(drlz_ctx* c, const uint8_t* ref, uint64_t n) {
     uint64_t padded = ((n + 15) & ~15ull) + 16;
     CK(c, c->stage[0].ensure(padded));
     if (n) CK(c, cudaMemcpyAsync(c->stage[0].p, ref, n, cudaMemcpyHostToDevice, s));
-    uint64_t words = n / 32 + 3;
-    int k = c->opt_k ? c->opt_k : auto_k(n);
-    CK(c, alloc_index_blob(c, n, k));
+    // alphabet: pure {A,C,G,T} -> 2-bit fast path; otherwise the distinct bytes of the reference get dense
+    // order-preserving codes (suffix order under unsigned bytes is preserved), 4 bits if sigma <= 16 else 8 bits
+    uint8_t lut[512];
+    memset(lut, 0xFF, 256); memset(lut + 256, 0, 256);
+    uint32_t sigma = 4, bl = 1;
+    {
+        bool present[256] = {false};
+        for (uint64_t i = 0; i < n; ++i) present[ref[i]] = true;
+        bool acgt = true;
+        for (int b = 0; b < 256; ++b) if (present[b] && b != 'A' && b != 'C' && b != 'G' && b != 'T') acgt = false;
+        if (acgt) { const char* a4 = "ACGT"; for (int q = 0; q < 4; ++q) { lut[(uint8_t)a4[q]] = (uint8_t)q; lut[256 + q] = (uint8_t)a4[q]; } }
+        else {
+            sigma = 0;
+            for (int b = 0; b < 256; ++b) if (present[b]) { lut[b] = (uint8_t)sigma; lut[256 + sigma] = (uint8_t)b; ++sigma; }
+            bl = sigma <= 16 ? 2 : 3;
+            if (sigma == 256) { c->err = "reference uses all 256 byte values (0xFF is reserved)"; for (int i = 0; i < 5; ++i) cudaEventDestroy(e[i]); return DRLZ_E_ALPHABET; }
+        }
+    }
+    uint64_t words = (n >> (6 - bl)) + 8;
+    int k = c->opt_k ? c->opt_k : auto_k(n, sigma, bl);
+    if (k > (int)(64u >> bl)) k = (int)(64u >> bl);
+    while (k > 1 && table_entries(sigma, k) > (1ull << 30)) --k;
+    CK(c, alloc_index_blob(c, n, k, sigma, bl));
+    CK(c, cudaMemcpyAsync(c->d_lut, lut, 512, cudaMemcpyHostToDevice, s));
     CK(c, c->sa.ensure(n * 4 + 4));
     CK(c, c->isa.ensure(n * 4 + 4));
     cudaEventRecord(e[0], s);
@@ -443,25 +492,38 @@ int drlz_build_index(drlz_ctx* c, const uint8_t* ref, uint64_t n) {
         job.m_out = c->mdev.as<uint64_t>(); job.exc_cnt = c->exccnt.as<uint64_t>();
         job.exc_pos = c->excpos.as<uint32_t>(); job.exc_byte = c->excbyte.as<uint8_t>(); job.exc_stride = 64;
         job.flags = c->flags.as<uint32_t>(); job.gapless = nullptr; job.gapless_off = dm + 3;
+        uint32_t GT = (uint32_t)((n + kPackGTileBytes - 1) / kPackGTileBytes); if (!GT) GT = 1;
+        if (bl != 1) {
+            CK(c, c->gtile_cnt.ensure((size_t)GT * 4)); CK(c, c->gtile_exc.ensure((size_t)GT * 4));
+            CK(c, c->gtile_off.ensure((size_t)GT * 8)); CK(c, c->gtile_excoff.ensure((size_t)GT * 8));
+            CK(c, c->gscan_tmp.ensure(scan_tmp_elems(GT) * 8 * 2));
+        }
+        job.bl = bl; job.b2c = c->d_lut; job.gtiles_per_row = GT;
+        job.gtile_cnt = c->gtile_cnt.as<uint32_t>(); job.gtile_exc = c->gtile_exc.as<uint32_t>();
+        job.gtile_off = c->gtile_off.as<uint64_t>(); job.gtile_excoff = c->gtile_excoff.as<uint64_t>();
+        job.gscan_tmp = c->gscan_tmp.as<uint64_t>();
         launch_pack(job, s, nullptr);
         uint64_t* sh = c->small_host.as<uint64_t>();
         CK(c, cudaMemcpyAsync(sh, c->exccnt.p, 8, cudaMemcpyDeviceToHost, s));
         CK(c, cudaStreamSynchronize(s));
-        if (sh[0] != 0) { c->err = "reference contains bytes outside {A,C,G,T}"; for (int i = 0; i < 5; ++i) cudaEventDestroy(e[i]); return DRLZ_E_ALPHABET; }
+        if (sh[0] != 0) { c->err = "internal: reference byte without a code"; for (int i = 0; i < 5; ++i) cudaEventDestroy(e[i]); return DRLZ_E_INTERNAL; }
     }
     (void)off0; (void)m; (void)np; (void)tot;
     cudaEventRecord(e[1], s);
     char ebuf[256]; ebuf[0] = 0;
-    int rc = build_suffix_array(c->d_text, n, c->sa.as<uint32_t>(), c->isa.as<uint32_t>(), s, &c->sa_rounds, ebuf, sizeof ebuf);
+    int rc = build_suffix_array(c->d_text, n, bl, c->sa.as<uint32_t>(), c->isa.as<uint32_t>(), s, &c->sa_rounds, ebuf, sizeof ebuf);
     if (rc != 0) { c->err = std::string("suffix array: ") + ebuf; for (int i = 0; i < 5; ++i) cudaEventDestroy(e[i]); return rc == (int)cudaErrorMemoryAllocation ? DRLZ_E_NOMEM : DRLZ_E_CUDA; }
     cudaEventRecord(e[2], s);
 
-    rc = build_kmer_table(c->d_text, n, c->sa.as<uint32_t>(), k, c->d_tab, s);
+    {
+        IndexView tix{c->d_text, c->sa.as<uint32_t>(), nullptr, n, k, nullptr, bl, sigma, c->d_lut + 256};
+        rc = build_kmer_table(tix, c->d_tab, s);
+    }
     if (rc != 0) { c->err = "k-mer table build failed"; for (int i = 0; i < 5; ++i) cudaEventDestroy(e[i]); return DRLZ_E_CUDA; }
     cudaEventRecord(e[3], s);
     {   // LCP (kept only on request) and the uniqueness array derived from it
         CK(c, c->lcp.ensure(n * 4 + 8));
-        rc = build_lcp(c->d_text, n, c->sa.as<uint32_t>(), c->isa.as<uint32_t>(), c->lcp.as<uint32_t>(), s);
+        rc = build_lcp(c->d_text, n, bl, c->sa.as<uint32_t>(), c->isa.as<uint32_t>(), c->lcp.as<uint32_t>(), s);
         if (rc == 0) rc = build_uniq(n, c->isa.as<uint32_t>(), c->lcp.as<uint32_t>(), c->d_uniq, s);
         if (rc != 0) { c->err = "lcp / uniqueness build failed"; for (int i = 0; i < 5; ++i) cudaEventDestroy(e[i]); return DRLZ_E_CUDA; }
     }
@@ -489,8 +551,8 @@ int drlz_index_get(drlz_ctx* c, int what, void* host_out, uint64_t bytes) {
         case 0: src = c->sa.p; need = c->n * 4; break;
         case 1: src = c->isa.p; need = c->n * 4; if (!c->isa.p) return DRLZ_E_STATE; break;
         case 2: if (!c->opt_lcp || !c->lcp.p) { c->err = "lcp not built (option lcp=1)"; return DRLZ_E_STATE; } src = c->lcp.p; need = c->n * 4; break;
-        case 3: src = c->d_tab; need = ((1ull << (2 * c->k)) + 1) * 4; break;
-        case 4: src = c->d_text; need = ((c->n + 31) / 32) * 8; break;
+        case 3: src = c->d_tab; need = table_entries(c->sigma, c->k) * 4; break;
+        case 4: src = c->d_text; need = ((c->n + (64u >> c->bl) - 1) >> (6 - c->bl)) * 8; break;
         default: return DRLZ_E_ARG;
     }
     if (bytes < need) { c->err = "host buffer too small"; return DRLZ_E_NOSPACE; }
@@ -501,8 +563,9 @@ int drlz_index_get(drlz_ctx* c, int what, void* host_out, uint64_t bytes) {
 
 int drlz_index_info(const drlz_ctx* c, uint64_t info[4]) {
     if (!c || !info) return DRLZ_E_ARG;
-    info[0] = c->n; info[1] = (uint64_t)c->k; info[2] = (uint64_t)c->sa_rounds;
-    info[3] = c->have_index ? (c->n / 32 + 3) * 8 + c->n * 4 + ((1ull << (2 * c->k)) + 1) * 4 : 0;
+    info[0] = c->n; info[1] = (uint64_t)c->k | ((uint64_t)c->bl << 8) | ((uint64_t)c->sigma << 16);
+    info[2] = (uint64_t)c->sa_rounds;
+    info[3] = c->have_index ? c->blob_bytes + c->n * 4 : 0;
     return DRLZ_OK;
 }
 
@@ -512,13 +575,16 @@ int drlz_index_timings(const drlz_ctx* c, double ms[5]) {
     return DRLZ_OK;
 }
 
-int drlz_index_reserve(drlz_ctx* c, uint64_t n, int k) {
-    if (!c || k < 1 || k > 15) return DRLZ_E_ARG;
+int drlz_index_reserve(drlz_ctx* c, uint64_t n, int kinfo) {
+    int k = kinfo & 0xFF;
+    uint32_t bl = (uint32_t)(kinfo >> 8) & 0xFF, sigma = (uint32_t)kinfo >> 16;
+    if (bl == 0 && sigma == 0) { bl = 1; sigma = 4; }          // plain k: pure-ACGT index
+    if (!c || k < 1 || k > 32 || bl < 1 || bl > 3 || sigma < 1 || sigma > 256) return DRLZ_E_ARG;
     std::lock_guard<std::recursive_mutex> lk_(c->mu);
     if (n > kMaxLen) return DRLZ_E_LIMIT;
     CK(c, cudaSetDevice(c->device));
     c->have_index = false;
-    CK(c, alloc_index_blob(c, n, k));
+    CK(c, alloc_index_blob(c, n, k, sigma, bl));
     CK(c, c->sa.ensure(n * 4 + 4));
     CK(c, cudaMemsetAsync(c->d_text, 0, c->text_bytes, c->stream));
     CK(c, cudaStreamSynchronize(c->stream));
@@ -530,9 +596,9 @@ int drlz_index_buffers(drlz_ctx* c, void* dev_ptrs[3], uint64_t bytes[3]) {
     if (!c || !dev_ptrs || !bytes) return DRLZ_E_ARG;
     std::lock_guard<std::recursive_mutex> lk_(c->mu);
     if (!c->d_text || !c->d_tab) { c->err = "no index buffers (build or reserve first)"; return DRLZ_E_STATE; }
-    dev_ptrs[0] = c->d_text; bytes[0] = c->text_bytes + c->uniq_bytes;      // packed text followed by the uniqueness array
+    dev_ptrs[0] = c->d_text; bytes[0] = c->text_bytes + c->uniq_bytes + 512;   // packed text, uniqueness array, byte<->code tables
     dev_ptrs[1] = c->sa.p; bytes[1] = c->n * 4;
-    dev_ptrs[2] = c->d_tab; bytes[2] = ((1ull << (2 * c->k)) + 1) * 4;
+    dev_ptrs[2] = c->d_tab; bytes[2] = table_entries(c->sigma, c->k) * 4;
     return DRLZ_OK;
 }
 
@@ -716,9 +782,9 @@ int drlz_matching_stats(drlz_ctx* c, const uint8_t* x, uint64_t m, uint32_t* ms_
     uint64_t* sh = c->small_host.as<uint64_t>();
     CK(c, cudaMemcpyAsync(sh, c->exccnt.p, 8, cudaMemcpyDeviceToHost, s));
     CK(c, cudaStreamSynchronize(s));
-    if (sh[0] != 0) { c->err = "sequence contains bytes outside {A,C,G,T}"; return DRLZ_E_ALPHABET; }
+    if (sh[0] != 0) { c->err = "sequence contains bytes outside the reference alphabet"; return DRLZ_E_ALPHABET; }
     CK(c, c->ms_a.ensure(m * 4)); CK(c, c->ms_b.ensure(m * 4));
-    IndexView ix{c->d_text, c->sa.as<uint32_t>(), c->d_tab, c->n, c->k, nullptr};
+    IndexView ix{c->d_text, c->sa.as<uint32_t>(), c->d_tab, c->n, c->k, nullptr, c->bl, c->sigma, c->d_lut + 256};
     launch_ms_dense(ix, c->X.as<uint64_t>(), m, c->ms_a.as<uint32_t>(), c->ms_b.as<uint32_t>(), s);
     CK(c, cudaMemcpyAsync(ms_out, c->ms_a.p, m * 4, cudaMemcpyDeviceToHost, s));
     CK(c, cudaMemcpyAsync(pos_out, c->ms_b.p, m * 4, cudaMemcpyDeviceToHost, s));

@@ -8,6 +8,7 @@ namespace drlz {
 
 extern unsigned long long g_launches;
 
+static const int kPackGTileBytes = 4096;     // tile of the generic-alphabet pack kernels (256 threads x 16 B)
 static const int kPackTileBytes = 16384;     // MSA bytes per CTA in the strip/pack kernel (256 threads x 64 B; 8 KB and 32 KB measured slower)
 
 // ---- strip + pack (pack.cu) --------------------------------------------------------------------
@@ -31,6 +32,15 @@ struct PackJob {
     uint8_t* exc_byte;            // [H*exc_stride]
     uint64_t exc_stride;
     uint32_t* flags;              // bit 0: a row has more exceptions than exc_stride; bit 1: look-back timed out
+    // generic alphabets (bl > 1): byte -> code table and the buffers of the two-pass generic kernels
+    uint32_t bl;                  // log2(bits per symbol) of the packed output: 1 (ACGT fast path), 2 or 3
+    const uint8_t* b2c;           // [256] byte -> code, 0xFF = not in the reference alphabet (device)
+    uint32_t gtiles_per_row;      // ceil(max cols / kPackGTileBytes)
+    uint32_t* gtile_cnt;          // [H*gtiles_per_row]
+    uint32_t* gtile_exc;          // [H*gtiles_per_row]
+    uint64_t* gtile_off;          // [H*gtiles_per_row]
+    uint64_t* gtile_excoff;       // [H*gtiles_per_row]
+    uint64_t* gscan_tmp;          // 2 * scan_tmp_elems(H*gtiles_per_row)
     uint8_t* gapless;             // optional gapless bytes out (device) or null
     const uint64_t* gapless_off;  // [H] byte offsets into gapless
 };
@@ -40,12 +50,13 @@ void launch_pack(const PackJob& job, cudaStream_t s, cudaEvent_t* ev);
 // ---- suffix array + k-mer table (sa_build.cu) ---------------------------------------------------
 struct SaWorkspace;   // opaque
 // Builds SA (uint32[n]) of the packed text and, when isa != null, the inverse.  Returns 0 or a cudaError.
-int build_suffix_array(const uint64_t* text, uint64_t n, uint32_t* sa, uint32_t* isa, cudaStream_t s,
+// bl = log2(bits per symbol) of the packed text
+int build_suffix_array(const uint64_t* text, uint64_t n, uint32_t bl, uint32_t* sa, uint32_t* isa, cudaStream_t s,
                        int* rounds_out, char* err, int errlen);
-// tab: 4^k + 1 entries
-int build_kmer_table(const uint64_t* text, uint64_t n, const uint32_t* sa, int k, uint32_t* tab, cudaStream_t s);
+// tab: sigma^k + 1 entries (ix.tab is ignored, ix.text / ix.sa / ix.k / ix.bl / ix.sigma are used)
+int build_kmer_table(const IndexView& ix, uint32_t* tab, cudaStream_t s);
 // LCP[j] = lcp(suffix SA[j-1], suffix SA[j]), LCP[0] = 0
-int build_lcp(const uint64_t* text, uint64_t n, const uint32_t* sa, const uint32_t* isa, uint32_t* lcp,
+int build_lcp(const uint64_t* text, uint64_t n, uint32_t bl, const uint32_t* sa, const uint32_t* isa, uint32_t* lcp,
               cudaStream_t s);
 // uniq[p] = min(65535, max(LCP[ISA[p]], LCP[ISA[p]+1]))
 int build_uniq(uint64_t n, const uint32_t* isa, const uint32_t* lcp, uint16_t* uniq, cudaStream_t s);

@@ -271,8 +271,123 @@ __global__ void __launch_bounds__(kPackThreads) k_pack(PackJob job, uint32_t n_t
     pack_tile(job, s_ticket[1], s_ticket[2], sbits, sm, s_bcast, s_wlast);
 }
 
+// ---- generic alphabets (references with N, soft-masking, IUPAC codes ...): 4 or 8 bits per symbol ----------------
+// Two passes (count, scan, write) with a byte -> code table; slower than k_pack (the MSA bytes are read twice) but
+// alphabet-agnostic.  Bytes outside the reference alphabet become exceptions exactly as in the 2-bit path.
+__global__ void __launch_bounds__(256) k_packg_count(PackJob job) {
+    __shared__ uint32_t sm[33];
+    uint32_t h = blockIdx.y, t = blockIdx.x;
+    uint64_t cols = job.cols[h];
+    uint64_t off = (uint64_t)t * kPackGTileBytes + (uint64_t)threadIdx.x * 16;
+    const uint8_t* rowp = job.rows + job.row_off[h];
+    uint32_t cnt = 0, exc = 0;
+    for (int b = 0; b < 16; ++b) {
+        uint64_t o = off + b;
+        if (o >= cols) break;
+        uint32_t byte = rowp[o];
+        if (job.strip && byte == '-') continue;
+        ++cnt;
+        if (job.b2c[byte] == 0xFF) ++exc;
+    }
+    uint32_t total;
+    block_exclusive_scan<uint32_t, OpSum>(cnt | (exc << 16), OpSum(), 0u, &total, sm);
+    if (threadIdx.x == 0) {
+        job.gtile_cnt[(uint64_t)h * job.gtiles_per_row + t] = total & 0xFFFFu;
+        job.gtile_exc[(uint64_t)h * job.gtiles_per_row + t] = total >> 16;
+    }
+}
+
+__global__ void k_packg_rows(PackJob job, const uint64_t* total_cnt, const uint64_t* total_exc) {
+    uint32_t h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= job.H) return;
+    uint64_t T = job.gtiles_per_row, nt = (uint64_t)job.H * T;
+    uint64_t a = job.gtile_off[h * T], b = (uint64_t)(h + 1) * T < nt ? job.gtile_off[(uint64_t)(h + 1) * T] : *total_cnt;
+    uint64_t ea = job.gtile_excoff[h * T], eb = (uint64_t)(h + 1) * T < nt ? job.gtile_excoff[(uint64_t)(h + 1) * T] : *total_exc;
+    job.m_out[h] = b - a;
+    job.exc_cnt[h] = eb - ea;
+    if (eb - ea > job.exc_stride) atomicOr(job.flags, 1u);
+}
+
+__global__ void __launch_bounds__(256) k_packg_write(PackJob job) {
+    __shared__ uint8_t scode[kPackGTileBytes];
+    __shared__ uint32_t sm[33];
+    uint32_t h = blockIdx.y, t = blockIdx.x;
+    uint64_t cols = job.cols[h];
+    uint64_t tile_start = (uint64_t)t * kPackGTileBytes;
+    if (tile_start >= cols) return;
+    const uint8_t* rowp = job.rows + job.row_off[h];
+    uint64_t off = tile_start + (uint64_t)threadIdx.x * 16;
+    uint8_t code[16], raw[16];
+    uint32_t cnt = 0, exc = 0;
+    for (int b = 0; b < 16; ++b) {
+        uint64_t o = off + b;
+        if (o >= cols) break;
+        uint32_t byte = rowp[o];
+        if (job.strip && byte == '-') continue;
+        uint32_t c = job.b2c[byte];
+        if (c == 0xFF) { ++exc; }
+        code[cnt] = (uint8_t)c; raw[cnt] = (uint8_t)byte;
+        ++cnt;
+    }
+    uint32_t total;
+    uint32_t ex = block_exclusive_scan<uint32_t, OpSum>(cnt | (exc << 16), OpSum(), 0u, &total, sm);
+    const uint32_t lo = ex & 0xFFFFu, elo = ex >> 16, T = total & 0xFFFFu;
+    uint64_t gidx = (uint64_t)h * job.gtiles_per_row + t, g0 = (uint64_t)h * job.gtiles_per_row;
+    uint64_t o = job.gtile_off[gidx] - job.gtile_off[g0];            // first output symbol of the tile in the row
+    uint64_t e = job.gtile_excoff[gidx] - job.gtile_excoff[g0] + elo;
+    uint8_t* gl = job.gapless ? job.gapless + job.gapless_off[h] : nullptr;
+    uint32_t* ep = job.exc_pos + (uint64_t)h * job.exc_stride;
+    uint8_t* eb = job.exc_byte + (uint64_t)h * job.exc_stride;
+    for (uint32_t q = 0; q < cnt; ++q) {
+        uint32_t c = code[q];
+        if (c == 0xFF) {
+            if (e < job.exc_stride) { ep[e] = (uint32_t)(o + lo + q); eb[e] = raw[q]; }
+            ++e; c = 0;
+        }
+        scode[lo + q] = (uint8_t)c;
+        if (gl) gl[o + lo + q] = raw[q];
+    }
+    __syncthreads();
+    if (T == 0) return;
+    const uint32_t bl = job.bl, sl = 6 - bl, spw = 1u << sl, B = 1u << bl;
+    uint64_t* X = job.X + job.xoff[h];
+    const uint32_t lead = (uint32_t)(o & (spw - 1));
+    const uint64_t W0 = o >> sl;
+    uint32_t nwords = (lead + T + spw - 1) >> sl;
+    for (uint32_t j = threadIdx.x; j < nwords; j += 256) {
+        uint64_t val = 0;
+        for (uint32_t q = 0; q < spw; ++q) {
+            int64_t li = (int64_t)j * spw + q - (int64_t)lead;
+            if (li >= 0 && li < (int64_t)T) val |= (uint64_t)scode[li] << (64 - B - B * q);
+        }
+        bool first_partial = j == 0 && lead != 0;
+        bool last_partial = j == nwords - 1 && ((lead + T) & (spw - 1)) != 0;
+        if (first_partial || last_partial) atomicOr(reinterpret_cast<unsigned long long*>(&X[W0 + j]), (unsigned long long)val);
+        else X[W0 + j] = val;
+    }
+}
+
+static void launch_pack_generic(const PackJob& job, cudaStream_t s, cudaEvent_t* ev) {
+    dim3 grid(job.gtiles_per_row, job.H);
+    uint64_t nt = (uint64_t)job.H * job.gtiles_per_row;
+    if (ev) { cudaEventRecord(ev[0], s); cudaEventRecord(ev[1], s); }
+    g_launches += 3;
+    k_packg_count<<<grid, 256, 0, s>>>(job);
+    uint64_t* tmp1 = job.gscan_tmp;
+    uint64_t* tmp2 = job.gscan_tmp + scan_tmp_elems(nt);
+    device_scan<uint64_t, LoadArr<uint32_t, uint64_t>, StoreArr<uint64_t>, OpSum, false>(
+        LoadArr<uint32_t, uint64_t>{job.gtile_cnt}, StoreArr<uint64_t>{job.gtile_off}, nt, tmp1, OpSum(), 0ull, s);
+    device_scan<uint64_t, LoadArr<uint32_t, uint64_t>, StoreArr<uint64_t>, OpSum, false>(
+        LoadArr<uint32_t, uint64_t>{job.gtile_exc}, StoreArr<uint64_t>{job.gtile_excoff}, nt, tmp2, OpSum(), 0ull, s);
+    uint64_t nts = (nt + kScanTile - 1) / kScanTile;
+    k_packg_rows<<<(job.H + 127) / 128, 128, 0, s>>>(job, tmp1 + nts, tmp2 + nts);
+    k_packg_write<<<grid, 256, 0, s>>>(job);
+    if (ev) cudaEventRecord(ev[2], s);
+}
+
 void launch_pack(const PackJob& job, cudaStream_t s, cudaEvent_t* ev) {
     if (job.H == 0 || job.tiles_per_row == 0) { if (ev) for (int i = 0; i < 3; ++i) cudaEventRecord(ev[i], s); return; }
+    if (job.bl != 1) { launch_pack_generic(job, s, ev); return; }
     uint64_t nt = (uint64_t)job.H * job.tiles_per_row;
     cudaMemsetAsync(job.desc_cnt, 0, nt * 8, s);
     cudaMemsetAsync(job.desc_exc, 0, nt * 8, s);

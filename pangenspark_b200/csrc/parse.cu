@@ -62,20 +62,21 @@ __global__ void __launch_bounds__(128) k_diag_w(ParseView pv) {
     const uint32_t p = (uint32_t)p0, len = (uint32_t)(e - s);
     const uint32_t avail = (uint32_t)pv.ix.n - p;
     const uint32_t cmplen = len < avail ? len : avail;
-    const uint64_t* __restrict__ xw = hv.x + (s >> 5);
+    const uint32_t bl = pv.ix.bl, sl = 6 - bl, spw = 1u << sl, B = 1u << bl, slab = 32u << sl;   // slab = 32 words
+    const uint64_t* __restrict__ xw = hv.x + (s >> sl);
     const uint64_t* __restrict__ D = pv.ix.text;
     uint32_t cnt = 0, V = len;
     bool full = false;
-    for (uint32_t o0 = 0; o0 < cmplen && !full; o0 += 4096) {        // 4 slabs of 1024 bases per iteration
+    for (uint32_t o0 = 0; o0 < cmplen && !full; o0 += 4 * slab) {    // 4 slabs of 32 words per iteration
         uint64_t xr[4];
 #pragma unroll
         for (int r = 0; r < 4; ++r) {                                // all 8 loads of the lane are independent
-            const uint32_t o = o0 + 1024u * r + 32u * (uint32_t)lane;
+            const uint32_t o = o0 + slab * r + spw * (uint32_t)lane;
             xr[r] = 0;
             if (o < cmplen) {
-                xr[r] = xw[o >> 5] ^ get64u(D, p + o);
-                uint32_t nb = cmplen - o < 32u ? cmplen - o : 32u;
-                if (nb < 32) xr[r] &= ~0ull << (64 - 2 * nb);
+                xr[r] = xw[o >> sl] ^ get64u(D, p + o, bl);
+                uint32_t nb = cmplen - o < spw ? cmplen - o : spw;
+                if (nb < spw) xr[r] &= ~0ull << (64 - B * nb);
             }
         }
         if (!__any_sync(0xffffffffu, (xr[0] | xr[1] | xr[2] | xr[3]) != 0)) continue;
@@ -86,13 +87,13 @@ __global__ void __launch_bounds__(128) k_diag_w(ParseView pv) {
                 const int src = __ffs(bal) - 1;
                 bal &= bal - 1;
                 uint64_t w = __shfl_sync(0xffffffffu, xr[r], src);
-                const uint32_t ob = o0 + 1024u * r + 32u * (uint32_t)src;
+                const uint32_t ob = o0 + slab * r + spw * (uint32_t)src;
                 while (w) {
-                    uint32_t b = (uint32_t)(clz64(w) >> 1);
+                    uint32_t b = (uint32_t)(clz64(w) >> bl);
                     if (cnt == (uint32_t)kMmMax) { V = ob + b; full = true; break; }
                     if (lane == 0) mm[2 + cnt] = (uint16_t)(ob + b);
                     ++cnt;
-                    w &= ~(3ull << (62 - 2 * b));
+                    w &= ~(((1ull << B) - 1) << (64 - B - B * b));
                 }
             }
         }
@@ -366,7 +367,7 @@ __global__ void __launch_bounds__(128) k_ms_dense(IndexView ix, const uint64_t* 
     if (i >= m) return;
     bool open;
     Match mt = lookup(ix, X, i, (uint32_t)(m - i), (uint32_t)(m - i), &open);
-    if (mt.len == 0) mt.pos = (uint32_t)("ACGT"[base_at(X, i)]);
+    if (mt.len == 0) mt.pos = (uint32_t)ix.c2b[base_at(X, i, ix.bl)];
     ms[i] = mt.len; pos[i] = mt.pos;
 }
 void launch_ms_dense(const IndexView& ix, const uint64_t* X, uint64_t m, uint32_t* ms, uint32_t* pos, cudaStream_t s) {

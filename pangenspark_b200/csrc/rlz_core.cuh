@@ -10,14 +10,16 @@
 //   greedy: i += max(1, L)                                                                  (:226-240)
 //
 // Data layout (all in HBM):
-//   text / haplotypes : 2 bits per base (A,C,G,T -> 0..3), 32 bases per 64-bit word, first base in the
-//                       most significant bits, so integer order of words == lexicographic order of bases;
-//                       arrays carry >= 2 zero pad words.
+//   text / haplotypes : B = 2, 4 or 8 bits per symbol (B = 1 << bl), 64/B symbols per 64-bit word, first symbol in
+//                       the most significant bits, so integer order of words == lexicographic order of symbols;
+//                       arrays carry >= 2 zero pad words.  B = 2: A,C,G,T -> 0..3 (pure-ACGT references, the fast
+//                       path).  Otherwise the sigma distinct bytes of the reference get order-preserving codes
+//                       0..sigma-1 (4 bits if sigma <= 16, else 8 bits).
 //   SA                : uint32 suffix array of the reference (n < 2^32 - 1024)
-//   tab               : 4^k + 1 entries; tab[K] = #suffixes whose zero-padded k-mer key is < K
+//   tab               : sigma^k + 1 entries; tab[K] = #suffixes whose zero-padded radix-sigma k-mer key is < K
 //                       (a jump table replacing the top ~2k levels of the SA binary search)
-//   exceptions        : sorted positions (+ bytes) of haplotype bytes outside {A,C,G,T}; such a byte can
-//                       never match a pure-ACGT reference, so it ends the running phrase and is a literal.
+//   exceptions        : sorted positions (+ bytes) of haplotype bytes outside the reference alphabet; such a byte
+//                       can never match, so it ends the running phrase and is a literal.
 #pragma once
 #include <stdint.h>
 
@@ -50,27 +52,49 @@ DRLZ_HD int clz64(uint64_t v) {
 #endif
 }
 
-// 32 bases starting at base `pos`
-DRLZ_HD uint64_t get64(const uint64_t* __restrict__ w, uint64_t pos) {
-    uint64_t wi = pos >> 5;
-    unsigned sh = (unsigned)(pos & 31) * 2;
+// one word of symbols (64 / B of them) starting at symbol `pos`;  bl = log2(B)
+DRLZ_HD uint64_t get64(const uint64_t* __restrict__ w, uint64_t pos, uint32_t bl) {
+    const uint32_t sl = 6 - bl;
+    uint64_t wi = pos >> sl;
+    unsigned sh = (unsigned)(pos & ((1u << sl) - 1)) << bl;
     uint64_t a = w[wi];
     if (sh == 0) return a;
     return (a << sh) | (w[wi + 1] >> (64 - sh));
 }
 
-DRLZ_HD unsigned base_at(const uint64_t* __restrict__ w, uint64_t pos) {
-    return (unsigned)(w[pos >> 5] >> (62 - 2 * (pos & 31))) & 3u;
+DRLZ_HD unsigned base_at(const uint64_t* __restrict__ w, uint64_t pos, uint32_t bl) {
+    const uint32_t sl = 6 - bl, B = 1u << bl;
+    return (unsigned)(w[pos >> sl] >> (64 - B - ((unsigned)(pos & ((1u << sl) - 1)) << bl))) & ((1u << B) - 1u);
 }
 
 struct IndexView {
     const uint64_t* text;   // packed reference
     const uint32_t* sa;
-    const uint32_t* tab;    // 4^k + 1
+    const uint32_t* tab;    // sigma^k + 1
     uint64_t n;
     int k;
     const uint16_t* uniq;   // [n] min(65535, longest repeat starting at p) = max(LCP[ISA[p]], LCP[ISA[p]+1]); may be null
+    uint32_t bl;            // log2(bits per symbol): 1, 2 or 3
+    uint32_t sigma;         // alphabet size (4 when bl == 1)
+    const uint8_t* c2b;     // code -> byte (literal phrases)
 };
+
+// key of the first kk symbols of the word xw padded with code 0 to k symbols, and the number of keys sharing that
+// prefix: the table brackets are tab[lokey] and tab[lokey + span]
+DRLZ_HD void prefix_keys(const IndexView& ix, uint64_t xw, uint32_t kk, uint64_t* lokey, uint64_t* span) {
+    const int k = ix.k;
+    if (ix.bl == 1) {
+        uint64_t kmer = xw >> (64 - 2 * k);
+        uint64_t lowmask = (1ull << (2 * (k - (int)kk))) - 1;
+        *lokey = kmer & ~lowmask; *span = lowmask + 1;
+        return;
+    }
+    const uint32_t B = 1u << ix.bl;
+    uint64_t key = 0, sp = 1;
+    for (uint32_t t = 0; t < kk; ++t) key = key * ix.sigma + ((xw >> (64 - B * (t + 1))) & ((1ull << B) - 1));
+    for (uint32_t t = kk; t < (uint32_t)k; ++t) { key *= ix.sigma; sp *= ix.sigma; }
+    *lokey = key; *span = sp;
+}
 
 struct HapView {
     const uint64_t* x;        // packed haplotype
@@ -89,9 +113,10 @@ struct Match {
 DRLZ_HD uint64_t funnel64(uint64_t a, uint64_t b, unsigned sh) { return sh ? (a << sh) | (b >> (64 - sh)) : a; }
 
 // get64 with a 32-bit position (n, m < 2^32: half the integer work of the 64-bit form)
-DRLZ_HD uint64_t get64u(const uint64_t* __restrict__ w, uint32_t pos) {
-    uint32_t wi = pos >> 5;
-    unsigned sh = (pos & 31u) * 2;
+DRLZ_HD uint64_t get64u(const uint64_t* __restrict__ w, uint32_t pos, uint32_t bl) {
+    const uint32_t sl = 6 - bl;
+    uint32_t wi = pos >> sl;
+    unsigned sh = (pos & ((1u << sl) - 1)) << bl;
     uint64_t a = w[wi];
     if (sh == 0) return a;
     return (a << sh) | (w[wi + 1] >> (64 - sh));
@@ -99,25 +124,26 @@ DRLZ_HD uint64_t get64u(const uint64_t* __restrict__ w, uint32_t pos) {
 
 // lcp(x[i..i+maxlen), d[p..n)) and whether the suffix d[p..] sorts before the pattern; xw0 = get64u(X, i).
 // The first 32 bases are compared alone (most probes differ there); longer matches stream 128 bases per
-// iteration: 4 new words per stream with a carry word, 8 independent loads in flight, one OR-reduced test.
+// iteration (4 words per stream with a carry word, 8 independent loads in flight, one OR-reduced test).
 DRLZ_HD uint32_t cmp_suffix_w(uint64_t xw0, const uint64_t* __restrict__ X, uint32_t i, const uint64_t* __restrict__ D,
-                              uint32_t p, uint32_t n, uint32_t maxlen, bool* less) {
+                              uint32_t p, uint32_t n, uint32_t maxlen, bool* less, uint32_t bl) {
+    const uint32_t sl = 6 - bl, spw = 1u << sl;          // symbols per word
     uint32_t rem = n - p;
     uint32_t lim = rem < maxlen ? rem : maxlen;
     uint32_t l = 0;
     bool diff_less = false, found = false;
     if (lim > 0) {
-        uint64_t b = get64u(D, p);
+        uint64_t b = get64u(D, p, bl);
         uint64_t xr = xw0 ^ b;
-        if (xr) { l = (uint32_t)(clz64(xr) >> 1); diff_less = b < xw0; found = true; }
-        else l = 32;
+        if (xr) { l = (uint32_t)(clz64(xr) >> bl); diff_less = b < xw0; found = true; }
+        else l = spw;
     }
-    if (!found && l + 128 <= lim) {
-        const unsigned shx = ((i + l) & 31u) * 2, shd = ((p + l) & 31u) * 2;
-        const uint64_t* xp = X + ((i + l) >> 5);
-        const uint64_t* dp = D + ((p + l) >> 5);
+    if (!found && l + 4 * spw <= lim) {
+        const unsigned shx = ((i + l) & (spw - 1)) << bl, shd = ((p + l) & (spw - 1)) << bl;
+        const uint64_t* xp = X + ((i + l) >> sl);
+        const uint64_t* dp = D + ((p + l) >> sl);
         uint64_t cx = xp[0], cd = dp[0];
-        while (l + 128 <= lim) {
+        while (l + 4 * spw <= lim) {
             uint64_t x1 = xp[1], x2 = xp[2], x3 = xp[3], x4 = xp[4];
             uint64_t d1 = dp[1], d2 = dp[2], d3 = dp[3], d4 = dp[4];
             uint64_t r0 = funnel64(cx, x1, shx) ^ funnel64(cd, d1, shd);
@@ -125,14 +151,14 @@ DRLZ_HD uint32_t cmp_suffix_w(uint64_t xw0, const uint64_t* __restrict__ X, uint
             uint64_t r2 = funnel64(x2, x3, shx) ^ funnel64(d2, d3, shd);
             uint64_t r3 = funnel64(x3, x4, shx) ^ funnel64(d3, d4, shd);
             if (r0 | r1 | r2 | r3) break;                 // the word loop below locates the mismatch
-            l += 128; xp += 4; dp += 4; cx = x4; cd = d4;
+            l += 4 * spw; xp += 4; dp += 4; cx = x4; cd = d4;
         }
     }
     while (!found && l < lim) {
-        uint64_t a = get64u(X, i + l), b = get64u(D, p + l);
+        uint64_t a = get64u(X, i + l, bl), b = get64u(D, p + l, bl);
         uint64_t xr = a ^ b;
-        if (xr) { l += (uint32_t)(clz64(xr) >> 1); diff_less = b < a; found = true; }
-        else l += 32;
+        if (xr) { l += (uint32_t)(clz64(xr) >> bl); diff_less = b < a; found = true; }
+        else l += spw;
     }
     if (l >= lim) {
         l = lim;
@@ -145,8 +171,8 @@ DRLZ_HD uint32_t cmp_suffix_w(uint64_t xw0, const uint64_t* __restrict__ X, uint
 }
 
 DRLZ_HD uint32_t cmp_suffix(const uint64_t* __restrict__ X, uint64_t i, const uint64_t* __restrict__ D,
-                            uint64_t p, uint64_t n, uint32_t maxlen, bool* less) {
-    return cmp_suffix_w(get64u(X, (uint32_t)i), X, (uint32_t)i, D, (uint32_t)p, (uint32_t)n, maxlen, less);
+                            uint64_t p, uint64_t n, uint32_t maxlen, bool* less, uint32_t bl) {
+    return cmp_suffix_w(get64u(X, (uint32_t)i, bl), X, (uint32_t)i, D, (uint32_t)p, (uint32_t)n, maxlen, less, bl);
 }
 
 // Longest match of x[i..i+maxlen) in d with the reference's tie-break.  maxlen >= 1.
@@ -162,15 +188,15 @@ DRLZ_HD Match lookup(const IndexView& ix, const uint64_t* __restrict__ X, uint64
     const uint64_t* __restrict__ D = ix.text;
     const uint32_t* __restrict__ SA = ix.sa;
     *open = false;
-    const uint64_t xw = get64u(X, i);
-    const uint64_t kmer = xw >> (64 - 2 * k);
+    const uint32_t bl = ix.bl;
+    const uint64_t xw = get64u(X, i, bl);
     Match mt;
     uint32_t plen = cap < maxlen ? cap : maxlen;
     for (int pass = 0; pass < 2; ++pass) {
         uint32_t kk = plen < (uint32_t)k ? plen : (uint32_t)k;
-        uint64_t lowmask = (1ull << (2 * (k - (int)kk))) - 1;
-        uint64_t lokey = kmer & ~lowmask, hikey = kmer | lowmask;
-        uint32_t lo = ix.tab[lokey], hi = ix.tab[hikey + 1];
+        uint64_t lokey, span;
+        prefix_keys(ix, xw, kk, &lokey, &span);
+        uint32_t lo = ix.tab[lokey], hi = ix.tab[lokey + span];
         // r = #suffixes < pattern lies in [lo, hi]
         uint32_t l = lo, h = hi;
         uint32_t lcp_left = 0, lcp_right = 0, sar = 0;
@@ -179,23 +205,23 @@ DRLZ_HD Match lookup(const IndexView& ix, const uint64_t* __restrict__ X, uint64
             uint32_t mid = l + ((h - l) >> 1);
             bool less;
             uint32_t pm = SA[mid];
-            uint32_t c = cmp_suffix_w(xw, X, i, D, pm, n, plen, &less);
+            uint32_t c = cmp_suffix_w(xw, X, i, D, pm, n, plen, &less, bl);
             if (less) { l = mid + 1; lcp_left = c; have_left = true; }
             else { h = mid; lcp_right = c; have_right = true; sar = pm; }
         }
         uint32_t r = l;
         bool dummy;
         uint32_t l1 = 0, l2 = 0;
-        if (r > 0) l1 = have_left ? lcp_left : cmp_suffix_w(xw, X, i, D, SA[r - 1], n, plen, &dummy);
+        if (r > 0) l1 = have_left ? lcp_left : cmp_suffix_w(xw, X, i, D, SA[r - 1], n, plen, &dummy, bl);
         if (r < n) {
-            if (!have_right) { sar = SA[r]; lcp_right = cmp_suffix_w(xw, X, i, D, sar, n, plen, &dummy); }
+            if (!have_right) { sar = SA[r]; lcp_right = cmp_suffix_w(xw, X, i, D, sar, n, plen, &dummy, bl); }
             l2 = lcp_right;
         }
         if (l2 > l1) {
             if (l2 == plen && plen < maxlen) {
                 // capped: is SA[r] the only suffix carrying the capped pattern?
                 bool multi = false;
-                if (r + 1 < n) multi = cmp_suffix_w(xw, X, i, D, SA[r + 1], n, plen, &dummy) >= plen;
+                if (r + 1 < n) multi = cmp_suffix_w(xw, X, i, D, SA[r + 1], n, plen, &dummy, bl) >= plen;
                 if (multi) { plen = maxlen; continue; }
                 *open = true;
             }
@@ -207,13 +233,14 @@ DRLZ_HD Match lookup(const IndexView& ix, const uint64_t* __restrict__ X, uint64
         uint32_t Lk = L < (uint32_t)k ? L : (uint32_t)k;
         uint32_t a = lo;
         if (Lk != kk) {
-            uint64_t m2 = (1ull << (2 * (k - (int)Lk))) - 1;
-            a = ix.tab[kmer & ~m2];
+            uint64_t lk2, sp2;
+            prefix_keys(ix, xw, Lk, &lk2, &sp2);
+            a = ix.tab[lk2];
         }
         uint32_t b = r - 1;
         while (a < b) {
             uint32_t mid = a + ((b - a) >> 1);
-            uint32_t c = cmp_suffix_w(xw, X, i, D, SA[mid], n, L, &dummy);
+            uint32_t c = cmp_suffix_w(xw, X, i, D, SA[mid], n, L, &dummy, bl);
             if (c >= L) b = mid; else a = mid + 1;
         }
         mt.len = L; mt.pos = SA[a];
@@ -380,7 +407,7 @@ DRLZ_HD Match phrase_capped(const ParseView& pv, const HapView& hv, uint64_t i, 
             uint32_t c;
             bool less;
             if (!(pv.mm && g != kEmpty && pv.hint[g / kHintGroup] == *diag && list_extent(pv, g, s, i, plen, &c)))
-                c = cmp_suffix_w(get64u(hv.x, (uint32_t)i), hv.x, (uint32_t)i, pv.ix.text, p, (uint32_t)pv.ix.n, plen, &less);
+                c = cmp_suffix_w(get64u(hv.x, (uint32_t)i, pv.ix.bl), hv.x, (uint32_t)i, pv.ix.text, p, (uint32_t)pv.ix.n, plen, &less, pv.ix.bl);
             if (c > 0) {
                 uint32_t u = pv.ix.uniq[p];
                 if (u != 0xFFFFu && c > u) {
@@ -392,7 +419,7 @@ DRLZ_HD Match phrase_capped(const ParseView& pv, const HapView& hv, uint64_t i, 
         }
     }
     mt = lookup(pv.ix, hv.x, i, maxlen, cap, open);
-    if (mt.len == 0) mt.pos = (uint32_t)("ACGT"[base_at(hv.x, i)]);
+    if (mt.len == 0) mt.pos = (uint32_t)pv.ix.c2b[base_at(hv.x, i, pv.ix.bl)];
     else if (mt.len >= kDiagMinLen) *diag = (int64_t)mt.pos - (int64_t)i;
     return mt;
 }
@@ -417,7 +444,7 @@ DRLZ_HD uint32_t foreign_run(const ParseView& pv, const HapView& hv, uint64_t i,
     uint32_t cap = maxlen < pv.foreign_cap ? maxlen : pv.foreign_cap;
     bool less;
     uint64_t p = (uint64_t)mt.pos + (j - i);
-    uint32_t l = cap ? cmp_suffix(hv.x, j, pv.ix.text, p, pv.ix.n, cap, &less) : 0;
+    uint32_t l = cap ? cmp_suffix(hv.x, j, pv.ix.text, p, pv.ix.n, cap, &less, pv.ix.bl) : 0;
     if (l == cap && cap < maxlen) pv.counters[0] = 3;        // too long for one thread: take the exact fallback
     return l;
 }
@@ -523,15 +550,16 @@ DRLZ_HD void diag_scan_chunk(const ParseView& pv, uint32_t g) {
     uint32_t cmplen = len < avail ? len : avail;
     uint32_t cnt = 0, V = len;
     bool full = false;
-    for (uint32_t o = 0; o < cmplen && !full; o += 32) {
-        uint64_t xr = get64u(hv.x, (uint32_t)s + o) ^ get64u(pv.ix.text, p + o);
-        uint32_t nb = cmplen - o < 32u ? cmplen - o : 32u;
-        if (nb < 32) xr &= ~0ull << (64 - 2 * nb);
+    const uint32_t bl = pv.ix.bl, B = 1u << bl, spw = 64u >> bl;
+    for (uint32_t o = 0; o < cmplen && !full; o += spw) {
+        uint64_t xr = get64u(hv.x, (uint32_t)s + o, bl) ^ get64u(pv.ix.text, p + o, bl);
+        uint32_t nb = cmplen - o < spw ? cmplen - o : spw;
+        if (nb < spw) xr &= ~0ull << (64 - B * nb);
         while (xr) {
-            uint32_t b = (uint32_t)(clz64(xr) >> 1);
+            uint32_t b = (uint32_t)(clz64(xr) >> bl);
             if (cnt == (uint32_t)kMmMax) { V = o + b; full = true; break; }
             mm[2 + cnt++] = (uint16_t)(o + b);
-            xr &= ~(3ull << (62 - 2 * b));
+            xr &= ~(((1ull << B) - 1) << (64 - B - B * b));
         }
     }
     if (!full && cmplen < len) {
@@ -559,7 +587,7 @@ DRLZ_HD void snp_lookup(const ParseView& pv, uint32_t g, uint32_t t) {
     uint32_t cap = to_end > (uint64_t)pv.min_cap ? (to_end > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)to_end) : pv.min_cap;
     bool open;
     Match mt = lookup(pv.ix, hv.x, i, maxlen, cap, &open);
-    if (mt.len == 0) mt.pos = (uint32_t)("ACGT"[base_at(hv.x, i)]);
+    if (mt.len == 0) mt.pos = (uint32_t)pv.ix.c2b[base_at(hv.x, i, pv.ix.bl)];
     *out = make_uint2(mt.pos, mt.len | (open ? 0x80000000u : 0u));
 }
 

@@ -2,13 +2,13 @@
 // table derived from it, and the LCP array.  Replaces the external `radixSA` binary
 // (DistributedRLZ.scala:45,52) and the text SA load (:55).
 //
-//   round 0 : key = first 29 bases (58 bits) | min(remaining, 29) (6 bits)  -> 8-pass LSD radix sort.
-//             The length field makes every suffix shorter than 29 unique and sorts a proper prefix first,
-//             which is exactly the "shorter suffix first" order of the reference's SA.
+//   round 0 : key = first S0 symbols (S0 = 58 / bits per symbol: 29 bases at 2 bits) | min(remaining, S0) (6 bits)
+//             -> 8-pass LSD radix sort.  The length field makes every suffix shorter than S0 unique and sorts a
+//             proper prefix first, which is exactly the "shorter suffix first" order of the reference's SA.
 //   round r : only suffixes whose group is not yet a singleton stay active (early retirement);
 //             key = (group head index << 32) | (rank of suffix i+h, 0 past the end), radix sorted over the
 //             significant bits only; positions come back through the (sorted) list of active SA slots.
-//             h = 29, 58, 116, ...   One 8-byte device->host read per round decides termination.
+//             h = S0, 2 S0, 4 S0, ...   One 8-byte device->host read per round decides termination.
 //   rank[]  is the inverse suffix array once every group is a singleton.
 #include <stdio.h>
 #include "drlz_internal.h"
@@ -17,16 +17,17 @@
 
 namespace drlz {
 
-static const int kH0 = 29;
 
 #define SA_CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { snprintf(err, errlen, "%s: %s", #x, cudaGetErrorString(e_)); rc = (int)e_; goto done; } } while (0)
 
-__global__ void k_sa_init_keys(const uint64_t* __restrict__ text, uint64_t n, uint64_t* keys, uint32_t* vals) {
+__global__ void k_sa_init_keys(const uint64_t* __restrict__ text, uint64_t n, uint64_t* keys, uint32_t* vals, uint32_t bl) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    const uint32_t s0 = 58u >> bl;                              // symbols in the first key
+    const uint64_t keep = ~((1ull << (64 - (s0 << bl))) - 1);   // their bits (58 or 56 of them)
     uint64_t rem = n - i;
-    uint64_t len = rem < (uint64_t)kH0 ? rem : (uint64_t)kH0;
-    keys[i] = (get64(text, i) & ~0x3Full) | len;
+    uint64_t len = rem < (uint64_t)s0 ? rem : (uint64_t)s0;
+    keys[i] = (get64(text, i, bl) & keep) | len;
     vals[i] = (uint32_t)i;
 }
 
@@ -95,7 +96,7 @@ struct StoreRound {
 
 static int bits_for(uint64_t v) { int b = 0; while (v) { ++b; v >>= 1; } return b ? b : 1; }
 
-int build_suffix_array(const uint64_t* text, uint64_t n, uint32_t* sa, uint32_t* isa_out, cudaStream_t s,
+int build_suffix_array(const uint64_t* text, uint64_t n, uint32_t bl, uint32_t* sa, uint32_t* isa_out, cudaStream_t s,
                        int* rounds_out, char* err, int errlen) {
     int rc = 0;
     if (rounds_out) *rounds_out = 0;
@@ -119,7 +120,7 @@ int build_suffix_array(const uint64_t* text, uint64_t n, uint32_t* sa, uint32_t*
         const unsigned T = 256;
         unsigned nb = (unsigned)((n + T - 1) / T);
         g_launches += 1;
-        k_sa_init_keys<<<nb, T, 0, s>>>(text, n, keys_a, vals_a);
+        k_sa_init_keys<<<nb, T, 0, s>>>(text, n, keys_a, vals_a, bl);
         radix_sort_pairs<uint64_t>(&keys_a, &keys_b, &vals_a, &vals_b, n, 0, 64, hist, scan_tmp, s);
         // ranks = group head index (inclusive running max of head indices); SA = sorted values
         device_scan<uint32_t, LoadHeadIdx, StoreRank, OpMax, true>(LoadHeadIdx{keys_a}, StoreRank{vals_a, sa, isa}, n,
@@ -133,7 +134,7 @@ int build_suffix_array(const uint64_t* text, uint64_t n, uint32_t* sa, uint32_t*
         SA_CK(cudaStreamSynchronize(s));
         na32 = *(uint32_t*)tot_host;
         uint64_t na = na32;
-        uint64_t h = kH0;
+        uint64_t h = 58u >> bl;
         int rounds = 0;
         int rank_bits = bits_for(n);        // ranks+1 <= n
         while (na > 0) {
@@ -172,25 +173,28 @@ __global__ void k_tab_fill(uint32_t* tab, uint64_t cnt, uint32_t v) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < cnt) tab[i] = v;
 }
-__global__ void k_tab_mark(const uint64_t* __restrict__ text, uint64_t n, const uint32_t* __restrict__ sa, int k, uint32_t* tab) {
+__global__ void k_tab_mark(IndexView ix, uint32_t* tab) {
     uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n) return;
-    uint64_t key = get64(text, sa[j]) >> (64 - 2 * k);
-    bool first = j == 0 || (get64(text, sa[j - 1]) >> (64 - 2 * k)) != key;
-    if (first) tab[key] = (uint32_t)j;
+    if (j >= ix.n) return;
+    uint64_t key, span, prev = 0;
+    prefix_keys(ix, get64(ix.text, ix.sa[j], ix.bl), (uint32_t)ix.k, &key, &span);
+    if (j) prefix_keys(ix, get64(ix.text, ix.sa[j - 1], ix.bl), (uint32_t)ix.k, &prev, &span);
+    if (j == 0 || prev != key) tab[key] = (uint32_t)j;
 }
 // right-to-left running minimum: element e of the scan is table entry (cnt-1-e)
 struct LoadRev { const uint32_t* tab; uint64_t cnt; __device__ __forceinline__ uint32_t operator()(uint64_t e) const { return tab[cnt - 1 - e]; } };
 struct StoreRev { uint32_t* tab; uint64_t cnt; __device__ __forceinline__ void operator()(uint64_t e, uint32_t v) const { tab[cnt - 1 - e] = v; } };
 
-int build_kmer_table(const uint64_t* text, uint64_t n, const uint32_t* sa, int k, uint32_t* tab, cudaStream_t s) {
-    uint64_t cnt = (1ull << (2 * k)) + 1;
+int build_kmer_table(const IndexView& ix, uint32_t* tab, cudaStream_t s) {
+    uint64_t cnt = 1;
+    for (int t = 0; t < ix.k; ++t) cnt *= ix.sigma;
+    cnt += 1;
     uint32_t* tmp = nullptr;
     cudaError_t e = cudaMalloc(&tmp, scan_tmp_elems(cnt) * 4 + 64);
     if (e != cudaSuccess) return (int)e;
     g_launches += 2;
-    k_tab_fill<<<(unsigned)((cnt + 255) / 256), 256, 0, s>>>(tab, cnt, (uint32_t)n);
-    if (n) k_tab_mark<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(text, n, sa, k, tab);
+    k_tab_fill<<<(unsigned)((cnt + 255) / 256), 256, 0, s>>>(tab, cnt, (uint32_t)ix.n);
+    if (ix.n) k_tab_mark<<<(unsigned)((ix.n + 255) / 256), 256, 0, s>>>(ix, tab);
     device_scan<uint32_t, LoadRev, StoreRev, OpMin, true>(LoadRev{tab, cnt}, StoreRev{tab, cnt}, cnt, tmp, OpMin(),
                                                           0xFFFFFFFFu, s);
     e = cudaStreamSynchronize(s);
@@ -201,7 +205,7 @@ int build_kmer_table(const uint64_t* text, uint64_t n, const uint32_t* sa, int k
 // ---- LCP (Kasai order inside fixed blocks of text positions) ----------------------------------------
 static const int kLcpBlock = 64;
 __global__ void k_lcp(const uint64_t* __restrict__ text, uint64_t n, const uint32_t* __restrict__ sa,
-                      const uint32_t* __restrict__ isa, uint32_t* __restrict__ lcp) {
+                      const uint32_t* __restrict__ isa, uint32_t* __restrict__ lcp, uint32_t bl) {
     uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     uint64_t i0 = b * kLcpBlock;
     if (i0 >= n) return;
@@ -214,9 +218,9 @@ __global__ void k_lcp(const uint64_t* __restrict__ text, uint64_t n, const uint3
         // extend from hh (Kasai: lcp of the successor suffix is at least lcp-1)
         uint64_t lim = n - (i > j ? i : j);
         while (hh < lim) {
-            uint64_t xr = get64(text, i + hh) ^ get64(text, j + hh);
-            if (xr) { hh += (uint64_t)(clz64(xr) >> 1); break; }
-            hh += 32;
+            uint64_t xr = get64(text, i + hh, bl) ^ get64(text, j + hh, bl);
+            if (xr) { hh += (uint64_t)(clz64(xr) >> bl); break; }
+            hh += 64u >> bl;
         }
         if (hh > lim) hh = lim;
         lcp[r] = (uint32_t)hh;
@@ -224,11 +228,11 @@ __global__ void k_lcp(const uint64_t* __restrict__ text, uint64_t n, const uint3
     }
 }
 
-int build_lcp(const uint64_t* text, uint64_t n, const uint32_t* sa, const uint32_t* isa, uint32_t* lcp, cudaStream_t s) {
+int build_lcp(const uint64_t* text, uint64_t n, uint32_t bl, const uint32_t* sa, const uint32_t* isa, uint32_t* lcp, cudaStream_t s) {
     if (n == 0) return 0;
     uint64_t nb = (n + kLcpBlock - 1) / kLcpBlock;
     g_launches += 1;
-    k_lcp<<<(unsigned)((nb + 127) / 128), 128, 0, s>>>(text, n, sa, isa, lcp);
+    k_lcp<<<(unsigned)((nb + 127) / 128), 128, 0, s>>>(text, n, sa, isa, lcp, bl);
     return (int)cudaGetLastError();
 }
 

@@ -149,7 +149,9 @@ class Drlz:
     def index_info(self):
         a = (C.c_uint64 * 4)()
         self._ck(self._lib.drlz_index_info(self._h, a))
-        return {"n": int(a[0]), "k": int(a[1]), "sa_rounds": int(a[2]), "bytes": int(a[3])}
+        kinfo = int(a[1])           # k | log2(bits per symbol) << 8 | alphabet size << 16
+        return {"n": int(a[0]), "k": kinfo & 0xFF, "bits": 1 << ((kinfo >> 8) & 0xFF), "sigma": kinfo >> 16, "kinfo": kinfo,
+                "sa_rounds": int(a[2]), "bytes": int(a[3])}
 
     def index_timings(self):
         a = (C.c_double * 5)()
@@ -159,8 +161,9 @@ class Drlz:
     def index_get(self, what: str) -> np.ndarray:
         info = self.index_info()
         n, k = info["n"], info["k"]
+        spw = 64 // info["bits"]
         kinds = {"sa": (0, np.uint32, n), "isa": (1, np.uint32, n), "lcp": (2, np.uint32, n),
-                 "tab": (3, np.uint32, 4 ** k + 1), "text": (4, np.uint64, (n + 31) // 32)}
+                 "tab": (3, np.uint32, info["sigma"] ** k + 1), "text": (4, np.uint64, (n + spw - 1) // spw)}
         code, dt, cnt = kinds[what]
         out = np.empty(cnt, dtype=dt)
         self._ck(self._lib.drlz_index_get(self._h, code, out.ctypes.data_as(C.c_void_p), out.nbytes))

@@ -5,30 +5,54 @@
 #include <cstdlib>
 #include <cstring>
 #include <vector>
+#include <cmath>
 #include "../../pangenspark_b200/csrc/rlz_core.cuh"
 
 using namespace drlz;
 
-static int code_of(uint8_t b) { return b == 'A' ? 0 : b == 'C' ? 1 : b == 'G' ? 2 : b == 'T' ? 3 : -1; }
+struct Alphabet {
+    uint32_t bl, sigma;
+    uint8_t b2c[256], c2b[256];
+};
 
-static void pack_seq(const uint8_t* s, uint64_t m, std::vector<uint64_t>& w, std::vector<uint32_t>* ep,
+// same rule as the library: pure ACGT -> fixed 2-bit codes; else order-preserving dense codes, 4 bits if sigma <= 16
+static Alphabet make_alphabet(const uint8_t* ref, uint64_t n) {
+    Alphabet a; memset(a.b2c, 0xFF, 256); memset(a.c2b, 0, 256);
+    bool present[256] = {false};
+    for (uint64_t i = 0; i < n; ++i) present[ref[i]] = true;
+    bool acgt = true;
+    for (int b = 0; b < 256; ++b) if (present[b] && b != 'A' && b != 'C' && b != 'G' && b != 'T') acgt = false;
+    if (acgt) {
+        a.bl = 1; a.sigma = 4;
+        const char* s = "ACGT";
+        for (int c = 0; c < 4; ++c) { a.b2c[(uint8_t)s[c]] = (uint8_t)c; a.c2b[c] = (uint8_t)s[c]; }
+        return a;
+    }
+    uint32_t sg = 0;
+    for (int b = 0; b < 256; ++b) if (present[b]) { a.b2c[b] = (uint8_t)sg; a.c2b[sg] = (uint8_t)b; ++sg; }
+    a.sigma = sg; a.bl = sg <= 16 ? 2 : 3;
+    return a;
+}
+
+static void pack_seq(const Alphabet& al, const uint8_t* s, uint64_t m, std::vector<uint64_t>& w, std::vector<uint32_t>* ep,
                      std::vector<uint8_t>* eb) {
-    w.assign(m / 32 + 3, 0);
+    const uint32_t B = 1u << al.bl, spw = 64 / B;
+    w.assign(m / spw + 8, 0);
     for (uint64_t i = 0; i < m; ++i) {
-        int c = code_of(s[i]);
-        if (c < 0) { if (ep) { ep->push_back((uint32_t)i); eb->push_back(s[i]); } c = 0; }
-        w[i >> 5] |= (uint64_t)c << (62 - 2 * (i & 31));
+        uint32_t c = al.b2c[s[i]];
+        if (c == 0xFF) { if (ep) { ep->push_back((uint32_t)i); eb->push_back(s[i]); } c = 0; }
+        w[i / spw] |= (uint64_t)c << (64 - B - B * (i % spw));
     }
 }
 
-static void build_tab(const std::vector<uint64_t>& text, uint64_t n, const std::vector<uint32_t>& sa, int k,
-                      std::vector<uint32_t>& tab) {
-    uint64_t nk = 1ull << (2 * k);
-    tab.assign(nk + 1, (uint32_t)n);
+static void build_tab(const IndexView& ix, const std::vector<uint32_t>& sa, std::vector<uint32_t>& tab) {
+    uint64_t nk = 1;
+    for (int t = 0; t < ix.k; ++t) nk *= ix.sigma;
+    tab.assign(nk + 1, (uint32_t)ix.n);
     uint64_t prev = 0;  // next K to fill
-    for (uint64_t j = 0; j < n; ++j) {
-        uint64_t key = get64(text.data(), sa[j]) >> (64 - 2 * k);
-        // bases past n are zero in `text`, i.e. the zero-padded key
+    for (uint64_t j = 0; j < ix.n; ++j) {
+        uint64_t key, span;
+        prefix_keys(ix, get64(ix.text, sa[j], ix.bl), (uint32_t)ix.k, &key, &span);   // symbols past n are code 0
         for (uint64_t K = prev; K <= key; ++K) tab[K] = (uint32_t)j;
         if (key + 1 > prev) prev = key + 1;
     }
@@ -42,13 +66,14 @@ void emu_free(void* p) { free(p); }
 int emu_parse(const uint8_t* ref, uint64_t n, const int64_t* sa64, int k, uint32_t chunk, uint32_t min_cap, uint32_t foreign_cap, int use_uniq, int H,
               const uint8_t* const* rows, const uint64_t* cols, int64_t** pairs_out, uint64_t* npairs,
               uint64_t* m_out, int* rounds_out) {
-    for (uint64_t i = 0; i < n; ++i) if (code_of(ref[i]) < 0) return 1;
+    Alphabet al = make_alphabet(ref, n);
+    const uint32_t spw = 64u >> al.bl;
+    while (k > 1 && ((uint32_t)k > spw || pow((double)al.sigma, k) > 3e7)) --k;
     uint32_t chunk_shift = 0;
     while ((2u << chunk_shift) <= chunk && chunk_shift < 31) ++chunk_shift;     // round down to a power of two
     chunk = 1u << chunk_shift;
-    std::vector<uint64_t> text; pack_seq(ref, n, text, nullptr, nullptr);
+    std::vector<uint64_t> text; pack_seq(al, ref, n, text, nullptr, nullptr);
     std::vector<uint32_t> sa(n); for (uint64_t i = 0; i < n; ++i) sa[i] = (uint32_t)sa64[i];
-    std::vector<uint32_t> tab; build_tab(text, n, sa, k, tab);
     // uniqueness array: longest repeat starting at p (Kasai LCP on the host; test harness only)
     std::vector<uint16_t> uniq(n + 1, 0);
     {
@@ -69,7 +94,9 @@ int emu_parse(const uint8_t* ref, uint64_t n, const int64_t* sa64, int k, uint32
             uniq[p] = (uint16_t)(u > 65535u ? 65535u : u);
         }
     }
-    IndexView ix{text.data(), sa.data(), tab.data(), n, k, use_uniq ? uniq.data() : nullptr};
+    IndexView ix{text.data(), sa.data(), nullptr, n, k, use_uniq ? uniq.data() : nullptr, al.bl, al.sigma, al.c2b};
+    std::vector<uint32_t> tab; build_tab(ix, sa, tab);
+    ix.tab = tab.data();
 
     std::vector<std::vector<uint64_t>> xs(H);
     std::vector<std::vector<uint32_t>> eps(H);
@@ -81,7 +108,7 @@ int emu_parse(const uint8_t* ref, uint64_t n, const int64_t* sa64, int k, uint32
         uint64_t c = cols[h];
         while (c > 0 && (rows[h][c - 1] == '\n' || rows[h][c - 1] == '\r')) --c;
         for (uint64_t t = 0; t < c; ++t) if (rows[h][t] != '-') g.push_back(rows[h][t]);
-        pack_seq(g.data(), g.size(), xs[h], &eps[h], &ebs[h]);
+        pack_seq(al, g.data(), g.size(), xs[h], &eps[h], &ebs[h]);
         haps[h] = HapView{xs[h].data(), (uint64_t)g.size(), eps[h].data(), ebs[h].data(), (uint32_t)eps[h].size()};
         m_out[h] = g.size();
         base[h + 1] = base[h] + (uint32_t)((g.size() + chunk - 1) / chunk);

@@ -8,13 +8,14 @@ from tests.emu import emu
 from tests.util import random_case
 
 
-def check(d, rows, k, chunk, min_cap=64, foreign_cap=1 << 20, use_uniq=1):
+def check(d, rows, k, chunk, min_cap=64, foreign_cap=1 << 20, use_uniq=1, clean=False):
     sa = orc.sa_build(d)
+    lcp = orc.lcp_build(d, sa) if clean else None
     rc, res, m, rounds = emu.parse(d, sa, rows, k, chunk, min_cap, foreign_cap, use_uniq)
     assert rc == 0, (rc, rounds)
     for h, r in enumerate(rows):
         x = orc.strip_gaps(r).tobytes()
-        a1, _ = orc.encode_literal(d, sa, x)
+        a1 = orc.encode_a3(d, sa, lcp, x) if clean else orc.encode_literal(d, sa, x)[0]
         assert m[h] == len(x)
         assert res[h].tolist() == a1.tolist(), (d, r, k, chunk)
     return rounds
@@ -34,6 +35,46 @@ def test_random_small(seed):
         chunk = int(rng.choice([1, 2, 3, 5, 8, 16, 64]))
         min_cap = int(rng.choice([1, 2, 4, 64]))
         check(d, [x, x[::-1], b"", d, d[3:]], k, chunk, min_cap, use_uniq=int(rng.integers(0, 2)))
+
+
+@pytest.mark.parametrize("alphabet", [b"ACGTN", b"ACGTNacgtn", b"AB", bytes(range(60, 100))])
+def test_generic_alphabets(alphabet):
+    """references outside {A,C,G,T}: 4-bit (sigma <= 16) and 8-bit symbol paths, order-preserving codes"""
+    rng = np.random.default_rng(len(alphabet))
+    for it in range(150):
+        d, x = random_case(rng, alphabet, 120, 200)
+        xb = bytearray(x)
+        if rng.random() < 0.5:
+            for _ in range(int(rng.integers(1, 4))):
+                xb.insert(int(rng.integers(0, len(xb) + 1)), int(rng.choice(list(b"-#z"))))
+        k = int(rng.integers(1, 5))
+        chunk = int(rng.choice([1, 4, 16, 32, 64, 256]))
+        check(d, [bytes(xb), bytes(xb)[::-1], d, b""], k, chunk, int(rng.choice([1, 4, 64])))
+    # N runs: long single-symbol stretches in the reference and the haplotype
+    d = b"ACGTTGCA" * 50 + b"N" * 700 + b"GATTACA" * 40 + b"N" * 90 + b"ACGT" * 30
+    x = d[:300] + b"N" * 650 + d[1100:] + b"NNNNACGTNN"
+    check(d, [x, d, x[::-1]], 3, 64)
+    check(d, [x, d], 3, 1024)
+
+
+@pytest.mark.parametrize("alphabet", [bytes(range(40, 60)), b"\x00\x01\xfe\xff!", b"01"])
+def test_alphabets_below_the_reference_sentinel(alphabet):
+    """Reference bytes <= '1': DistributedRLZ.scala:118-122 compares positions past the end of the text as the
+    byte '1', which contradicts the SA order (shorter suffix first) for such bytes, so the reference's result
+    depends on the search trajectory there.  The product follows the clean specification (longest match, leftmost
+    SA index = A3 = brute force), pinned here; test_oracle pins that A1 == A3 whenever all bytes are > '1'."""
+    from tests.util import brute_parse
+    rng = np.random.default_rng(len(alphabet) + 7)
+    for it in range(120):
+        d, x = random_case(rng, alphabet, 100, 160)
+        k = int(rng.integers(1, 4))
+        chunk = int(rng.choice([1, 8, 64, 256]))
+        check(d, [x, x[::-1], d], k, chunk, int(rng.choice([1, 64])), clean=True)
+        if it < 25:
+            sa = orc.sa_build(d)
+            xs = orc.strip_gaps(x).tobytes()
+            a3 = orc.encode_a3(d, sa, orc.lcp_build(d, sa), xs)
+            assert a3.tolist() == brute_parse(d, xs).tolist()
 
 
 def test_low_complexity_never_merging():

@@ -68,7 +68,7 @@ def _check_index(ctx, d: bytes, k=None):
     return sa_ref
 
 
-@pytest.mark.parametrize("alphabet", [b"ACGT", b"AC", b"A"])
+@pytest.mark.parametrize("alphabet", [b"ACGT", b"AC", b"A", b"ACGTN", b"ACGNTacgnt", bytes(range(33, 73)), b"AB"])
 def test_suffix_array_small(ctx, alphabet):
     rng = np.random.default_rng(len(alphabet))
     for n in list(range(1, 70)) + [100, 257, 1000, 4097, 20000]:
@@ -109,13 +109,17 @@ def test_kmer_table_and_text(ctx):
     assert int(text[0]) == w0
 
 
-def _check_rows(ctx, d: bytes, rows, sa=None):
+def _check_rows(ctx, d: bytes, rows, sa=None, clean=False):
+    """clean=False: against A1, the literal restatement of the reference's binary search.  clean=True: against A3
+    (longest match, leftmost SA index), for reference texts with bytes <= '1': there the reference's own search
+    compares past-the-end as the byte '1' (DistributedRLZ.scala:118-122) and is inconsistent with its SA order."""
     if sa is None:
         sa = orc.sa_build(d)
+    lcp = orc.lcp_build(d, sa) if clean else None
     res, m, gl = ctx.parse_batch(rows, strip_gaps=True, want_gapless=True)
     for h, r in enumerate(rows):
         x = orc.strip_gaps(r).tobytes()
-        a1, _ = orc.encode_literal(d, sa, x)
+        a1 = orc.encode_a3(d, sa, lcp, x) if clean else orc.encode_literal(d, sa, x)[0]
         assert int(m[h]) == len(x)
         assert gl[h].tobytes() == x
         assert orc.lz_bytes(res[h]) == orc.lz_bytes(a1), (h, len(x), res[h][:5], a1[:5])
@@ -240,13 +244,62 @@ def test_submit_wait_and_threads(ctx):
 
 def test_errors(ctx):
     with pytest.raises(D.DrlzError) as e:
-        ctx.build_index(b"ACGTNACGT")
+        ctx.build_index(bytes(range(256)) * 2)          # every byte value in use: no code left for "not in reference"
     assert e.value.code == -5
     c2 = D.Drlz(0)
     with pytest.raises(D.DrlzError) as e:
         c2.parse_batch([b"ACGT"])
     assert e.value.code == -6
     c2.close()
+
+
+@pytest.mark.parametrize("alphabet", [b"ACGTN", b"ACGNTacgnt", bytes(range(50, 100)), b"AB", bytes(range(40, 90)), b"\x00\x01\xfe\xff!"])
+def test_generic_alphabet_parse(ctx, alphabet):
+    """references outside {A,C,G,T}: 4-bit and 8-bit symbol layouts against the byte-wise oracle"""
+    rng = np.random.default_rng(len(alphabet) + 100)
+    for it in range(6):
+        n = int(rng.choice([50, 300, 5000, 70000]))
+        d = bytes(rng.choice(list(alphabet), size=n).astype(np.uint8))
+        if it % 2:
+            d = d + d[n // 4: n // 2] + alphabet[:1] * 300 + d[: n // 3]
+        rows = []
+        for r in range(5):
+            x = bytearray(d[int(rng.integers(0, max(1, len(d) // 2))):])
+            for _ in range(int(rng.integers(0, 30))):
+                p = int(rng.integers(0, len(x) + 1)); op = int(rng.integers(0, 4))
+                if op == 0 and p < len(x): x[p] = int(rng.choice(list(alphabet)))
+                elif op == 1: x.insert(p, int(rng.choice(list(alphabet + b"-#"))))
+                elif op == 2 and p < len(x): del x[p:p + int(rng.integers(1, 9))]
+                else: x[p:p] = b"-" * int(rng.integers(1, 40))
+            rows.append(bytes(x))
+        rows += [d, b"", b"-", d[::-1]]
+        ctx.set_option("kmer", int(rng.integers(0, 4)))
+        ctx.set_option("chunk", int(rng.choice([64, 1024, 8192])))
+        ctx.build_index(d)
+        info = ctx.index_info()
+        assert info["sigma"] == len(set(d)) and info["bits"] == (4 if len(set(d)) <= 16 else 8)
+        _check_rows(ctx, d, rows, clean=min(alphabet) <= ord("1"))
+    ctx.set_option("kmer", 0); ctx.set_option("chunk", 0)
+
+
+def test_generic_alphabet_genome_like(ctx):
+    """ACGT reference with N runs and soft-masked (lower-case) stretches, 2 Mbp, haplotypes with SNPs/indels/gaps"""
+    seed = orc.seed_for(1)
+    d = bytearray(orc.syn_reference(seed, 2_000_000).tobytes())
+    rng = np.random.default_rng(5)
+    for _ in range(5):
+        p = int(rng.integers(0, len(d) - 60000)); L = int(rng.integers(1000, 50000)); d[p:p + L] = b"N" * L
+    for _ in range(8):
+        p = int(rng.integers(0, len(d) - 60000)); L = int(rng.integers(100, 20000)); d[p:p + L] = bytes(d[p:p + L]).lower()
+    d = bytes(d)
+    rows = [r.tobytes() for r in orc.syn_rows(seed, np.frombuffer(d, dtype=np.uint8), 0, 6, 1e-3, 1e-4, 1e-4)]
+    ctx.build_index(d)
+    assert ctx.index_info()["bits"] == 4
+    _check_rows(ctx, d, rows)
+    ms, pos = ctx.matching_stats(rows[1][:3000].replace(b"-", b""))
+    sa = orc.sa_build(d); lcp = orc.lcp_build(d, sa)
+    ms_ref, pos_ref = orc.ms_all(d, sa, lcp, rows[1][:3000].replace(b"-", b""))
+    assert (ms.astype(np.int64) == ms_ref).all() and (pos.astype(np.int64) == pos_ref).all()
 
 
 def test_dense_matching_stats(ctx):

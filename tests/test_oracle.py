@@ -42,7 +42,29 @@ def test_sa_repetitive_medium():
     assert dd.size == sa.size
 
 
-@pytest.mark.parametrize("alphabet,seed", [(b"AC", 1), (b"ACGT", 2), (b"ACGTN", 3)])
+def test_q6_end_of_text_sentinel():
+    """DistributedRLZ.scala:118-122 reads positions past the end of the text as the byte '1'.  Every sequence byte
+    (letters, digits 2-9) is > '1', so the sentinel sorts first like the SA's "shorter suffix first" and A1 is the
+    clean spec.  With reference bytes <= '1' the two orders disagree and A1 can miss the longest match -- still a
+    valid, decodable parse, but trajectory-dependent; the CUDA path follows the clean spec (A3) there."""
+    rng = np.random.default_rng(6)
+    differ = 0
+    for _ in range(300):
+        d, x = random_case(rng, b"()*+", 30, 30)
+        sa = orc.sa_build(d)
+        a1, _ = orc.encode_literal(d, sa, x)
+        a3 = orc.encode_a3(d, sa, orc.lcp_build(d, sa), x)
+        assert a3.tolist() == brute_parse(d, x).tolist()
+        assert orc.decode(d, a1) == x
+        differ += a1.tolist() != a3.tolist()
+    assert differ > 0
+    for _ in range(300):
+        d, x = random_case(rng, b"23Zz", 30, 30)
+        sa = orc.sa_build(d)
+        assert orc.encode_literal(d, sa, x)[0].tolist() == orc.encode_a3(d, sa, orc.lcp_build(d, sa), x).tolist()
+
+
+@pytest.mark.parametrize("alphabet,seed", [(b"AC", 1), (b"ACGT", 2), (b"ACGTN", 3), (b"ACGTNacgtnRYKM", 4)])
 def test_a1_equals_a3_equals_brute(alphabet, seed):
     rng = np.random.default_rng(seed)
     checked = thrown = 0
