@@ -42,7 +42,7 @@ def test_sa_repetitive_medium():
     assert dd.size == sa.size
 
 
-def test_q6_end_of_text_sentinel():
+def test_q5_end_of_text_sentinel():
     """DistributedRLZ.scala:118-122 reads positions past the end of the text as the byte '1'.  Every sequence byte
     (letters, digits 2-9) is > '1', so the sentinel sorts first like the SA's "shorter suffix first" and A1 is the
     clean spec.  With reference bytes <= '1' the two orders disagree and A1 can miss the longest match -- still a

@@ -15,6 +15,9 @@ import bench  # noqa: E402
 
 def main():
     wl = bench.workload(0)
+    for key in ("p_snp", "p_ins", "p_del"):          # e.g. SWEEP_P_SNP=8e-3 SWEEP_P_INS=1e-3 SWEEP_P_DEL=1e-3: config-5-like divergence
+        if os.environ.get("SWEEP_" + key.upper()):
+            wl[key] = float(os.environ["SWEEP_" + key.upper()])
     d = orc.syn_reference(orc.seed_for(wl["cfg"]), wl["n"])
     rows_arr, M, stride = bench.gen_rows(orc, wl, d)
     H = wl["H"]
