@@ -54,7 +54,7 @@ struct drlz_ctx {
     cudaEvent_t ev_stage[12] = {};
     std::string err;
     // options
-    int opt_k = 0; uint32_t opt_chunk = 8192; uint32_t opt_min_cap = 64; uint32_t opt_foreign_cap = 1u << 20; uint64_t opt_group_bytes = 256ull << 20; int opt_lcp = 0;
+    int opt_occ_pack = 8; uint32_t opt_prefetch = 1200; int opt_k = 0; uint32_t opt_chunk = 8192; uint32_t opt_min_cap = 64; uint32_t opt_foreign_cap = 1u << 20; uint64_t opt_group_bytes = 256ull << 20; int opt_lcp = 0;
     // index
     bool have_index = false; uint64_t n = 0; int k = 0; int sa_rounds = 0;
     DevBuf blob, sa, isa, lcp;             // blob = [k-mer table | packed text] (one L2 access-policy window)
@@ -202,6 +202,8 @@ int drlz_set_option(drlz_ctx* c, const char* key, int64_t v) {
     else if (!strcmp(key, "spec_store")) { if (v < 0 || v > 4096) return DRLZ_E_ARG; c->opt_spec_store = (uint32_t)v; }
     else if (!strcmp(key, "tickets")) c->opt_tickets = v != 0;
     else if (!strcmp(key, "predict")) c->opt_predict = v != 0;
+    else if (!strcmp(key, "occ_pack")) c->opt_occ_pack = (int)v;
+    else if (!strcmp(key, "prefetch")) { if (v < 0 || v > (1 << 20)) return DRLZ_E_ARG; c->opt_prefetch = (uint32_t)v; }
     else if (!strcmp(key, "min_cap")) { if (v < 0 || v > 0x7FFFFFFF) return DRLZ_E_ARG; c->opt_min_cap = v ? (uint32_t)v : 64; }
     else if (!strcmp(key, "foreign_cap")) { if (v < 0 || v > 0x7FFFFFFF) return DRLZ_E_ARG; c->opt_foreign_cap = v ? (uint32_t)v : (1u << 20); }
     else return DRLZ_E_ARG;
@@ -310,7 +312,7 @@ static int run_device_group(drlz_ctx* c, const uint8_t* rows_dev, const uint64_t
         job.rows = rows_dev; job.row_off = d_row_off; job.cols = d_cols; job.H = H; job.tiles_per_row = T; job.strip = strip;
         job.desc_cnt = c->desc_cnt.as<uint64_t>(); job.desc_exc = c->desc_exc.as<uint64_t>();
         job.tile_counter = c->tile_counter.as<uint32_t>(); job.X = c->X.as<uint64_t>(); job.xoff = d_xoff;
-        job.use_tickets = c->opt_tickets;
+        job.occ = c->opt_occ_pack; job.prefetch = c->opt_prefetch; job.use_tickets = c->opt_tickets;
         job.m_out = c->mdev.as<uint64_t>(); job.exc_cnt = c->exccnt.as<uint64_t>();
         job.exc_pos = c->excpos.as<uint32_t>(); job.exc_byte = c->excbyte.as<uint8_t>(); job.exc_stride = exc_stride;
         job.flags = c->flags.as<uint32_t>();
@@ -488,7 +490,7 @@ int drlz_build_index(drlz_ctx* c, const uint8_t* ref, uint64_t n) {
         job.rows = c->stage[0].as<uint8_t>(); job.row_off = dm; job.cols = dm + 1; job.H = 1; job.tiles_per_row = T; job.strip = 0;
         job.desc_cnt = c->desc_cnt.as<uint64_t>(); job.desc_exc = c->desc_exc.as<uint64_t>();
         job.tile_counter = c->tile_counter.as<uint32_t>(); job.X = c->d_text; job.xoff = dm + 2;
-        job.use_tickets = 1;
+        job.occ = c->opt_occ_pack; job.prefetch = 0; job.use_tickets = 1;
         job.m_out = c->mdev.as<uint64_t>(); job.exc_cnt = c->exccnt.as<uint64_t>();
         job.exc_pos = c->excpos.as<uint32_t>(); job.exc_byte = c->excbyte.as<uint8_t>(); job.exc_stride = 64;
         job.flags = c->flags.as<uint32_t>(); job.gapless = nullptr; job.gapless_off = dm + 3;

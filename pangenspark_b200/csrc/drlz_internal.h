@@ -23,6 +23,8 @@ struct PackJob {
     uint64_t* desc_cnt;           // [H*tiles_per_row] look-back descriptors: non-gap bytes   (zeroed by launch_pack)
     uint64_t* desc_exc;           // [H*tiles_per_row] look-back descriptors: exceptions
     uint32_t* tile_counter;       // [1] dynamic tile ids
+    int occ;                      // min CTAs per SM the kernel is compiled for (6 or 8)
+    uint32_t prefetch;            // L2 prefetch distance in tiles (0 = off): CTA i prefetches the bytes of tile i + prefetch
     int use_tickets;              // 1: tile ids from the atomic counter; 0: from blockIdx (dispatch order), guarded by a timeout
     uint64_t* X;                  // packed output, zero-filled by the caller
     const uint64_t* xoff;         // [H] word offset of haplotype h inside X (device)
