@@ -24,9 +24,18 @@
 
 namespace drlz {
 
+// The symbol width is a run-time field of the index (2, 4 or 8 bits), but nearly every batch runs on a pure ACGT
+// index: the hot kernels carry a copy of their body in which the width is a compile-time constant (shifts and
+// masks fold, the generic key arithmetic disappears) and fall back to the run-time body otherwise.
+#define DRLZ_WITH_BL(pv, PV, ...)                                                               \
+    do {                                                                                         \
+        if ((pv).ix.bl == 1) { ParseView PV = (pv); PV.ix.bl = 1; PV.ix.sigma = 4; __VA_ARGS__; } \
+        else { const ParseView& PV = (pv); __VA_ARGS__; }                                        \
+    } while (0)
+
 __global__ void __launch_bounds__(128) k_link(ParseView pv) {
     uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g < pv.n_chunks) link_chunk(pv, g);
+    if (g < pv.n_chunks) DRLZ_WITH_BL(pv, q, link_chunk(q, g));
 }
 
 __global__ void k_rank(const uint32_t* __restrict__ link_in, const uint32_t* __restrict__ run_in, uint32_t* link_out,
@@ -37,14 +46,15 @@ __global__ void k_rank(const uint32_t* __restrict__ link_in, const uint32_t* __r
 
 __global__ void __launch_bounds__(128) k_hint(ParseView pv, int64_t* hint, uint32_t nq) {
     uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q < nq) hint_group(pv, hint, q);
+    if (q < nq) DRLZ_WITH_BL(pv, v, hint_group(v, hint, q));
 }
 
 // D: one warp per chunk; lane l compares packed word l of each 1024-base slab (the haplotype side is word aligned
 // because chunks start at multiples of 32 bases), so both streams are read with coalesced 256-byte requests at
 // 32 active lanes -- this is the whole streaming compare of the parse, done once.  Mismatching words are decoded
 // in lane order (ballot), which keeps the offsets sorted.  Same result as diag_scan_chunk().
-__global__ void __launch_bounds__(128) k_diag_w(ParseView pv) {
+template <int BL>        // BL = 1: 2-bit symbols known at compile time; 0: width read from the index
+__global__ void __launch_bounds__(128, 16) k_diag_w(ParseView pv) {
     const uint32_t g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (g >= pv.n_chunks) return;
@@ -62,32 +72,39 @@ __global__ void __launch_bounds__(128) k_diag_w(ParseView pv) {
     const uint32_t p = (uint32_t)p0, len = (uint32_t)(e - s);
     const uint32_t avail = (uint32_t)pv.ix.n - p;
     const uint32_t cmplen = len < avail ? len : avail;
-    const uint32_t bl = pv.ix.bl, sl = 6 - bl, spw = 1u << sl, B = 1u << bl, slab = 32u << sl;   // slab = 32 words
+    const uint32_t bl = BL ? (uint32_t)BL : pv.ix.bl, sl = 6 - bl, spw = 1u << sl, B = 1u << bl, slab = 32u << sl;   // slab = 32 words
     const uint64_t* __restrict__ xw = hv.x + (s >> sl);
-    const uint64_t* __restrict__ D = pv.ix.text;
+    // the reference side: same word grid shifted by a bit offset that is constant along the diagonal
+    const uint64_t* __restrict__ Dw = pv.ix.text + (p >> sl);
+    const uint32_t dsh = (p & (spw - 1)) << bl;                        // 0..62
+    const uint32_t nfull = cmplen >> sl, rem = cmplen & (spw - 1);     // whole words, symbols of the last partial word
+    const uint32_t nwords = nfull + (rem ? 1u : 0u);
+    const uint64_t tailmask = rem ? ~0ull << (64 - B * rem) : ~0ull;
     uint32_t cnt = 0, V = len;
     bool full = false;
-    for (uint32_t o0 = 0; o0 < cmplen && !full; o0 += 4 * slab) {    // 4 slabs of 32 words per iteration
-        uint64_t xr[4];
+    constexpr int kSlabs = 4;                                        // 4 slabs of 32 words per iteration, all 12 loads of a
+    for (uint32_t w0 = 0; w0 < nwords && !full; w0 += 32 * kSlabs) { // lane in flight at once (8 slabs: same time, 50 registers)
+        uint64_t xr[kSlabs];
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {                                // all 8 loads of the lane are independent
-            const uint32_t o = o0 + slab * r + spw * (uint32_t)lane;
+        for (int r = 0; r < kSlabs; ++r) {
+            const uint32_t wi = w0 + 32u * r + (uint32_t)lane;
             xr[r] = 0;
-            if (o < cmplen) {
-                xr[r] = xw[o >> sl] ^ get64u(D, p + o, bl);
-                uint32_t nb = cmplen - o < spw ? cmplen - o : spw;
-                if (nb < spw) xr[r] &= ~0ull << (64 - B * nb);
+            if (wi < nwords) {
+                const uint64_t a = Dw[wi], b = Dw[wi + 1];           // the text has two zero pad words
+                const uint64_t d = (a << dsh) | ((b >> 1) >> (63 - dsh));
+                xr[r] = xw[wi] ^ d;
+                if (wi == nfull) xr[r] &= tailmask;
             }
         }
         if (!__any_sync(0xffffffffu, (xr[0] | xr[1] | xr[2] | xr[3]) != 0)) continue;
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
+        for (int r = 0; r < kSlabs; ++r) {
             unsigned bal = __ballot_sync(0xffffffffu, xr[r] != 0);
             while (bal && !full) {
                 const int src = __ffs(bal) - 1;
                 bal &= bal - 1;
                 uint64_t w = __shfl_sync(0xffffffffu, xr[r], src);
-                const uint32_t ob = o0 + slab * r + spw * (uint32_t)src;
+                const uint32_t ob = (w0 + 32u * r + (uint32_t)src) << sl;
                 while (w) {
                     uint32_t b = (uint32_t)(clz64(w) >> bl);
                     if (cnt == (uint32_t)kMmMax) { V = ob + b; full = true; break; }
@@ -114,17 +131,17 @@ __global__ void __launch_bounds__(128, 8) k_snp(ParseView pv) {
 
 __global__ void __launch_bounds__(128) k_resolve(ParseView pv) {
     uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g < pv.n_chunks) resolve_chunk(pv, g);
+    if (g < pv.n_chunks) DRLZ_WITH_BL(pv, q, resolve_chunk(q, g));
 }
 template <int MINB>
 __global__ void __launch_bounds__(128, MINB) k_spec(ParseView pv) {
     uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g < pv.n_chunks) spec_parse_chunk(pv, g);
+    if (g < pv.n_chunks) DRLZ_WITH_BL(pv, q, spec_parse_chunk(q, g));
 }
 template <int MINB>
 __global__ void __launch_bounds__(128, MINB) k_fix(ParseView pv, uint32_t round) {
     uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r < pv.n_chunks * kAltSlots) fix_parse_record(pv, r / kAltSlots, (int)(r % kAltSlots), round);
+    if (r < pv.n_chunks * kAltSlots) DRLZ_WITH_BL(pv, q, fix_parse_record(q, r / kAltSlots, (int)(r % kAltSlots), round));
 }
 
 // ---- J: marking the true chain, two levels ------------------------------------------------------------------
@@ -272,7 +289,8 @@ int parse_stage_count(ParseBuffers& pb, cudaStream_t s, int* rounds_out, cudaEve
         if (pb.mm && pv.chunk_shift >= 5 && pv.chunk_shift <= 15) {   // D: mismatch lists along the hinted diagonals
             pv.mm = pb.mm;
             g_launches += 1;
-            k_diag_w<<<(unsigned)(((uint64_t)NC * 32 + 127) / 128), 128, 0, s>>>(pv);
+            if (pv.ix.bl == 1) k_diag_w<1><<<(unsigned)(((uint64_t)NC * 32 + 127) / 128), 128, 0, s>>>(pv);
+            else k_diag_w<0><<<(unsigned)(((uint64_t)NC * 32 + 127) / 128), 128, 0, s>>>(pv);
             if (pb.ml) {                    // S: the short phrase after every listed mismatch, looked up convergently
                 pv.ml = pb.ml;
                 g_launches += 1;
