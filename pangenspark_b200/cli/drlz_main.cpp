@@ -30,18 +30,31 @@
 #include <thread>
 #include <vector>
 
+#include <zlib.h>
+
 #include "drlz.h"
 
+// Reads a file whole; gzip files (the legacy flow globs *.NN.gz, create.sh:27 -- Spark's text reader inflates them
+// transparently) are inflated, anything else is read as it is (zlib's gzread passes plain bytes through).
 static bool read_file(const std::string& path, std::vector<uint8_t>& out) {
-    FILE* f = fopen(path.c_str(), "rb");
+    gzFile f = gzopen(path.c_str(), "rb");
     if (!f) return false;
-    fseek(f, 0, SEEK_END);
-    long sz = ftell(f);
-    fseek(f, 0, SEEK_SET);
-    out.resize(sz > 0 ? (size_t)sz : 0);
-    size_t got = sz > 0 ? fread(out.data(), 1, (size_t)sz, f) : 0;
-    fclose(f);
-    return got == out.size();
+    gzbuffer(f, 1 << 20);
+    struct stat st;
+    size_t cap = stat(path.c_str(), &st) == 0 && st.st_size > 0 ? (size_t)st.st_size + 1 : (size_t)1 << 16;
+    out.resize(cap);
+    size_t got = 0;
+    for (;;) {
+        if (got == out.size()) out.resize(out.size() * 2);
+        size_t want = out.size() - got;
+        if (want > (1u << 30)) want = 1u << 30;
+        int n = gzread(f, out.data() + got, (unsigned)want);
+        if (n < 0) { gzclose(f); return false; }
+        if (n == 0) break;
+        got += (size_t)n;
+    }
+    out.resize(got);
+    return gzclose(f) == Z_OK;
 }
 
 static bool write_file_atomic(const std::string& path, const void* a, size_t na, const void* b = nullptr, size_t nb = 0,

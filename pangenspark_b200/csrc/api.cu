@@ -62,11 +62,11 @@ struct drlz_ctx {
     size_t blob_bytes = 0, text_bytes = 0, uniq_bytes = 0, tab_bytes = 0;
     uint32_t bl = 1, sigma = 4;        // symbol width (log2 bits) and alphabet size of the index
     int opt_predict = 1;
-    cudaStream_t l2_stream = nullptr; int opt_l2persist = 0; int opt_occ = 8; int opt_occ_fix = 10; int opt_tickets = 1; int opt_hint = 1; int opt_diag = 1; int opt_snp = 0; uint32_t opt_spec_store = 0;
+    cudaStream_t l2_stream = nullptr; int opt_l2persist = 0; int opt_occ = 8; int opt_occ_fix = 10; int opt_tickets = 1; int opt_hint = 1; int opt_diag = 1; uint32_t opt_spec_store = 0;
     double idx_ms[5] = {0, 0, 0, 0, 0};
     // batch scratch (grow-only)
     DevBuf stage[2], meta_dev, desc_cnt, desc_exc, tile_counter, X, mdev, exccnt, excpos, excbyte,
-        flags, haps, gapless, gtile_cnt, gtile_exc, gtile_off, gtile_excoff, gscan_tmp, chunk_hap, first_pos, first_len, run_a, run_b, link_a, link_b, open_i, open_pos, open_len, spec_cnt, spec_exit, alt_entry, alt_cnt, alt_exit, alt_round, alt_own, alt_merge, spec_ph, alt_ph, hint, mm, ml, true_slot, counters, jump_a,
+        flags, haps, gapless, gtile_cnt, gtile_exc, gtile_off, gtile_excoff, gscan_tmp, chunk_hap, first_pos, first_len, run_a, run_b, link_a, link_b, open_i, open_pos, open_len, spec_cnt, spec_exit, alt_entry, alt_cnt, alt_exit, alt_round, alt_own, alt_merge, spec_ph, alt_ph, hint, mm, true_slot, counters, jump_a,
         jump_b, mark, true_cnt, true_entry, true_off, scan_tmp, hap_pairs, out, ms_a, ms_b;
     HostBuf meta_host, small_host;
     uint64_t exc_stride_hint = 0;
@@ -166,7 +166,7 @@ void drlz_destroy(drlz_ctx* c) {
     DevBuf* bufs[] = {&c->blob, &c->sa, &c->isa, &c->lcp, &c->stage[0], &c->stage[1], &c->meta_dev, &c->desc_cnt,
                       &c->desc_exc, &c->tile_counter, &c->X, &c->mdev, &c->exccnt, &c->excpos,
                       &c->excbyte, &c->flags, &c->haps, &c->gapless, &c->gtile_cnt, &c->gtile_exc, &c->gtile_off, &c->gtile_excoff, &c->gscan_tmp, &c->chunk_hap, &c->first_pos, &c->first_len, &c->run_a, &c->run_b, &c->link_a, &c->link_b, &c->open_i, &c->open_pos, &c->open_len, &c->spec_cnt, &c->spec_exit,
-                      &c->alt_entry, &c->alt_cnt, &c->alt_exit, &c->alt_round, &c->alt_own, &c->alt_merge, &c->spec_ph, &c->alt_ph, &c->hint, &c->mm, &c->ml, &c->true_slot, &c->counters, &c->jump_a, &c->jump_b,
+                      &c->alt_entry, &c->alt_cnt, &c->alt_exit, &c->alt_round, &c->alt_own, &c->alt_merge, &c->spec_ph, &c->alt_ph, &c->hint, &c->mm, &c->true_slot, &c->counters, &c->jump_a, &c->jump_b,
                       &c->mark, &c->true_cnt, &c->true_entry, &c->true_off, &c->scan_tmp, &c->hap_pairs, &c->out, &c->ms_a, &c->ms_b};
     for (DevBuf* b : bufs) b->release();
     c->meta_host.release(); c->small_host.release();
@@ -198,7 +198,6 @@ int drlz_set_option(drlz_ctx* c, const char* key, int64_t v) {
     else if (!strcmp(key, "occ_fix")) c->opt_occ_fix = (int)v;
     else if (!strcmp(key, "hint")) c->opt_hint = v != 0;
     else if (!strcmp(key, "diag")) c->opt_diag = v != 0;
-    else if (!strcmp(key, "snp")) c->opt_snp = v != 0;
     else if (!strcmp(key, "spec_store")) { if (v < 0 || v > 4096) return DRLZ_E_ARG; c->opt_spec_store = (uint32_t)v; }
     else if (!strcmp(key, "tickets")) c->opt_tickets = v != 0;
     else if (!strcmp(key, "predict")) c->opt_predict = v != 0;
@@ -336,7 +335,7 @@ static int run_device_group(drlz_ctx* c, const uint8_t* rows_dev, const uint64_t
         uint32_t spec_store = c->opt_spec_store ? c->opt_spec_store : (C / 32 > 16 ? C / 32 : 16);   // 2 phrases per SNP: covers ~1.5 % divergence
         if (single_chunk) spec_store = 1;
         CK(c, c->spec_ph.ensure((size_t)NC * spec_store * 8 + 8)); CK(c, c->alt_ph.ensure(na * kAltStore * 8 + 8));
-        CK(c, c->hint.ensure(((size_t)NC / kHintGroup + 2) * 8)); CK(c, c->mm.ensure(((size_t)NC + 1) * kMmStride * 2)); CK(c, c->ml.ensure(((size_t)NC + 1) * kMmMax * 8));
+        CK(c, c->hint.ensure(((size_t)NC / kHintGroup + 2) * 8)); CK(c, c->mm.ensure(((size_t)NC + 1) * kMmStride * 2));
         CK(c, c->true_slot.ensure((size_t)NC * 4 + 4));
         CK(c, c->alt_round.ensure(na * 4 + 4)); CK(c, c->counters.ensure(sizeof(uint32_t) * (2 + kMaxRounds)));
         CK(c, c->jump_a.ensure(nn * 4 + 4)); CK(c, c->jump_b.ensure(nn * 4 + 4)); CK(c, c->mark.ensure(nn + 4));
@@ -359,9 +358,8 @@ static int run_device_group(drlz_ctx* c, const uint8_t* rows_dev, const uint64_t
         pb.pv.alt_exit = c->alt_exit.as<uint32_t>(); pb.pv.alt_round = c->alt_round.as<uint32_t>();
         pb.pv.alt_own = c->alt_own.as<uint32_t>(); pb.pv.alt_merge = c->alt_merge.as<uint32_t>();
         pb.pv.spec_ph = c->spec_ph.as<uint2>(); pb.pv.alt_ph = c->alt_ph.as<uint2>();
-        pb.pv.spec_store = spec_store; pb.pv.hint = nullptr; pb.pv.mm = nullptr; pb.pv.ml = nullptr;
+        pb.pv.spec_store = spec_store; pb.pv.hint = nullptr; pb.pv.mm = nullptr;
         pb.mm = (c->opt_hint && c->opt_diag && !single_chunk) ? c->mm.as<uint16_t>() : nullptr;
-        pb.ml = (pb.mm && c->opt_snp) ? c->ml.as<uint2>() : nullptr;
         pb.hint = (c->opt_hint && !single_chunk) ? c->hint.as<int64_t>() : nullptr;
         pb.true_slot = c->true_slot.as<uint32_t>();
         pb.pv.counters = c->counters.as<uint32_t>();

@@ -72,7 +72,6 @@ struct ParseBuffers {
     int occ_fix;                  // same for k_fix
     int64_t* hint;                // [ceil(NC / kHintGroup)] diagonal hints (null = no hint pass)
     uint16_t* mm;                 // [NC*kMmStride] mismatch lists (null = no diagonal pre-scan)
-    uint2* ml;                    // [NC*kMmMax] phrases at the listed mismatch positions (null = looked up inline)
     uint32_t* link_b;             // [NC] second buffers of the list ranking
     uint32_t* run_b;              // [NC]
     uint32_t* jump_a;             // [NC*(kAltSlots+1)]

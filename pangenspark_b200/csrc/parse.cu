@@ -2,7 +2,6 @@
 //
 //   k_hint      H : a 64-base lookup at every chunk start gives the chunk's predicted diagonal
 //   k_diag_w    D : mismatch offsets of every chunk along that diagonal (the streaming compare, done once, up front)
-//   k_snp       S : the phrase at every listed mismatch position (the short phrase after a SNP), one thread each
 //   k_spec      P1: one thread per chunk, speculative greedy parse from the chunk's first base with chunk-capped
 //                   lookups; phrases stored; the first phrase doubles as stage A's phrase at the chunk start
 //   k_link      A : open first phrases linked to the chunk their match continues in
@@ -18,7 +17,9 @@
 //
 // Two warp-synchronous variants of k_spec (a lock-step per-lane state machine, and cooperative 1024-base
 // extension) were built and measured slower (2.7 ms / 1.6 ms vs 1.2 ms per step): the parse is bound by chains
-// of dependent cache misses, and divergent scalar lanes overlap those chains better (profiles/README.md).
+// of dependent cache misses, and divergent scalar lanes overlap those chains better (profiles/README.md).  So was
+// a kernel that did the lookups at the listed mismatch positions up front, one thread each (0.35 ms for 2.3 M
+// lookups, k_spec only 0.08 ms faster).
 #include "drlz_internal.h"
 #include "scan.cuh"
 
@@ -120,13 +121,6 @@ __global__ void __launch_bounds__(128, 16) k_diag_w(ParseView pv) {
         else { if (lane == 0) mm[2 + cnt] = (uint16_t)cmplen; ++cnt; }
     }
     if (lane == 0) { mm[0] = (uint16_t)cnt; mm[1] = (uint16_t)V; }
-}
-
-// S: one thread per listed mismatch position
-__global__ void __launch_bounds__(128, 8) k_snp(ParseView pv) {
-    uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t g = (uint32_t)(idx / kMmMax), t = (uint32_t)(idx % kMmMax);
-    if (g < pv.n_chunks) snp_lookup(pv, g, t);
 }
 
 __global__ void __launch_bounds__(128) k_resolve(ParseView pv) {
@@ -291,13 +285,8 @@ int parse_stage_count(ParseBuffers& pb, cudaStream_t s, int* rounds_out, cudaEve
             g_launches += 1;
             if (pv.ix.bl == 1) k_diag_w<1><<<(unsigned)(((uint64_t)NC * 32 + 127) / 128), 128, 0, s>>>(pv);
             else k_diag_w<0><<<(unsigned)(((uint64_t)NC * 32 + 127) / 128), 128, 0, s>>>(pv);
-            if (pb.ml) {                    // S: the short phrase after every listed mismatch, looked up convergently
-                pv.ml = pb.ml;
-                g_launches += 1;
-                k_snp<<<(unsigned)(((uint64_t)NC * kMmMax + 127) / 128), 128, 0, s>>>(pv);
-            } else pv.ml = nullptr;
-        } else { pv.mm = nullptr; pv.ml = nullptr; }
-    } else { pv.hint = nullptr; pv.mm = nullptr; pv.ml = nullptr; }
+        } else pv.mm = nullptr;
+    } else { pv.hint = nullptr; pv.mm = nullptr; }
     if (ev) cudaEventRecord(ev[5], s);
     g_launches += 1;
     if (pb.occ >= 16) k_spec<16><<<(NC + 127) / 128, 128, 0, s>>>(pv);

@@ -313,7 +313,6 @@ struct ParseView {
     uint32_t spec_store;            // phrases of a chunk's speculative parse kept for emission
     const int64_t* hint;            // [ceil(NC / kHintGroup)] predicted diagonal of each chunk group (kNoDiag = none); may be null
     uint16_t* mm;                   // [NC*kMmStride] mismatch offsets of each chunk along its hinted diagonal; may be null
-    uint2* ml;                      // [NC*kMmMax] phrase (pos, len | open << 31) at each listed mismatch position; may be null
     uint2* alt_ph;                  // [NC*kAltSlots*kAltStore] own phrases of the alternative records
     uint32_t* counters;             // [0] overflow flag, [1 + r] records created for round r
 };
@@ -383,22 +382,6 @@ DRLZ_HD Match phrase_capped(const ParseView& pv, const HapView& hv, uint64_t i, 
     uint64_t to_end = (((i >> pv.chunk_shift) + 1) << pv.chunk_shift) - i;
     uint32_t cap = to_end > (uint64_t)pv.min_cap ? (to_end > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)to_end) : pv.min_cap;
     Match mt;
-    if (pv.ml && g != kEmpty) {                  // the lookup at a listed mismatch position was done up front (snp_lookup)
-        const uint16_t* mm = pv.mm + (size_t)g * kMmStride;
-        uint32_t cnt = mm[0], off = (uint32_t)(i - s);
-        if (off < mm[1])
-            for (uint32_t t = 0; t < cnt; ++t) {
-                uint32_t mo = mm[2 + t];
-                if (mo > off) break;
-                if (mo == off) {
-                    uint2 r = pv.ml[(size_t)g * kMmMax + t];
-                    mt.pos = r.x; mt.len = r.y & 0x7FFFFFFFu;
-                    *open = (r.y >> 31) != 0;
-                    if (mt.len >= kDiagMinLen) *diag = (int64_t)mt.pos - (int64_t)i;
-                    return mt;
-                }
-            }
-    }
     if (pv.ix.uniq && *diag != kNoDiag) {
         int64_t p64 = (int64_t)i + *diag;
         if (p64 >= 0 && (uint64_t)p64 < pv.ix.n) {
@@ -566,29 +549,6 @@ DRLZ_HD void diag_scan_chunk(const ParseView& pv, uint32_t g) {
         if (cnt == (uint32_t)kMmMax) V = cmplen; else mm[2 + cnt++] = (uint16_t)cmplen;
     }
     mm[0] = (uint16_t)cnt; mm[1] = (uint16_t)V;
-}
-
-// S: the phrase at the t-th listed mismatch position of chunk g (the short phrase that follows a SNP): exactly what
-// phrase_capped() computes there, done by one thread per position in its own kernel so that every lane of a warp
-// runs the same lookup code.
-DRLZ_HD void snp_lookup(const ParseView& pv, uint32_t g, uint32_t t) {
-    const uint16_t* mm = pv.mm + (size_t)g * kMmStride;
-    if (t >= mm[0]) return;
-    uint32_t h = pv.chunk_hap[g];
-    const HapView& hv = pv.haps[h];
-    uint64_t s = (uint64_t)(g - pv.hap_chunk_base[h]) << pv.chunk_shift;
-    uint64_t i = s + mm[2 + t];
-    uint2* out = pv.ml + (size_t)g * kMmMax + t;
-    uint32_t cur = hv.n_exc ? exc_lower_bound(hv, i) : 0;
-    uint64_t stop = stop_after(hv, i, &cur);
-    if (stop == i) { *out = make_uint2(hv.exc_byte[cur], 0u); return; }
-    uint32_t maxlen = (uint32_t)(stop - i);
-    uint64_t to_end = (((i >> pv.chunk_shift) + 1) << pv.chunk_shift) - i;
-    uint32_t cap = to_end > (uint64_t)pv.min_cap ? (to_end > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)to_end) : pv.min_cap;
-    bool open;
-    Match mt = lookup(pv.ix, hv.x, i, maxlen, cap, &open);
-    if (mt.len == 0) mt.pos = (uint32_t)pv.ix.c2b[base_at(hv.x, i, pv.ix.bl)];
-    *out = make_uint2(mt.pos, mt.len | (open ? 0x80000000u : 0u));
 }
 
 // P1 for global chunk g: speculative greedy parse from the chunk's first base with chunk-capped lookups.  Only

@@ -38,14 +38,23 @@ def shard(items, rank: int, world: int):
 
 def read_reference(path: str) -> bytes:
     """DistributedRLZ.scala:61: all lines concatenated."""
-    with open(path, "rb") as f:
-        raw = f.read()
+    raw = read_bytes(path)
     return raw.replace(b"\n", b"").replace(b"\r", b"")
 
 
-def read_row(path: str) -> bytes:
+def read_bytes(path: str) -> bytes:
+    """gzip files (the legacy flow globs *.NN.gz, create.sh:27; Spark's text reader inflates them transparently)
+    are inflated, anything else is read as it is."""
     with open(path, "rb") as f:
         raw = f.read()
+    if raw[:2] == b"\x1f\x8b":
+        import gzip
+        raw = gzip.decompress(raw)
+    return raw
+
+
+def read_row(path: str) -> bytes:
+    raw = read_bytes(path)
     body = raw.rstrip(b"\r\n")
     if b"\n" in body:
         raise ValueError(f"{path}: more than one line; every line would overwrite the same .lz in the reference "

@@ -124,19 +124,16 @@ int emu_parse(const uint8_t* ref, uint64_t n, const int64_t* sa64, int k, uint32
     std::vector<uint2> spec_ph((size_t)NC * spec_store), alt_ph((size_t)NC * kAltSlots * kAltStore);
     std::vector<int64_t> hint(NC / kHintGroup + 1, kNoDiag);
     std::vector<uint16_t> mm((size_t)NC * kMmStride + 16, 0);
-    std::vector<uint2> ml((size_t)NC * kMmMax + 1);
     ParseView pv{ix, haps.data(), chunk_hap.data(), base.data(), chunk, chunk_shift, NC, min_cap, foreign_cap,
                  first_pos.data(), first_len.data(), run_a.data(), link_a.data(), open_i.data(), open_pos.data(), open_len.data(), spec_cnt.data(), spec_exit.data(),
                  alt_entry.data(), alt_cnt.data(), alt_exit.data(), alt_round.data(), alt_own.data(), alt_merge.data(),
-                 spec_ph.data(), spec_store, nullptr, nullptr, nullptr, alt_ph.data(), counters.data()};
+                 spec_ph.data(), spec_store, nullptr, nullptr, alt_ph.data(), counters.data()};
     uint32_t maxc0 = 1;
     for (int h = 0; h < H; ++h) if (base[h + 1] - base[h] > maxc0) maxc0 = base[h + 1] - base[h];
     if (use_uniq && chunk_shift >= 5 && chunk_shift <= 15) {
         for (uint32_t q = 0; q * kHintGroup < NC; ++q) hint_group(pv, hint.data(), q);
         pv.hint = hint.data(); pv.mm = mm.data();
         for (uint32_t g = 0; g < NC; ++g) diag_scan_chunk(pv, g);
-        pv.ml = ml.data();
-        for (uint32_t g = 0; g < NC; ++g) for (uint32_t t = 0; t < (uint32_t)kMmMax; ++t) snp_lookup(pv, g, t);
     }
     for (uint32_t g = 0; g < NC; ++g) spec_parse_chunk(pv, g);
     for (uint32_t g = 0; g < NC; ++g) link_chunk(pv, g);

@@ -38,3 +38,25 @@ def test_python_mirror(tmp_path):
                         tmp + "/msa/*.01", "", tmp + "/drlz", tmp + "/gapless"], capture_output=True, text=True, cwd=ROOT, timeout=300)
     assert r.returncode == 0, r.stderr
     check_outputs(tmp, d, rows)
+
+
+def test_native_cli_gzip_rows(tmp_path):
+    """gzip rows through the native CLI (zlib): same records as the plain files"""
+    import gzip
+    from oracle import oracle as orc
+    tmp = str(tmp_path)
+    d, rows = make_dataset(tmp, H=3, n=100_000)
+    for h in range(3):
+        src = os.path.join(tmp, "msa", "H%05d.01" % h)
+        with open(src, "rb") as f, gzip.open(src + ".gz", "wb") as g:
+            g.write(f.read())
+        os.remove(src)
+    exe = os.path.join(ROOT, "pangenspark_b200", "bin", "drlz")
+    r = subprocess.run([exe, tmp + "/radix", tmp + "/ref.txt", tmp + "/msa/*.01.gz", "", tmp + "/drlz", tmp + "/gapless"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    sa = orc.sa_build(d)
+    for h in range(3):
+        x = orc.strip_gaps(rows[h]).tobytes()
+        lz = open(os.path.join(tmp, "drlz", "H%05d.01.gz.lz" % h), "rb").read()
+        assert lz == orc.lz_bytes(orc.encode_literal(d, sa, x)[0])

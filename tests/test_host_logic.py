@@ -73,6 +73,28 @@ def test_merged_outputs(tmp_path, monkeypatch):
     assert fa.count(b">") == 4 and fa.startswith(b">H00000.01\n")
 
 
+def test_gzip_rows(tmp_path):
+    """legacy inputs are gzip files (create.sh:27 globs *.NN.gz); the output keeps the input's full basename + .lz
+    (DistributedRLZ.scala:257)"""
+    import gzip
+    tmp = str(tmp_path)
+    d, rows = make_dataset(tmp, H=3)
+    for h in range(3):
+        src = os.path.join(tmp, "msa", "H%05d.01" % h)
+        with open(src, "rb") as f, gzip.open(src + ".gz", "wb") as g:
+            g.write(f.read())
+        os.remove(src)
+    rc = drz.main([tmp + "/radix", tmp + "/ref.txt", tmp + "/msa/*.01.gz", "", tmp + "/drlz", tmp + "/gapless"],
+                  parser=oracle_parser, rank=0, world=1)
+    assert rc == 0
+    sa = orc.sa_build(d)
+    for h in range(3):
+        x = orc.strip_gaps(rows[h]).tobytes()
+        lz = open(os.path.join(tmp, "drlz", "H%05d.01.gz.lz" % h), "rb").read()
+        assert lz == orc.lz_bytes(orc.encode_literal(d, sa, x)[0])
+        assert open(os.path.join(tmp, "gapless", "part-%05d" % h), "rb").read() == b">H%05d.01.gz\n" % h + x + b"\n"
+
+
 def test_shards_cover_everything():
     for n in range(0, 40):
         for w in (1, 2, 3, 8):
