@@ -123,8 +123,7 @@ DRLZ_HD uint64_t get64u(const uint64_t* __restrict__ w, uint32_t pos, uint32_t b
 }
 
 // lcp(x[i..i+maxlen), d[p..n)) and whether the suffix d[p..] sorts before the pattern; xw0 = get64u(X, i).
-// The first 32 bases are compared alone (most probes differ there); longer matches stream 128 bases per
-// iteration (4 words per stream with a carry word, 8 independent loads in flight, one OR-reduced test).
+// The first word is compared alone (most probes differ there); longer matches stream 4 words per iteration.
 DRLZ_HD uint32_t cmp_suffix_w(uint64_t xw0, const uint64_t* __restrict__ X, uint32_t i, const uint64_t* __restrict__ D,
                               uint32_t p, uint32_t n, uint32_t maxlen, bool* less, uint32_t bl) {
     const uint32_t sl = 6 - bl, spw = 1u << sl;          // symbols per word
@@ -138,27 +137,33 @@ DRLZ_HD uint32_t cmp_suffix_w(uint64_t xw0, const uint64_t* __restrict__ X, uint
         if (xr) { l = (uint32_t)(clz64(xr) >> bl); diff_less = b < xw0; found = true; }
         else l = spw;
     }
-    if (!found && l + 4 * spw <= lim) {
-        const unsigned shx = ((i + l) & (spw - 1)) << bl, shd = ((p + l) & (spw - 1)) << bl;
-        const uint64_t* xp = X + ((i + l) >> sl);
-        const uint64_t* dp = D + ((p + l) >> sl);
-        uint64_t cx = xp[0], cd = dp[0];
-        while (l + 4 * spw <= lim) {
-            uint64_t x1 = xp[1], x2 = xp[2], x3 = xp[3], x4 = xp[4];
+    if (!found && l < lim) {
+        // Continue on the grid of the haplotype's packed words: position i + l lies q symbols into a word, and those q
+        // symbols were just verified equal, so whole haplotype words are compared and only the reference is shifted
+        // onto that grid (one funnel shift per word).
+        const uint32_t q = (i + l) & (spw - 1);
+        uint32_t base = l - q;                                // pattern offset of that word's first symbol (l == spw > q)
+        const uint64_t* xp = X + ((i + base) >> sl);
+        const uint32_t pd = p + base;
+        const unsigned shd = (pd & (spw - 1)) << bl;
+        const uint64_t* dp = D + (pd >> sl);
+        uint64_t cd = dp[0];
+        while (base + 4 * spw <= lim) {                       // 128 bases per iteration, 8 independent loads in flight
+            uint64_t x0 = xp[0], x1 = xp[1], x2 = xp[2], x3 = xp[3];
             uint64_t d1 = dp[1], d2 = dp[2], d3 = dp[3], d4 = dp[4];
-            uint64_t r0 = funnel64(cx, x1, shx) ^ funnel64(cd, d1, shd);
-            uint64_t r1 = funnel64(x1, x2, shx) ^ funnel64(d1, d2, shd);
-            uint64_t r2 = funnel64(x2, x3, shx) ^ funnel64(d2, d3, shd);
-            uint64_t r3 = funnel64(x3, x4, shx) ^ funnel64(d3, d4, shd);
-            if (r0 | r1 | r2 | r3) break;                 // the word loop below locates the mismatch
-            l += 4 * spw; xp += 4; dp += 4; cx = x4; cd = d4;
+            uint64_t r0 = x0 ^ funnel64(cd, d1, shd), r1 = x1 ^ funnel64(d1, d2, shd);
+            uint64_t r2 = x2 ^ funnel64(d2, d3, shd), r3 = x3 ^ funnel64(d3, d4, shd);
+            if (r0 | r1 | r2 | r3) break;                     // the word loop below locates the mismatch
+            base += 4 * spw; xp += 4; dp += 4; cd = d4;
         }
-    }
-    while (!found && l < lim) {
-        uint64_t a = get64u(X, i + l, bl), b = get64u(D, p + l, bl);
-        uint64_t xr = a ^ b;
-        if (xr) { l += (uint32_t)(clz64(xr) >> bl); diff_less = b < a; found = true; }
-        else l += spw;
+        while (base < lim) {
+            const uint64_t a = xp[0], d1 = dp[1];
+            const uint64_t b = funnel64(cd, d1, shd);
+            const uint64_t xr = a ^ b;
+            if (xr) { base += (uint32_t)(clz64(xr) >> bl); diff_less = b < a; found = true; break; }
+            base += spw; ++xp; ++dp; cd = d1;
+        }
+        l = base;
     }
     if (l >= lim) {
         l = lim;
