@@ -91,8 +91,8 @@ __global__ void __launch_bounds__(128, 16) k_diag_w(ParseView pv) {
             const uint32_t wi = w0 + 32u * r + (uint32_t)lane;
             xr[r] = 0;
             if (wi < nwords) {
-                const uint64_t a = Dw[wi], b = Dw[wi + 1];           // the text has two zero pad words
-                const uint64_t d = (a << dsh) | ((b >> 1) >> (63 - dsh));
+                const uint64_t a = Dw[wi], b = Dw[wi + 1];           // the text ends in zero pad words
+                const uint64_t d = dsh >= 32 ? funnel_fixed<true>(a, b, dsh & 31) : funnel_fixed<false>(a, b, dsh & 31);
                 xr[r] = xw[wi] ^ d;
                 if (wi == nfull) xr[r] &= tailmask;
             }

@@ -109,17 +109,65 @@ struct Match {
     uint32_t pos;   // SA[leftmost] or the literal byte
 };
 
-// shifted word: bases [pos, pos+32) from two consecutive packed words a (holding pos) and b
-DRLZ_HD uint64_t funnel64(uint64_t a, uint64_t b, unsigned sh) { return sh ? (a << sh) | (b >> (64 - sh)) : a; }
+// high 32 bits of (hi:lo) << s, s in 0..31: one funnel-shift instruction on the device
+DRLZ_HD uint32_t fsl32(uint32_t hi, uint32_t lo, unsigned s) {
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_l(lo, hi, s);
+#else
+    return s ? (hi << s) | (lo >> (32 - s)) : hi;
+#endif
+}
 
-// get64 with a 32-bit position (n, m < 2^32: half the integer work of the 64-bit form)
+// shifted word: the 64 bits that start sh bits (0..63) into the 128-bit string a:b.  Done on 32-bit halves: the
+// string is four halves, the result two funnel shifts of three of them (no 64-bit shifts, no special case for 0).
+DRLZ_HD uint64_t funnel64(uint64_t a, uint64_t b, unsigned sh) {
+    const uint32_t ah = (uint32_t)(a >> 32), al = (uint32_t)a, bh = (uint32_t)(b >> 32), bl_ = (uint32_t)b;
+    const bool odd = sh >= 32;
+    const unsigned s = sh & 31;
+    const uint32_t w0 = odd ? al : ah, w1 = odd ? bh : al, w2 = odd ? bl_ : bh;
+    return ((uint64_t)fsl32(w0, w1, s) << 32) | fsl32(w1, w2, s);
+}
+
+// get64 with a 32-bit position (n, m < 2^32: half the integer work of the 64-bit form).  Always reads the next word
+// too (every packed array ends in zero pad words): no branch on the alignment.
 DRLZ_HD uint64_t get64u(const uint64_t* __restrict__ w, uint32_t pos, uint32_t bl) {
     const uint32_t sl = 6 - bl;
     uint32_t wi = pos >> sl;
     unsigned sh = (pos & ((1u << sl) - 1)) << bl;
-    uint64_t a = w[wi];
-    if (sh == 0) return a;
-    return (a << sh) | (w[wi + 1] >> (64 - sh));
+    return funnel64(w[wi], w[wi + 1], sh);
+}
+
+// funnel64 for a shift that is fixed along a stream: ODD = (sh >= 32) picks the halves at compile time, s = sh & 31
+template <bool ODD>
+DRLZ_HD uint64_t funnel_fixed(uint64_t a, uint64_t b, unsigned s) {
+    const uint32_t ah = (uint32_t)(a >> 32), al = (uint32_t)a, bh = (uint32_t)(b >> 32), bl_ = (uint32_t)b;
+    return ODD ? ((uint64_t)fsl32(al, bh, s) << 32) | fsl32(bh, bl_, s)
+               : ((uint64_t)fsl32(ah, al, s) << 32) | fsl32(al, bh, s);
+}
+
+// Streaming part of cmp_suffix_w: whole haplotype words xp[0..] against the reference words dp[0..] shifted by a
+// fixed amount, from pattern offset `base` up to lim.  Returns the offset of the first difference (>= lim if none).
+template <bool ODD>
+DRLZ_HD uint32_t cmp_stream(const uint64_t* __restrict__ xp, const uint64_t* __restrict__ dp, unsigned s, uint32_t base,
+                            uint32_t lim, uint32_t bl, bool* found, bool* diff_less) {
+    const uint32_t spw = 64u >> bl;
+    uint64_t cd = dp[0];
+    while (base + 4 * spw <= lim) {                           // 4 words per iteration, 8 independent loads in flight
+        uint64_t x0 = xp[0], x1 = xp[1], x2 = xp[2], x3 = xp[3];
+        uint64_t d1 = dp[1], d2 = dp[2], d3 = dp[3], d4 = dp[4];
+        uint64_t r0 = x0 ^ funnel_fixed<ODD>(cd, d1, s), r1 = x1 ^ funnel_fixed<ODD>(d1, d2, s);
+        uint64_t r2 = x2 ^ funnel_fixed<ODD>(d2, d3, s), r3 = x3 ^ funnel_fixed<ODD>(d3, d4, s);
+        if (r0 | r1 | r2 | r3) break;                         // the word loop below locates the mismatch
+        base += 4 * spw; xp += 4; dp += 4; cd = d4;
+    }
+    while (base < lim) {
+        const uint64_t a = xp[0], d1 = dp[1];
+        const uint64_t b = funnel_fixed<ODD>(cd, d1, s);
+        const uint64_t xr = a ^ b;
+        if (xr) { base += (uint32_t)(clz64(xr) >> bl); *diff_less = b < a; *found = true; break; }
+        base += spw; ++xp; ++dp; cd = d1;
+    }
+    return base;
 }
 
 // lcp(x[i..i+maxlen), d[p..n)) and whether the suffix d[p..] sorts before the pattern; xw0 = get64u(X, i).
@@ -147,22 +195,8 @@ DRLZ_HD uint32_t cmp_suffix_w(uint64_t xw0, const uint64_t* __restrict__ X, uint
         const uint32_t pd = p + base;
         const unsigned shd = (pd & (spw - 1)) << bl;
         const uint64_t* dp = D + (pd >> sl);
-        uint64_t cd = dp[0];
-        while (base + 4 * spw <= lim) {                       // 128 bases per iteration, 8 independent loads in flight
-            uint64_t x0 = xp[0], x1 = xp[1], x2 = xp[2], x3 = xp[3];
-            uint64_t d1 = dp[1], d2 = dp[2], d3 = dp[3], d4 = dp[4];
-            uint64_t r0 = x0 ^ funnel64(cd, d1, shd), r1 = x1 ^ funnel64(d1, d2, shd);
-            uint64_t r2 = x2 ^ funnel64(d2, d3, shd), r3 = x3 ^ funnel64(d3, d4, shd);
-            if (r0 | r1 | r2 | r3) break;                     // the word loop below locates the mismatch
-            base += 4 * spw; xp += 4; dp += 4; cd = d4;
-        }
-        while (base < lim) {
-            const uint64_t a = xp[0], d1 = dp[1];
-            const uint64_t b = funnel64(cd, d1, shd);
-            const uint64_t xr = a ^ b;
-            if (xr) { base += (uint32_t)(clz64(xr) >> bl); diff_less = b < a; found = true; break; }
-            base += spw; ++xp; ++dp; cd = d1;
-        }
+        base = shd >= 32 ? cmp_stream<true>(xp, dp, shd & 31, base, lim, bl, &found, &diff_less)
+                         : cmp_stream<false>(xp, dp, shd & 31, base, lim, bl, &found, &diff_less);
         l = base;
     }
     if (l >= lim) {
