@@ -54,7 +54,7 @@ struct drlz_ctx {
     cudaEvent_t ev_stage[12] = {};
     std::string err;
     // options
-    int opt_occ_pack = 8; uint32_t opt_prefetch = 1200; int opt_k = 0; uint32_t opt_chunk = 8192; uint32_t opt_min_cap = 64; uint32_t opt_foreign_cap = 1u << 20; uint64_t opt_group_bytes = 256ull << 20; int opt_lcp = 0;
+    int opt_blind_rounds = 2; int opt_occ_pack = 8; uint32_t opt_prefetch = 1200; int opt_k = 0; uint32_t opt_chunk = 8192; uint32_t opt_min_cap = 64; uint32_t opt_foreign_cap = 1u << 20; uint64_t opt_group_bytes = 256ull << 20; int opt_lcp = 0;
     // index
     bool have_index = false; uint64_t n = 0; int k = 0; int sa_rounds = 0;
     DevBuf blob, sa, isa, lcp;             // blob = [k-mer table | packed text] (one L2 access-policy window)
@@ -202,6 +202,7 @@ int drlz_set_option(drlz_ctx* c, const char* key, int64_t v) {
     else if (!strcmp(key, "tickets")) c->opt_tickets = v != 0;
     else if (!strcmp(key, "predict")) c->opt_predict = v != 0;
     else if (!strcmp(key, "occ_pack")) c->opt_occ_pack = (int)v;
+    else if (!strcmp(key, "blind_rounds")) c->opt_blind_rounds = (int)v;
     else if (!strcmp(key, "prefetch")) { if (v < 0 || v > (1 << 20)) return DRLZ_E_ARG; c->opt_prefetch = (uint32_t)v; }
     else if (!strcmp(key, "min_cap")) { if (v < 0 || v > 0x7FFFFFFF) return DRLZ_E_ARG; c->opt_min_cap = v ? (uint32_t)v : 64; }
     else if (!strcmp(key, "foreign_cap")) { if (v < 0 || v > 0x7FFFFFFF) return DRLZ_E_ARG; c->opt_foreign_cap = v ? (uint32_t)v : (1u << 20); }
@@ -363,7 +364,7 @@ static int run_device_group(drlz_ctx* c, const uint8_t* rows_dev, const uint64_t
         pb.hint = (c->opt_hint && !single_chunk) ? c->hint.as<int64_t>() : nullptr;
         pb.true_slot = c->true_slot.as<uint32_t>();
         pb.pv.counters = c->counters.as<uint32_t>();
-        pb.H = H; pb.max_chunks_per_hap = maxc ? maxc : 1; pb.occ = c->opt_occ; pb.occ_fix = c->opt_occ_fix;
+        pb.H = H; pb.max_chunks_per_hap = maxc ? maxc : 1; pb.occ = c->opt_occ; pb.occ_fix = c->opt_occ_fix; pb.blind_rounds = c->opt_blind_rounds;
         pb.jump_a = c->jump_a.as<uint32_t>(); pb.jump_b = c->jump_b.as<uint32_t>(); pb.mark = c->mark.as<uint8_t>();
         pb.true_cnt = c->true_cnt.as<uint32_t>(); pb.true_entry = c->true_entry.as<uint32_t>(); pb.true_off = c->true_off.as<uint64_t>();
         pb.scan_tmp = c->scan_tmp.as<uint64_t>(); pb.hap_pairs = c->hap_pairs.as<uint64_t>();

@@ -70,6 +70,7 @@ struct ParseBuffers {
     uint32_t max_chunks_per_hap;
     int occ;                      // min CTAs per SM of k_spec (0 = compiler default; 8 / 10 / 12 / 16)
     int occ_fix;                  // same for k_fix
+    int blind_rounds;             // fix-up rounds launched without reading the counters back (see parse_stage_count)
     int64_t* hint;                // [ceil(NC / kHintGroup)] diagonal hints (null = no hint pass)
     uint16_t* mm;                 // [NC*kMmStride] mismatch lists (null = no diagonal pre-scan)
     uint32_t* link_b;             // [NC] second buffers of the list ranking

@@ -313,37 +313,55 @@ int parse_stage_count(ParseBuffers& pb, cudaStream_t s, int* rounds_out, cudaEve
     }
     k_resolve<<<(NC + 127) / 128, 128, 0, s>>>(pv);
     if (ev) cudaEventRecord(ev[4], s);
+    // F: fix-up rounds.  Whether another round is needed is known on the device only (counters[1 + r] = records
+    // created for round r); reading it back after every round idles the GPU for a round trip each time.  So the
+    // usual number of rounds is launched blind (a round without records is an empty launch), the marking and the
+    // compaction follow in the same breath, and one read-back at the end tells whether that was enough.  If not
+    // (never seen on real rates), the remaining rounds run with a read-back each and J is redone.
+    auto launch_fix = [&](int r) {
+        uint32_t nr = NC * kAltSlots;
+        g_launches += 1;
+        if (pb.occ_fix >= 16) k_fix<16><<<(nr + 127) / 128, 128, 0, s>>>(pv, (uint32_t)r);
+        else if (pb.occ_fix >= 10) k_fix<10><<<(nr + 127) / 128, 128, 0, s>>>(pv, (uint32_t)r);
+        else k_fix<1><<<(nr + 127) / 128, 128, 0, s>>>(pv, (uint32_t)r);
+    };
     int round = 1;
-    for (;;) {
+    const int blind = pb.blind_rounds < 0 ? 0 : (pb.blind_rounds >= kMaxRounds ? kMaxRounds - 1 : pb.blind_rounds);
+    for (; round <= blind; ++round) launch_fix(round);
+    const uint32_t nn = NC * (kAltSlots + 1);
+    const uint32_t nmb = (nn + kMarkNodes - 1) / kMarkNodes;
+    const uint64_t nt = ((uint64_t)NC + kScanTile - 1) / kScanTile;
+    for (int pass = 0;; ++pass) {
+        if (ev && pass == 0) cudaEventRecord(ev[2], s);
+        pv.parsed_rounds = (uint32_t)(round - 1);
+        g_launches += 4;
+        cudaMemsetAsync(pb.mark, 0, nn, s);
+        k_mark_local<<<nmb, 256, 0, s>>>(pv, pb.jump_a, pb.jump_b);
+        k_mark_walk<<<(pb.H + 127) / 128, 128, 0, s>>>(pv, pb.H, pb.jump_a, pb.jump_b, pb.mark);
+        k_mark_spread<<<nmb, 256, 0, s>>>(pv, pb.jump_a, pb.mark, pb.true_cnt, pb.true_entry, pb.true_slot);
+        device_scan<uint64_t, LoadArr<uint32_t, uint64_t>, StoreArr<uint64_t>, OpSum, false>(
+            LoadArr<uint32_t, uint64_t>{pb.true_cnt}, StoreArr<uint64_t>{pb.true_off}, NC, pb.scan_tmp, OpSum(), 0ull, s);
+        k_hap_pairs<<<(pb.H + 1 + 127) / 128, 128, 0, s>>>(pv, pb.H, pb.true_off, pb.scan_tmp + nt, pb.hap_pairs);
+        if (ev && pass == 0) cudaEventRecord(ev[3], s);
+        cudaMemcpyAsync(pb.host_total, pb.scan_tmp + nt, sizeof(uint64_t), cudaMemcpyDeviceToHost, s);
         cudaMemcpyAsync(pb.host_counters, pv.counters, sizeof(uint32_t) * (2 + kMaxRounds), cudaMemcpyDeviceToHost, s);
         cudaStreamSynchronize(s);
         if (pb.host_counters[0]) return 2;
-        if (round >= kMaxRounds) return 2;
-        if (pb.host_counters[1 + round] == 0) break;
-        uint32_t nr = NC * kAltSlots;
-        g_launches += 1;
-        if (pb.occ_fix >= 16) k_fix<16><<<(nr + 127) / 128, 128, 0, s>>>(pv, (uint32_t)round);
-        else if (pb.occ_fix >= 10) k_fix<10><<<(nr + 127) / 128, 128, 0, s>>>(pv, (uint32_t)round);
-        else k_fix<1><<<(nr + 127) / 128, 128, 0, s>>>(pv, (uint32_t)round);
-        ++round;
+        if (pb.host_counters[1 + round] == 0) break;        // nothing was registered for the next round: converged
+        while (pb.host_counters[1 + round] != 0) {           // rare: more rounds than launched blind
+            if (round >= kMaxRounds) return 2;
+            launch_fix(round);
+            ++round;
+            cudaMemcpyAsync(pb.host_counters, pv.counters, sizeof(uint32_t) * (2 + kMaxRounds), cudaMemcpyDeviceToHost, s);
+            cudaStreamSynchronize(s);
+            if (pb.host_counters[0]) return 2;
+        }
     }
-    if (rounds_out) *rounds_out = round;
-    if (ev) cudaEventRecord(ev[2], s);
-    uint32_t nn = NC * (kAltSlots + 1);
-    uint32_t nmb = (nn + kMarkNodes - 1) / kMarkNodes;
-    g_launches += 4;
-    cudaMemsetAsync(pb.mark, 0, nn, s);
-    k_mark_local<<<nmb, 256, 0, s>>>(pv, pb.jump_a, pb.jump_b);
-    k_mark_walk<<<(pb.H + 127) / 128, 128, 0, s>>>(pv, pb.H, pb.jump_a, pb.jump_b, pb.mark);
-    k_mark_spread<<<nmb, 256, 0, s>>>(pv, pb.jump_a, pb.mark, pb.true_cnt, pb.true_entry, pb.true_slot);
-    device_scan<uint64_t, LoadArr<uint32_t, uint64_t>, StoreArr<uint64_t>, OpSum, false>(
-        LoadArr<uint32_t, uint64_t>{pb.true_cnt}, StoreArr<uint64_t>{pb.true_off}, NC, pb.scan_tmp, OpSum(), 0ull, s);
-    uint64_t nt = ((uint64_t)NC + kScanTile - 1) / kScanTile;
-    k_hap_pairs<<<(pb.H + 1 + 127) / 128, 128, 0, s>>>(pv, pb.H, pb.true_off, pb.scan_tmp + nt, pb.hap_pairs);
-    if (ev) cudaEventRecord(ev[3], s);
-    cudaMemcpyAsync(pb.host_total, pb.scan_tmp + nt, sizeof(uint64_t), cudaMemcpyDeviceToHost, s);
-    cudaMemcpyAsync(pb.host_counters, pv.counters, sizeof(uint32_t) * 2, cudaMemcpyDeviceToHost, s);
-    cudaStreamSynchronize(s);
+    if (rounds_out) {                                        // rounds that had work + 1, as before
+        int r = 1;
+        while (r < kMaxRounds && pb.host_counters[1 + r] != 0) ++r;
+        *rounds_out = r;
+    }
     if (pb.host_counters[0]) return 2;
     return 0;
 }

@@ -354,6 +354,7 @@ struct ParseView {
     uint16_t* mm;                   // [NC*kMmStride] mismatch offsets of each chunk along its hinted diagonal; may be null
     uint2* alt_ph;                  // [NC*kAltSlots*kAltStore] own phrases of the alternative records
     uint32_t* counters;             // [0] overflow flag, [1 + r] records created for round r
+    uint32_t parsed_rounds;         // fix-up rounds run so far: records registered for a later round are not parsed yet
 };
 
 DRLZ_HD uint32_t atomic_cas_u32(uint32_t* p, uint32_t cmp, uint32_t val) {
@@ -696,7 +697,9 @@ DRLZ_HD uint32_t node_succ(const ParseView& pv, uint32_t node) {
     uint64_t x;
     if (r == 0) x = pv.spec_exit[g];
     else {
-        if (pv.alt_entry[g * kAltSlots + r - 1] == kEmpty) return node;
+        // unused slot, or a record whose fix-up round has not run (possible only while the host launches rounds blind
+        // and checks convergence afterwards): no exit yet, a terminal
+        if (pv.alt_entry[g * kAltSlots + r - 1] == kEmpty || pv.alt_round[g * kAltSlots + r - 1] > pv.parsed_rounds) return node;
         x = pv.alt_exit[g * kAltSlots + r - 1];
     }
     if (x >= hv.m) return node;                              // terminal: self loop

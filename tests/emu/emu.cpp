@@ -127,7 +127,7 @@ int emu_parse(const uint8_t* ref, uint64_t n, const int64_t* sa64, int k, uint32
     ParseView pv{ix, haps.data(), chunk_hap.data(), base.data(), chunk, chunk_shift, NC, min_cap, foreign_cap,
                  first_pos.data(), first_len.data(), run_a.data(), link_a.data(), open_i.data(), open_pos.data(), open_len.data(), spec_cnt.data(), spec_exit.data(),
                  alt_entry.data(), alt_cnt.data(), alt_exit.data(), alt_round.data(), alt_own.data(), alt_merge.data(),
-                 spec_ph.data(), spec_store, nullptr, nullptr, alt_ph.data(), counters.data()};
+                 spec_ph.data(), spec_store, nullptr, nullptr, alt_ph.data(), counters.data(), (uint32_t)kMaxRounds};
     uint32_t maxc0 = 1;
     for (int h = 0; h < H; ++h) if (base[h + 1] - base[h] > maxc0) maxc0 = base[h + 1] - base[h];
     if (use_uniq && chunk_shift >= 5 && chunk_shift <= 15) {
