@@ -370,6 +370,11 @@ static int run_device_group(drlz_ctx* c, const uint8_t* rows_dev, const uint64_t
         pb.scan_tmp = c->scan_tmp.as<uint64_t>(); pb.hap_pairs = c->hap_pairs.as<uint64_t>();
         pb.host_counters = sh_counters; pb.host_total = sh_total;
         int rounds = 0;
+        pb.spec_out = c->out.as<int64_t>(); pb.spec_out_cap = c->out.cap >= 32 ? (c->out.cap - 16) / 16 : 0;
+        pb.ev_emitted = c->ev_stage[11]; pb.emitted = false;
+        pb.n_tail = 4;
+        pb.tail[0] = {sh_m, c->mdev.p, (size_t)H * 8}; pb.tail[1] = {sh_pairs, c->hap_pairs.p, ((size_t)H + 1) * 8};
+        pb.tail[2] = {sh_exccnt, c->exccnt.p, (size_t)H * 8}; pb.tail[3] = {sh_flags, c->flags.p, 4};
         int prc = parse_stage_count(pb, s, &rounds, &c->ev_stage[5]);   // ev 5,6,7,8 and 9 (after stage A)
         CK(c, cudaGetLastError());
         if (prc == 2) {
@@ -378,14 +383,12 @@ static int run_device_group(drlz_ctx* c, const uint8_t* rows_dev, const uint64_t
             continue;
         }
         uint64_t total = *sh_total;
-        CK(c, c->out.ensure(total * 16 + 16));
-        parse_stage_emit(pb, c->out.as<int64_t>(), s);
-        cudaEventRecord(c->ev_stage[11], s);
-        CK(c, cudaMemcpyAsync(sh_m, c->mdev.p, (size_t)H * 8, cudaMemcpyDeviceToHost, s));
-        CK(c, cudaMemcpyAsync(sh_pairs, c->hap_pairs.p, ((size_t)H + 1) * 8, cudaMemcpyDeviceToHost, s));
-        CK(c, cudaMemcpyAsync(sh_exccnt, c->exccnt.p, (size_t)H * 8, cudaMemcpyDeviceToHost, s));
-        CK(c, cudaMemcpyAsync(sh_flags, c->flags.p, 4, cudaMemcpyDeviceToHost, s));
-        CK(c, cudaStreamSynchronize(s));
+        if (!pb.emitted || total > pb.spec_out_cap) {                    // first batch, or more records than ever before
+            CK(c, c->out.ensure(total * 16 + total * 2 + 16));
+            parse_stage_emit(pb, c->out.as<int64_t>(), s);
+            cudaEventRecord(c->ev_stage[11], s);
+            CK(c, cudaStreamSynchronize(s));
+        }
         if (*sh_flags & 2u) {           // look-back timed out (CTAs not dispatched in index order): redo with tickets
             c->opt_tickets = 1;
             continue;

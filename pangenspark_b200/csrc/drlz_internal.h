@@ -70,6 +70,12 @@ struct ParseBuffers {
     uint32_t max_chunks_per_hap;
     int occ;                      // min CTAs per SM of k_spec (0 = compiler default; 8 / 10 / 12 / 16)
     int occ_fix;                  // same for k_fix
+    struct TailCopy { void* dst; const void* src; size_t bytes; } tail[4];   // device -> host copies issued before the
+    int n_tail;                   // final sync of parse_stage_count
+    int64_t* spec_out;            // where parse_stage_count may emit the records right away (null = do not)
+    uint64_t spec_out_cap;        // its capacity in records
+    cudaEvent_t ev_emitted;       // recorded after that emission (nullable)
+    bool emitted;                 // out: the records were emitted (valid if the total fits spec_out_cap)
     int blind_rounds;             // fix-up rounds launched without reading the counters back (see parse_stage_count)
     int64_t* hint;                // [ceil(NC / kHintGroup)] diagonal hints (null = no hint pass)
     uint16_t* mm;                 // [NC*kMmStride] mismatch lists (null = no diagonal pre-scan)

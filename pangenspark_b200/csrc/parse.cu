@@ -252,11 +252,12 @@ __global__ void k_hap_pairs(ParseView pv, uint32_t H, const uint64_t* true_off, 
 }
 
 __global__ void __launch_bounds__(128) k_emit(ParseView pv, const uint32_t* true_cnt, const uint32_t* true_entry,
-                                              const uint32_t* true_slot, const uint64_t* true_off, int64_t* out) {
+                                              const uint32_t* true_slot, const uint64_t* true_off, int64_t* out, uint64_t cap) {
     uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= pv.n_chunks) return;
     uint32_t c = true_cnt[g];
     if (!c) return;
+    if (true_off[g] + c > cap) return;                       // speculative launch into a buffer that may be too small
     int64_t* o = out + 2 * true_off[g];
     if (!emit_stored(pv, g, true_slot[g], c, o)) emit_chunk(pv, g, true_entry[g], c, o);
 }
@@ -269,6 +270,7 @@ int parse_stage_count(ParseBuffers& pb, cudaStream_t s, int* rounds_out, cudaEve
     if (NC == 0) {
         if (ev) for (int i = 0; i < 6; ++i) cudaEventRecord(ev[i], s);
         cudaMemsetAsync(pb.hap_pairs, 0, sizeof(uint64_t) * (pb.H + 1), s);
+        for (int k = 0; k < pb.n_tail; ++k) cudaMemcpyAsync(pb.tail[k].dst, pb.tail[k].src, pb.tail[k].bytes, cudaMemcpyDeviceToHost, s);
         cudaStreamSynchronize(s);
         return 0;
     }
@@ -343,8 +345,19 @@ int parse_stage_count(ParseBuffers& pb, cudaStream_t s, int* rounds_out, cudaEve
             LoadArr<uint32_t, uint64_t>{pb.true_cnt}, StoreArr<uint64_t>{pb.true_off}, NC, pb.scan_tmp, OpSum(), 0ull, s);
         k_hap_pairs<<<(pb.H + 1 + 127) / 128, 128, 0, s>>>(pv, pb.H, pb.true_off, pb.scan_tmp + nt, pb.hap_pairs);
         if (ev && pass == 0) cudaEventRecord(ev[3], s);
+        pb.emitted = false;
+        if (pb.spec_out && pb.spec_out_cap) {
+            // E without waiting for the host: the records go to the caller's buffer if they fit (checked per chunk on
+            // the device, and by the host once the total is known; too small => the host grows it and emits again)
+            g_launches += 1;
+            k_emit<<<(NC + 127) / 128, 128, 0, s>>>(pv, pb.true_cnt, pb.true_entry, pb.true_slot, pb.true_off, pb.spec_out, pb.spec_out_cap);
+            if (pb.ev_emitted) cudaEventRecord(pb.ev_emitted, s);
+            pb.emitted = true;
+        }
         cudaMemcpyAsync(pb.host_total, pb.scan_tmp + nt, sizeof(uint64_t), cudaMemcpyDeviceToHost, s);
         cudaMemcpyAsync(pb.host_counters, pv.counters, sizeof(uint32_t) * (2 + kMaxRounds), cudaMemcpyDeviceToHost, s);
+        for (int k = 0; k < pb.n_tail; ++k)                  // the caller's small result read-backs ride on the same sync
+            cudaMemcpyAsync(pb.tail[k].dst, pb.tail[k].src, pb.tail[k].bytes, cudaMemcpyDeviceToHost, s);
         cudaStreamSynchronize(s);
         if (pb.host_counters[0]) return 2;
         if (pb.host_counters[1 + round] == 0) break;        // nothing was registered for the next round: converged
@@ -370,7 +383,7 @@ void parse_stage_emit(ParseBuffers& pb, int64_t* out, cudaStream_t s) {
     uint32_t NC = pb.pv.n_chunks;
     if (NC == 0) return;
     g_launches += 1;
-    k_emit<<<(NC + 127) / 128, 128, 0, s>>>(pb.pv, pb.true_cnt, pb.true_entry, pb.true_slot, pb.true_off, out);
+    k_emit<<<(NC + 127) / 128, 128, 0, s>>>(pb.pv, pb.true_cnt, pb.true_entry, pb.true_slot, pb.true_off, out, ~0ull);
 }
 
 __global__ void k_fill_chunk_hap(uint32_t* chunk_hap, const uint32_t* __restrict__ base, uint32_t H, uint32_t NC) {
