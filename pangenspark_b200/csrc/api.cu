@@ -262,7 +262,8 @@ static int run_device_group(drlz_ctx* c, const uint8_t* rows_dev, const uint64_t
         h_goff[h] = gbytes; gbytes += (cols[h] + 15) & ~15ull;
         if (gapless_off_out) gapless_off_out[h] = h_goff[h];
     }
-    CK(c, c->small_host.ensure(sizeof(uint64_t) * (3 * (size_t)H + 8) + sizeof(uint32_t) * (4 + kMaxRounds)));
+    const size_t res_bytes = sizeof(uint64_t) * (3 * (size_t)H + 2) + sizeof(uint32_t) * (4 + kMaxRounds);   // see k_results
+    CK(c, c->small_host.ensure(res_bytes + 64));
     uint64_t* sh_m = c->small_host.as<uint64_t>();            // [H]
     uint64_t* sh_pairs = sh_m + H;                            // [H+1]
     uint64_t* sh_total = sh_pairs + H + 1;                    // [1]
@@ -341,7 +342,7 @@ static int run_device_group(drlz_ctx* c, const uint8_t* rows_dev, const uint64_t
         CK(c, c->alt_round.ensure(na * 4 + 4)); CK(c, c->counters.ensure(sizeof(uint32_t) * (2 + kMaxRounds)));
         CK(c, c->jump_a.ensure(nn * 4 + 4)); CK(c, c->jump_b.ensure(nn * 4 + 4)); CK(c, c->mark.ensure(nn + 4));
         CK(c, c->true_cnt.ensure((size_t)NC * 4 + 4)); CK(c, c->true_entry.ensure((size_t)NC * 4 + 4)); CK(c, c->true_off.ensure((size_t)NC * 8 + 8));
-        CK(c, c->scan_tmp.ensure(scan_tmp_elems(NC) * 8)); CK(c, c->hap_pairs.ensure(((size_t)H + 1) * 8));
+        CK(c, c->scan_tmp.ensure(scan_tmp_elems(NC) * 8)); CK(c, c->hap_pairs.ensure(res_bytes + 64));
         launch_fill_chunk_hap(c->chunk_hap.as<uint32_t>(), d_base, H, NC, s);
 
         ParseBuffers pb;
@@ -367,14 +368,13 @@ static int run_device_group(drlz_ctx* c, const uint8_t* rows_dev, const uint64_t
         pb.H = H; pb.max_chunks_per_hap = maxc ? maxc : 1; pb.occ = c->opt_occ; pb.occ_fix = c->opt_occ_fix; pb.blind_rounds = c->opt_blind_rounds;
         pb.jump_a = c->jump_a.as<uint32_t>(); pb.jump_b = c->jump_b.as<uint32_t>(); pb.mark = c->mark.as<uint8_t>();
         pb.true_cnt = c->true_cnt.as<uint32_t>(); pb.true_entry = c->true_entry.as<uint32_t>(); pb.true_off = c->true_off.as<uint64_t>();
-        pb.scan_tmp = c->scan_tmp.as<uint64_t>(); pb.hap_pairs = c->hap_pairs.as<uint64_t>();
+        pb.scan_tmp = c->scan_tmp.as<uint64_t>();
+        pb.res = c->hap_pairs.as<uint64_t>(); pb.host_res = sh_m; pb.res_bytes = res_bytes;
+        pb.m_dev = c->mdev.as<uint64_t>(); pb.exccnt_dev = c->exccnt.as<uint64_t>(); pb.flags_dev = c->flags.as<uint32_t>();
         pb.host_counters = sh_counters; pb.host_total = sh_total;
         int rounds = 0;
         pb.spec_out = c->out.as<int64_t>(); pb.spec_out_cap = c->out.cap >= 32 ? (c->out.cap - 16) / 16 : 0;
         pb.ev_emitted = c->ev_stage[11]; pb.emitted = false;
-        pb.n_tail = 4;
-        pb.tail[0] = {sh_m, c->mdev.p, (size_t)H * 8}; pb.tail[1] = {sh_pairs, c->hap_pairs.p, ((size_t)H + 1) * 8};
-        pb.tail[2] = {sh_exccnt, c->exccnt.p, (size_t)H * 8}; pb.tail[3] = {sh_flags, c->flags.p, 4};
         int prc = parse_stage_count(pb, s, &rounds, &c->ev_stage[5]);   // ev 5,6,7,8 and 9 (after stage A)
         CK(c, cudaGetLastError());
         if (prc == 2) {

@@ -70,8 +70,8 @@ struct ParseBuffers {
     uint32_t max_chunks_per_hap;
     int occ;                      // min CTAs per SM of k_spec (0 = compiler default; 8 / 10 / 12 / 16)
     int occ_fix;                  // same for k_fix
-    struct TailCopy { void* dst; const void* src; size_t bytes; } tail[4];   // device -> host copies issued before the
-    int n_tail;                   // final sync of parse_stage_count
+    uint64_t* res; void* host_res; size_t res_bytes;   // result block (layout at k_results) and its pinned host mirror
+    const uint64_t* m_dev; const uint64_t* exccnt_dev; const uint32_t* flags_dev;   // what k_pack left for it
     int64_t* spec_out;            // where parse_stage_count may emit the records right away (null = do not)
     uint64_t spec_out_cap;        // its capacity in records
     cudaEvent_t ev_emitted;       // recorded after that emission (nullable)
@@ -89,7 +89,6 @@ struct ParseBuffers {
     uint32_t* true_slot;          // [NC] 0 = speculative record, 1+s = alternative record s
     uint64_t* true_off;           // [NC]
     uint64_t* scan_tmp;           // scan_tmp_elems(NC)
-    uint64_t* hap_pairs;          // [H+1]: [h] phrases of haplotype h's start offset, [H] = total
     uint32_t* host_counters;      // pinned host mirror of pv.counters (2 + kMaxRounds)
     uint64_t* host_total;         // pinned host: total phrase count
 };

@@ -244,11 +244,28 @@ struct StoreRunRev {
     __device__ __forceinline__ void operator()(uint64_t e, uint64_t v) const { out[nc - 1 - e] = (uint32_t)v; }
 };
 
-__global__ void k_hap_pairs(ParseView pv, uint32_t H, const uint64_t* true_off, const uint64_t* total, uint64_t* hap_pairs) {
-    uint32_t h = blockIdx.x * blockDim.x + threadIdx.x;
-    if (h > H) return;
-    uint32_t g = h < H ? pv.hap_chunk_base[h] : pv.n_chunks;
-    hap_pairs[h] = g < pv.n_chunks ? true_off[g] : *total;
+// Everything the host reads back after a batch, gathered into one block so that it is one device-to-host copy:
+//   u64 [0, H) gapless lengths | [H, 2H+1) first record of each haplotype, [2H] = total | [2H+1] total |
+//   [2H+2, 3H+2) exceptions per row | u32 flags[2] | u32 counters[2 + kMaxRounds]        (same layout on the host)
+__global__ void k_results(ParseView pv, uint32_t H, const uint64_t* true_off, const uint64_t* total, const uint64_t* m,
+                          const uint64_t* exccnt, const uint32_t* flags, uint64_t* res) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t tot = total ? *total : 0;
+    if (t < H) { res[t] = m[t]; res[2 * (size_t)H + 2 + t] = exccnt[t]; }
+    if (t <= H) {
+        uint32_t g = t < H ? pv.hap_chunk_base[t] : pv.n_chunks;
+        res[(size_t)H + t] = g < pv.n_chunks ? true_off[g] : tot;
+    }
+    if (t == 0) res[2 * (size_t)H + 1] = tot;
+    uint32_t* r32 = reinterpret_cast<uint32_t*>(res + 3 * (size_t)H + 2);
+    if (t < 2) r32[t] = flags[t];
+    if (t < 2u + (uint32_t)kMaxRounds) r32[2 + t] = pv.counters[t];
+}
+static void launch_results(ParseBuffers& pb, const uint64_t* total, cudaStream_t s) {
+    uint32_t nthr = pb.H + 1 > 2u + (uint32_t)kMaxRounds ? pb.H + 1 : 2u + (uint32_t)kMaxRounds;
+    g_launches += 1;
+    k_results<<<(nthr + 127) / 128, 128, 0, s>>>(pb.pv, pb.H, pb.true_off, total, pb.m_dev, pb.exccnt_dev, pb.flags_dev, pb.res);
+    cudaMemcpyAsync(pb.host_res, pb.res, pb.res_bytes, cudaMemcpyDeviceToHost, s);
 }
 
 __global__ void __launch_bounds__(128) k_emit(ParseView pv, const uint32_t* true_cnt, const uint32_t* true_entry,
@@ -269,8 +286,8 @@ int parse_stage_count(ParseBuffers& pb, cudaStream_t s, int* rounds_out, cudaEve
     if (rounds_out) *rounds_out = 0;
     if (NC == 0) {
         if (ev) for (int i = 0; i < 6; ++i) cudaEventRecord(ev[i], s);
-        cudaMemsetAsync(pb.hap_pairs, 0, sizeof(uint64_t) * (pb.H + 1), s);
-        for (int k = 0; k < pb.n_tail; ++k) cudaMemcpyAsync(pb.tail[k].dst, pb.tail[k].src, pb.tail[k].bytes, cudaMemcpyDeviceToHost, s);
+        cudaMemsetAsync(pv.counters, 0, sizeof(uint32_t) * (2 + kMaxRounds), s);
+        launch_results(pb, nullptr, s);
         cudaStreamSynchronize(s);
         return 0;
     }
@@ -336,14 +353,13 @@ int parse_stage_count(ParseBuffers& pb, cudaStream_t s, int* rounds_out, cudaEve
     for (int pass = 0;; ++pass) {
         if (ev && pass == 0) cudaEventRecord(ev[2], s);
         pv.parsed_rounds = (uint32_t)(round - 1);
-        g_launches += 4;
+        g_launches += 3;
         cudaMemsetAsync(pb.mark, 0, nn, s);
         k_mark_local<<<nmb, 256, 0, s>>>(pv, pb.jump_a, pb.jump_b);
         k_mark_walk<<<(pb.H + 127) / 128, 128, 0, s>>>(pv, pb.H, pb.jump_a, pb.jump_b, pb.mark);
         k_mark_spread<<<nmb, 256, 0, s>>>(pv, pb.jump_a, pb.mark, pb.true_cnt, pb.true_entry, pb.true_slot);
         device_scan<uint64_t, LoadArr<uint32_t, uint64_t>, StoreArr<uint64_t>, OpSum, false>(
             LoadArr<uint32_t, uint64_t>{pb.true_cnt}, StoreArr<uint64_t>{pb.true_off}, NC, pb.scan_tmp, OpSum(), 0ull, s);
-        k_hap_pairs<<<(pb.H + 1 + 127) / 128, 128, 0, s>>>(pv, pb.H, pb.true_off, pb.scan_tmp + nt, pb.hap_pairs);
         if (ev && pass == 0) cudaEventRecord(ev[3], s);
         pb.emitted = false;
         if (pb.spec_out && pb.spec_out_cap) {
@@ -354,10 +370,7 @@ int parse_stage_count(ParseBuffers& pb, cudaStream_t s, int* rounds_out, cudaEve
             if (pb.ev_emitted) cudaEventRecord(pb.ev_emitted, s);
             pb.emitted = true;
         }
-        cudaMemcpyAsync(pb.host_total, pb.scan_tmp + nt, sizeof(uint64_t), cudaMemcpyDeviceToHost, s);
-        cudaMemcpyAsync(pb.host_counters, pv.counters, sizeof(uint32_t) * (2 + kMaxRounds), cudaMemcpyDeviceToHost, s);
-        for (int k = 0; k < pb.n_tail; ++k)                  // the caller's small result read-backs ride on the same sync
-            cudaMemcpyAsync(pb.tail[k].dst, pb.tail[k].src, pb.tail[k].bytes, cudaMemcpyDeviceToHost, s);
+        launch_results(pb, pb.scan_tmp + nt, s);             // totals, per-haplotype offsets, lengths, flags, counters: one copy
         cudaStreamSynchronize(s);
         if (pb.host_counters[0]) return 2;
         if (pb.host_counters[1 + round] == 0) break;        // nothing was registered for the next round: converged
