@@ -116,7 +116,7 @@ int drlz_parse_batch_device(drlz_ctx* ctx, const uint8_t* rows_dev, const uint64
 int drlz_copy_to_host(drlz_ctx* ctx, void* dst_host, const void* src_dev, uint64_t bytes);
 
 /* Per-kernel timings (ms, CUDA events on the context's stream) summed over the groups of the last parse call:
- * [0] zero-fill of the packed buffer, [1] pre-scan (k_hint + k_diag_w), [2] unused, [3] k_pack (single pass), [4] k_spec (speculative
+ * [0] zero-fill of the packed buffer, [1] pre-scan (k_hint + k_diag_w), [2] host time of the last group outside the GPU work (before its first launch + after its last synchronisation), [3] k_pack (single pass), [4] k_spec (speculative
  * parse), [5] k_fix rounds, [6] pointer jumping + compaction scan, [7] k_emit (incl. the host read of the phrase
  * total), [8] whole device pipeline, [9] stage A (k_link + list ranking + k_resolve), [10] fix-up rounds executed,
  * [11] kernels launched. */

@@ -5,6 +5,7 @@
 #include <condition_variable>
 #include <deque>
 #include <mutex>
+#include <chrono>
 #include <string>
 #include <thread>
 #include <vector>
@@ -228,6 +229,7 @@ static int run_device_group(drlz_ctx* c, const uint8_t* rows_dev, const uint64_t
                             int strip, bool want_gapless, uint64_t* m_out, uint64_t* n_pairs, uint64_t* total_pairs,
                             uint64_t* gapless_off_out /*[H], host*/) {
     cudaStream_t s = c->stream;
+    const auto t_entry = std::chrono::steady_clock::now();
     *total_pairs = 0;
     if (H == 0) return DRLZ_OK;
     apply_l2_policy(c);
@@ -306,6 +308,7 @@ static int run_device_group(drlz_ctx* c, const uint8_t* rows_dev, const uint64_t
         const uint32_t* d_base = reinterpret_cast<const uint32_t*>(d_row_off + 4 * H);
 
         cudaEventRecord(c->ev_stage[0], s);
+        const auto t_first = std::chrono::steady_clock::now();
         CK(c, cudaMemsetAsync(c->X.p, 0, xwords * 8, s));
         CK(c, cudaMemsetAsync(c->flags.p, 0, 16, s));
         cudaEventRecord(c->ev_stage[1], s);
@@ -382,12 +385,14 @@ static int run_device_group(drlz_ctx* c, const uint8_t* rows_dev, const uint64_t
             single_chunk = true;        // exact sequential fallback on the device: one chunk per haplotype
             continue;
         }
+        auto t_done = std::chrono::steady_clock::now();            // parse_stage_count returned after its sync
         uint64_t total = *sh_total;
         if (!pb.emitted || total > pb.spec_out_cap) {                    // first batch, or more records than ever before
             CK(c, c->out.ensure(total * 16 + total * 2 + 16));
             parse_stage_emit(pb, c->out.as<int64_t>(), s);
             cudaEventRecord(c->ev_stage[11], s);
             CK(c, cudaStreamSynchronize(s));
+            t_done = std::chrono::steady_clock::now();
         }
         if (*sh_flags & 2u) {           // look-back timed out (CTAs not dispatched in index order): redo with tickets
             c->opt_tickets = 1;
@@ -410,6 +415,9 @@ static int run_device_group(drlz_ctx* c, const uint8_t* rows_dev, const uint64_t
         static const int iv[10][2] = {{0, 1}, {5, 10}, {2, 3}, {3, 4}, {10, 6}, {9, 7}, {7, 8}, {8, 11}, {0, 11}, {6, 9}};
         for (int i = 0; i < 10; ++i) { cudaEventElapsedTime(&t, c->ev_stage[iv[i][0]], c->ev_stage[iv[i][1]]); pm[i] += t; }
         pm[10] += rounds; pm[11] += (double)(g_launches - launches0);
+        // [2]: host time of this call during which the GPU had nothing of it to run (before the first launch, after the last sync)
+        pm[2] = std::chrono::duration<double, std::milli>(t_first - t_entry).count() +
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_done).count();
         return DRLZ_OK;
     }
     c->err = "exception list kept overflowing";

@@ -269,7 +269,7 @@ class Drlz:
     def parse_timings(self):
         a = (C.c_double * 12)()
         self._ck(self._lib.drlz_parse_timings(self._h, a))
-        keys = ["memset_ms", "prescan_ms", "unused_ms", "pack_write_ms", "spec_ms", "fix_ms", "jump_ms", "emit_ms",
+        keys = ["memset_ms", "prescan_ms", "host_ms", "pack_write_ms", "spec_ms", "fix_ms", "jump_ms", "emit_ms",
                 "device_ms", "first_ms", "fix_rounds", "launches"]
         return dict(zip(keys, list(a)))
 
