@@ -172,15 +172,16 @@ DRLZ_HD uint32_t cmp_stream(const uint64_t* __restrict__ xp, const uint64_t* __r
 
 // lcp(x[i..i+maxlen), d[p..n)) and whether the suffix d[p..] sorts before the pattern; xw0 = get64u(X, i).
 // The first word is compared alone (most probes differ there); longer matches stream 4 words per iteration.
-DRLZ_HD uint32_t cmp_suffix_w(uint64_t xw0, const uint64_t* __restrict__ X, uint32_t i, const uint64_t* __restrict__ D,
-                              uint32_t p, uint32_t n, uint32_t maxlen, bool* less, uint32_t bl) {
+// dw0 = get64u(D, p): the caller may have requested it together with other candidates' first words
+DRLZ_HD uint32_t cmp_suffix_pre(uint64_t xw0, uint64_t dw0, const uint64_t* __restrict__ X, uint32_t i,
+                                const uint64_t* __restrict__ D, uint32_t p, uint32_t n, uint32_t maxlen, bool* less, uint32_t bl) {
     const uint32_t sl = 6 - bl, spw = 1u << sl;          // symbols per word
     uint32_t rem = n - p;
     uint32_t lim = rem < maxlen ? rem : maxlen;
     uint32_t l = 0;
     bool diff_less = false, found = false;
     if (lim > 0) {
-        uint64_t b = get64u(D, p, bl);
+        uint64_t b = dw0;
         uint64_t xr = xw0 ^ b;
         if (xr) { l = (uint32_t)(clz64(xr) >> bl); diff_less = b < xw0; found = true; }
         else l = spw;
@@ -207,6 +208,11 @@ DRLZ_HD uint32_t cmp_suffix_w(uint64_t xw0, const uint64_t* __restrict__ X, uint
         *less = diff_less;
     }
     return l;
+}
+
+DRLZ_HD uint32_t cmp_suffix_w(uint64_t xw0, const uint64_t* __restrict__ X, uint32_t i, const uint64_t* __restrict__ D,
+                              uint32_t p, uint32_t n, uint32_t maxlen, bool* less, uint32_t bl) {
+    return cmp_suffix_pre(xw0, get64u(D, p, bl), X, i, D, p, n, maxlen, less, bl);
 }
 
 DRLZ_HD uint32_t cmp_suffix(const uint64_t* __restrict__ X, uint64_t i, const uint64_t* __restrict__ D,
@@ -251,16 +257,25 @@ DRLZ_HD Match lookup(const IndexView& ix, const uint64_t* __restrict__ X, uint64
         uint32_t r = l;
         bool dummy;
         uint32_t l1 = 0, l2 = 0;
-        if (r > 0) l1 = have_left ? lcp_left : cmp_suffix_w(xw, X, i, D, SA[r - 1], n, plen, &dummy, bl);
+        // the candidates are the neighbours r-1 and r (and r+1 for the uniqueness test of a capped match): their SA
+        // entries share a line and their first reference words are requested together, so the compares below start
+        // from data that arrives in two round trips instead of six
+        const bool needL = r > 0 && !have_left, needR = r < n && !have_right, haveN = r + 1 < n;
+        const uint32_t pL = needL ? SA[r - 1] : 0u;
+        if (needR) sar = SA[r];
+        const uint32_t pN = haveN ? SA[r + 1] : 0u;
+        const uint64_t wL = needL ? get64u(D, pL, bl) : 0ull, wR = needR ? get64u(D, sar, bl) : 0ull;
+        const uint64_t wN = haveN ? get64u(D, pN, bl) : 0ull;
+        if (r > 0) l1 = have_left ? lcp_left : cmp_suffix_pre(xw, wL, X, i, D, pL, n, plen, &dummy, bl);
         if (r < n) {
-            if (!have_right) { sar = SA[r]; lcp_right = cmp_suffix_w(xw, X, i, D, sar, n, plen, &dummy, bl); }
+            if (!have_right) lcp_right = cmp_suffix_pre(xw, wR, X, i, D, sar, n, plen, &dummy, bl);
             l2 = lcp_right;
         }
         if (l2 > l1) {
             if (l2 == plen && plen < maxlen) {
                 // capped: is SA[r] the only suffix carrying the capped pattern?
                 bool multi = false;
-                if (r + 1 < n) multi = cmp_suffix_w(xw, X, i, D, SA[r + 1], n, plen, &dummy, bl) >= plen;
+                if (haveN) multi = cmp_suffix_pre(xw, wN, X, i, D, pN, n, plen, &dummy, bl) >= plen;
                 if (multi) { plen = maxlen; continue; }
                 *open = true;
             }
