@@ -444,10 +444,10 @@ DRLZ_HD Match phrase_capped(const ParseView& pv, const HapView& hv, uint64_t i, 
             uint32_t plen = cap < maxlen ? cap : maxlen;
             uint32_t c;
             bool less;
+            const uint32_t u = pv.ix.uniq[p];                // a DRAM miss as a rule: requested before the list scan, used after it
             if (!(pv.mm && g != kEmpty && pv.hint[g / kHintGroup] == *diag && list_extent(pv, g, s, i, plen, &c)))
                 c = cmp_suffix_w(get64u(hv.x, (uint32_t)i, pv.ix.bl), hv.x, (uint32_t)i, pv.ix.text, p, (uint32_t)pv.ix.n, plen, &less, pv.ix.bl);
             if (c > 0) {
-                uint32_t u = pv.ix.uniq[p];
                 if (u != 0xFFFFu && c > u) {
                     mt.len = c; mt.pos = p;
                     *open = (c == plen && plen < maxlen);
