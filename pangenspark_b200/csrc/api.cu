@@ -55,7 +55,7 @@ struct drlz_ctx {
     cudaEvent_t ev_stage[12] = {};
     std::string err;
     // options
-    int opt_blind_rounds = 2; int opt_occ_pack = 8; uint32_t opt_prefetch = 1200; int opt_k = 0; uint32_t opt_chunk = 8192; uint32_t opt_min_cap = 64; uint32_t opt_foreign_cap = 1u << 20; uint64_t opt_group_bytes = 256ull << 20; int opt_lcp = 0;
+    uint64_t x_zeroed = 0; bool keep_x = false; int opt_postzero = 1; int opt_blind_rounds = 2; int opt_occ_pack = 8; uint32_t opt_prefetch = 1200; int opt_k = 0; uint32_t opt_chunk = 8192; uint32_t opt_min_cap = 64; uint32_t opt_foreign_cap = 1u << 20; uint64_t opt_group_bytes = 256ull << 20; int opt_lcp = 0;
     // index
     bool have_index = false; uint64_t n = 0; int k = 0; int sa_rounds = 0;
     DevBuf blob, sa, isa, lcp;             // blob = [k-mer table | packed text] (one L2 access-policy window)
@@ -204,6 +204,7 @@ int drlz_set_option(drlz_ctx* c, const char* key, int64_t v) {
     else if (!strcmp(key, "predict")) c->opt_predict = v != 0;
     else if (!strcmp(key, "occ_pack")) c->opt_occ_pack = (int)v;
     else if (!strcmp(key, "blind_rounds")) c->opt_blind_rounds = (int)v;
+    else if (!strcmp(key, "postzero")) c->opt_postzero = v != 0;
     else if (!strcmp(key, "prefetch")) { if (v < 0 || v > (1 << 20)) return DRLZ_E_ARG; c->opt_prefetch = (uint32_t)v; }
     else if (!strcmp(key, "min_cap")) { if (v < 0 || v > 0x7FFFFFFF) return DRLZ_E_ARG; c->opt_min_cap = v ? (uint32_t)v : 64; }
     else if (!strcmp(key, "foreign_cap")) { if (v < 0 || v > 0x7FFFFFFF) return DRLZ_E_ARG; c->opt_foreign_cap = v ? (uint32_t)v : (1u << 20); }
@@ -274,7 +275,11 @@ static int run_device_group(drlz_ctx* c, const uint8_t* rows_dev, const uint64_t
     uint32_t* sh_counters = sh_flags + 2;                     // [2 + kMaxRounds]
 
     CK(c, c->desc_cnt.ensure(nt * 8)); CK(c, c->desc_exc.ensure(nt * 8)); CK(c, c->tile_counter.ensure(16));
-    CK(c, c->X.ensure(xwords * 8 + 256));
+    {
+        void* before = c->X.p;
+        CK(c, c->X.ensure(xwords * 8 + 256));
+        if (c->X.p != before) c->x_zeroed = 0;
+    }
     uint32_t GT = (uint32_t)((maxcols + kPackGTileBytes - 1) / kPackGTileBytes); if (GT == 0) GT = 1;
     if (c->bl != 1) {
         uint64_t gnt = (uint64_t)H * GT;
@@ -309,7 +314,10 @@ static int run_device_group(drlz_ctx* c, const uint8_t* rows_dev, const uint64_t
 
         cudaEventRecord(c->ev_stage[0], s);
         const auto t_first = std::chrono::steady_clock::now();
-        CK(c, cudaMemsetAsync(c->X.p, 0, xwords * 8, s));
+        // the packed buffer must be zero where k_pack ORs in the words at tile borders; in the steady state the previous
+        // batch left it zeroed behind its last kernel (below), while the host was busy between the two calls
+        if (c->x_zeroed < xwords) CK(c, cudaMemsetAsync(c->X.p, 0, xwords * 8, s));
+        c->x_zeroed = 0;
         CK(c, cudaMemsetAsync(c->flags.p, 0, 16, s));
         cudaEventRecord(c->ev_stage[1], s);
         PackJob job;
@@ -409,6 +417,10 @@ static int run_device_group(drlz_ctx* c, const uint8_t* rows_dev, const uint64_t
             if (n_pairs) n_pairs[h] = sh_pairs[h + 1] - sh_pairs[h];
         }
         *total_pairs = total;
+        if (c->opt_postzero && !c->keep_x) {      // nothing reads the packed haplotypes any more: zero them for the next batch, unawaited
+            CK(c, cudaMemsetAsync(c->X.p, 0, xwords * 8, s));
+            c->x_zeroed = xwords;
+        }
         // timings
         float t;
         double* pm = c->parse_ms;
@@ -789,7 +801,9 @@ int drlz_matching_stats(drlz_ctx* c, const uint8_t* x, uint64_t m, uint32_t* ms_
     CK(c, cudaMemcpyAsync(c->stage[0].p, x, m, cudaMemcpyHostToDevice, s));
     uint64_t off = 0, mm = 0, np = 0, total = 0;
     // run the normal group path to get the packed haplotype (its phrase output is ignored)
+    c->keep_x = true;                       // k_ms_dense below reads the packed sequence
     int rc = run_device_group(c, c->stage[0].as<uint8_t>(), &off, &m, 1, 0, false, &mm, &np, &total, nullptr);
+    c->keep_x = false;
     if (rc != DRLZ_OK) return rc;
     uint64_t* sh = c->small_host.as<uint64_t>();
     CK(c, cudaMemcpyAsync(sh, c->exccnt.p, 8, cudaMemcpyDeviceToHost, s));
