@@ -3,8 +3,9 @@
 // Per pass: (1) per-tile digit histograms in shared memory -> digit-major matrix in HBM,
 //           (2) exclusive scan of the matrix (scan.cuh),
 //           (3) stable scatter: warp-level multisplit with __match_any_sync, warp-private digit
-//               counters in shared memory, cross-warp prefix per digit, then coalesced-as-possible
-//               stores (a tile of 4096 keys puts ~16 consecutive keys into each of the 256 runs).
+//               counters in shared memory, cross-warp prefix per digit, the tile staged in digit order in
+//               shared memory, then stores of contiguous pieces (a tile of 4096 keys puts ~16 consecutive
+//               keys into each of the 256 runs).
 // Passes whose digit is constant over all keys are skipped by the caller through the bit range.
 // Used by the suffix-array prefix doubling (sa_build.cu).
 #pragma once
@@ -35,18 +36,27 @@ k_sort_hist(const K* __restrict__ keys, uint64_t n, int shift, uint32_t* __restr
     hist[(uint64_t)threadIdx.x * ntiles + blockIdx.x] = h[threadIdx.x];
 }
 
+// Stable scatter of one tile.  Ranks come from a warp-level multisplit (__match_any_sync) with warp-private digit
+// counters; the tile is then put in digit order in shared memory, so that the stores to the 256 output runs are
+// contiguous pieces (~16 keys each) written by consecutive threads instead of 32 unrelated 8-byte stores per warp.
 template <typename K>
-__global__ void __launch_bounds__(kSortThreads)
+__global__ void __launch_bounds__(kSortThreads, 4)      // 64 registers: 4 CTAs per SM also fit their 43 KB of shared memory
 k_sort_scatter(const K* __restrict__ keys, const uint32_t* __restrict__ vals, K* __restrict__ okeys,
                uint32_t* __restrict__ ovals, uint64_t n, int shift, const uint32_t* __restrict__ offs,
                uint32_t ntiles) {
     __shared__ uint32_t wcnt[kSortWarps][256];
+    __shared__ uint32_t dstart[256];          // first tile-local slot of each digit
+    __shared__ uint32_t goff[256];            // global slot of that first element
+    __shared__ uint32_t sm[33];
+    __shared__ K stage[kSortTile];            // the tile in digit order (keys first, then reused for the values)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < kSortWarps * 256; i += kSortThreads) (&wcnt[0][0])[i] = 0;
     __syncthreads();
     // warp w owns the contiguous slice [w*512, w*512+512) of the tile; item k of lane l sits at k*32+l,
     // so (k, lane) order == memory order == stable order.
-    uint64_t base = (uint64_t)blockIdx.x * kSortTile + (uint64_t)warp * (32 * kSortItems);
+    const uint64_t tile0 = (uint64_t)blockIdx.x * kSortTile;
+    const uint64_t base = tile0 + (uint64_t)warp * (32 * kSortItems);
+    const uint32_t tile_n = (uint32_t)(n - tile0 < (uint64_t)kSortTile ? n - tile0 : (uint64_t)kSortTile);
     K key[kSortItems];
     uint32_t rank[kSortItems];
     const uint32_t lt = (1u << lane) - 1u;
@@ -65,22 +75,52 @@ k_sort_scatter(const K* __restrict__ keys, const uint32_t* __restrict__ vals, K*
         __syncwarp();
     }
     __syncthreads();
-    {   // digit t: exclusive prefix over warps + global offset of (digit, tile)
-        int t = threadIdx.x;
-        uint32_t run = offs[(uint64_t)t * ntiles + blockIdx.x];
+    {   // digit t: exclusive prefix over warps (tile-local), digit totals -> exclusive scan over digits
+        const int t = threadIdx.x;
+        uint32_t run = 0;
 #pragma unroll
         for (int w = 0; w < kSortWarps; ++w) { uint32_t c = wcnt[w][t]; wcnt[w][t] = run; run += c; }
+        uint32_t total;
+        uint32_t ds = block_exclusive_scan<uint32_t, OpSum>(run, OpSum(), 0u, &total, sm);
+        dstart[t] = ds;
+        goff[t] = offs[(uint64_t)t * ntiles + blockIdx.x];
+    }
+    __syncthreads();
+    uint32_t slot[kSortItems];
+#pragma unroll
+    for (int k = 0; k < kSortItems; ++k) {
+        uint64_t i = base + (uint64_t)k * 32 + lane;
+        slot[k] = 0;
+        if (i < n) {
+            unsigned d = (unsigned)(key[k] >> shift) & 255u;
+            slot[k] = dstart[d] + wcnt[warp][d] + rank[k];
+            stage[slot[k]] = key[k];
+        }
+    }
+    __syncthreads();
+    uint32_t dst[kSortItems];
+#pragma unroll
+    for (int k = 0; k < kSortItems; ++k) {
+        const uint32_t j = (uint32_t)k * kSortThreads + threadIdx.x;      // consecutive threads, consecutive slots
+        if (j < tile_n) {
+            const K kk = stage[j];
+            const unsigned d = (unsigned)(kk >> shift) & 255u;
+            dst[k] = goff[d] + (j - dstart[d]);
+            okeys[dst[k]] = kk;
+        }
+    }
+    __syncthreads();
+    uint32_t* vstage = reinterpret_cast<uint32_t*>(stage);
+#pragma unroll
+    for (int k = 0; k < kSortItems; ++k) {
+        uint64_t i = base + (uint64_t)k * 32 + lane;
+        if (i < n) vstage[slot[k]] = vals[i];
     }
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < kSortItems; ++k) {
-        uint64_t i = base + (uint64_t)k * 32 + lane;
-        if (i < n) {
-            unsigned d = (unsigned)(key[k] >> shift) & 255u;
-            uint32_t dst = wcnt[warp][d] + rank[k];
-            okeys[dst] = key[k];
-            ovals[dst] = vals[i];
-        }
+        const uint32_t j = (uint32_t)k * kSortThreads + threadIdx.x;
+        if (j < tile_n) ovals[dst[k]] = vstage[j];
     }
 }
 
