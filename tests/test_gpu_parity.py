@@ -144,6 +144,37 @@ def test_parse_random_small(ctx, seed):
     ctx.set_option("min_cap", 0)
 
 
+@pytest.mark.parametrize("blind", [0, 1, 2, 6])
+def test_fix_rounds_blind_or_not(ctx, blind):
+    """The fix-up rounds are launched without a read-back in between (option blind_rounds, default 2) and one
+    read-back afterwards decides whether more are needed; with tiny chunks many rounds are needed, so every mix of
+    blind and checked rounds -- and the redone marking after an insufficient blind guess -- must give the same parse."""
+    rng = np.random.default_rng(4242)
+    ctx.set_option("blind_rounds", blind)
+    try:
+        for it in range(25):
+            d, x = random_case(rng, b"ACGT", 300, 600)
+            ctx.set_option("chunk", int(rng.choice([2, 4, 16, 64])))
+            ctx.set_option("kmer", int(rng.integers(1, 6)))
+            ctx.build_index(d)
+            _check_rows(ctx, d, [x, x[::-1], d, x + x])
+            assert ctx.parse_timings()["fix_rounds"] >= 1
+    finally:
+        ctx.set_option("blind_rounds", 2); ctx.set_option("chunk", 0); ctx.set_option("kmer", 0)
+
+
+def test_repeated_batches_reuse_buffers(ctx):
+    """steady state of a streaming caller: the zero-fill behind a batch serves the next one, records are emitted into
+    the previous batch's buffer; batches of different sizes and shapes in a row must not see each other's leftovers"""
+    seed = orc.seed_for(1)
+    d = orc.syn_reference(seed, 300_000)
+    rows = [r.tobytes() for r in orc.syn_rows(seed, d, 0, 6, 2e-3, 2e-4, 2e-4)]
+    ctx.build_index(d.tobytes())
+    sa = orc.sa_build(d.tobytes())
+    for batch in ([rows[1]], rows, [rows[3][:1000], rows[2]], rows[:2], [b"", rows[5]], rows):
+        _check_rows(ctx, d.tobytes(), batch, sa=sa)
+
+
 def test_parse_golden(ctx):
     for f in sorted(os.listdir(GOLD)):
         if not f.endswith(".npz"):
