@@ -63,7 +63,7 @@ struct drlz_ctx {
     size_t blob_bytes = 0, text_bytes = 0, uniq_bytes = 0, tab_bytes = 0;
     uint32_t bl = 1, sigma = 4;        // symbol width (log2 bits) and alphabet size of the index
     int opt_predict = 1;
-    cudaStream_t l2_stream = nullptr; int opt_l2persist = 0; int opt_occ = 8; int opt_occ_fix = 10; int opt_tickets = 1; int opt_pack_v = 2; int opt_hint = 1; int opt_diag = 1; uint32_t opt_spec_store = 0;
+    cudaStream_t l2_stream = nullptr; int opt_l2persist = 0; int opt_occ = 8; int opt_occ_fix = 10; int opt_tickets = 1; int opt_hint = 1; int opt_diag = 1; uint32_t opt_spec_store = 0;
     double idx_ms[5] = {0, 0, 0, 0, 0};
     // batch scratch (grow-only)
     DevBuf stage[2], meta_dev, desc_cnt, desc_exc, tile_counter, X, mdev, exccnt, excpos, excbyte,
@@ -201,7 +201,6 @@ int drlz_set_option(drlz_ctx* c, const char* key, int64_t v) {
     else if (!strcmp(key, "diag")) c->opt_diag = v != 0;
     else if (!strcmp(key, "spec_store")) { if (v < 0 || v > 4096) return DRLZ_E_ARG; c->opt_spec_store = (uint32_t)v; }
     else if (!strcmp(key, "tickets")) c->opt_tickets = v != 0;
-    else if (!strcmp(key, "pack_v")) { if (v != 1 && v != 2) return DRLZ_E_ARG; c->opt_pack_v = (int)v; }
     else if (!strcmp(key, "predict")) c->opt_predict = v != 0;
     else if (!strcmp(key, "occ_pack")) c->opt_occ_pack = (int)v;
     else if (!strcmp(key, "blind_rounds")) c->opt_blind_rounds = (int)v;
@@ -325,7 +324,7 @@ static int run_device_group(drlz_ctx* c, const uint8_t* rows_dev, const uint64_t
         job.rows = rows_dev; job.row_off = d_row_off; job.cols = d_cols; job.H = H; job.tiles_per_row = T; job.strip = strip;
         job.desc_cnt = c->desc_cnt.as<uint64_t>(); job.desc_exc = c->desc_exc.as<uint64_t>();
         job.tile_counter = c->tile_counter.as<uint32_t>(); job.X = c->X.as<uint64_t>(); job.xoff = d_xoff;
-        job.occ = c->opt_occ_pack; job.prefetch = c->opt_prefetch; job.use_tickets = c->opt_tickets; job.variant = c->opt_pack_v;
+        job.occ = c->opt_occ_pack; job.prefetch = c->opt_prefetch; job.use_tickets = c->opt_tickets;
         job.m_out = c->mdev.as<uint64_t>(); job.exc_cnt = c->exccnt.as<uint64_t>();
         job.exc_pos = c->excpos.as<uint32_t>(); job.exc_byte = c->excbyte.as<uint8_t>(); job.exc_stride = exc_stride;
         job.flags = c->flags.as<uint32_t>();
@@ -513,7 +512,7 @@ int drlz_build_index(drlz_ctx* c, const uint8_t* ref, uint64_t n) {
         job.rows = c->stage[0].as<uint8_t>(); job.row_off = dm; job.cols = dm + 1; job.H = 1; job.tiles_per_row = T; job.strip = 0;
         job.desc_cnt = c->desc_cnt.as<uint64_t>(); job.desc_exc = c->desc_exc.as<uint64_t>();
         job.tile_counter = c->tile_counter.as<uint32_t>(); job.X = c->d_text; job.xoff = dm + 2;
-        job.occ = c->opt_occ_pack; job.prefetch = 0; job.use_tickets = 1; job.variant = c->opt_pack_v;
+        job.occ = c->opt_occ_pack; job.prefetch = 0; job.use_tickets = 1;
         job.m_out = c->mdev.as<uint64_t>(); job.exc_cnt = c->exccnt.as<uint64_t>();
         job.exc_pos = c->excpos.as<uint32_t>(); job.exc_byte = c->excbyte.as<uint8_t>(); job.exc_stride = 64;
         job.flags = c->flags.as<uint32_t>(); job.gapless = nullptr; job.gapless_off = dm + 3;

@@ -26,7 +26,6 @@ struct PackJob {
     int occ;                      // min CTAs per SM the kernel is compiled for (6 or 8)
     uint32_t prefetch;            // L2 prefetch distance in tiles (0 = off): CTA i prefetches the bytes of tile i + prefetch
     int use_tickets;              // 1: tile ids from the atomic counter; 0: from blockIdx (dispatch order), guarded by a timeout
-    int variant;                  // 1: k_pack, 2: k_pack2 (leaner instruction stream, warp-private irregular path)
     uint64_t* X;                  // packed output, zero-filled by the caller
     const uint64_t* xoff;         // [H] word offset of haplotype h inside X (device)
     uint64_t* m_out;              // [H] gapless lengths (device)

@@ -8,25 +8,15 @@
 // non-gap bytes before it in the row) comes from a decoupled look-back over per-tile descriptors
 // {status:2, value:62} in the same kernel (tiles take their ids from an atomic counter, so every predecessor is
 // already running): the MSA bytes are read from HBM exactly once.  ACGT validation and code extraction are
-// SIMD-in-register (~15 integer ops per 4 bytes).  Tiles without gaps or foreign bytes (the common case) assemble
-// their 64-bit output words in registers with one shuffle; other tiles go through a shared-memory bit buffer.
-// The first / last partially covered output word of a tile is OR-ed atomically into the zero-filled output.
+// SIMD-in-register (~11 instructions per 4 bytes).  Every warp whose 2 KB hold neither a gap nor a foreign byte
+// assembles its 64-bit output words in registers with one shuffle; a warp that holds irregular bytes goes through
+// its own shared-memory bit buffer.  Partially covered words at tile / warp borders are OR-ed atomically into the
+// zero-filled output (in a tile without any irregular byte only the tile's two edge words are).
 // HBM traffic = M read + m/4 written (+ m/4 zero fill): the algorithmic bytes of SURVEY.md 8(d).
 #include "drlz_internal.h"
 #include "scan.cuh"
 
 namespace drlz {
-
-// 4 ASCII bytes -> per-byte 2-bit codes (A0 C1 G2 T3) in the low 2 bits of each byte; *ok = all four valid
-__device__ __forceinline__ uint32_t codes4(uint32_t w, bool* ok) {
-    uint32_t c = (w >> 1) & 0x03030303u;                  // A0 C1 T2 G3
-    uint32_t m = (c >> 1) & ~c & 0x01010101u;             // 1 where T
-    uint32_t expect = 0x41414141u + (c << 1) + (m << 4) - m;
-    *ok = expect == w;
-    return c ^ ((c >> 1) & 0x01010101u);                  // swap 2 <-> 3
-}
-// four per-byte codes (first byte = lowest address) -> 8 bits, first base in the top bits
-__device__ __forceinline__ uint32_t squeeze4(uint32_t c) { return (c * 0x40100401u) >> 24; }
 
 struct Seg16 {
     uint32_t cnt;      // non-gap bytes
@@ -35,34 +25,6 @@ struct Seg16 {
 };
 
 __device__ __forceinline__ uint4 load16(const uint8_t* p) { return *reinterpret_cast<const uint4*>(p); }
-
-__device__ __forceinline__ Seg16 classify16(uint4 v, int nvalid, int strip) {
-    Seg16 s;
-    bool k0, k1, k2, k3;
-    uint32_t c0 = codes4(v.x, &k0), c1 = codes4(v.y, &k1), c2 = codes4(v.z, &k2), c3 = codes4(v.w, &k3);
-    if (nvalid == 16 && k0 && k1 && k2 && k3) {
-        s.cnt = 16; s.exc = 0;
-        s.codes = (squeeze4(c0) << 24) | (squeeze4(c1) << 16) | (squeeze4(c2) << 8) | squeeze4(c3);
-        return s;
-    }
-    uint32_t w[4] = {v.x, v.y, v.z, v.w};
-    uint32_t cnt = 0, exc = 0, codes = 0;
-#pragma unroll
-    for (int b = 0; b < 16; ++b) {
-        uint32_t byte = (w[b >> 2] >> (8 * (b & 3))) & 255u;
-        bool gap = b >= nvalid || (strip && byte == '-');
-        if (!gap) {
-            uint32_t c = (byte >> 1) & 3u; c ^= c >> 1;
-            bool valid = byte == 'A' || byte == 'C' || byte == 'G' || byte == 'T';
-            if (!valid) { c = 0; ++exc; }
-            codes = (codes << 2) | c;
-            ++cnt;
-        }
-    }
-    s.cnt = cnt; s.exc = exc;
-    s.codes = cnt ? codes << (2 * (16 - cnt)) : 0u;
-    return s;
-}
 
 static const uint64_t kDescAgg = 1ull << 62, kDescPrefix = 2ull << 62, kDescMask = (1ull << 62) - 1;
 
@@ -102,197 +64,15 @@ __device__ __forceinline__ uint64_t lookback(uint64_t* desc_row, uint32_t t, uin
     return excl;
 }
 
-static const int kTilesPerCta = 1;            // (kept for the record, see below)            // tiles per atomic ticket (4 was measured 18x slower: a tile is published only after
-                                              // its CTA finished the earlier ones, which serialises every row's look-back chain)
-
 static const int kPackThreads = kPackTileBytes / 64;
 
-__device__ __forceinline__ void pack_tile(const PackJob& job, uint32_t h, uint32_t t, uint32_t* sbits, uint32_t* sm,
-                                          uint64_t* s_bcast, uint64_t* s_wlast) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint64_t cols = job.cols[h];
-    const uint64_t tile_start = (uint64_t)t * kPackTileBytes;
-    uint64_t* dcnt = job.desc_cnt + (uint64_t)h * job.tiles_per_row;
-    uint64_t* dexc = job.desc_exc + (uint64_t)h * job.tiles_per_row;
-    const bool last_tile = t + 1 == job.tiles_per_row;
-
-    // ---- load and classify 64 bytes per thread -------------------------------------------------------------
-    const uint64_t off = tile_start + (uint64_t)tid * 64;
-    Seg16 sg[4];
-    uint32_t cnt = 0, exc = 0;
-    const uint8_t* rowp = job.rows + job.row_off[h];
-    if (tile_start + kPackTileBytes <= cols) {            // interior tile (block-uniform): no bounds logic at all
-        const uint4* src = reinterpret_cast<const uint4*>(rowp + off);
-        uint4 v0 = src[0], v1 = src[1], v2 = src[2], v3 = src[3];
-        sg[0] = classify16(v0, 16, job.strip); sg[1] = classify16(v1, 16, job.strip);
-        sg[2] = classify16(v2, 16, job.strip); sg[3] = classify16(v3, 16, job.strip);
-        cnt = sg[0].cnt + sg[1].cnt + sg[2].cnt + sg[3].cnt;
-        exc = sg[0].exc + sg[1].exc + sg[2].exc + sg[3].exc;
-    } else {
-        uint4 v[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            uint64_t o = off + 16u * q;
-            v[q] = make_uint4(0, 0, 0, 0);
-            if (o < cols) v[q] = load16(rowp + o);
-        }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            uint64_t o = off + 16u * q;
-            sg[q].cnt = 0; sg[q].exc = 0; sg[q].codes = 0;
-            if (o < cols) {
-                int nvalid = cols - o >= 16 ? 16 : (int)(cols - o);
-                sg[q] = classify16(v[q], nvalid, job.strip);
-            }
-            cnt += sg[q].cnt; exc += sg[q].exc;
-        }
-    }
-    // the bit buffer of the general path is cleared before the scan; the scan's barriers order it before the ORs
-    for (int i = tid; i < kPackTileBytes / 16 + 8; i += kPackThreads) sbits[i] = 0;
-    uint32_t total;
-    uint32_t ex = block_exclusive_scan<uint32_t, OpSum>(cnt | (exc << 16), OpSum(), 0u, &total, sm);
-    const uint32_t lo = ex & 0xFFFFu, elo = ex >> 16;     // local base offset, local exception offset
-    const uint32_t T = total & 0xFFFFu, TE = total >> 16;
-    const bool fast = T == kPackTileBytes && TE == 0;        // no gap, no foreign byte, full tile
-
-    // ---- tile offset inside the row: decoupled look-back by warp 0, while the other warps assemble the tile's
-    //      bases in the shared-memory bit buffer (that needs local offsets only) ------------------------------------
-    if (warp == 0) {
-        uint64_t o = lookback(dcnt, t, T, job.flags);
-        uint64_t eo = 0;
-        if (TE || last_tile) eo = lookback(dexc, t, TE, job.flags);
-        else if (lane == 0) st_desc(&dexc[t], (t == 0 ? kDescPrefix : kDescAgg) | 0ull);
-        if (lane == 0) {
-            s_bcast[1] = o; s_bcast[2] = eo;
-            if (last_tile) {
-                job.m_out[h] = o + T;
-                uint64_t ne = eo + TE;
-                job.exc_cnt[h] = ne;
-                if (ne > job.exc_stride) atomicOr(job.flags, 1u);
-            }
-        }
-    }
-    if (!fast) {
-        uint32_t l = lo;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            if (sg[q].cnt) {
-                uint32_t wi = l >> 4, sh = (l & 15u) * 2;
-                atomicOr(&sbits[wi], sg[q].codes >> sh);
-                if (sh && sg[q].cnt > 16 - (l & 15u)) atomicOr(&sbits[wi + 1], sg[q].codes << (32 - sh));
-                l += sg[q].cnt;
-            }
-        }
-    }
-    __syncthreads();
-    const uint64_t o = s_bcast[1];
-    if (T == 0) return;
-    uint64_t* X = job.X + job.xoff[h];
-    const uint32_t lead = (uint32_t)(o & 31);
-    const uint64_t W0 = o >> 5;
-
-    if (job.gapless || exc) {          // optional gapless bytes / rare exceptions: plain byte loops
-        uint64_t e = s_bcast[2] + elo;
-        uint64_t p = o + lo;
-        uint8_t* gl = job.gapless ? job.gapless + job.gapless_off[h] : nullptr;
-        uint32_t* ep = job.exc_pos + (uint64_t)h * job.exc_stride;
-        uint8_t* eb = job.exc_byte + (uint64_t)h * job.exc_stride;
-        for (int q = 0; q < 4; ++q) {
-            uint64_t ob = off + 16u * q;
-            int nvalid = ob >= cols ? 0 : (cols - ob >= 16 ? 16 : (int)(cols - ob));
-            for (int b = 0; b < nvalid; ++b) {
-                uint32_t byte = rowp[ob + b];              // rare path: re-read (L1/L2 hit)
-                if (job.strip && byte == '-') continue;
-                bool valid = byte == 'A' || byte == 'C' || byte == 'G' || byte == 'T';
-                if (!valid) {
-                    if (e < job.exc_stride) { ep[e] = (uint32_t)p; eb[e] = (uint8_t)byte; }
-                    ++e;
-                }
-                if (gl) gl[p] = (uint8_t)byte;
-                ++p;
-            }
-        }
-    }
-
-    if (fast) {
-        // thread owns local 64-bit words 2*tid, 2*tid+1; global word j = (local[j-1] << 2(32-lead)) | (local[j] >> 2 lead)
-        uint64_t w0 = ((uint64_t)sg[0].codes << 32) | sg[1].codes;
-        uint64_t w1 = ((uint64_t)sg[2].codes << 32) | sg[3].codes;
-        if (lane == 31) s_wlast[warp] = w1;
-        uint64_t prev = __shfl_up_sync(0xffffffffu, w1, 1);
-        __syncthreads();
-        if (lane == 0) prev = warp ? s_wlast[warp - 1] : 0ull;
-        uint64_t g0, g1;
-        if (lead == 0) { g0 = w0; g1 = w1; }
-        else {
-            unsigned sh = 2 * lead;
-            g0 = (prev << (64 - sh)) | (w0 >> sh);
-            g1 = (w0 << (64 - sh)) | (w1 >> sh);
-        }
-        uint64_t* dst = X + W0 + 2 * (uint64_t)tid;
-        if (tid == 0 && lead != 0) atomicOr(reinterpret_cast<unsigned long long*>(dst), (unsigned long long)g0);
-        else dst[0] = g0;
-        dst[1] = g1;
-        if (tid == kPackThreads - 1 && lead != 0)
-            atomicOr(reinterpret_cast<unsigned long long*>(dst + 2), (unsigned long long)(w1 << (64 - 2 * lead)));
-        return;
-    }
-
-    // ---- general path: the bases were assembled in the shared-memory bit buffer above ----------------------------
-    uint32_t nwords = (lead + T + 31) >> 5;
-    for (uint32_t j = tid; j < nwords; j += kPackThreads) {
-        int64_t lb = (int64_t)j * 32 - (int64_t)lead;      // local base index of the word's first base
-        uint32_t b0 = lb < 0 ? 0u : (uint32_t)lb;
-        uint32_t wi = b0 >> 4, sh = (b0 & 15u) * 2;
-        uint64_t hi = ((uint64_t)sbits[wi] << 32) | sbits[wi + 1];
-        uint64_t val = sh ? (hi << sh) | ((uint64_t)sbits[wi + 2] >> (32 - sh)) : hi;
-        if (lb < 0) val >>= 2 * lead;
-        bool first_partial = j == 0 && lead != 0;
-        bool last_partial = j == nwords - 1 && ((lead + T) & 31u) != 0;
-        if (first_partial || last_partial) atomicOr(reinterpret_cast<unsigned long long*>(&X[W0 + j]), (unsigned long long)val);
-        else X[W0 + j] = val;
-    }
-}
-
-// MINB = 8 (32 registers, ~100 bytes of spills) measured 8 % faster than 6 (40 registers): the kernel hides its
-// barrier and look-back waits with resident warps.
-template <int MINB>
-__global__ void __launch_bounds__(kPackThreads, MINB) k_pack(PackJob job, uint32_t n_tiles) {
-    __shared__ uint32_t sbits[kPackTileBytes / 16 + 8];
-    __shared__ uint32_t sm[33];
-    __shared__ uint64_t s_bcast[4];
-    __shared__ uint64_t s_wlast[kPackThreads / 32];
-    __shared__ uint32_t s_ticket[5];
-    // rows interleaved: consecutive ids are the same tile index of consecutive rows, so each row has only a few
-    // tiles in flight and its look-back resolves within one 32-descriptor window.  Thread 0 takes the ticket and
-    // does the one integer division of the CTA.
-    if (threadIdx.x == 0) {
-        uint32_t id = job.use_tickets ? atomicAdd(job.tile_counter, 1u) : blockIdx.x;
-        s_ticket[0] = id; s_ticket[1] = id % job.H; s_ticket[2] = id / job.H;
-        const uint32_t idp = id + job.prefetch;          // the tile a CTA launched ~one CTA lifetime from now will load
-        s_ticket[3] = idp % job.H; s_ticket[4] = (job.prefetch && idp < n_tiles) ? idp / job.H : 0xFFFFFFFFu;
-    }
-    __syncthreads();
-    if (s_ticket[0] >= n_tiles) return;
-    if (s_ticket[4] != 0xFFFFFFFFu && threadIdx.x < kPackTileBytes / 128) {
-        // software prefetch into L2: by the time that tile's CTA starts, its bytes are one L2 hit away
-        const uint32_t hp = s_ticket[3];
-        const uint64_t o = (uint64_t)s_ticket[4] * kPackTileBytes + (uint64_t)threadIdx.x * 128;
-        if (o < job.cols[hp]) asm volatile("prefetch.global.L2 [%0];" ::"l"(job.rows + job.row_off[hp] + o));
-    }
-    pack_tile(job, s_ticket[1], s_ticket[2], sbits, sm, s_bcast, s_wlast);
-}
-
-// ---- k_pack2: same tile scheme, leaner instruction stream ---------------------------------------------------------
-// What changed against k_pack (the kernel is bound by integer issue, profiles/README.md item 13):
+// ---- classification -------------------------------------------------------------------------------------------------
+// The kernel is bound by integer issue (profiles/README.md items 13 and 18), hence:
 //   * ACGT validation from the masked byte itself: (b & 0xF9) == 0x41 for A, C, G and 0x50 for T, where "T" is
 //     bits 2:1 == 10 -- two shifts, four logic operations and two multiply-adds per 4 bytes;
-//   * block scan with one barrier (every warp sums the 8 warp totals itself);
-//   * no tile-wide bit buffer: inside a tile that contains a gap or a foreign byte, every warp whose 2 KB are clean
-//     still assembles its words in registers (its two edge words are OR-ed into the output), and only the warps that
-//     hold the irregular bytes go through a warp-private bit buffer;
-//   * a 16-byte segment with a gap is compacted word by word (clean words are appended 4 codes at a time).
-__device__ __forceinline__ uint32_t codes4b(uint32_t w, uint32_t* bad) {
+//   * a 16-byte segment with a gap is compacted word by word (clean words are appended 4 codes at a time);
+//   * block scan with one barrier (every warp sums the 8 warp totals itself).
+__device__ __forceinline__ uint32_t codes4(uint32_t w, uint32_t* bad) {
     const uint32_t s1 = w >> 1, s2 = w >> 2;
     const uint32_t t = s2 & ~s1 & 0x01010101u;                        // bits 2:1 == 10: 'T' among the valid bytes
     *bad = (w & 0xF9F9F9F9u) ^ (t * 15u + 0x41414141u);               // per byte: zero iff the byte is A, C, G or T
@@ -303,10 +83,10 @@ __device__ __forceinline__ uint32_t top_bytes(uint32_t p0, uint32_t p1, uint32_t
     return __byte_perm(__byte_perm(p3, p2, 0x0073), __byte_perm(p1, p0, 0x0073), 0x5410);
 }
 
-__device__ __forceinline__ Seg16 classify16b(uint4 v, int nvalid, int strip) {
+__device__ __forceinline__ Seg16 classify16(uint4 v, int nvalid, int strip) {
     Seg16 s;
     uint32_t b0, b1, b2, b3;
-    const uint32_t c0 = codes4b(v.x, &b0), c1 = codes4b(v.y, &b1), c2 = codes4b(v.z, &b2), c3 = codes4b(v.w, &b3);
+    const uint32_t c0 = codes4(v.x, &b0), c1 = codes4(v.y, &b1), c2 = codes4(v.z, &b2), c3 = codes4(v.w, &b3);
     const uint32_t p0 = c0 * 0x40100401u, p1 = c1 * 0x40100401u, p2 = c2 * 0x40100401u, p3 = c3 * 0x40100401u;
     if (nvalid == 16 && (b0 | b1 | b2 | b3) == 0) {
         s.cnt = 16; s.exc = 0; s.codes = top_bytes(p0, p1, p2, p3);
@@ -356,7 +136,7 @@ __device__ __forceinline__ void flush_bits(const uint32_t* sb, uint64_t* X, uint
     }
 }
 
-__device__ __forceinline__ void pack_tile2(const PackJob& job, uint32_t h, uint32_t t, uint32_t* sbits, uint32_t* sm,
+__device__ __forceinline__ void pack_tile(const PackJob& job, uint32_t h, uint32_t t, uint32_t* sbits, uint32_t* sm,
                                            uint64_t* s_bcast, uint64_t* s_wlast) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint64_t cols = job.cols[h];
@@ -373,8 +153,8 @@ __device__ __forceinline__ void pack_tile2(const PackJob& job, uint32_t h, uint3
     if (tile_start + kPackTileBytes <= cols) {            // interior tile (block-uniform): no bounds logic at all
         const uint4* src = reinterpret_cast<const uint4*>(rowp + off);
         uint4 v0 = src[0], v1 = src[1], v2 = src[2], v3 = src[3];
-        sg[0] = classify16b(v0, 16, job.strip); sg[1] = classify16b(v1, 16, job.strip);
-        sg[2] = classify16b(v2, 16, job.strip); sg[3] = classify16b(v3, 16, job.strip);
+        sg[0] = classify16(v0, 16, job.strip); sg[1] = classify16(v1, 16, job.strip);
+        sg[2] = classify16(v2, 16, job.strip); sg[3] = classify16(v3, 16, job.strip);
         cnt = sg[0].cnt + sg[1].cnt + sg[2].cnt + sg[3].cnt;
         exc = sg[0].exc + sg[1].exc + sg[2].exc + sg[3].exc;
     } else {
@@ -391,7 +171,7 @@ __device__ __forceinline__ void pack_tile2(const PackJob& job, uint32_t h, uint3
             sg[q].cnt = 0; sg[q].exc = 0; sg[q].codes = 0;
             if (o < cols) {
                 int nvalid = cols - o >= 16 ? 16 : (int)(cols - o);
-                sg[q] = classify16b(v[q], nvalid, job.strip);
+                sg[q] = classify16(v[q], nvalid, job.strip);
             }
             cnt += sg[q].cnt; exc += sg[q].exc;
         }
@@ -506,7 +286,7 @@ __device__ __forceinline__ void pack_tile2(const PackJob& job, uint32_t h, uint3
 }
 
 template <int MINB>
-__global__ void __launch_bounds__(kPackThreads, MINB) k_pack2(PackJob job, uint32_t n_tiles) {
+__global__ void __launch_bounds__(kPackThreads, MINB) k_pack(PackJob job, uint32_t n_tiles) {
     __shared__ uint32_t sbits[kPackWarps * kWarpBits];
     __shared__ uint32_t sm[kPackWarps];
     __shared__ uint64_t s_bcast[4];
@@ -525,7 +305,7 @@ __global__ void __launch_bounds__(kPackThreads, MINB) k_pack2(PackJob job, uint3
         const uint64_t o = (uint64_t)s_ticket[4] * kPackTileBytes + (uint64_t)threadIdx.x * 128;
         if (o < job.cols[hp]) asm volatile("prefetch.global.L2 [%0];" ::"l"(job.rows + job.row_off[hp] + o));
     }
-    pack_tile2(job, s_ticket[1], s_ticket[2], sbits, sm, s_bcast, s_wlast);
+    pack_tile(job, s_ticket[1], s_ticket[2], sbits, sm, s_bcast, s_wlast);
 }
 
 // ---- generic alphabets (references with N, soft-masking, IUPAC codes ...): 4 or 8 bits per symbol ----------------
@@ -651,11 +431,9 @@ void launch_pack(const PackJob& job, cudaStream_t s, cudaEvent_t* ev) {
     cudaMemsetAsync(job.tile_counter, 0, 4, s);
     if (ev) { cudaEventRecord(ev[0], s); cudaEventRecord(ev[1], s); }
     g_launches += 1;
-    const unsigned grid = (unsigned)((nt + kTilesPerCta - 1) / kTilesPerCta);
-    if (job.variant == 2) {
-        if (job.occ >= 8) k_pack2<8><<<grid, kPackThreads, 0, s>>>(job, (uint32_t)nt);
-        else k_pack2<6><<<grid, kPackThreads, 0, s>>>(job, (uint32_t)nt);
-    } else if (job.occ >= 8) k_pack<8><<<grid, kPackThreads, 0, s>>>(job, (uint32_t)nt);
+    const unsigned grid = (unsigned)nt;          // one tile per CTA (4 per ticket measured 18x slower: a tile is published only
+                                                 // after its CTA finished the earlier ones, which serialises every row's look-back)
+    if (job.occ >= 8) k_pack<8><<<grid, kPackThreads, 0, s>>>(job, (uint32_t)nt);
     else k_pack<6><<<grid, kPackThreads, 0, s>>>(job, (uint32_t)nt);
     if (ev) cudaEventRecord(ev[2], s);
 }
