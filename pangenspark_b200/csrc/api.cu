@@ -63,7 +63,7 @@ struct drlz_ctx {
     size_t blob_bytes = 0, text_bytes = 0, uniq_bytes = 0, tab_bytes = 0;
     uint32_t bl = 1, sigma = 4;        // symbol width (log2 bits) and alphabet size of the index
     int opt_predict = 1;
-    cudaStream_t l2_stream = nullptr; int opt_l2persist = 0; int opt_occ = 8; int opt_occ_fix = 10; int opt_tickets = 1; int opt_hint = 1; int opt_diag = 1; uint32_t opt_spec_store = 0;
+    cudaStream_t l2_stream = nullptr; int opt_l2persist = 0; int opt_occ = 8; int opt_occ_fix = 10; int opt_occ_diag = 12; int opt_tickets = 1; int opt_hint = 1; int opt_diag = 1; uint32_t opt_spec_store = 0;
     double idx_ms[5] = {0, 0, 0, 0, 0};
     // batch scratch (grow-only)
     DevBuf stage[2], meta_dev, desc_cnt, desc_exc, tile_counter, X, mdev, exccnt, excpos, excbyte,
@@ -197,6 +197,7 @@ int drlz_set_option(drlz_ctx* c, const char* key, int64_t v) {
     else if (!strcmp(key, "l2persist")) { c->opt_l2persist = v != 0; c->l2_stream = nullptr; }
     else if (!strcmp(key, "occ")) c->opt_occ = (int)v;
     else if (!strcmp(key, "occ_fix")) c->opt_occ_fix = (int)v;
+    else if (!strcmp(key, "occ_diag")) c->opt_occ_diag = (int)v;
     else if (!strcmp(key, "hint")) c->opt_hint = v != 0;
     else if (!strcmp(key, "diag")) c->opt_diag = v != 0;
     else if (!strcmp(key, "spec_store")) { if (v < 0 || v > 4096) return DRLZ_E_ARG; c->opt_spec_store = (uint32_t)v; }
@@ -376,7 +377,7 @@ static int run_device_group(drlz_ctx* c, const uint8_t* rows_dev, const uint64_t
         pb.hint = (c->opt_hint && !single_chunk) ? c->hint.as<int64_t>() : nullptr;
         pb.true_slot = c->true_slot.as<uint32_t>();
         pb.pv.counters = c->counters.as<uint32_t>();
-        pb.H = H; pb.max_chunks_per_hap = maxc ? maxc : 1; pb.occ = c->opt_occ; pb.occ_fix = c->opt_occ_fix; pb.blind_rounds = c->opt_blind_rounds;
+        pb.H = H; pb.max_chunks_per_hap = maxc ? maxc : 1; pb.occ = c->opt_occ; pb.occ_fix = c->opt_occ_fix; pb.occ_diag = c->opt_occ_diag; pb.blind_rounds = c->opt_blind_rounds;
         pb.jump_a = c->jump_a.as<uint32_t>(); pb.jump_b = c->jump_b.as<uint32_t>(); pb.mark = c->mark.as<uint8_t>();
         pb.true_cnt = c->true_cnt.as<uint32_t>(); pb.true_entry = c->true_entry.as<uint32_t>(); pb.true_off = c->true_off.as<uint64_t>();
         pb.scan_tmp = c->scan_tmp.as<uint64_t>();

@@ -70,6 +70,7 @@ struct ParseBuffers {
     uint32_t max_chunks_per_hap;
     int occ;                      // min CTAs per SM of k_spec (0 = compiler default; 8 / 10 / 12 / 16)
     int occ_fix;                  // same for k_fix
+    int occ_diag;                 // same for k_diag_w (16 / 12 / 10)
     uint64_t* res; void* host_res; size_t res_bytes;   // result block (layout at k_results) and its pinned host mirror
     const uint64_t* m_dev; const uint64_t* exccnt_dev; const uint32_t* flags_dev;   // what k_pack left for it
     int64_t* spec_out;            // where parse_stage_count may emit the records right away (null = do not)

@@ -54,8 +54,80 @@ __global__ void __launch_bounds__(128) k_hint(ParseView pv, int64_t* hint, uint3
 // because chunks start at multiples of 32 bases), so both streams are read with coalesced 256-byte requests at
 // 32 active lanes -- this is the whole streaming compare of the parse, done once.  Mismatching words are decoded
 // in lane order (ballot), which keeps the offsets sorted.  Same result as diag_scan_chunk().
-template <int BL>        // BL = 1: 2-bit symbols known at compile time; 0: width read from the index
-__global__ void __launch_bounds__(128, 16) k_diag_w(ParseView pv) {
+//
+// The compare is bound by instruction issue, so the loop over complete slabs carries nothing but the loads, the
+// funnel shift and the XOR: two running pointers, the half of the funnel fixed at compile time (ODD), no bounds or
+// tail-mask logic (that lives in the loop over the last, partial group of slabs).
+struct DiagList {            // the chunk's mismatch list under construction (warp-uniform)
+    uint16_t* mm; uint32_t cnt, V; bool full;
+};
+template <int BL>
+__device__ __forceinline__ void diag_decode(DiagList& L, const uint64_t (&xr)[4], uint32_t w0, uint32_t bl, int lane) {
+    const uint32_t sl = 6 - bl, B = 1u << bl;
+    const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const bool hit = xr[r] != 0;
+        unsigned bal = __ballot_sync(0xffffffffu, hit);
+        if (!bal || L.full) continue;
+        // the usual case -- one mismatching symbol per mismatching word, and room in the list for all of them: every
+        // lane stores its own offset at its rank among the mismatching lanes (lane order == offset order)
+        const uint32_t b1 = hit ? (uint32_t)(clz64(xr[r]) >> bl) : 0u;
+        const uint64_t rest = hit ? xr[r] & ~(((1ull << B) - 1) << (64 - B - B * b1)) : 0ull;
+        const uint32_t nb = (uint32_t)__popc(bal);
+        if (L.cnt + nb <= (uint32_t)kMmMax && !__any_sync(0xffffffffu, rest != 0)) {
+            if (hit) L.mm[2 + L.cnt + __popc(bal & lt)] = (uint16_t)(((w0 + 32u * r + (uint32_t)lane) << sl) + b1);
+            L.cnt += nb;
+            continue;
+        }
+        while (bal && !L.full) {
+            const int src = __ffs(bal) - 1;
+            bal &= bal - 1;
+            uint64_t w = __shfl_sync(0xffffffffu, xr[r], src);
+            const uint32_t ob = (w0 + 32u * r + (uint32_t)src) << sl;
+            while (w) {
+                uint32_t b = (uint32_t)(clz64(w) >> bl);
+                if (L.cnt == (uint32_t)kMmMax) { L.V = ob + b; L.full = true; break; }
+                if (lane == 0) L.mm[2 + L.cnt] = (uint16_t)(ob + b);
+                ++L.cnt;
+                w &= ~(((1ull << B) - 1) << (64 - B - B * b));
+            }
+        }
+    }
+}
+template <int BL, bool ODD>
+__device__ __forceinline__ void diag_compare(DiagList& L, const uint64_t* __restrict__ xw, const uint64_t* __restrict__ Dw,
+                                             unsigned s5, uint32_t nfull, uint32_t rem, uint32_t bl, int lane) {
+    const uint32_t B = 1u << bl;
+    const uint32_t nwords = nfull + (rem ? 1u : 0u);
+    const uint64_t* __restrict__ xl = xw + lane;
+    const uint64_t* __restrict__ dl = Dw + lane;
+    uint32_t w0 = 0;
+    for (; w0 + 128u <= nfull && !L.full; w0 += 128u, xl += 128, dl += 128) {      // four complete slabs of 32 words
+        uint64_t xr[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) xr[r] = xl[32 * r] ^ funnel_fixed<ODD>(dl[32 * r], dl[32 * r + 1], s5);
+        if (!__any_sync(0xffffffffu, (xr[0] | xr[1] | xr[2] | xr[3]) != 0)) continue;
+        diag_decode<BL>(L, xr, w0, bl, lane);
+    }
+    if (w0 < nwords && !L.full) {                                  // the last, partial group (the text ends in zero pad words)
+        const uint64_t tailmask = rem ? ~0ull << (64 - B * rem) : ~0ull;
+        uint64_t xr[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const uint32_t wi = w0 + 32u * r + (uint32_t)lane;
+            xr[r] = 0;
+            if (wi < nwords) {
+                xr[r] = xl[32 * r] ^ funnel_fixed<ODD>(dl[32 * r], dl[32 * r + 1], s5);
+                if (wi == nfull) xr[r] &= tailmask;
+            }
+        }
+        if (__any_sync(0xffffffffu, (xr[0] | xr[1] | xr[2] | xr[3]) != 0)) diag_decode<BL>(L, xr, w0, bl, lane);
+    }
+}
+
+template <int BL, int MINB>        // BL = 1: 2-bit symbols known at compile time; 0: width read from the index
+__global__ void __launch_bounds__(128, MINB) k_diag_w(ParseView pv) {
     const uint32_t g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (g >= pv.n_chunks) return;
@@ -73,54 +145,20 @@ __global__ void __launch_bounds__(128, 16) k_diag_w(ParseView pv) {
     const uint32_t p = (uint32_t)p0, len = (uint32_t)(e - s);
     const uint32_t avail = (uint32_t)pv.ix.n - p;
     const uint32_t cmplen = len < avail ? len : avail;
-    const uint32_t bl = BL ? (uint32_t)BL : pv.ix.bl, sl = 6 - bl, spw = 1u << sl, B = 1u << bl, slab = 32u << sl;   // slab = 32 words
+    const uint32_t bl = BL ? (uint32_t)BL : pv.ix.bl, sl = 6 - bl, spw = 1u << sl;
     const uint64_t* __restrict__ xw = hv.x + (s >> sl);
     // the reference side: same word grid shifted by a bit offset that is constant along the diagonal
     const uint64_t* __restrict__ Dw = pv.ix.text + (p >> sl);
     const uint32_t dsh = (p & (spw - 1)) << bl;                        // 0..62
     const uint32_t nfull = cmplen >> sl, rem = cmplen & (spw - 1);     // whole words, symbols of the last partial word
-    const uint32_t nwords = nfull + (rem ? 1u : 0u);
-    const uint64_t tailmask = rem ? ~0ull << (64 - B * rem) : ~0ull;
-    uint32_t cnt = 0, V = len;
-    bool full = false;
-    constexpr int kSlabs = 4;                                        // 4 slabs of 32 words per iteration, all 12 loads of a
-    for (uint32_t w0 = 0; w0 < nwords && !full; w0 += 32 * kSlabs) { // lane in flight at once (8 slabs: same time, 50 registers)
-        uint64_t xr[kSlabs];
-#pragma unroll
-        for (int r = 0; r < kSlabs; ++r) {
-            const uint32_t wi = w0 + 32u * r + (uint32_t)lane;
-            xr[r] = 0;
-            if (wi < nwords) {
-                const uint64_t a = Dw[wi], b = Dw[wi + 1];           // the text ends in zero pad words
-                const uint64_t d = dsh >= 32 ? funnel_fixed<true>(a, b, dsh & 31) : funnel_fixed<false>(a, b, dsh & 31);
-                xr[r] = xw[wi] ^ d;
-                if (wi == nfull) xr[r] &= tailmask;
-            }
-        }
-        if (!__any_sync(0xffffffffu, (xr[0] | xr[1] | xr[2] | xr[3]) != 0)) continue;
-#pragma unroll
-        for (int r = 0; r < kSlabs; ++r) {
-            unsigned bal = __ballot_sync(0xffffffffu, xr[r] != 0);
-            while (bal && !full) {
-                const int src = __ffs(bal) - 1;
-                bal &= bal - 1;
-                uint64_t w = __shfl_sync(0xffffffffu, xr[r], src);
-                const uint32_t ob = (w0 + 32u * r + (uint32_t)src) << sl;
-                while (w) {
-                    uint32_t b = (uint32_t)(clz64(w) >> bl);
-                    if (cnt == (uint32_t)kMmMax) { V = ob + b; full = true; break; }
-                    if (lane == 0) mm[2 + cnt] = (uint16_t)(ob + b);
-                    ++cnt;
-                    w &= ~(((1ull << B) - 1) << (64 - B - B * b));
-                }
-            }
-        }
+    DiagList L; L.mm = mm; L.cnt = 0; L.V = len; L.full = false;
+    if (dsh >= 32) diag_compare<BL, true>(L, xw, Dw, dsh & 31, nfull, rem, bl, lane);
+    else diag_compare<BL, false>(L, xw, Dw, dsh & 31, nfull, rem, bl, lane);
+    if (!L.full && cmplen < len) {
+        if (L.cnt == (uint32_t)kMmMax) L.V = cmplen;
+        else { if (lane == 0) mm[2 + L.cnt] = (uint16_t)cmplen; ++L.cnt; }
     }
-    if (!full && cmplen < len) {
-        if (cnt == (uint32_t)kMmMax) V = cmplen;
-        else { if (lane == 0) mm[2 + cnt] = (uint16_t)cmplen; ++cnt; }
-    }
-    if (lane == 0) { mm[0] = (uint16_t)cnt; mm[1] = (uint16_t)V; }
+    if (lane == 0) { mm[0] = (uint16_t)L.cnt; mm[1] = (uint16_t)L.V; }
 }
 
 __global__ void __launch_bounds__(128) k_resolve(ParseView pv) {
@@ -302,8 +340,11 @@ int parse_stage_count(ParseBuffers& pb, cudaStream_t s, int* rounds_out, cudaEve
         if (pb.mm && pv.chunk_shift >= 5 && pv.chunk_shift <= 15) {   // D: mismatch lists along the hinted diagonals
             pv.mm = pb.mm;
             g_launches += 1;
-            if (pv.ix.bl == 1) k_diag_w<1><<<(unsigned)(((uint64_t)NC * 32 + 127) / 128), 128, 0, s>>>(pv);
-            else k_diag_w<0><<<(unsigned)(((uint64_t)NC * 32 + 127) / 128), 128, 0, s>>>(pv);
+            const unsigned nb = (unsigned)(((uint64_t)NC * 32 + 127) / 128);
+            if (pv.ix.bl != 1) k_diag_w<0, 16><<<nb, 128, 0, s>>>(pv);
+            else if (pb.occ_diag >= 16) k_diag_w<1, 16><<<nb, 128, 0, s>>>(pv);
+            else if (pb.occ_diag >= 12) k_diag_w<1, 12><<<nb, 128, 0, s>>>(pv);
+            else k_diag_w<1, 10><<<nb, 128, 0, s>>>(pv);
         } else pv.mm = nullptr;
     } else { pv.hint = nullptr; pv.mm = nullptr; }
     if (ev) cudaEventRecord(ev[5], s);
