@@ -306,15 +306,56 @@ static void launch_results(ParseBuffers& pb, const uint64_t* total, cudaStream_t
     cudaMemcpyAsync(pb.host_res, pb.res, pb.res_bytes, cudaMemcpyDeviceToHost, s);
 }
 
-__global__ void __launch_bounds__(128) k_emit(ParseView pv, const uint32_t* true_cnt, const uint32_t* true_entry,
-                                              const uint32_t* true_slot, const uint64_t* true_off, int64_t* out, uint64_t cap) {
-    uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= pv.n_chunks) return;
-    uint32_t c = true_cnt[g];
-    if (!c) return;
-    if (true_off[g] + c > cap) return;                       // speculative launch into a buffer that may be too small
-    int64_t* o = out + 2 * true_off[g];
-    if (!emit_stored(pv, g, true_slot[g], c, o)) emit_chunk(pv, g, true_entry[g], c, o);
+// E: one warp per 32 consecutive chunks.  The lanes first fetch the 32 chunks' (count, offset, slot) in one coalesced
+// round trip; then the warp goes through the chunks, lane t copying stored phrase t of the chunk's true record into
+// record t of its output run, so that the 8-byte phrase reads and the 16-byte record writes of a warp instruction are
+// contiguous (one thread per chunk wrote 32 separate runs per instruction).  Same selection as emit_stored(); a
+// record whose phrases were not all stored is re-parsed by its lane first (emit_chunk).
+__device__ __noinline__ void emit_chunk_slow(const ParseView& pv, uint32_t g, uint32_t entry, uint32_t cnt, int64_t* out) {
+    emit_chunk(pv, g, entry, cnt, out);
+}
+__global__ void __launch_bounds__(128, 16) k_emit(ParseView pv, const uint32_t* __restrict__ true_cnt, const uint32_t* __restrict__ true_entry,
+                                              const uint32_t* __restrict__ true_slot, const uint64_t* __restrict__ true_off,
+                                              int64_t* out, uint64_t cap) {
+    const uint32_t g0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32u;
+    const uint32_t lane = threadIdx.x & 31;
+    if (g0 >= pv.n_chunks) return;
+    const uint32_t gl = g0 + lane;
+    uint32_t c_l = 0, slot_l = 0, own_l = 0, mg_l = kEmpty;
+    uint64_t o_l = 0;
+    if (gl < pv.n_chunks) c_l = true_cnt[gl];
+    if (c_l) {
+        o_l = true_off[gl]; slot_l = true_slot[gl];
+        if (o_l + c_l > cap) c_l = 0;                        // speculative launch into a buffer that may be too small
+    }
+    if (c_l) {
+        bool stored;
+        if (slot_l == 0) stored = c_l <= pv.spec_store;
+        else {
+            const uint32_t rid = gl * kAltSlots + slot_l - 1;
+            own_l = pv.alt_own[rid]; mg_l = pv.alt_merge[rid];
+            const uint32_t sc = mg_l != kEmpty ? pv.spec_cnt[gl] : 0u;
+            stored = own_l <= (uint32_t)kAltStore && sc <= pv.spec_store;
+        }
+        if (!stored) { emit_chunk_slow(pv, gl, true_entry[gl], c_l, out + 2 * o_l); c_l = 0; }
+    }
+    unsigned todo = __ballot_sync(0xffffffffu, c_l != 0);
+    while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const uint32_t c = __shfl_sync(0xffffffffu, c_l, src), slot = __shfl_sync(0xffffffffu, slot_l, src);
+        const uint64_t o = __shfl_sync(0xffffffffu, o_l, src);
+        const uint32_t g = g0 + (uint32_t)src;
+        const uint2* __restrict__ sp = pv.spec_ph + (size_t)g * pv.spec_store;
+        int64_t* dst = out + 2 * o;
+        if (slot == 0) {
+            for (uint32_t t = lane; t < c; t += 32) put_record(dst, t, sp[t]);
+        } else {
+            const uint32_t own = __shfl_sync(0xffffffffu, own_l, src), mg = __shfl_sync(0xffffffffu, mg_l, src);
+            const uint2* __restrict__ ap = pv.alt_ph + (size_t)(g * kAltSlots + slot - 1) * kAltStore;
+            for (uint32_t t = lane; t < c; t += 32) put_record(dst, t, t < own ? ap[t] : sp[mg + (t - own)]);
+        }
+    }
 }
 
 int parse_stage_count(ParseBuffers& pb, cudaStream_t s, int* rounds_out, cudaEvent_t* ev) {
