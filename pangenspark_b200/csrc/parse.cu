@@ -183,6 +183,7 @@ __global__ void __launch_bounds__(128, MINB) k_fix(ParseView pv, uint32_t round)
 // the true chain enters each block, and k_mark_spread propagates those marks inside the blocks (again in shared
 // memory) and picks each chunk's true record.  3 launches instead of 2 + log2(chunks) global passes.
 static const int kMarkChunks = 1024;
+static const int kMarkThreads = 1024;     // one thread per chunk of the block: the 10 jumping rounds are latency, not work (256 threads: 62 us for both kernels)
 static const int kMarkNodes = kMarkChunks * (kAltSlots + 1);
 
 __device__ __forceinline__ void mark_load_links(const ParseView& pv, const uint32_t* succ_in, uint32_t* succ_out, uint32_t base,
@@ -199,7 +200,7 @@ __device__ __forceinline__ void mark_load_links(const ParseView& pv, const uint3
     }
 }
 
-__global__ void __launch_bounds__(256) k_mark_local(ParseView pv, uint32_t* succ_glob, uint32_t* block_last) {
+__global__ void __launch_bounds__(kMarkThreads) k_mark_local(ParseView pv, uint32_t* succ_glob, uint32_t* block_last) {
     __shared__ uint16_t ja[kMarkNodes], jb[kMarkNodes];
     const uint32_t nn = pv.n_chunks * (kAltSlots + 1);
     const uint32_t base = blockIdx.x * kMarkNodes;
@@ -230,7 +231,7 @@ __global__ void k_mark_walk(ParseView pv, uint32_t H, const uint32_t* __restrict
     }
 }
 
-__global__ void __launch_bounds__(256) k_mark_spread(ParseView pv, const uint32_t* __restrict__ succ_glob,
+__global__ void __launch_bounds__(kMarkThreads) k_mark_spread(ParseView pv, const uint32_t* __restrict__ succ_glob,
                                                       const uint8_t* __restrict__ mark_in, uint32_t* true_cnt,
                                                       uint32_t* true_entry, uint32_t* true_slot) {
     __shared__ uint16_t ja[kMarkNodes], jb[kMarkNodes];
@@ -437,9 +438,9 @@ int parse_stage_count(ParseBuffers& pb, cudaStream_t s, int* rounds_out, cudaEve
         pv.parsed_rounds = (uint32_t)(round - 1);
         g_launches += 3;
         cudaMemsetAsync(pb.mark, 0, nn, s);
-        k_mark_local<<<nmb, 256, 0, s>>>(pv, pb.jump_a, pb.jump_b);
+        k_mark_local<<<nmb, kMarkThreads, 0, s>>>(pv, pb.jump_a, pb.jump_b);
         k_mark_walk<<<(pb.H + 127) / 128, 128, 0, s>>>(pv, pb.H, pb.jump_a, pb.jump_b, pb.mark);
-        k_mark_spread<<<nmb, 256, 0, s>>>(pv, pb.jump_a, pb.mark, pb.true_cnt, pb.true_entry, pb.true_slot);
+        k_mark_spread<<<nmb, kMarkThreads, 0, s>>>(pv, pb.jump_a, pb.mark, pb.true_cnt, pb.true_entry, pb.true_slot);
         device_scan<uint64_t, LoadArr<uint32_t, uint64_t>, StoreArr<uint64_t>, OpSum, false>(
             LoadArr<uint32_t, uint64_t>{pb.true_cnt}, StoreArr<uint64_t>{pb.true_off}, NC, pb.scan_tmp, OpSum(), 0ull, s);
         if (ev && pass == 0) cudaEventRecord(ev[3], s);
