@@ -231,6 +231,60 @@ def test_parse_synth_medium(ctx):
     ctx.set_option("group_bytes", 0)
 
 
+def _gapped_row(rng, d: np.ndarray, events):
+    """MSA row over the reference d: events = sorted [(reference position, kind, length)], kind 'g' = a run of gap
+    columns in front of that base, 'd' = that many reference bases deleted (written as '-'), 's' = SNP, 'n' = an N."""
+    out, i = [], 0
+    for pos, kind, ln in events:
+        out.append(d[i:pos]); i = pos
+        if kind == "g":
+            out.append(np.full(ln, ord("-"), dtype=np.uint8))
+        elif kind == "d":
+            out.append(np.full(ln, ord("-"), dtype=np.uint8)); i = min(len(d), pos + ln)
+        elif kind == "s":
+            out.append(np.array([b"ACGT"[(b"ACGT".index(bytes([d[pos]])) + 1 + int(rng.integers(0, 3))) % 4]], dtype=np.uint8)); i = pos + 1
+        else:
+            out.append(np.array([ord("N")], dtype=np.uint8)); i = pos + 1
+    out.append(d[i:])
+    return np.concatenate(out)
+
+
+def test_pack_gap_patterns(ctx):
+    """k_pack: gaps, deletions and foreign bytes at and around the borders of the 2 KB warp spans and the 16 KB tiles,
+    gap runs that empty whole warps and whole tiles, rows of different lengths in one batch (tile ids interleave
+    the rows), every alignment of the packed output against the 32-base words."""
+    rng = np.random.default_rng(77)
+    d = orc.syn_reference(orc.seed_for(3), 70_000)
+    ctx.build_index(d)
+    sa = orc.sa_build(d)
+    rows = []
+    for r in range(10):
+        ev, used = [], set()
+        marks = [2048 * k + o for k in range(1, 34) for o in (-33, -32, -17, -16, -1, 0, 1, 15, 16, 31, 32)]
+        for pos in rng.choice(marks, size=14, replace=False):
+            pos = int(pos)
+            if pos <= 0 or pos >= len(d) - 9 or any(abs(pos - u) < 12 for u in used):
+                continue
+            used.add(pos)
+            kind = "gdsn"[int(rng.integers(0, 4))]
+            ln = int(rng.choice([1, 2, 3, 7, 15, 16, 17, 31, 33])) if kind == "g" else int(rng.integers(1, 9))
+            ev.append((pos, kind, ln))
+        if r % 3 == 0:       # long gap runs: a whole warp span, more than a tile, and one that starts mid-word
+            for pos, ln in ((5000 + r, 2048), (21000 + 3 * r, 16384 + 2048 + 5), (40001, 4099)):
+                if not any(abs(pos - u) < 12 for u in used):
+                    used.add(pos); ev.append((pos, "g", ln))
+        ev.sort()
+        row = _gapped_row(rng, d, ev)
+        if r % 4 == 1:
+            row = row[: int(rng.integers(16384, len(row)))]        # rows of different lengths, ending anywhere in a tile
+        if r == 7:
+            row = np.concatenate([np.full(16384 + 77, ord("-"), dtype=np.uint8), row])     # leading empty tile
+        rows.append(row.tobytes())
+    rows.append(b"-" * 40000)                                      # nothing but gaps: an empty haplotype among the others
+    _check_rows(ctx, d.tobytes(), rows, sa)
+    _check_rows(ctx, d.tobytes(), rows[3:5], sa)                   # the same rows at other positions of the tile order
+
+
 def test_divergent_haplotype(ctx):
     seed = orc.seed_for(5)
     d = orc.syn_reference(seed, 300_000)
