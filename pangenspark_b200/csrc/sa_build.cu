@@ -2,11 +2,9 @@
 // table derived from it, and the LCP array.  Replaces the external `radixSA` binary
 // (DistributedRLZ.scala:45,52) and the text SA load (:55).
 //
-//   round 0 : key = first S0 symbols (S0 = 34 / bits per symbol: 17 bases at 2 bits) | min(remaining, S0) (6 bits)
-//             -> 40 key bits, 5 LSD radix passes.  The length field makes every suffix shorter than S0 unique and
-//             sorts a proper prefix first, which is exactly the "shorter suffix first" order of the reference's SA.
-//             (29 bases / 8 passes left nothing for the rounds on a random 48 Mbp text, but three more passes over
-//             all n keys cost more than one round over the ~0.3 % of the suffixes that share their first 17 bases.)
+//   round 0 : key = first S0 symbols (S0 = 58 / bits per symbol: 29 bases at 2 bits) | min(remaining, S0) (6 bits)
+//             -> 8-pass LSD radix sort.  The length field makes every suffix shorter than S0 unique and sorts a
+//             proper prefix first, which is exactly the "shorter suffix first" order of the reference's SA.
 //   round r : only suffixes whose group is not yet a singleton stay active (early retirement);
 //             key = (group head index << 32) | (rank of suffix i+h, 0 past the end), radix sorted over the
 //             significant bits only; positions come back through the (sorted) list of active SA slots.
@@ -22,15 +20,14 @@ namespace drlz {
 
 #define SA_CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { snprintf(err, errlen, "%s: %s", #x, cudaGetErrorString(e_)); rc = (int)e_; goto done; } } while (0)
 
-static const uint32_t kSaKeyBits = 34;      // symbol bits of the round-0 key (+ 6 bits of length = 5 radix passes)
-
 __global__ void k_sa_init_keys(const uint64_t* __restrict__ text, uint64_t n, uint64_t* keys, uint32_t* vals, uint32_t bl) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const uint32_t s0 = kSaKeyBits >> bl;                       // symbols in the first key
+    const uint32_t s0 = 58u >> bl;                              // symbols in the first key
+    const uint64_t keep = ~((1ull << (64 - (s0 << bl))) - 1);   // their bits (58 or 56 of them)
     uint64_t rem = n - i;
     uint64_t len = rem < (uint64_t)s0 ? rem : (uint64_t)s0;
-    keys[i] = ((get64(text, i, bl) >> (64 - (s0 << bl))) << 6) | len;     // symbols above the 6-bit length field
+    keys[i] = (get64(text, i, bl) & keep) | len;
     vals[i] = (uint32_t)i;
 }
 
@@ -124,7 +121,7 @@ int build_suffix_array(const uint64_t* text, uint64_t n, uint32_t bl, uint32_t* 
         unsigned nb = (unsigned)((n + T - 1) / T);
         g_launches += 1;
         k_sa_init_keys<<<nb, T, 0, s>>>(text, n, keys_a, vals_a, bl);
-        radix_sort_pairs<uint64_t>(&keys_a, &keys_b, &vals_a, &vals_b, n, 0, 6 + (int)((kSaKeyBits >> bl) << bl), hist, scan_tmp, s);
+        radix_sort_pairs<uint64_t>(&keys_a, &keys_b, &vals_a, &vals_b, n, 0, 64, hist, scan_tmp, s);
         // ranks = group head index (inclusive running max of head indices); SA = sorted values
         device_scan<uint32_t, LoadHeadIdx, StoreRank, OpMax, true>(LoadHeadIdx{keys_a}, StoreRank{vals_a, sa, isa}, n,
                                                                    scan_tmp, OpMax(), 0u, s);
@@ -137,7 +134,7 @@ int build_suffix_array(const uint64_t* text, uint64_t n, uint32_t bl, uint32_t* 
         SA_CK(cudaStreamSynchronize(s));
         na32 = *(uint32_t*)tot_host;
         uint64_t na = na32;
-        uint64_t h = kSaKeyBits >> bl;
+        uint64_t h = 58u >> bl;
         int rounds = 0;
         int rank_bits = bits_for(n);        // ranks+1 <= n
         while (na > 0) {
