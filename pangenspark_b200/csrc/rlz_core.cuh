@@ -292,6 +292,14 @@ DRLZ_HD Match lookup(const IndexView& ix, const uint64_t* __restrict__ X, uint64
             a = ix.tab[lk2];
         }
         uint32_t b = r - 1;
+        if (a < b) {
+            // The suffixes that start with the pattern's first L symbols are the whole table bracket of that prefix,
+            // except for at most L-1 shorter suffixes at its start whose zero padding imitates it: the bracket's
+            // first entry is the answer nearly always -- one probe instead of log2(bracket) dependent SA / text misses.
+            const uint32_t pa = SA[a];
+            if (cmp_suffix_w(xw, X, i, D, pa, n, L, &dummy, bl) >= L) { mt.len = L; mt.pos = pa; return mt; }
+            ++a;
+        }
         while (a < b) {
             uint32_t mid = a + ((b - a) >> 1);
             uint32_t c = cmp_suffix_w(xw, X, i, D, SA[mid], n, L, &dummy, bl);

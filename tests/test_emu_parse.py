@@ -77,6 +77,23 @@ def test_alphabets_below_the_reference_sentinel(alphabet):
             assert a3.tolist() == brute_parse(d, xs).tolist()
 
 
+def test_bracket_start_probe_with_imitating_short_suffixes():
+    """lookup(): the leftmost suffix that shares L < k symbols with the pattern is the first entry of the table
+    bracket of that L-prefix, unless suffixes shorter than L sit at the start of the bracket because their zero
+    padding imitates the prefix (reference ends in A's = code 0).  The probe must then fall back to the search."""
+    rng = np.random.default_rng(5)
+    for it in range(300):
+        n = int(rng.integers(4, 40))
+        d = bytes(rng.choice(list(b"AC"), size=n).astype(np.uint8)) + b"A" * int(rng.integers(1, 7))
+        rows = []
+        for _ in range(4):
+            m = int(rng.integers(1, 30))
+            x = bytearray(rng.choice(list(b"AC"), size=m).astype(np.uint8))
+            x += b"A" * int(rng.integers(0, 6)) + bytes(rng.choice(list(b"ACG"), size=int(rng.integers(0, 4))).astype(np.uint8))
+            rows.append(bytes(x))
+        check(d, rows, int(rng.integers(3, 9)), int(rng.choice([4, 64])), int(rng.choice([1, 64])), use_uniq=int(rng.integers(0, 2)))
+
+
 def test_low_complexity_never_merging():
     # parses started at different offsets of a homopolymer never share a phrase start:
     # the fix-up must still converge (one extra record per round) or report overflow, never be wrong
