@@ -420,8 +420,7 @@ static const uint32_t kDiagMinLen = 32;   // phrases at least this long update t
 // table -> SA -> text probe chain.  Anything else falls through to lookup().
 // verified length of the match of x[i..i+plen) along the chunk's hinted diagonal, from the pre-scanned mismatch list;
 // returns false if the list cannot answer (position past the classified range, or plen reaches beyond the chunk)
-DRLZ_HD bool list_extent(const ParseView& pv, uint32_t g, uint64_t s, uint64_t i, uint32_t plen, uint32_t* c_out) {
-    const uint16_t* mm = pv.mm + (size_t)g * kMmStride;
+DRLZ_HD bool list_extent(const uint16_t* mm, uint64_t s, uint64_t i, uint32_t plen, uint32_t* c_out) {
     uint32_t cnt = mm[0], V = mm[1];
     uint32_t off = (uint32_t)(i - s);
     if (off >= V) return false;
@@ -436,8 +435,10 @@ DRLZ_HD bool list_extent(const ParseView& pv, uint32_t g, uint64_t s, uint64_t i
     return false;                                            // classified range ends before the pattern does
 }
 
-DRLZ_HD Match phrase_capped(const ParseView& pv, const HapView& hv, uint64_t i, uint32_t* cursor, bool* open, int64_t* diag,
-                            uint32_t g, uint64_t s) {
+// mml / hint_g: the chunk's mismatch record and hinted diagonal (mml == nullptr: none).  k_spec keeps its copy of the
+// record in shared memory -- it is read once per predicted phrase, and in L1 it does not survive between two of them.
+DRLZ_HD Match phrase_capped_l(const ParseView& pv, const HapView& hv, uint64_t i, uint32_t* cursor, bool* open, int64_t* diag,
+                              const uint16_t* mml, int64_t hint_g, uint64_t s) {
     *open = false;
     uint64_t stop = stop_after(hv, i, cursor);
     if (stop == i) { Match mt; mt.len = 0; mt.pos = hv.exc_byte[*cursor]; return mt; }
@@ -453,7 +454,7 @@ DRLZ_HD Match phrase_capped(const ParseView& pv, const HapView& hv, uint64_t i, 
             uint32_t c;
             bool less;
             const uint32_t u = pv.ix.uniq[p];                // a DRAM miss as a rule: requested before the list scan, used after it
-            if (!(pv.mm && g != kEmpty && pv.hint[g / kHintGroup] == *diag && list_extent(pv, g, s, i, plen, &c)))
+            if (!(mml && hint_g == *diag && list_extent(mml, s, i, plen, &c)))
                 c = cmp_suffix_w(get64u(hv.x, (uint32_t)i, pv.ix.bl), hv.x, (uint32_t)i, pv.ix.text, p, (uint32_t)pv.ix.n, plen, &less, pv.ix.bl);
             if (c > 0) {
                 if (u != 0xFFFFu && c > u) {
@@ -468,6 +469,13 @@ DRLZ_HD Match phrase_capped(const ParseView& pv, const HapView& hv, uint64_t i, 
     if (mt.len == 0) mt.pos = (uint32_t)pv.ix.c2b[base_at(hv.x, i, pv.ix.bl)];
     else if (mt.len >= kDiagMinLen) *diag = (int64_t)mt.pos - (int64_t)i;
     return mt;
+}
+
+DRLZ_HD Match phrase_capped(const ParseView& pv, const HapView& hv, uint64_t i, uint32_t* cursor, bool* open, int64_t* diag,
+                            uint32_t g, uint64_t s) {
+    const bool listed = pv.mm && g != kEmpty;
+    return phrase_capped_l(pv, hv, i, cursor, open, diag, listed ? pv.mm + (size_t)g * kMmStride : nullptr,
+                           listed ? pv.hint[g / kHintGroup] : kNoDiag, s);
 }
 
 // Where an open match (start i, verified len, position pos) continues: the last chunk start j <= i+len.
@@ -618,7 +626,7 @@ DRLZ_HD void diag_scan_chunk(const ParseView& pv, uint32_t g) {
 // the last phrase of a chunk can be open (it reaches the chunk end); its total length -- hence the exit of the
 // chunk -- is filled in by resolve_chunk() once the diagonal runs are ranked.  The first phrase doubles as
 // stage A's "phrase at the chunk start" (first_pos / first_len / run_len).
-DRLZ_HD void spec_parse_chunk(const ParseView& pv, uint32_t g) {
+DRLZ_HD void spec_parse_chunk(const ParseView& pv, uint32_t g, const uint16_t* mm_copy = nullptr) {
     uint32_t h = pv.chunk_hap[g];
     const HapView& hv = pv.haps[h];
     uint64_t s = (uint64_t)(g - pv.hap_chunk_base[h]) << pv.chunk_shift;
@@ -633,9 +641,11 @@ DRLZ_HD void spec_parse_chunk(const ParseView& pv, uint32_t g) {
     uint64_t i = s; uint32_t cnt = 0;
     uint32_t cur = hv.n_exc ? exc_lower_bound(hv, i) : 0;
     bool open = false;
-    int64_t diag = pv.hint ? pv.hint[g / kHintGroup] : kNoDiag;
+    const int64_t hint_g = pv.hint ? pv.hint[g / kHintGroup] : kNoDiag;
+    int64_t diag = hint_g;
+    const uint16_t* mml = !pv.mm ? nullptr : (mm_copy ? mm_copy : pv.mm + (size_t)g * kMmStride);
     while (i < e) {
-        Match mt = phrase_capped(pv, hv, i, &cur, &open, &diag, g, s);
+        Match mt = phrase_capped_l(pv, hv, i, &cur, &open, &diag, mml, hint_g, s);
         if (i == s) { pv.first_pos[g] = mt.pos; pv.first_len[g] = mt.len; pv.run_len[g] = open ? kEmpty : mt.len; }
         if (cnt < pv.spec_store) pv.spec_ph[(size_t)g * pv.spec_store + cnt] = make_uint2(mt.pos, mt.len);
         ++cnt;
