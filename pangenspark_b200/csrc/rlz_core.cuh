@@ -628,7 +628,7 @@ DRLZ_HD void diag_scan_chunk(const ParseView& pv, uint32_t g) {
 // stage A's "phrase at the chunk start" (first_pos / first_len / run_len).
 DRLZ_HD void spec_parse_chunk(const ParseView& pv, uint32_t g, const uint16_t* mm_copy = nullptr) {
     uint32_t h = pv.chunk_hap[g];
-    const HapView& hv = pv.haps[h];
+    const HapView hv = pv.haps[h];          // by value: the fields stay in registers instead of being re-read through L1
     uint64_t s = (uint64_t)(g - pv.hap_chunk_base[h]) << pv.chunk_shift;
     uint64_t e = s + (1ull << pv.chunk_shift); if (e > hv.m) e = hv.m;
     pv.link[g] = kEmpty;
