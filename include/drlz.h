@@ -45,7 +45,7 @@ int drlz_set_stream(drlz_ctx* ctx, void* cuda_stream);
  *          "group_bytes" (host-path pipeline granularity), "lcp" (1 = also build the LCP array),
  *          "min_cap" (lower bound of the per-lookup compare cap, default 64), "foreign_cap" (longest off-chain
  *          diagonal compare a single thread may do before the exact sequential fallback is taken),
- *          tuning / A-B switches: "occ", "occ_fix" (min CTAs per SM of k_spec / k_fix), "predict" (uniqueness-array
+ *          tuning / A-B switches: "occ", "occ_fix", "occ_diag" (min CTAs per SM of k_spec / k_fix / k_diag_w), "predict" (uniqueness-array
  *          prediction), "hint" + "diag" (per-chunk diagonal hint and mismatch pre-scan), "tickets" (1 = atomic tile tickets in k_pack), "occ_pack" (6 | 8 CTAs per SM k_pack is
  *          compiled for), "prefetch" (L2 prefetch distance of k_pack in tiles, 0 = off),
  *          "spec_store", "l2persist".  None of them changes results. */

@@ -66,6 +66,7 @@ struct drlz_ctx {
     cudaStream_t l2_stream = nullptr; int opt_l2persist = 0; int opt_occ = 8; int opt_occ_fix = 10; int opt_occ_diag = 12; int opt_tickets = 1; int opt_hint = 1; int opt_diag = 1; uint32_t opt_spec_store = 0;
     double idx_ms[5] = {0, 0, 0, 0, 0};
     // batch scratch (grow-only)
+    SaWorkspace sa_ws;
     DevBuf stage[2], meta_dev, desc_cnt, desc_exc, tile_counter, X, mdev, exccnt, excpos, excbyte,
         flags, haps, gapless, gtile_cnt, gtile_exc, gtile_off, gtile_excoff, gscan_tmp, chunk_hap, first_pos, first_len, run_a, run_b, link_a, link_b, open_i, open_pos, open_len, spec_cnt, spec_exit, alt_entry, alt_cnt, alt_exit, alt_round, alt_own, alt_merge, spec_ph, alt_ph, hint, mm, true_slot, counters, jump_a,
         jump_b, mark, true_cnt, true_entry, true_off, scan_tmp, hap_pairs, out, ms_a, ms_b;
@@ -164,6 +165,7 @@ void drlz_destroy(drlz_ctx* c) {
     }
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
+    c->sa_ws.release();
     DevBuf* bufs[] = {&c->blob, &c->sa, &c->isa, &c->lcp, &c->stage[0], &c->stage[1], &c->meta_dev, &c->desc_cnt,
                       &c->desc_exc, &c->tile_counter, &c->X, &c->mdev, &c->exccnt, &c->excpos,
                       &c->excbyte, &c->flags, &c->haps, &c->gapless, &c->gtile_cnt, &c->gtile_exc, &c->gtile_off, &c->gtile_excoff, &c->gscan_tmp, &c->chunk_hap, &c->first_pos, &c->first_len, &c->run_a, &c->run_b, &c->link_a, &c->link_b, &c->open_i, &c->open_pos, &c->open_len, &c->spec_cnt, &c->spec_exit,
@@ -536,7 +538,11 @@ int drlz_build_index(drlz_ctx* c, const uint8_t* ref, uint64_t n) {
     (void)off0; (void)m; (void)np; (void)tot;
     cudaEventRecord(e[1], s);
     char ebuf[256]; ebuf[0] = 0;
-    int rc = build_suffix_array(c->d_text, n, bl, c->sa.as<uint32_t>(), c->isa.as<uint32_t>(), s, &c->sa_rounds, ebuf, sizeof ebuf);
+    int rc = build_suffix_array(c->d_text, n, bl, c->sa.as<uint32_t>(), c->isa.as<uint32_t>(), s, &c->sa_rounds, ebuf, sizeof ebuf, &c->sa_ws);
+    if (c->sa_ws.bytes() > (16ull << 30)) {          // whole-genome scale: the parse needs that memory back
+        cudaStreamSynchronize(s);
+        c->sa_ws.release();
+    }
     if (rc != 0) { c->err = std::string("suffix array: ") + ebuf; for (int i = 0; i < 5; ++i) cudaEventDestroy(e[i]); return rc == (int)cudaErrorMemoryAllocation ? DRLZ_E_NOMEM : DRLZ_E_CUDA; }
     cudaEventRecord(e[2], s);
 

@@ -50,11 +50,33 @@ struct PackJob {
 void launch_pack(const PackJob& job, cudaStream_t s, cudaEvent_t* ev);
 
 // ---- suffix array + k-mer table (sa_build.cu) ---------------------------------------------------
-struct SaWorkspace;   // opaque
+// Scratch of build_suffix_array (sort keys / values, active-slot lists, histograms: ~32 bytes per reference base).
+// Kept by the caller between builds, grow-only, so that only the first build of a context allocates; cudaMalloc and
+// cudaFree of gigabytes otherwise sit inside the build (measured: 14 ms of kernels became 34 - 101 ms on some boxes).
+struct SaWorkspace {
+    void* p[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    size_t cap[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    void* host = nullptr;                  // 8 pinned bytes for the per-round read-back
+    cudaError_t ensure(int i, size_t bytes) {
+        if (bytes <= cap[i]) return cudaSuccess;
+        if (p[i]) cudaFree(p[i]);
+        p[i] = nullptr; cap[i] = 0;
+        cudaError_t e = cudaMalloc(&p[i], bytes + 256);
+        if (e == cudaSuccess) cap[i] = bytes;
+        return e;
+    }
+    size_t bytes() const { size_t t = 0; for (int i = 0; i < 9; ++i) t += cap[i]; return t; }
+    void release() {
+        for (int i = 0; i < 9; ++i) { if (p[i]) cudaFree(p[i]); p[i] = nullptr; cap[i] = 0; }
+        if (host) cudaFreeHost(host);
+        host = nullptr;
+    }
+};
 // Builds SA (uint32[n]) of the packed text and, when isa != null, the inverse.  Returns 0 or a cudaError.
 // bl = log2(bits per symbol) of the packed text
+// ws: scratch kept by the caller (null = allocated and freed inside the call)
 int build_suffix_array(const uint64_t* text, uint64_t n, uint32_t bl, uint32_t* sa, uint32_t* isa, cudaStream_t s,
-                       int* rounds_out, char* err, int errlen);
+                       int* rounds_out, char* err, int errlen, SaWorkspace* ws = nullptr);
 // tab: sigma^k + 1 entries (ix.tab is ignored, ix.text / ix.sa / ix.k / ix.bl / ix.sigma are used)
 int build_kmer_table(const IndexView& ix, uint32_t* tab, cudaStream_t s);
 // LCP[j] = lcp(suffix SA[j-1], suffix SA[j]), LCP[0] = 0

@@ -349,7 +349,8 @@ __global__ void __launch_bounds__(128, 16) k_emit(ParseView pv, const uint32_t* 
             const uint32_t rid = gl * kAltSlots + slot_l - 1;
             own_l = pv.alt_own[rid]; mg_l = pv.alt_merge[rid];
             const uint32_t sc = mg_l != kEmpty ? pv.spec_cnt[gl] : 0u;
-            stored = own_l <= (uint32_t)kAltStore && sc <= pv.spec_store;
+            stored = own_l <= (uint32_t)kAltStore && sc <= pv.spec_store && (mg_l == kEmpty || mg_l <= sc) &&
+                     own_l + (mg_l != kEmpty ? sc - mg_l : 0u) == c_l;         // the copy below trusts these three
         }
         if (!stored) { emit_chunk_slow(pv, gl, true_entry[gl], c_l, out + 2 * o_l); c_l = 0; }
     }

@@ -754,7 +754,13 @@ DRLZ_HD uint32_t chunk_true_record(const ParseView& pv, const uint8_t* m4, uint3
         return pv.spec_cnt[g];
     }
     for (int s = 0; s < kAltSlots; ++s)
-        if (m4[1 + s]) { *entry = pv.alt_entry[g * kAltSlots + s]; *slot = 1 + s; return pv.alt_cnt[g * kAltSlots + s]; }
+        if (m4[1 + s]) {
+            // a record registered for a round that has not run yet (blind rounds, see parse_stage_count) has no phrases:
+            // its counters are whatever an earlier batch left there, and this marking pass is provisional anyway
+            const uint32_t rid = g * kAltSlots + s;
+            *entry = pv.alt_entry[rid]; *slot = 1 + s;
+            return pv.alt_round[rid] > pv.parsed_rounds ? 0u : pv.alt_cnt[rid];
+        }
     *entry = 0;
     return 0;
 }

@@ -97,25 +97,31 @@ struct StoreRound {
 static int bits_for(uint64_t v) { int b = 0; while (v) { ++b; v >>= 1; } return b ? b : 1; }
 
 int build_suffix_array(const uint64_t* text, uint64_t n, uint32_t bl, uint32_t* sa, uint32_t* isa_out, cudaStream_t s,
-                       int* rounds_out, char* err, int errlen) {
+                       int* rounds_out, char* err, int errlen, SaWorkspace* ws_in) {
     int rc = 0;
     if (rounds_out) *rounds_out = 0;
     if (n == 0) return 0;
+    SaWorkspace local;
+    SaWorkspace& ws = ws_in ? *ws_in : local;
     uint64_t *keys_a = nullptr, *keys_b = nullptr, *tot_host = nullptr;
     uint32_t *vals_a = nullptr, *vals_b = nullptr, *hist = nullptr, *scan_tmp = nullptr, *slots_a = nullptr,
              *slots_b = nullptr, *isa = nullptr;
     uint64_t hist_n = sort_hist_elems(n);
     uint64_t tmp_n = scan_tmp_elems(hist_n > n ? hist_n : n) + 8;
-    SA_CK(cudaMalloc(&keys_a, n * 8));
-    SA_CK(cudaMalloc(&keys_b, n * 8));
-    SA_CK(cudaMalloc(&vals_a, n * 4));
-    SA_CK(cudaMalloc(&vals_b, n * 4));
-    SA_CK(cudaMalloc(&hist, hist_n * 4 + 64));
-    SA_CK(cudaMalloc(&scan_tmp, tmp_n * 4));
-    SA_CK(cudaMalloc(&slots_a, n * 4));
-    SA_CK(cudaMalloc(&slots_b, n * 4));
-    if (isa_out) isa = isa_out; else SA_CK(cudaMalloc(&isa, n * 4));
-    SA_CK(cudaMallocHost(&tot_host, 8));
+    SA_CK(ws.ensure(0, n * 8));
+    SA_CK(ws.ensure(1, n * 8));
+    SA_CK(ws.ensure(2, n * 4));
+    SA_CK(ws.ensure(3, n * 4));
+    SA_CK(ws.ensure(4, hist_n * 4 + 64));
+    SA_CK(ws.ensure(5, tmp_n * 4));
+    SA_CK(ws.ensure(6, n * 4));
+    SA_CK(ws.ensure(7, n * 4));
+    if (!isa_out) SA_CK(ws.ensure(8, n * 4));
+    if (!ws.host) SA_CK(cudaMallocHost(&ws.host, 8));
+    keys_a = (uint64_t*)ws.p[0]; keys_b = (uint64_t*)ws.p[1]; vals_a = (uint32_t*)ws.p[2]; vals_b = (uint32_t*)ws.p[3];
+    hist = (uint32_t*)ws.p[4]; scan_tmp = (uint32_t*)ws.p[5]; slots_a = (uint32_t*)ws.p[6]; slots_b = (uint32_t*)ws.p[7];
+    isa = isa_out ? isa_out : (uint32_t*)ws.p[8];
+    tot_host = (uint64_t*)ws.host;
     {
         const unsigned T = 256;
         unsigned nb = (unsigned)((n + T - 1) / T);
@@ -161,10 +167,7 @@ int build_suffix_array(const uint64_t* text, uint64_t n, uint32_t bl, uint32_t* 
         SA_CK(cudaGetLastError());
     }
 done:
-    cudaFree(keys_a); cudaFree(keys_b); cudaFree(vals_a); cudaFree(vals_b); cudaFree(hist); cudaFree(scan_tmp);
-    cudaFree(slots_a); cudaFree(slots_b);
-    if (!isa_out) cudaFree(isa);
-    if (tot_host) cudaFreeHost(tot_host);
+    if (!ws_in) { cudaStreamSynchronize(s); local.release(); }
     return rc;
 }
 
