@@ -148,6 +148,35 @@ int emu_parse(const uint8_t* ref, uint64_t n, const int64_t* sa64, int k, uint32
     }
     for (uint32_t g = 0; g < NC; ++g) resolve_chunk(pv, g);
     if (counters[0]) return 2;
+    {   // A provisional marking pass before any fix-up round has run (what the library does when it launches fewer
+        // rounds blind than the input needs): records registered for round 1 are not parsed yet, their counters are
+        // whatever an earlier batch left behind -- poisoned here.  Such a record must count zero phrases; a nonzero
+        // count can only be a speculative record's.
+        ParseView pq = pv; pq.parsed_rounds = 0;
+        std::fill(alt_cnt.begin(), alt_cnt.end(), 0xDEADBEEFu);
+        std::fill(alt_own.begin(), alt_own.end(), 0xDEADBEEFu);
+        std::fill(alt_merge.begin(), alt_merge.end(), 0x00ADBEEFu);
+        uint32_t NNp = NC * (kAltSlots + 1);
+        std::vector<uint32_t> jp(NNp), jp2(NNp);
+        std::vector<uint8_t> mk(NNp, 0);
+        const uint32_t c0 = counters[0];
+        for (uint32_t v = 0; v < NNp; ++v) jp[v] = node_succ(pq, v);
+        counters[0] = c0;                  // links into records that do not exist yet are expected in this pass
+        uint32_t mc = 1;
+        for (int h = 0; h < H; ++h) { if (base[h + 1] > base[h]) mk[base[h] * (kAltSlots + 1)] = 1; if (base[h + 1] - base[h] > mc) mc = base[h + 1] - base[h]; }
+        for (uint32_t span = 1; span < 2 * mc; span *= 2) {
+            for (uint32_t v = 0; v < NNp; ++v) { uint32_t j = jp[v]; if (mk[v]) mk[j] = 1; jp2[v] = jp[j]; }
+            jp.swap(jp2);
+        }
+        for (uint32_t g = 0; g < NC; ++g) {
+            uint32_t e, sl;
+            uint32_t c = chunk_true_record(pq, mk.data() + (size_t)g * (kAltSlots + 1), g, &e, &sl);
+            if (c != 0 && !(sl == 0 && c == spec_cnt[g])) return 3;
+        }
+        std::fill(alt_cnt.begin(), alt_cnt.end(), 0u);
+        std::fill(alt_own.begin(), alt_own.end(), 0u);
+        std::fill(alt_merge.begin(), alt_merge.end(), kEmpty);
+    }
     int round = 1;
     while (counters[1 + round] > 0 && round < kMaxRounds) {
         for (uint32_t g = 0; g < NC; ++g) for (int s = 0; s < kAltSlots; ++s) fix_parse_record(pv, g, s, round);
