@@ -142,3 +142,40 @@ def test_world_size_2_gloo(tmp_path):
     for p in procs:
         assert p.wait(timeout=300) == 0
     check_outputs(tmp, d, rows)
+
+
+def test_pack_classification_arithmetic():
+    """The SIMD-in-register ACGT test and code extraction of k_pack (pack.cu::codes4, top_bytes), restated in numpy
+    with the constants read from the source, over every byte value in every position of a 32-bit word: a byte's lane
+    of `bad` is zero exactly for A, C, G, T, valid bytes get the codes 0..3 in alphabet order, and the multiply gathers
+    the four codes into the top byte, first base first."""
+    import re
+    src = open(os.path.join(ROOT, "pangenspark_b200", "csrc", "pack.cu")).read()
+    body = src[src.index("uint32_t codes4(uint32_t w, uint32_t* bad)"):]
+    body = body[:body.index("}")]
+    for const in ("0x01010101u", "0xF9F9F9F9u", "15u", "0x41414141u", "0x03030303u"):
+        assert const in body, const
+    assert re.search(r"c\d \* 0x40100401u", src)
+    u = np.uint32
+    rng = np.random.default_rng(9)
+    code = {65: 0, 67: 1, 71: 2, 84: 3}
+    words = []
+    for pos in range(4):
+        for b in range(256):
+            for _ in range(8):
+                bs = [int(x) for x in (rng.choice([65, 67, 71, 84], 4) if rng.random() < 0.7 else rng.integers(0, 256, 4))]
+                bs[pos] = b
+                words.append(bs)
+    W = np.array(words, dtype=np.uint64)
+    w = (W[:, 0] | (W[:, 1] << 8) | (W[:, 2] << 16) | (W[:, 3] << 24)).astype(u)
+    s1, s2 = w >> u(1), w >> u(2)
+    t = s2 & ~s1 & u(0x01010101)
+    bad = (w & u(0xF9F9F9F9)) ^ (t * u(15) + u(0x41414141))
+    c = (s1 ^ (s2 & u(0x01010101))) & u(0x03030303)
+    top = ((c.astype(np.uint64) * 0x40100401) & 0xFFFFFFFF) >> 24
+    for row, bd, cc, tp in zip(words, bad.tolist(), c.tolist(), top.tolist()):
+        for i, v in enumerate(row):
+            assert (((bd >> (8 * i)) & 255) == 0) == (v in code), (row, i)
+        if all(v in code for v in row):
+            assert [(cc >> (8 * i)) & 3 for i in range(4)] == [code[v] for v in row]
+            assert tp == (code[row[0]] << 6) | (code[row[1]] << 4) | (code[row[2]] << 2) | code[row[3]]
