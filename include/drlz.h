@@ -68,7 +68,8 @@ int drlz_index_get(drlz_ctx* ctx, int what, void* host_out, uint64_t bytes);
 /* info[0]=n, [1]=k | log2(bits per symbol) << 8 | alphabet size sigma << 16, [2]=prefix-doubling rounds,
  * [3]=index bytes on device */
 int drlz_index_info(const drlz_ctx* ctx, uint64_t info[4]);
-/* time of the last drlz_build_index in ms: [0] total, [1] pack, [2] suffix array, [3] k-mer table, [4] lcp */
+/* time of the last drlz_build_index in ms (CUDA events on the context stream): [0] total, from before the host->device
+ * copy of the reference to the last kernel, [1] copy + alphabet scan + pack, [2] suffix array, [3] k-mer table, [4] lcp */
 int drlz_index_timings(const drlz_ctx* ctx, double ms[5]);
 
 /* Multi-GPU: rank 0 builds, the others call drlz_index_reserve(n, info[1] of rank 0) and receive the three

@@ -14,7 +14,7 @@
 #include "scan.cuh"
 
 namespace drlz {
-unsigned long long g_launches = 0;
+thread_local unsigned long long g_launches = 0;   // kernels launched by the calling thread (a parse call runs on one thread)
 
 struct DevBuf {
     void* p = nullptr; size_t cap = 0;
@@ -69,7 +69,7 @@ struct drlz_ctx {
     SaWorkspace sa_ws;
     DevBuf stage[2], meta_dev, desc_cnt, desc_exc, tile_counter, X, mdev, exccnt, excpos, excbyte,
         flags, haps, gapless, gtile_cnt, gtile_exc, gtile_off, gtile_excoff, gscan_tmp, chunk_hap, first_pos, first_len, run_a, run_b, link_a, link_b, open_i, open_pos, open_len, spec_cnt, spec_exit, alt_entry, alt_cnt, alt_exit, alt_round, alt_own, alt_merge, spec_ph, alt_ph, hint, mm, true_slot, counters, jump_a,
-        jump_b, mark, true_cnt, true_entry, true_off, scan_tmp, hap_pairs, out, ms_a, ms_b;
+        jump_b, mark, true_cnt, true_entry, true_off, scan_tmp, hap_pairs, out, ms_a, ms_b, tab_tmp;
     HostBuf meta_host, small_host;
     uint64_t exc_stride_hint = 0;
     // thread safety: every entry point takes `mu` (calls from several threads are serialised on the device)
@@ -79,6 +79,7 @@ struct drlz_ctx {
                  uint64_t* m_out; int64_t* pairs; uint64_t cap; uint64_t* n_pairs; };
     std::mutex qmu; std::condition_variable qcv, done_cv;
     std::deque<Job> queue; std::vector<std::pair<uint64_t, int>> done;
+    std::vector<uint64_t> outstanding;      // tickets submitted and not yet collected by drlz_wait
     std::thread worker; bool worker_started = false, stopping = false; uint64_t next_ticket = 1;
     double parse_ms[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 };
@@ -170,7 +171,7 @@ void drlz_destroy(drlz_ctx* c) {
                       &c->desc_exc, &c->tile_counter, &c->X, &c->mdev, &c->exccnt, &c->excpos,
                       &c->excbyte, &c->flags, &c->haps, &c->gapless, &c->gtile_cnt, &c->gtile_exc, &c->gtile_off, &c->gtile_excoff, &c->gscan_tmp, &c->chunk_hap, &c->first_pos, &c->first_len, &c->run_a, &c->run_b, &c->link_a, &c->link_b, &c->open_i, &c->open_pos, &c->open_len, &c->spec_cnt, &c->spec_exit,
                       &c->alt_entry, &c->alt_cnt, &c->alt_exit, &c->alt_round, &c->alt_own, &c->alt_merge, &c->spec_ph, &c->alt_ph, &c->hint, &c->mm, &c->true_slot, &c->counters, &c->jump_a, &c->jump_b,
-                      &c->mark, &c->true_cnt, &c->true_entry, &c->true_off, &c->scan_tmp, &c->hap_pairs, &c->out, &c->ms_a, &c->ms_b};
+                      &c->mark, &c->true_cnt, &c->true_entry, &c->true_off, &c->scan_tmp, &c->hap_pairs, &c->out, &c->ms_a, &c->ms_b, &c->tab_tmp};
     for (DevBuf* b : bufs) b->release();
     c->meta_host.release(); c->small_host.release();
     for (int i = 0; i < 2; ++i) if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]);
@@ -185,7 +186,14 @@ const char* drlz_last_error(const drlz_ctx* c) { return c ? c->err.c_str() : "nu
 int drlz_set_stream(drlz_ctx* c, void* s) {
     if (!c) return DRLZ_E_ARG;
     std::lock_guard<std::recursive_mutex> lk_(c->mu);
-    c->stream = s ? (cudaStream_t)s : c->own_stream;
+    cudaStream_t ns = s ? (cudaStream_t)s : c->own_stream;
+    if (ns != c->stream) {
+        // work may still be queued on the old stream (the zero-fill of the packed buffer behind the last batch is not
+        // awaited): the first kernel on the new stream must not overtake it
+        CK(c, cudaSetDevice(c->device));
+        CK(c, cudaStreamSynchronize(c->stream));
+        c->stream = ns;
+    }
     return DRLZ_OK;
 }
 
@@ -295,7 +303,12 @@ static int run_device_group(drlz_ctx* c, const uint8_t* rows_dev, const uint64_t
     if (want_gapless) CK(c, c->gapless.ensure(gbytes + 16));
     if (c->exc_stride_hint < maxcols / 256 + 256) c->exc_stride_hint = maxcols / 256 + 256;
 
-    for (int attempt = 0; attempt < 4; ++attempt) {
+    // a group is redone when (a) the fix-up did not converge with chunks (once: one chunk per haplotype, always exact),
+    // (b) the look-back of k_pack timed out under blockIdx tile ids (once: atomic tickets cannot time out), (c) a row
+    // has more exceptions than the list holds (the list is then sized from the exact counts; twice at most, the
+    // second time only if a ticket retry came in between).  Each cause has its own budget and its own message.
+    int retry_ticket = 0, retry_exc = 0;
+    for (;;) {
         uint64_t exc_stride = c->exc_stride_hint;
         CK(c, c->excpos.ensure(exc_stride * H * 4)); CK(c, c->excbyte.ensure(exc_stride * H));
         // chunk layout (upper bound from cols; chunks past the gapless length stay empty)
@@ -406,10 +419,12 @@ static int run_device_group(drlz_ctx* c, const uint8_t* rows_dev, const uint64_t
             t_done = std::chrono::steady_clock::now();
         }
         if (*sh_flags & 2u) {           // look-back timed out (CTAs not dispatched in index order): redo with tickets
+            if (c->opt_tickets || ++retry_ticket > 1) { c->err = "strip/pack look-back timed out although tile ids come from atomic tickets (is the GPU shared with another process?)"; return DRLZ_E_INTERNAL; }
             c->opt_tickets = 1;
             continue;
         }
-        if (*sh_flags & 1u) {           // exception list overflowed: grow and redo the group
+        if (*sh_flags & 1u) {           // exception list overflowed: size it from the exact counts and redo the group
+            if (++retry_exc > 3) { c->err = "exception list kept overflowing"; return DRLZ_E_INTERNAL; }
             uint64_t mx = 0;
             for (uint32_t h = 0; h < H; ++h) if (sh_exccnt[h] > mx) mx = sh_exccnt[h];
             c->exc_stride_hint = mx + mx / 8 + 1024;
@@ -435,8 +450,6 @@ static int run_device_group(drlz_ctx* c, const uint8_t* rows_dev, const uint64_t
                 std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_done).count();
         return DRLZ_OK;
     }
-    c->err = "exception list kept overflowing";
-    return DRLZ_E_INTERNAL;
 }
 
 extern "C" {
@@ -464,18 +477,28 @@ int drlz_build_index(drlz_ctx* c, const uint8_t* ref, uint64_t n) {
     c->have_index = false;
     cudaEvent_t e[5];
     for (int i = 0; i < 5; ++i) cudaEventCreate(&e[i]);
+    // everything from here on is inside idx_ms[0]: the host->device copy of the reference, the alphabet scan, the
+    // packing, the suffix sort, the table and the uniqueness array
+    cudaEventRecord(e[0], s);
     // stage the reference and pack it with the row kernels (no gap stripping)
     uint64_t padded = ((n + 15) & ~15ull) + 16;
     CK(c, c->stage[0].ensure(padded));
     if (n) CK(c, cudaMemcpyAsync(c->stage[0].p, ref, n, cudaMemcpyHostToDevice, s));
     // alphabet: pure {A,C,G,T} -> 2-bit fast path; otherwise the distinct bytes of the reference get dense
-    // order-preserving codes (suffix order under unsigned bytes is preserved), 4 bits if sigma <= 16 else 8 bits
+    // order-preserving codes (suffix order under unsigned bytes is preserved), 4 bits if sigma <= 16 else 8 bits.
+    // Which byte values occur is found on the device (one HBM pass; a host loop over 3.1 Gbp takes seconds).
     uint8_t lut[512];
     memset(lut, 0xFF, 256); memset(lut + 256, 0, 256);
     uint32_t sigma = 4, bl = 1;
     {
-        bool present[256] = {false};
-        for (uint64_t i = 0; i < n; ++i) present[ref[i]] = true;
+        CK(c, c->counters.ensure(sizeof(uint32_t) * (2 + kMaxRounds) > 32 ? sizeof(uint32_t) * (2 + kMaxRounds) : 32));
+        CK(c, c->small_host.ensure(64));
+        launch_byte_presence(c->stage[0].as<uint8_t>(), n, c->counters.as<uint32_t>(), s);
+        uint32_t* hp = c->small_host.as<uint32_t>();
+        CK(c, cudaMemcpyAsync(hp, c->counters.p, 32, cudaMemcpyDeviceToHost, s));
+        CK(c, cudaStreamSynchronize(s));
+        bool present[256];
+        for (int b = 0; b < 256; ++b) present[b] = (hp[b >> 5] >> (b & 31)) & 1u;
         bool acgt = true;
         for (int b = 0; b < 256; ++b) if (present[b] && b != 'A' && b != 'C' && b != 'G' && b != 'T') acgt = false;
         if (acgt) { const char* a4 = "ACGT"; for (int q = 0; q < 4; ++q) { lut[(uint8_t)a4[q]] = (uint8_t)q; lut[256 + q] = (uint8_t)a4[q]; } }
@@ -491,10 +514,10 @@ int drlz_build_index(drlz_ctx* c, const uint8_t* ref, uint64_t n) {
     if (k > (int)(64u >> bl)) k = (int)(64u >> bl);
     while (k > 1 && table_entries(sigma, k) > (1ull << 30)) --k;
     CK(c, alloc_index_blob(c, n, k, sigma, bl));
+    CK(c, c->tab_tmp.ensure(kmer_table_tmp_bytes(table_entries(sigma, k))));
     CK(c, cudaMemcpyAsync(c->d_lut, lut, 512, cudaMemcpyHostToDevice, s));
     CK(c, c->sa.ensure(n * 4 + 4));
     CK(c, c->isa.ensure(n * 4 + 4));
-    cudaEventRecord(e[0], s);
     c->n = 0; c->k = 1;
     uint64_t off0 = 0, m = 0, np = 0, tot = 0;
     // pack through the generic group path needs an index view only for parsing; call the pack pieces directly
@@ -548,7 +571,7 @@ int drlz_build_index(drlz_ctx* c, const uint8_t* ref, uint64_t n) {
 
     {
         IndexView tix{c->d_text, c->sa.as<uint32_t>(), nullptr, n, k, nullptr, bl, sigma, c->d_lut + 256};
-        rc = build_kmer_table(tix, c->d_tab, s);
+        rc = build_kmer_table(tix, c->d_tab, c->tab_tmp.as<uint32_t>(), s);
     }
     if (rc != 0) { c->err = "k-mer table build failed"; for (int i = 0; i < 5; ++i) cudaEventDestroy(e[i]); return DRLZ_E_CUDA; }
     cudaEventRecord(e[3], s);
@@ -763,6 +786,7 @@ int drlz_submit(drlz_ctx* c, const uint8_t* const* rows, const uint64_t* cols, u
     if (!c->worker_started) { c->worker = std::thread(drlz_worker, c); c->worker_started = true; }
     drlz_ctx::Job j{c->next_ticket++, rows, cols, H, strip_gaps, gapless_out, m_out, pairs_out, pairs_cap, n_pairs};
     *ticket = j.ticket;
+    c->outstanding.push_back(j.ticket);
     c->queue.push_back(j);
     c->qcv.notify_one();
     return DRLZ_OK;
@@ -771,7 +795,11 @@ int drlz_submit(drlz_ctx* c, const uint8_t* const* rows, const uint64_t* cols, u
 int drlz_wait(drlz_ctx* c, uint64_t ticket) {
     if (!c || ticket == 0) return DRLZ_E_ARG;
     std::unique_lock<std::mutex> lk(c->qmu);
-    if (ticket >= c->next_ticket) return DRLZ_E_ARG;
+    // unknown ticket, or one that was collected already (waiting for it again would never return)
+    size_t oi = 0;
+    while (oi < c->outstanding.size() && c->outstanding[oi] != ticket) ++oi;
+    if (oi == c->outstanding.size()) return DRLZ_E_ARG;
+    c->outstanding.erase(c->outstanding.begin() + oi);
     for (;;) {
         for (size_t i = 0; i < c->done.size(); ++i)
             if (c->done[i].first == ticket) { int rc = c->done[i].second; c->done.erase(c->done.begin() + i); return rc; }

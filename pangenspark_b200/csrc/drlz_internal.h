@@ -6,7 +6,7 @@
 
 namespace drlz {
 
-extern unsigned long long g_launches;
+extern thread_local unsigned long long g_launches;
 
 static const int kPackGTileBytes = 4096;     // tile of the generic-alphabet pack kernels (256 threads x 16 B)
 static const int kPackTileBytes = 16384;     // MSA bytes per CTA in the strip/pack kernel (256 threads x 64 B; 8 KB and 32 KB measured slower)
@@ -49,6 +49,9 @@ struct PackJob {
 // ev (nullable): 3 events: [0],[1] before the kernel, [2] after it
 void launch_pack(const PackJob& job, cudaStream_t s, cudaEvent_t* ev);
 
+// presence[8]: bit b of the 256-bit set = byte value b occurs in bytes[0, n) (bytes 16-byte aligned)
+void launch_byte_presence(const uint8_t* bytes, uint64_t n, uint32_t* presence, cudaStream_t s);
+
 // ---- suffix array + k-mer table (sa_build.cu) ---------------------------------------------------
 // Scratch of build_suffix_array (sort keys / values, active-slot lists, histograms: ~32 bytes per reference base).
 // Kept by the caller between builds, grow-only, so that only the first build of a context allocates; cudaMalloc and
@@ -78,7 +81,9 @@ struct SaWorkspace {
 int build_suffix_array(const uint64_t* text, uint64_t n, uint32_t bl, uint32_t* sa, uint32_t* isa, cudaStream_t s,
                        int* rounds_out, char* err, int errlen, SaWorkspace* ws = nullptr);
 // tab: sigma^k + 1 entries (ix.tab is ignored, ix.text / ix.sa / ix.k / ix.bl / ix.sigma are used)
-int build_kmer_table(const IndexView& ix, uint32_t* tab, cudaStream_t s);
+// tmp: kmer_table_tmp_bytes(entries) bytes of scratch owned by the caller; the call does not synchronise
+size_t kmer_table_tmp_bytes(uint64_t entries);
+int build_kmer_table(const IndexView& ix, uint32_t* tab, uint32_t* tmp, cudaStream_t s);
 // LCP[j] = lcp(suffix SA[j-1], suffix SA[j]), LCP[0] = 0
 int build_lcp(const uint64_t* text, uint64_t n, uint32_t bl, const uint32_t* sa, const uint32_t* isa, uint32_t* lcp,
               cudaStream_t s);

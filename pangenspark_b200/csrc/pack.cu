@@ -438,6 +438,42 @@ void launch_pack(const PackJob& job, cudaStream_t s, cudaEvent_t* ev) {
     if (ev) cudaEventRecord(ev[2], s);
 }
 
+// ---- alphabet of the reference: which of the 256 byte values occur (drlz_build_index) --------------------------------
+// One bit per byte value, 8 words.  A thread looks at 16 bytes per step; a bit that is already set in the CTA's
+// shared copy costs a shared-memory read, so after the first few hundred bytes the kernel is a plain HBM read.
+__global__ void __launch_bounds__(256) k_byte_presence(const uint8_t* __restrict__ bytes, uint64_t n, uint32_t* __restrict__ presence) {
+    __shared__ uint32_t sp[8];
+    if (threadIdx.x < 8) sp[threadIdx.x] = 0;
+    __syncthreads();
+    const uint64_t nvec = n >> 4;
+    for (uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (uint64_t)gridDim.x * blockDim.x) {
+        const uint4 q = reinterpret_cast<const uint4*>(bytes)[v];
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const uint32_t c = (w[j] >> (8 * b)) & 255u;
+                if (!((sp[c >> 5] >> (c & 31u)) & 1u)) atomicOr(&sp[c >> 5], 1u << (c & 31u));
+            }
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 15)) {
+        const uint32_t c = bytes[(nvec << 4) + threadIdx.x];
+        atomicOr(&sp[c >> 5], 1u << (c & 31u));
+    }
+    __syncthreads();
+    if (threadIdx.x < 8 && sp[threadIdx.x]) atomicOr(&presence[threadIdx.x], sp[threadIdx.x]);
+}
+
+void launch_byte_presence(const uint8_t* bytes, uint64_t n, uint32_t* presence, cudaStream_t s) {
+    cudaMemsetAsync(presence, 0, 32, s);
+    if (n == 0) return;
+    uint64_t want = (n / 16 + 255) / 256;
+    unsigned grid = (unsigned)(want < 148 * 8 ? (want ? want : 1) : 148 * 8);
+    g_launches += 1;
+    k_byte_presence<<<grid, 256, 0, s>>>(bytes, n, presence);
+}
+
 __global__ void k_make_hapviews(HapView* haps, const uint64_t* X, const uint64_t* xoff, const uint64_t* m,
                                 const uint32_t* exc_pos, const uint8_t* exc_byte, const uint64_t* exc_cnt,
                                 uint64_t exc_stride, uint32_t H) {

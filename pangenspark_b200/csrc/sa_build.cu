@@ -188,21 +188,18 @@ __global__ void k_tab_mark(IndexView ix, uint32_t* tab) {
 struct LoadRev { const uint32_t* tab; uint64_t cnt; __device__ __forceinline__ uint32_t operator()(uint64_t e) const { return tab[cnt - 1 - e]; } };
 struct StoreRev { uint32_t* tab; uint64_t cnt; __device__ __forceinline__ void operator()(uint64_t e, uint32_t v) const { tab[cnt - 1 - e] = v; } };
 
-int build_kmer_table(const IndexView& ix, uint32_t* tab, cudaStream_t s) {
+size_t kmer_table_tmp_bytes(uint64_t entries) { return scan_tmp_elems(entries) * 4 + 64; }
+
+int build_kmer_table(const IndexView& ix, uint32_t* tab, uint32_t* tmp, cudaStream_t s) {
     uint64_t cnt = 1;
     for (int t = 0; t < ix.k; ++t) cnt *= ix.sigma;
     cnt += 1;
-    uint32_t* tmp = nullptr;
-    cudaError_t e = cudaMalloc(&tmp, scan_tmp_elems(cnt) * 4 + 64);
-    if (e != cudaSuccess) return (int)e;
     g_launches += 2;
     k_tab_fill<<<(unsigned)((cnt + 255) / 256), 256, 0, s>>>(tab, cnt, (uint32_t)ix.n);
     if (ix.n) k_tab_mark<<<(unsigned)((ix.n + 255) / 256), 256, 0, s>>>(ix, tab);
     device_scan<uint32_t, LoadRev, StoreRev, OpMin, true>(LoadRev{tab, cnt}, StoreRev{tab, cnt}, cnt, tmp, OpMin(),
                                                           0xFFFFFFFFu, s);
-    e = cudaStreamSynchronize(s);
-    cudaFree(tmp);
-    return (int)e;
+    return (int)cudaGetLastError();
 }
 
 // ---- LCP (Kasai order inside fixed blocks of text positions) ----------------------------------------

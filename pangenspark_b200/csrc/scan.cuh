@@ -9,7 +9,7 @@
 
 namespace drlz {
 
-extern unsigned long long g_launches;      // kernels launched by this library (defined in api.cu)
+extern thread_local unsigned long long g_launches;      // kernels launched by the calling thread (defined in api.cu)
 
 static const int kScanThreads = 256;
 static const int kScanItems = 16;
