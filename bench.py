@@ -6,19 +6,30 @@
         bench.py --gpus N --steps K --warmup W
 
 A "step" = one pass of the hot path (gap strip + 2-bit pack + exact greedy RLZ parse + phrase records) over the
-rank's batch of haplotypes.  Workload at every N: BASELINE.json configs[1] per GPU (chr21-sized 48 Mbp synthetic
-reference, 50 haplotypes) -- haplotypes shard across ranks, no data-path collective, weak scaling; for N > 1 the
-index is built on rank 0 and broadcast with NCCL (reported separately, not part of the parse metric, as defined in
-SURVEY.md 8(d)).
+rank's batch of haplotypes.
+
+Primary line (`value`, `e2e`, `roofline`): BASELINE.json configs[1] per GPU (chr21-sized 48 Mbp synthetic reference,
+50 haplotypes) -- haplotypes shard across ranks, no data-path collective, weak scaling; for N > 1 the index is built
+on rank 0 and broadcast with NCCL (reported separately, as SURVEY.md 8(d) defines the metric on the parse phase).
   value : whole-job Gbp/s with the MSA rows resident in HBM (CUDA events, max over ranks)
-  e2e   : the same through drlz_parse_batch with pinned HOST rows in and HOST phrase records out
+  e2e   : the same through drlz_parse_batch with pinned HOST rows in and HOST phrase records out; next to it the raw
+          pinned host->device copy bandwidth of the same bytes on the same ranks at the same time (`h2d_ceiling_gbs`):
+          what the box's PCIe / host memory gives with nothing of ours involved
   roofline / cpu_baseline : see DESIGN.md "Measurement"
+`strong_config3`: BASELINE.json configs[2] -- chr1-sized 249 Mbp reference, 100 haplotypes in all, sharded over the
+N ranks (strong scaling), with a `job` figure that includes the index build and its broadcast (the serial term).
+`cli_e2e`: the drop-in itself -- MSA rows as files on tmpfs -> bin/drlz -> .lz + gapless FASTA files, wall clock.
+Parity gate at every N: every rank compares its (received) suffix array and phrase records of its own rows with the
+CPU oracle; a mismatch anywhere makes every rank exit non-zero.
 """
 import argparse
+import hashlib
 import json
 import os
+import shutil
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 
@@ -45,6 +56,15 @@ def workload(rank: int):
     H = int(os.environ.get("DRLZ_BENCH_H", 50))
     name = "configs[1]: chr21-sized %.0f Mbp synthetic reference, %d haplotypes per GPU (0.1%% SNP, 1e-5 indel), haplotype-sharded" % (n / 1e6, H)
     return {"n": n, "H": H, "p_snp": 1e-3, "p_ins": 1e-5, "p_del": 1e-5, "cfg": 2, "h0": rank * H, "name": name}
+
+
+def workload_cfg3(rank: int, world: int):
+    """configs[2]: 249 Mbp reference, 100 haplotypes in all; rank r takes the contiguous slice of the basename-sorted list"""
+    n = int(os.environ.get("DRLZ_BENCH_CFG3_N", 249_000_000))
+    Htot = int(os.environ.get("DRLZ_BENCH_CFG3_H", 100))
+    a, b = rank * Htot // world, (rank + 1) * Htot // world
+    name = "configs[2]: chr1-sized %.0f Mbp synthetic reference, %d haplotypes in all, sharded over %d GPU(s)" % (n / 1e6, Htot, world)
+    return {"n": n, "H": b - a, "Htot": Htot, "p_snp": 1e-3, "p_ins": 1e-5, "p_del": 1e-5, "cfg": 3, "h0": a, "name": name}
 
 
 def gen_rows(orc, wl, d, pinned_array=None, rows=None):
@@ -124,18 +144,6 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def cpu_baseline(orc, wl, d, rows_arr, M, sample_rows, threads, sa=None):
-    """Oracle (C restatement of DistributedRLZ.scala) on the host cores: one haplotype per task, all threads."""
-    t0 = time.time()
-    if sa is None:
-        sa = orc.sa_build(d)
-    t_sa = time.time() - t0
-    rows = [rows_arr[h, :M] for h in range(sample_rows)]
-    orc.encode_rows_mt(d, sa, rows, threads)                    # warm-up (thread pool, page faults)
-    res, m, wt, sec = orc.encode_rows_mt(d, sa, rows, threads)
-    return {"pairs": res, "m": m, "seconds": sec, "sa_seconds": t_sa, "bases": int(m.sum()), "would_throw": int(wt.sum()), "sa": sa}
-
-
 def run_reference(args):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
@@ -173,161 +181,240 @@ def run_reference(args):
     return 0
 
 
-def bind_to_gpu_numa(local_rank: int):
-    """Pin this rank to the CPUs next to its GPU (NVML affinity) BEFORE pinned host memory is allocated, so the
-    staging buffers live on the NUMA node that feeds the GPU's PCIe root port."""
-    try:
-        import pynvml
-        pynvml.nvmlInit()
-        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
-        ncpu = os.cpu_count() or 1
-        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
-        cpus = [64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1]
-        allowed = set(os.sched_getaffinity(0))
-        cpus = [c for c in cpus if c in allowed]
-        if cpus:
-            os.sched_setaffinity(0, cpus)
-        return len(cpus)
-    except Exception:
-        return 0
-
-
 class _Raw:
     def __init__(self, ptr, nbytes):
         self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
 
 
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
-    from oracle import oracle as orc          # input generator + (rank 0, N=1) the cpu_baseline / parity checker
-    from pangenspark_b200 import drlz as D
+class Job:
+    """One rank of the benchmark: torch for device memory, streams and NCCL; the library for everything measured."""
 
-    rank = int(os.environ.get("RANK", 0))
-    world = int(os.environ.get("WORLD_SIZE", 1))
-    local = int(os.environ.get("LOCAL_RANK", 0))
-    torch.cuda.set_device(local)
-    ncpu_bound = bind_to_gpu_numa(local) if world > 1 else 0
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    wl = workload(rank)
-    seed = orc.seed_for(wl["cfg"])
-    d = orc.syn_reference(seed, wl["n"])
-    M = orc.syn_columns(seed, wl["n"], wl["p_ins"])
-    stride = (M + 15) // 16 * 16 + 16
-    H = wl["H"]
-    pin = D.PinnedBuffer(H * stride)
-    rows_arr, M, stride = gen_rows(orc, wl, d, pinned_array=pin.array)
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        from oracle import oracle as orc          # input generator + the cpu_baseline / parity checker
+        from pangenspark_b200 import drlz as D
+        self.torch, self.dist, self.orc, self.D, self.args = torch, dist, orc, D, args
+        self.rank = int(os.environ.get("RANK", 0))
+        self.world = int(os.environ.get("WORLD_SIZE", 1))
+        self.local = int(os.environ.get("LOCAL_RANK", 0))
+        torch.cuda.set_device(self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+        self.ctx = D.Drlz(self.local)
+        self.stream = torch.cuda.Stream()
+        self.ctx.set_stream(self.stream.cuda_stream)
+        for key in ("kmer", "chunk", "group_bytes"):
+            v = os.environ.get("DRLZ_" + key.upper())
+            if v:
+                self.ctx.set_option(key, int(v))
+        self.threads = max(1, _cores // self.world)
+        self.shm_tag = "drlz_bench_%s_%s" % (os.environ.get("MASTER_PORT", "0"), os.getppid() if self.world > 1 else os.getpid())
 
-    ctx = D.Drlz(local)
-    stream = torch.cuda.Stream()
-    ctx.set_stream(stream.cuda_stream)
-    for key in ("kmer", "chunk", "group_bytes"):
-        v = os.environ.get("DRLZ_" + key.upper())
-        if v:
-            ctx.set_option(key, int(v))
+    # ---- collectives (scalars) ----------------------------------------------------------------------------------
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
 
-    # ---- index: built on rank 0, NCCL broadcast to the other ranks ---------------------------------------
-    bcast_ms = 0.0
-    if rank == 0:
-        ctx.build_index(d)            # warm-up build (allocations, first-touch)
-        ctx.build_index(d)
-        idx_t = ctx.index_timings()
-        info = ctx.index_info()
-    if world > 1:
-        meta = torch.zeros(2, dtype=torch.int64, device="cuda")
-        if rank == 0:
-            meta[0], meta[1] = info["n"], info["kinfo"]
-        dist.broadcast(meta, 0)
-        if rank != 0:
-            ctx.index_reserve(int(meta[0]), int(meta[1]))
-        bufs = [torch.as_tensor(_Raw(p, nb), device="cuda") for p, nb in ctx.index_buffers()]
-        torch.cuda.synchronize(); dist.barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for b in bufs:
-            dist.broadcast(b, 0)
-        e1.record(); torch.cuda.synchronize()
-        bcast_ms = e0.elapsed_time(e1)
-        if rank != 0:
-            ctx.index_commit()
+    def _reduce(self, x, op):
+        if self.world == 1:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=op)
+        return float(t.item())
+
+    def reduce_max(self, x):
+        return self._reduce(x, self.dist.ReduceOp.MAX)
+
+    def reduce_min(self, x):
+        return self._reduce(x, self.dist.ReduceOp.MIN)
+
+    def reduce_sum(self, x):
+        return self._reduce(x, self.dist.ReduceOp.SUM)
+
+    # ---- index: built on rank 0, NCCL broadcast to the other ranks -------------------------------------------------
+    def index(self, d, warm=True):
+        torch, dist, ctx = self.torch, self.dist, self.ctx
+        info, idx_t, bcast_ms, wall_ms = None, None, 0.0, 0.0
+        if self.rank == 0:
+            if warm:
+                ctx.build_index(d)            # warm-up build (allocations, first touch)
+            t0 = time.time()
+            ctx.build_index(d)
+            wall_ms = (time.time() - t0) * 1e3
+            idx_t = ctx.index_timings()
             info = ctx.index_info()
-            idx_t = {"total_ms": 0.0, "pack_ms": 0.0, "sa_ms": 0.0, "table_ms": 0.0, "lcp_ms": 0.0}
+        if self.world > 1:
+            meta = torch.zeros(2, dtype=torch.int64, device="cuda")
+            if self.rank == 0:
+                meta[0], meta[1] = info["n"], info["kinfo"]
+            dist.broadcast(meta, 0)
+            if self.rank != 0:
+                ctx.index_reserve(int(meta[0]), int(meta[1]))
+            bufs = [torch.as_tensor(_Raw(p, nb), device="cuda") for p, nb in ctx.index_buffers()]
+            torch.cuda.synchronize(); dist.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for b in bufs:
+                dist.broadcast(b, 0)
+            e1.record(); torch.cuda.synchronize()
+            bcast_ms = self.reduce_max(e0.elapsed_time(e1))
+            if self.rank != 0:
+                ctx.index_commit()
+                info = ctx.index_info()
+                idx_t = {"total_ms": 0.0, "pack_ms": 0.0, "sa_ms": 0.0, "table_ms": 0.0, "lcp_ms": 0.0}
+        return info, idx_t, bcast_ms, wall_ms
 
-    # ---- rows resident in HBM ------------------------------------------------------------------------------
-    dev_rows = torch.empty(H * stride, dtype=torch.uint8, device="cuda")
-    dev_rows.copy_(torch.from_numpy(rows_arr.reshape(-1)), non_blocking=False)
-    row_off = np.arange(H, dtype=np.uint64) * np.uint64(stride)
-    cols = np.full(H, M, dtype=np.uint64)
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def reduce_max(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    def reduce_sum(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
-
-    sampler = ClockSampler(local)
-    # ---- value: device-resident ----------------------------------------------------------------------------
-    with torch.cuda.stream(stream):
-        for _ in range(args.warmup):
-            ptr, npairs, m = ctx.parse_batch_device(dev_rows.data_ptr(), row_off, cols)
-        barrier()
-        sampler.start()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        kt = {}
-        ev0.record(stream)
-        for _ in range(args.steps):
-            ptr, npairs, m = ctx.parse_batch_device(dev_rows.data_ptr(), row_off, cols)
-            for k_, v_ in ctx.parse_timings().items():
-                kt[k_] = kt.get(k_, 0.0) + v_
-        ev1.record(stream)
-        barrier()
-        ms_dev = ev0.elapsed_time(ev1) / args.steps
-    bases = int(m.sum())
-    phrases = int(npairs.sum())
-    ms_dev = reduce_max(ms_dev)
-    total_bases = reduce_sum(float(bases))
-    value = total_bases / (ms_dev * 1e-3) / 1e9
-
-    # ---- e2e: pinned host rows in, host phrase records out -----------------------------------------------------
-    out_pin = D.PinnedBuffer(16 * (phrases + 1024))
-    out_arr = out_pin.array.view(np.int64)
-    host_rows = [rows_arr[h, :M] for h in range(H)]
-    with torch.cuda.stream(stream):
-        for _ in range(args.warmup):
-            res, m2, _ = ctx.parse_batch(host_rows, pairs_cap=phrases + 1024, out=out_arr)
-        barrier()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # ---- one workload: device-resident value, end to end, raw copy ceiling ------------------------------------------
+    def measure(self, wl, d, steps, warmup, sampler=None):
+        torch, ctx, D, orc = self.torch, self.ctx, self.D, self.orc
+        seed = orc.seed_for(wl["cfg"])
+        M = orc.syn_columns(seed, wl["n"], wl["p_ins"])
+        stride = (M + 15) // 16 * 16 + 16
+        H = wl["H"]
         t0 = time.time()
-        ev0.record(stream)
-        for _ in range(args.steps):
-            res, m2, _ = ctx.parse_batch(host_rows, pairs_cap=phrases + 1024, out=out_arr)
-        ev1.record(stream)
-        barrier()
-        wall_e2e = (time.time() - t0) / args.steps * 1e3
-        ms_e2e = ev0.elapsed_time(ev1) / args.steps
-    clocks = sampler.stop()
-    ms_e2e = reduce_max(max(ms_e2e, 0.0))
-    e2e_val = total_bases / (ms_e2e * 1e-3) / 1e9
-    assert [r.shape[0] for r in res] == npairs.tolist() and (m2 == m).all()
+        pin = D.PinnedBuffer(max(1, H) * stride)
+        rows_arr, M, stride = gen_rows(orc, wl, d, pinned_array=pin.array)
+        gen_s = time.time() - t0
+        dev_rows = torch.empty(max(1, H) * stride, dtype=torch.uint8, device="cuda")
+        pin_t = torch.from_numpy(rows_arr.reshape(-1))
+        dev_rows[: H * stride].copy_(pin_t, non_blocking=False)
+        row_off = np.arange(H, dtype=np.uint64) * np.uint64(stride)
+        cols = np.full(H, M, dtype=np.uint64)
+        stream = self.stream
 
-    # ---- roofline of the dominant kernel (per-launch CUDA-event times measured above) ---------------------------
-    peak, peak_src = peaks()
-    steps = args.steps
+        # value: rows resident in HBM
+        with torch.cuda.stream(stream):
+            for _ in range(warmup):
+                ptr, npairs, m = ctx.parse_batch_device(dev_rows.data_ptr(), row_off, cols)
+            self.barrier()
+            if sampler:
+                sampler.start()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            kt = {}
+            ev0.record(stream)
+            for _ in range(steps):
+                ptr, npairs, m = ctx.parse_batch_device(dev_rows.data_ptr(), row_off, cols)
+                for k_, v_ in ctx.parse_timings().items():
+                    kt[k_] = kt.get(k_, 0.0) + v_
+            ev1.record(stream)
+            self.barrier()
+            ms_dev = ev0.elapsed_time(ev1) / steps
+        bases = int(m.sum())
+        phrases = int(npairs.sum())
+        ms_dev = self.reduce_max(ms_dev)
+        total_bases = self.reduce_sum(float(bases))
+        value = total_bases / (ms_dev * 1e-3) / 1e9
+
+        # e2e: pinned host rows in, host phrase records out
+        out_pin = D.PinnedBuffer(16 * (phrases + 1024))
+        out_arr = out_pin.array.view(np.int64)
+        host_rows = [rows_arr[h, :M] for h in range(H)]
+        with torch.cuda.stream(stream):
+            for _ in range(warmup):
+                res, m2, _ = ctx.parse_batch(host_rows, pairs_cap=phrases + 1024, out=out_arr)
+            self.barrier()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.time()
+            ev0.record(stream)
+            for _ in range(steps):
+                res, m2, _ = ctx.parse_batch(host_rows, pairs_cap=phrases + 1024, out=out_arr)
+            ev1.record(stream)
+            self.barrier()
+            wall_e2e = (time.time() - t0) / steps * 1e3
+            ms_e2e = ev0.elapsed_time(ev1) / steps
+        ms_e2e = self.reduce_max(max(ms_e2e, 0.0))
+        e2e_val = total_bases / (ms_e2e * 1e-3) / 1e9
+        assert [r.shape[0] for r in res] == npairs.tolist() and (m2 == m).all()
+
+        # the ceiling of that: nothing but the pinned host->device copy of the same rows, all ranks at once
+        with torch.cuda.stream(stream):
+            dev_rows[: H * stride].copy_(pin_t, non_blocking=True)
+            self.barrier()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record(stream)
+            for _ in range(steps):
+                dev_rows[: H * stride].copy_(pin_t, non_blocking=True)
+            ev1.record(stream)
+            self.barrier()
+            ms_copy = self.reduce_max(ev0.elapsed_time(ev1) / steps)
+        total_h2d = self.reduce_sum(float(H) * M)
+        total_copy = self.reduce_sum(float(H) * stride)
+        if sampler:
+            self.clocks = sampler.stop()
+        h2d_gbs = total_h2d / (ms_e2e * 1e-3) / 1e9
+        ceil_gbs = total_copy / (ms_copy * 1e-3) / 1e9
+        e2e = {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(H * M), "d2h_bytes_per_step": int(16 * phrases),
+               "ms_per_step": ms_e2e, "wall_ms_per_step": wall_e2e, "h2d_gbs": h2d_gbs, "h2d_ceiling_gbs": ceil_gbs,
+               "frac_of_h2d_ceiling": h2d_gbs / ceil_gbs if ceil_gbs else None,
+               "h2d_ceiling_how": "pinned host -> device copy of the same rows on every rank at the same time, nothing else running (whole job, GB/s)"}
+        return {"M": M, "stride": stride, "H": H, "rows_arr": rows_arr, "res": res, "m": m, "npairs": npairs, "kt": kt,
+                "ms_dev": ms_dev, "value": value, "total_bases": total_bases, "bases": bases, "phrases": phrases, "e2e": e2e,
+                "gen_s": gen_s, "_keep": (pin, out_pin, dev_rows)}
+
+    # ---- parity gate: every rank, its own rows and its own copy of the index -------------------------------------------
+    def parity(self, wl, d, ms, sample_rows, want_cpu_baseline):
+        """Rank 0 builds the CPU suffix array and leaves it in /dev/shm; every rank compares the suffix array in its
+        own GPU memory (built there on rank 0, received over NCCL elsewhere) with it and its phrase records of
+        `sample_rows` of its own rows with the oracle's.  Returns (rows checked in all, cpu_baseline | None, ok)."""
+        orc, ctx = self.orc, self.ctx
+        path = "/dev/shm/%s_cfg%d_sa.npy" % (self.shm_tag, wl["cfg"])
+        t_sa = 0.0
+        if self.rank == 0:
+            t0 = time.time()
+            sa = orc.sa_build(d)
+            t_sa = time.time() - t0
+            if self.world > 1:
+                np.save(path, sa)
+        self.barrier()
+        if self.rank != 0:
+            sa = np.load(path)
+        ok = True
+        sa_gpu = ctx.index_get("sa")
+        if sa_gpu.shape != sa.shape or not (sa_gpu == sa).all():
+            print("PARITY FAILURE (rank %d): suffix array differs from the oracle" % self.rank, file=sys.stderr)
+            ok = False
+        del sa_gpu
+        H, M = ms["H"], ms["M"]
+        sample = min(H, sample_rows)
+        # rows spread over the rank's slice (first, last, and evenly in between)
+        pick = sorted(set(int(round(i * (H - 1) / max(1, sample - 1))) for i in range(sample))) if sample else []
+        rows = [ms["rows_arr"][h, :M] for h in pick]
+        cpu = None
+        if ok and rows:
+            threads = _cores if self.world == 1 else self.threads
+            if want_cpu_baseline:
+                orc.encode_rows_mt(d, sa, rows, threads)                    # warm-up (thread pool, page faults)
+            cres, cm, wt, sec = orc.encode_rows_mt(d, sa, rows, threads)
+            for j, h in enumerate(pick):
+                if orc.lz_bytes(ms["res"][h]) != orc.lz_bytes(cres[j]) or int(cm[j]) != int(ms["m"][h]):
+                    print("PARITY FAILURE (rank %d): phrase records of row %d differ from the oracle" % (self.rank, wl["h0"] + h), file=sys.stderr)
+                    ok = False
+            if want_cpu_baseline:
+                cpu = {"value": float(cm.sum()) / sec / 1e9, "unit": UNIT, "cores": threads, "kind": "port",
+                       "sample": "%d of the %d haplotypes (%.0f Mbp), parse only, one haplotype per task; CPU SA build %.1f s excluded; "
+                                 "C restatement of DistributedRLZ.scala, not the JVM job" % (len(pick), H, float(cm.sum()) / 1e6, t_sa),
+                       "sa_build_s": t_sa}
+        self.barrier()
+        if self.rank == 0 and self.world > 1:
+            try:
+                os.remove(path)
+            except OSError:
+                pass
+        all_ok = self.reduce_min(1.0 if ok else 0.0) > 0.5
+        checked = int(self.reduce_sum(float(len(pick) if ok else 0)))
+        return checked, cpu, all_ok
+
+    def close(self):
+        self.ctx.close()
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+def roofline_of(ms, steps, peak, peak_src):
+    kt, H, M, bases, phrases = ms["kt"], ms["H"], ms["M"], ms["bases"], ms["phrases"]
     Mtot, mtot = float(H) * M, float(bases)
     per_launch = {   # name: (avg ms per launch, algorithmic bytes per launch)
         "k_pack": (kt["pack_write_ms"] / steps, Mtot + mtot / 4),
@@ -339,62 +426,148 @@ def run_ours(args):
     dom = max(per_launch, key=lambda k_: per_launch[k_][0])
     dom_ms, dom_bytes = per_launch[dom]
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
-    traffic = None
+    traffic, traffic_src = None, None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get(dom)
+            tj = json.load(open(tp))
+            traffic = tj.get(dom)
+            traffic_src = tj.get("_source", "profiles/traffic.json (hand-kept from the last ncu --set full capture)")
         except Exception:
             traffic = None
     alg_step = Mtot + mtot / 2 + 16.0 * phrases            # M + m/4 + m/4 + 16 P
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes,
-                "kernel_ms": dom_ms,
-                "step": {"algorithmic_bytes": alg_step, "achieved": alg_step / (ms_dev * 1e-3) / 1e9,
-                         "frac": alg_step / (ms_dev * 1e-3) / 1e9 / peak},
-                "kernel_ms_per_step": {k_: round(v_ / steps, 4) for k_, v_ in kt.items() if k_.endswith("_ms")}}
+    return {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes,
+            "kernel_ms": dom_ms,
+            "step": {"algorithmic_bytes": alg_step, "achieved": alg_step / (ms["ms_dev"] * 1e-3) / 1e9,
+                     "frac": alg_step / (ms["ms_dev"] * 1e-3) / 1e9 / peak},
+            "kernel_ms_per_step": {k_: round(v_ / steps, 4) for k_, v_ in kt.items() if k_.endswith("_ms")}}
 
-    # ---- CPU baseline + parity gate (rank 0, N = 1 only) ----------------------------------------------------------
-    cpu = None
-    parity_rows = 0
-    if rank == 0 and world == 1 and not os.environ.get("DRLZ_BENCH_SKIP_CPU"):
-        threads = _cores
-        sample = min(H, int(os.environ.get("DRLZ_BENCH_REF_ROWS", 16)))
-        sa_gpu = ctx.index_get("sa").astype(np.int64)
-        cb = cpu_baseline(orc, wl, d, rows_arr, M, sample, threads)
-        if not (cb["sa"] == sa_gpu).all():
-            print("PARITY FAILURE: suffix array differs from the oracle", file=sys.stderr)
+
+def cli_e2e(job, wl, d, ms):
+    """The drop-in itself (rank 0, N GPUs through DRLZ_GPUS): rows as files on tmpfs -> bin/drlz -> .lz + FASTA files."""
+    orc = job.orc
+    exe = os.path.join(ROOT, "pangenspark_b200", "bin", "drlz")
+    if not os.path.exists(exe) or not os.path.isdir("/dev/shm"):
+        return None
+    H, M = ms["H"], ms["M"]
+    rows = min(H, int(os.environ.get("DRLZ_BENCH_CLI_ROWS", H)))
+    tmp = tempfile.mkdtemp(prefix="drlz_cli_", dir="/dev/shm")
+    try:
+        os.makedirs(os.path.join(tmp, "msa"))
+        d.tofile(os.path.join(tmp, "ref.txt"))
+        for h in range(rows):
+            ms["rows_arr"][h, :M].tofile(os.path.join(tmp, "msa", "H%05d.21" % (wl["h0"] + h)))
+        env = dict(os.environ, DRLZ_GPUS="1", DRLZ_DEVICE=str(job.local), DRLZ_STATS=os.path.join(tmp, "stats.json"))
+        cmd = [exe, os.path.join(tmp, "radix"), os.path.join(tmp, "ref.txt"), os.path.join(tmp, "msa", "*.21"), "file:///",
+               os.path.join(tmp, "out"), os.path.join(tmp, "gapless")]
+        t0 = time.time()
+        p = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+        wall = time.time() - t0
+        if p.returncode != 0:
+            return {"error": (p.stderr or p.stdout)[-300:]}
+        stats = {}
+        try:
+            stats = json.load(open(os.path.join(tmp, "stats.json")))
+        except Exception:
+            pass
+        # sampled .lz files against the records of the library call above (themselves gated against the oracle)
+        ok = True
+        sha = []
+        for h in sorted(set([0, rows // 2, rows - 1])):
+            b = open(os.path.join(tmp, "out", "H%05d.21.lz" % (wl["h0"] + h)), "rb").read()
+            sha.append(hashlib.sha256(b).hexdigest()[:16])
+            ok = ok and b == orc.lz_bytes(ms["res"][h])
+        fa = open(os.path.join(tmp, "gapless", "part-00000"), "rb").read()
+        ok = ok and fa == b">H%05d.21\n" % wl["h0"] + orc.strip_gaps(ms["rows_arr"][0, :M]).tobytes() + b"\n"
+        bases = float(ms["m"][:rows].sum())
+        parse_s = stats.get("encode_s", wall)
+        return {"value": bases / parse_s / 1e9, "unit": UNIT, "wall_s": wall, "encode_s": parse_s, "rows": rows, "files_ok": bool(ok),
+                "lz_sha256_16": sha, "input_gbs": rows * M / parse_s / 1e9, "stats": stats,
+                "what": "rows as files on tmpfs -> bin/drlz (one GPU) -> .lz and gapless FASTA part files on tmpfs; `value` = bases / "
+                        "seconds of the encode phase (read + copy + parse + write, index build excluded as for `e2e`); wall_s = whole process"}
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
+def run_ours(args):
+    job = Job(args)
+    orc, torch = job.orc, job.torch
+    rank, world = job.rank, job.world
+    peak, peak_src = peaks()
+    steps = args.steps
+
+    # ================= primary: configs[1] per GPU =====================================================================
+    wl = workload(rank)
+    d = orc.syn_reference(orc.seed_for(wl["cfg"]), wl["n"])
+    info, idx_t, bcast_ms, idx_wall = job.index(d)
+    ms = job.measure(wl, d, steps, args.warmup, sampler=ClockSampler(job.local))
+    clocks = job.clocks
+    roofline = roofline_of(ms, steps, peak, peak_src)
+    skip_cpu = bool(os.environ.get("DRLZ_BENCH_SKIP_CPU"))
+    parity_rows, cpu, ok = 0, None, True
+    if not skip_cpu:
+        sample = int(os.environ.get("DRLZ_BENCH_REF_ROWS", 16 if world == 1 else 2))
+        parity_rows, cpu, ok = job.parity(wl, d, ms, sample, want_cpu_baseline=(world == 1))
+        if not ok:
+            job.close()
             return 3
-        for h in range(sample):
-            if orc.lz_bytes(res[h]) != orc.lz_bytes(cb["pairs"][h]):
-                print("PARITY FAILURE: phrase records of row %d differ from the oracle" % h, file=sys.stderr)
-                return 3
-        parity_rows = sample
-        cpu = {"value": cb["bases"] / cb["seconds"] / 1e9, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": "%d of the %d haplotypes (%.0f Mbp), parse only, one haplotype per task; CPU SA build %.1f s excluded; "
-                         "C restatement of DistributedRLZ.scala, not the JVM job" % (sample, H, cb["bases"] / 1e6, cb["sa_seconds"]),
-               "sa_build_s": cb["sa_seconds"]}
+    cli = None
+    if rank == 0 and not os.environ.get("DRLZ_BENCH_SKIP_CLI"):
+        try:
+            cli = cli_e2e(job, wl, d, ms)
+        except Exception as ex:       # the CLI leg never takes the kernel numbers down with it
+            cli = {"error": repr(ex)[:300]}
+    job.barrier()
+    primary_kt = ms["kt"]
+    H, M = ms["H"], ms["M"]
+    out = {"metric": METRIC, "value": ms["value"], "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": args.warmup,
+           "ms_per_step": ms["ms_dev"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
+           "data": "synthetic",
+           "config": {"workload": wl["name"], "l2": "inputs (%.2f GB of MSA rows per GPU) exceed the 126 MB L2; no explicit flush" % (H * M / 1e9),
+                      "bases_per_step": ms["total_bases"], "phrases_per_step_rank0": ms["phrases"], "kmer": info["k"],
+                      "index": "built once outside the step" + (", NCCL broadcast from rank 0" if world > 1 else "")},
+           "e2e": ms["e2e"], "gpu_launches": int(primary_kt["launches"]),
+           "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+           "index_build": {"total_ms": idx_t["total_ms"], "wall_ms": idx_wall, "sa_ms": idx_t["sa_ms"], "table_ms": idx_t["table_ms"],
+                           "pack_ms": idx_t["pack_ms"], "lcp_ms": idx_t["lcp_ms"], "rounds": info["sa_rounds"], "n": info["n"],
+                           "algorithmic_bytes": 9 * info["n"], "bcast_ms": bcast_ms,
+                           "achieved_gbs": 9 * info["n"] / max(idx_t["total_ms"], 1e-9) / 1e6,
+                           "frac": 9 * info["n"] / max(idx_t["total_ms"], 1e-9) / 1e6 / peak,
+                           "includes": "host->device copy of the reference, alphabet scan, pack, suffix array + inverse, k-mer table, LCP, uniqueness array",
+                           "ref_mbp_per_s": info["n"] / max(idx_t["total_ms"], 1e-9) / 1e3},
+           "parity_checked_rows": parity_rows, "fix_rounds_per_step": primary_kt["fix_rounds"] / steps,
+           "cli_e2e": cli}
+    del ms, d
+    import gc
+    gc.collect()
+
+    # ================= configs[2]: chr1-sized reference, 100 haplotypes in all, strong scaling ======================
+    if not os.environ.get("DRLZ_BENCH_SKIP_CFG3"):
+        w3 = workload_cfg3(rank, world)
+        d3 = orc.syn_reference(orc.seed_for(3), w3["n"])
+        info3, idx3, bcast3, wall3 = job.index(d3, warm=False)
+        s3 = max(1, min(steps, int(os.environ.get("DRLZ_BENCH_CFG3_STEPS", 3))))
+        m3 = job.measure(w3, d3, s3, 3)
+        chk3, _, ok3 = (0, None, True) if skip_cpu else job.parity(w3, d3, m3, 2, want_cpu_baseline=False)
+        if not ok3:
+            job.close()
+            return 3
+        job_ms = job.reduce_max(wall3) + bcast3 + m3["e2e"]["ms_per_step"]      # first (and only) build of a real job: allocations included
+        out["strong_config3"] = {
+            "workload": w3["name"], "scaling": "strong", "rows_per_rank_max": int(job.reduce_max(float(w3["H"]))),
+            "value": m3["value"], "unit": UNIT, "ms_per_step": m3["ms_dev"], "steps": s3, "warmup": 3,
+            "e2e": m3["e2e"], "bases_per_step": m3["total_bases"],
+            "index_build_ms": job.reduce_max(idx3["total_ms"]), "index_first_call_wall_ms": job.reduce_max(wall3), "bcast_ms": bcast3,
+            "job": {"value": m3["total_bases"] / (job_ms * 1e-3) / 1e9, "unit": UNIT, "ms": job_ms,
+                    "what": "index build on rank 0 + NCCL broadcast + one end-to-end pass over all rows (the serial terms included)"},
+            "roofline_step_frac": roofline_of(m3, s3, peak, peak_src)["step"]["frac"],
+            "kernel_ms_per_step": {k_: round(v_ / s3, 4) for k_, v_ in m3["kt"].items() if k_.endswith("_ms")},
+            "parity_checked_rows": chk3, "kmer": info3["k"]}
 
     if rank == 0:
-        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-               "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
-               "data": "synthetic",
-               "config": {"workload": wl["name"], "l2": "inputs (%.2f GB of MSA rows per GPU) exceed the 126 MB L2; no explicit flush" % (H * M / 1e9),
-                          "bases_per_step": total_bases, "cpus_bound_per_rank": ncpu_bound, "phrases_per_step_rank0": phrases, "kmer": info["k"],
-                          "index": "built once outside the step" + (", NCCL broadcast from rank 0" if world > 1 else "")},
-               "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(H * M), "d2h_bytes_per_step": int(16 * phrases),
-                       "ms_per_step": ms_e2e, "wall_ms_per_step": wall_e2e},
-               "gpu_launches": int(kt["launches"]),
-               "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
-               "index_build": {"total_ms": idx_t["total_ms"], "sa_ms": idx_t["sa_ms"], "table_ms": idx_t["table_ms"],
-                               "pack_ms": idx_t["pack_ms"], "rounds": info["sa_rounds"], "n": info["n"],
-                               "algorithmic_bytes": 9 * info["n"], "bcast_ms": bcast_ms,
-                               "ref_mbp_per_s": info["n"] / max(idx_t["total_ms"], 1e-9) / 1e3},
-               "parity_checked_rows": parity_rows, "fix_rounds_per_step": kt["fix_rounds"] / steps}
         _emit(json.dumps(out))
-    ctx.close()
-    if world > 1:
-        dist.destroy_process_group()
+    job.close()
     return 0
 
 

@@ -103,7 +103,19 @@ int drlz_parse_batch(drlz_ctx* ctx, const uint8_t* const* rows, const uint64_t* 
 int drlz_submit(drlz_ctx* ctx, const uint8_t* const* rows, const uint64_t* cols, uint32_t H, int strip_gaps,
                 uint8_t* const* gapless_out, uint64_t* m_out, int64_t* pairs_out, uint64_t pairs_cap, uint64_t* n_pairs,
                 uint64_t* ticket);
-int drlz_wait(drlz_ctx* ctx, uint64_t ticket);
+int drlz_wait(drlz_ctx* ctx, uint64_t ticket);     /* a ticket can be collected once; an unknown or collected one => DRLZ_E_ARG */
+
+/* drlz_parse_batch / drlz_submit that also return the gap-position side table of every row:
+ * one (int64 first column, int64 length) record per maximal run of '-' in the row, in column order -- what
+ * ScoreMatrix.scala:89-127 recomputes from the rows (`gap`, `consecutive`) to map gapless positions back to MSA
+ * columns.  Records of row h start at gaps_out + 2 * (n_gaps[0] + ... + n_gaps[h-1]); too small a gaps_cap =>
+ * DRLZ_E_NOSPACE with the required counts in n_gaps.  strip_gaps == 0 => no gaps by definition. */
+int drlz_parse_batch_gaps(drlz_ctx* ctx, const uint8_t* const* rows, const uint64_t* cols, uint32_t H, int strip_gaps,
+                          uint8_t* const* gapless_out, uint64_t* m_out, int64_t* pairs_out, uint64_t pairs_cap,
+                          uint64_t* n_pairs, int64_t* gaps_out, uint64_t gaps_cap, uint64_t* n_gaps);
+int drlz_submit_gaps(drlz_ctx* ctx, const uint8_t* const* rows, const uint64_t* cols, uint32_t H, int strip_gaps,
+                     uint8_t* const* gapless_out, uint64_t* m_out, int64_t* pairs_out, uint64_t pairs_cap, uint64_t* n_pairs,
+                     int64_t* gaps_out, uint64_t gaps_cap, uint64_t* n_gaps, uint64_t* ticket);
 
 /* Same with the rows already resident in device memory: row h = rows_dev + row_off[h]; every row_off is a
  * multiple of 16 and the buffer is readable up to the next multiple of 16 past each row's end; cols excludes

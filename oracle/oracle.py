@@ -166,6 +166,17 @@ def max_threads() -> int:
     return int(lib().orc_max_threads())
 
 
+def gap_runs(row) -> np.ndarray:
+    """Gap-position side table of one MSA row as [runs, 2] int64 (first column, length): the maximal runs of the
+    column list ScoreMatrix.scala:91-93 collects (`for i if row(i) == '-' yield i`), run lengths as its
+    `consecutive` helper counts them (:63-79)."""
+    row = _u8(row)
+    g = (row == ord("-")).astype(np.int8)
+    edge = np.diff(np.concatenate([[0], g, [0]]))
+    starts, ends = np.flatnonzero(edge == 1), np.flatnonzero(edge == -1)
+    return np.stack([starts, ends - starts], axis=1).astype(np.int64).reshape(-1, 2)
+
+
 def lz_bytes(pairs) -> bytes:
     """DistributedRLZ.scala:263-284: int64 LE pos, int64 LE len per phrase."""
     return np.ascontiguousarray(pairs, dtype="<i8").tobytes()

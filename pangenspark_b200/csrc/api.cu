@@ -69,14 +69,14 @@ struct drlz_ctx {
     SaWorkspace sa_ws;
     DevBuf stage[2], meta_dev, desc_cnt, desc_exc, tile_counter, X, mdev, exccnt, excpos, excbyte,
         flags, haps, gapless, gtile_cnt, gtile_exc, gtile_off, gtile_excoff, gscan_tmp, chunk_hap, first_pos, first_len, run_a, run_b, link_a, link_b, open_i, open_pos, open_len, spec_cnt, spec_exit, alt_entry, alt_cnt, alt_exit, alt_round, alt_own, alt_merge, spec_ph, alt_ph, hint, mm, true_slot, counters, jump_a,
-        jump_b, mark, true_cnt, true_entry, true_off, scan_tmp, hap_pairs, out, ms_a, ms_b, tab_tmp;
-    HostBuf meta_host, small_host;
+        jump_b, mark, true_cnt, true_entry, true_off, scan_tmp, hap_pairs, out, ms_a, ms_b, tab_tmp, gap_list, gap_scratch, gap_counter;
+    HostBuf meta_host, small_host, gap_host;
     uint64_t exc_stride_hint = 0;
     // thread safety: every entry point takes `mu` (calls from several threads are serialised on the device)
     std::recursive_mutex mu;
     // async form (drlz_submit / drlz_wait): one worker thread per context, FIFO
     struct Job { uint64_t ticket; const uint8_t* const* rows; const uint64_t* cols; uint32_t H; int strip; uint8_t* const* gapless;
-                 uint64_t* m_out; int64_t* pairs; uint64_t cap; uint64_t* n_pairs; };
+                 uint64_t* m_out; int64_t* pairs; uint64_t cap; uint64_t* n_pairs; int64_t* gaps; uint64_t gaps_cap; uint64_t* n_gaps; };
     std::mutex qmu; std::condition_variable qcv, done_cv;
     std::deque<Job> queue; std::vector<std::pair<uint64_t, int>> done;
     std::vector<uint64_t> outstanding;      // tickets submitted and not yet collected by drlz_wait
@@ -171,9 +171,9 @@ void drlz_destroy(drlz_ctx* c) {
                       &c->desc_exc, &c->tile_counter, &c->X, &c->mdev, &c->exccnt, &c->excpos,
                       &c->excbyte, &c->flags, &c->haps, &c->gapless, &c->gtile_cnt, &c->gtile_exc, &c->gtile_off, &c->gtile_excoff, &c->gscan_tmp, &c->chunk_hap, &c->first_pos, &c->first_len, &c->run_a, &c->run_b, &c->link_a, &c->link_b, &c->open_i, &c->open_pos, &c->open_len, &c->spec_cnt, &c->spec_exit,
                       &c->alt_entry, &c->alt_cnt, &c->alt_exit, &c->alt_round, &c->alt_own, &c->alt_merge, &c->spec_ph, &c->alt_ph, &c->hint, &c->mm, &c->true_slot, &c->counters, &c->jump_a, &c->jump_b,
-                      &c->mark, &c->true_cnt, &c->true_entry, &c->true_off, &c->scan_tmp, &c->hap_pairs, &c->out, &c->ms_a, &c->ms_b, &c->tab_tmp};
+                      &c->mark, &c->true_cnt, &c->true_entry, &c->true_off, &c->scan_tmp, &c->hap_pairs, &c->out, &c->ms_a, &c->ms_b, &c->tab_tmp, &c->gap_list, &c->gap_scratch, &c->gap_counter};
     for (DevBuf* b : bufs) b->release();
-    c->meta_host.release(); c->small_host.release();
+    c->meta_host.release(); c->small_host.release(); c->gap_host.release();
     for (int i = 0; i < 2; ++i) if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]);
     for (int i = 0; i < 12; ++i) if (c->ev_stage[i]) cudaEventDestroy(c->ev_stage[i]);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -681,8 +681,54 @@ int drlz_parse_batch_device(drlz_ctx* c, const uint8_t* rows_dev, const uint64_t
     return DRLZ_OK;
 }
 
-int drlz_parse_batch(drlz_ctx* c, const uint8_t* const* rows, const uint64_t* cols, uint32_t H, int strip_gaps,
-                     uint8_t* const* gapless_out, uint64_t* m_out, int64_t* pairs_out, uint64_t pairs_cap, uint64_t* n_pairs) {
+// Gap runs of the rows of the group that run_device_group has just parsed (its row offsets and column counts are still in
+// meta_dev): events on the device, sorted there, paired on the host.  Appends (column, length) records to gaps_out.
+static int collect_gap_runs(drlz_ctx* c, const uint8_t* rows_dev, const uint64_t* tc, uint32_t H, int64_t* gaps_out, uint64_t gaps_cap,
+                            uint64_t* done_gaps, uint64_t* n_gaps, bool* nospace) {
+    cudaStream_t s = c->stream;
+    uint64_t maxcols = 0, sumcols = 0;
+    for (uint32_t h = 0; h < H; ++h) { n_gaps[h] = 0; sumcols += tc[h]; if (tc[h] > maxcols) maxcols = tc[h]; }
+    const uint64_t* d_row_off = c->meta_dev.as<uint64_t>();
+    const uint64_t* d_cols = d_row_off + H;
+    CK(c, c->gap_counter.ensure(16));
+    uint64_t cap = sumcols / 256 + 4096;
+    if (c->gap_list.cap / 8 > cap) cap = c->gap_list.cap / 8;
+    uint64_t found = 0;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        CK(c, c->gap_list.ensure(cap * 8));
+        CK(c, c->gap_host.ensure(16));
+        launch_gap_events(rows_dev, d_row_off, d_cols, H, maxcols, c->gap_list.as<uint64_t>(), cap, c->gap_counter.as<unsigned long long>(), s);
+        CK(c, cudaMemcpyAsync(c->gap_host.p, c->gap_counter.p, 8, cudaMemcpyDeviceToHost, s));
+        CK(c, cudaStreamSynchronize(s));
+        found = *c->gap_host.as<uint64_t>();
+        if (found <= cap) break;
+        cap = found + found / 8;             // the exact count is known now
+    }
+    if (found == 0) return DRLZ_OK;
+    CK(c, c->gap_scratch.ensure(sort_keys_scratch_bytes(found)));
+    int bits = 33;
+    for (uint32_t hh = H - 1; hh; hh >>= 1) ++bits;
+    if (sort_keys_u64(c->gap_list.as<uint64_t>(), found, bits, c->gap_scratch.p, s) != 0) { c->err = "gap table: sort failed"; return DRLZ_E_CUDA; }
+    CK(c, c->gap_host.ensure(found * 8));
+    CK(c, cudaMemcpyAsync(c->gap_host.p, c->gap_list.p, found * 8, cudaMemcpyDeviceToHost, s));
+    CK(c, cudaStreamSynchronize(s));
+    const uint64_t* ev = c->gap_host.as<uint64_t>();
+    if (found & 1) { c->err = "gap table: odd number of run events"; return DRLZ_E_INTERNAL; }
+    for (uint64_t e = 0; e < found; e += 2) {
+        const uint64_t a = ev[e], b = ev[e + 1];
+        if ((a & 1) != 0 || (b & 1) != 1 || (a >> 33) != (b >> 33) || b < a) { c->err = "gap table: run events do not pair up"; return DRLZ_E_INTERNAL; }
+        const uint32_t h = (uint32_t)(a >> 33);
+        const uint64_t start = (a >> 1) & 0xFFFFFFFFull, end = (b >> 1) & 0xFFFFFFFFull;
+        if (*done_gaps < gaps_cap && gaps_out) { gaps_out[2 * *done_gaps] = (int64_t)start; gaps_out[2 * *done_gaps + 1] = (int64_t)(end - start + 1); }
+        else *nospace = true;
+        ++*done_gaps; ++n_gaps[h];
+    }
+    return DRLZ_OK;
+}
+
+static int parse_batch_impl(drlz_ctx* c, const uint8_t* const* rows, const uint64_t* cols, uint32_t H, int strip_gaps,
+                            uint8_t* const* gapless_out, uint64_t* m_out, int64_t* pairs_out, uint64_t pairs_cap, uint64_t* n_pairs,
+                            int64_t* gaps_out, uint64_t gaps_cap, uint64_t* n_gaps) {
     if (!c || (H && (!rows || !cols || !n_pairs))) return DRLZ_E_ARG;
     std::lock_guard<std::recursive_mutex> lk_(c->mu);
     if (!c->have_index) { c->err = "index not built"; return DRLZ_E_STATE; }
@@ -717,12 +763,19 @@ int drlz_parse_batch(drlz_ctx* c, const uint8_t* const* rows, const uint64_t* co
         for (uint32_t h = a; h < b; ++h) { goffs[gi][h - a] = bytes; bytes += ((tc[h] + 15) & ~15ull) + 16; }
         DevBuf& st = c->stage[gi & 1];
         CK(c, st.ensure(bytes + 16));
-        for (uint32_t h = a; h < b; ++h)
-            if (tc[h]) CK(c, cudaMemcpyAsync(st.as<uint8_t>() + goffs[gi][h - a], rows[h], tc[h], cudaMemcpyHostToDevice, c->copy_stream));
+        // rows that follow each other in host memory with the staging layout's own spacing (a caller that fills one
+        // pinned buffer, as the streaming CLI does) go over in one copy: thousands of small rows cost one call
+        for (uint32_t h = a; h < b;) {
+            uint32_t e = h + 1;
+            while (e < b && rows[e] == rows[h] + (goffs[gi][e - a] - goffs[gi][h - a])) ++e;
+            uint64_t span = goffs[gi][e - 1 - a] - goffs[gi][h - a] + tc[e - 1];
+            if (span) CK(c, cudaMemcpyAsync(st.as<uint8_t>() + goffs[gi][h - a], rows[h], span, cudaMemcpyHostToDevice, c->copy_stream));
+            h = e;
+        }
         CK(c, cudaEventRecord(c->ev_copied[gi & 1], c->copy_stream));
         return DRLZ_OK;
     };
-    uint64_t done_pairs = 0;
+    uint64_t done_pairs = 0, done_gaps = 0;
     bool nospace = false;
     if (G) { int rc = issue_copy(0); if (rc) return rc; }
     std::vector<uint64_t> gl_off;
@@ -747,11 +800,27 @@ int drlz_parse_batch(drlz_ctx* c, const uint8_t* const* rows, const uint64_t* co
                 if (gapless_out[h] && sh_m[h - a])
                     CK(c, cudaMemcpyAsync(gapless_out[h], c->gapless.as<uint8_t>() + gl_off[h - a], sh_m[h - a], cudaMemcpyDeviceToHost, c->stream));
         }
+        if (n_gaps) {
+            if (strip_gaps) { rc = collect_gap_runs(c, c->stage[gi & 1].as<uint8_t>(), tc.data() + a, b - a, gaps_out, gaps_cap, &done_gaps, n_gaps + a, &nospace); if (rc != DRLZ_OK) return rc; }
+            else for (uint32_t h = a; h < b; ++h) n_gaps[h] = 0;
+        }
         CK(c, cudaStreamSynchronize(c->stream));
         done_pairs += total;
     }
-    if (nospace) { c->err = "pairs_cap too small"; return DRLZ_E_NOSPACE; }
+    if (nospace) { c->err = "pairs_cap or gaps_cap too small"; return DRLZ_E_NOSPACE; }
     return DRLZ_OK;
+}
+
+int drlz_parse_batch(drlz_ctx* c, const uint8_t* const* rows, const uint64_t* cols, uint32_t H, int strip_gaps,
+                     uint8_t* const* gapless_out, uint64_t* m_out, int64_t* pairs_out, uint64_t pairs_cap, uint64_t* n_pairs) {
+    return parse_batch_impl(c, rows, cols, H, strip_gaps, gapless_out, m_out, pairs_out, pairs_cap, n_pairs, nullptr, 0, nullptr);
+}
+
+int drlz_parse_batch_gaps(drlz_ctx* c, const uint8_t* const* rows, const uint64_t* cols, uint32_t H, int strip_gaps,
+                          uint8_t* const* gapless_out, uint64_t* m_out, int64_t* pairs_out, uint64_t pairs_cap, uint64_t* n_pairs,
+                          int64_t* gaps_out, uint64_t gaps_cap, uint64_t* n_gaps) {
+    if (!n_gaps) return DRLZ_E_ARG;
+    return parse_batch_impl(c, rows, cols, H, strip_gaps, gapless_out, m_out, pairs_out, pairs_cap, n_pairs, gaps_out, gaps_cap, n_gaps);
 }
 
 int drlz_parse(drlz_ctx* c, const uint8_t* msa_row, uint64_t cols, int strip_gaps, uint8_t* gapless_out, uint64_t* m_out,
@@ -772,24 +841,30 @@ static void drlz_worker(drlz_ctx* c) {
             if (c->queue.empty()) return;
             j = c->queue.front(); c->queue.pop_front();
         }
-        int rc = drlz_parse_batch(c, j.rows, j.cols, j.H, j.strip, j.gapless, j.m_out, j.pairs, j.cap, j.n_pairs);
+        int rc = parse_batch_impl(c, j.rows, j.cols, j.H, j.strip, j.gapless, j.m_out, j.pairs, j.cap, j.n_pairs, j.gaps, j.gaps_cap, j.n_gaps);
         { std::lock_guard<std::mutex> lk(c->qmu); c->done.push_back(std::make_pair(j.ticket, rc)); }
         c->done_cv.notify_all();
     }
 }
 
-int drlz_submit(drlz_ctx* c, const uint8_t* const* rows, const uint64_t* cols, uint32_t H, int strip_gaps,
-                uint8_t* const* gapless_out, uint64_t* m_out, int64_t* pairs_out, uint64_t pairs_cap, uint64_t* n_pairs,
-                uint64_t* ticket) {
+int drlz_submit_gaps(drlz_ctx* c, const uint8_t* const* rows, const uint64_t* cols, uint32_t H, int strip_gaps,
+                     uint8_t* const* gapless_out, uint64_t* m_out, int64_t* pairs_out, uint64_t pairs_cap, uint64_t* n_pairs,
+                     int64_t* gaps_out, uint64_t gaps_cap, uint64_t* n_gaps, uint64_t* ticket) {
     if (!c || !ticket || (H && (!rows || !cols || !n_pairs))) return DRLZ_E_ARG;
     std::lock_guard<std::mutex> lk(c->qmu);
     if (!c->worker_started) { c->worker = std::thread(drlz_worker, c); c->worker_started = true; }
-    drlz_ctx::Job j{c->next_ticket++, rows, cols, H, strip_gaps, gapless_out, m_out, pairs_out, pairs_cap, n_pairs};
+    drlz_ctx::Job j{c->next_ticket++, rows, cols, H, strip_gaps, gapless_out, m_out, pairs_out, pairs_cap, n_pairs, gaps_out, gaps_cap, n_gaps};
     *ticket = j.ticket;
     c->outstanding.push_back(j.ticket);
     c->queue.push_back(j);
     c->qcv.notify_one();
     return DRLZ_OK;
+}
+
+int drlz_submit(drlz_ctx* c, const uint8_t* const* rows, const uint64_t* cols, uint32_t H, int strip_gaps,
+                uint8_t* const* gapless_out, uint64_t* m_out, int64_t* pairs_out, uint64_t pairs_cap, uint64_t* n_pairs,
+                uint64_t* ticket) {
+    return drlz_submit_gaps(c, rows, cols, H, strip_gaps, gapless_out, m_out, pairs_out, pairs_cap, n_pairs, nullptr, 0, nullptr, ticket);
 }
 
 int drlz_wait(drlz_ctx* c, uint64_t ticket) {

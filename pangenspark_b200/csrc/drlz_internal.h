@@ -49,6 +49,13 @@ struct PackJob {
 // ev (nullable): 3 events: [0],[1] before the kernel, [2] after it
 void launch_pack(const PackJob& job, cudaStream_t s, cudaEvent_t* ev);
 
+// gap runs of the rows of a group as unsorted events (see k_gap_events); *counter = events found (may exceed cap)
+void launch_gap_events(const uint8_t* rows, const uint64_t* row_off, const uint64_t* cols, uint32_t H, uint64_t maxcols,
+                       uint64_t* list, uint64_t cap, unsigned long long* counter, cudaStream_t s);
+// sorts n 64-bit keys in place over bits [0, end_bit) (hand-written LSD radix sort of sa_build.cu); scratch from the caller
+size_t sort_keys_scratch_bytes(uint64_t n);
+int sort_keys_u64(uint64_t* keys, uint64_t n, int end_bit, void* scratch, cudaStream_t s);
+
 // presence[8]: bit b of the 256-bit set = byte value b occurs in bytes[0, n) (bytes 16-byte aligned)
 void launch_byte_presence(const uint8_t* bytes, uint64_t n, uint32_t* presence, cudaStream_t s);
 

@@ -438,6 +438,47 @@ void launch_pack(const PackJob& job, cudaStream_t s, cudaEvent_t* ev) {
     if (ev) cudaEventRecord(ev[2], s);
 }
 
+// ---- gap-position side table (the consumer ScoreMatrix.scala:89-127 recomputes it from the rows) ----
+// Every maximal run of '-' in a row gives two events, (column of its first byte, 0) and (column of its last byte, 1),
+// appended to one list as keys  row << 33 | column << 1 | kind ; the caller sorts the list, after which every row's
+// events alternate start, end, start, end ... in column order.  An optional pass over the rows (they are read once
+// more; the product's hot path does not pay for it).
+__global__ void __launch_bounds__(256) k_gap_events(const uint8_t* __restrict__ rows, const uint64_t* __restrict__ row_off,
+                                                    const uint64_t* __restrict__ cols, uint64_t* __restrict__ list, uint64_t cap,
+                                                    unsigned long long* __restrict__ counter) {
+    const uint32_t h = blockIdx.y;
+    const uint64_t nc = cols[h];
+    const uint8_t* __restrict__ rowp = rows + row_off[h];
+    for (uint64_t o = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 16; o < nc; o += (uint64_t)gridDim.x * blockDim.x * 16) {
+        const uint4 q = load16(rowp + o);
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+        const uint32_t nvalid = nc - o >= 16 ? 16u : (uint32_t)(nc - o);
+        uint32_t mask = 0;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) if ((uint32_t)j < nvalid && ((w[j >> 2] >> (8 * (j & 3))) & 255u) == (uint32_t)'-') mask |= 1u << j;
+        if (!mask) continue;
+        const uint32_t prev = (mask & 1u) && o > 0 && rowp[o - 1] == '-';
+        const uint32_t next = (mask >> 15) && o + 16 < nc && rowp[o + 16] == '-';
+        uint32_t starts = mask & ~((mask << 1) | prev), ends = mask & ~((mask >> 1) | (next << 15));
+        const uint32_t cnt = (uint32_t)(__popc(starts) + __popc(ends));
+        if (!cnt) continue;
+        unsigned long long at = atomicAdd(counter, (unsigned long long)cnt);
+        const uint64_t hi = (uint64_t)h << 33;
+        while (starts) { const uint32_t b = (uint32_t)__ffs(starts) - 1; starts &= starts - 1; if (at < cap) list[at] = hi | ((o + b) << 1); ++at; }
+        while (ends) { const uint32_t b = (uint32_t)__ffs(ends) - 1; ends &= ends - 1; if (at < cap) list[at] = hi | ((o + b) << 1) | 1u; ++at; }
+    }
+}
+
+void launch_gap_events(const uint8_t* rows, const uint64_t* row_off, const uint64_t* cols, uint32_t H, uint64_t maxcols,
+                       uint64_t* list, uint64_t cap, unsigned long long* counter, cudaStream_t s) {
+    cudaMemsetAsync(counter, 0, 8, s);
+    if (H == 0 || maxcols == 0) return;
+    uint64_t want = (maxcols / 16 + 255) / 256;
+    dim3 grid((unsigned)(want < 592 ? (want ? want : 1) : 592), H);
+    g_launches += 1;
+    k_gap_events<<<grid, 256, 0, s>>>(rows, row_off, cols, list, cap, counter);
+}
+
 // ---- alphabet of the reference: which of the 256 byte values occur (drlz_build_index) --------------------------------
 // One bit per byte value, 8 words.  A thread looks at 16 bytes per step; a bit that is already set in the CTA's
 // shared copy costs a shared-memory read, so after the first few hundred bytes the kernel is a plain HBM read.

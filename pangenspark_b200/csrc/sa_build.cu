@@ -171,6 +171,27 @@ done:
     return rc;
 }
 
+// ---- plain key sort for other parts of the library (the gap-run events of pack.cu) ------------------------------------
+// scratch layout: keys_b[n] | vals_a[n] | vals_b[n] | hist | scan_tmp
+size_t sort_keys_scratch_bytes(uint64_t n) {
+    uint64_t hist_n = sort_hist_elems(n);
+    return (size_t)(n * 8 + n * 4 * 2 + hist_n * 4 + 64 + (scan_tmp_elems(hist_n) + 8) * 4 + 256);
+}
+int sort_keys_u64(uint64_t* keys, uint64_t n, int end_bit, void* scratch, cudaStream_t s) {
+    if (n <= 1) return 0;
+    uint64_t hist_n = sort_hist_elems(n);
+    uint8_t* p = (uint8_t*)scratch;
+    uint64_t* keys_b = (uint64_t*)p; p += n * 8;
+    uint32_t* vals_a = (uint32_t*)p; p += n * 4;
+    uint32_t* vals_b = (uint32_t*)p; p += n * 4;
+    uint32_t* hist = (uint32_t*)p; p += hist_n * 4 + 64;
+    uint32_t* tmp = (uint32_t*)p;
+    uint64_t* ka = keys; uint64_t* kb = keys_b;
+    int passes = radix_sort_pairs<uint64_t>(&ka, &kb, &vals_a, &vals_b, n, 0, end_bit, hist, tmp, s);
+    if (passes & 1) cudaMemcpyAsync(keys, ka, n * 8, cudaMemcpyDeviceToDevice, s);       // result sits in the scratch half
+    return (int)cudaGetLastError();
+}
+
 // ---- k-mer jump table ---------------------------------------------------------------------------
 __global__ void k_tab_fill(uint32_t* tab, uint64_t cnt, uint32_t v) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;

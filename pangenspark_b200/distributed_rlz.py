@@ -94,6 +94,9 @@ def main(argv, parser=None, rank: int | None = None, world: int | None = None, b
     os.makedirs(gapless_dir, exist_ok=True)
     ref = read_reference(localref)
     files = list_inputs(data_glob)
+    if not files:
+        print("no input matches %s (Path does not exist)" % data_glob, file=sys.stderr)      # Spark throws here
+        return 1
     mine = shard(files, rank, world)
     ctx = None
     if parser is None:
@@ -141,11 +144,37 @@ def merge_outputs(out_dir: str, gapless_dir: str, names):
         os.replace(lz + ".tmp", lz)
     if fa:
         parts = sorted(p for p in os.listdir(gapless_dir) if p.startswith("part-"))
-        with open(fa + ".tmp", "wb") as out:
+        at = 0
+        with open(fa + ".tmp", "wb") as out, open(fa + ".offsets", "w") as omap:
             for p in parts:
                 with open(os.path.join(gapless_dir, p), "rb") as f:
-                    out.write(f.read())
+                    rec = f.read()
+                out.write(rec)
+                name = rec[1:rec.index(b"\n")].decode()
+                hl = len(name) + 2
+                omap.write("%s\t%d\t%d\t%d\n" % (name, at, at + hl, max(0, len(rec) - hl - 1)))
+                at += len(rec)
         os.replace(fa + ".tmp", fa)
+
+
+def read_offsets(path: str):
+    """<chrNN.fa>.offsets: name, offset of '>', offset of the first base, number of bases -- one
+    line per haplotype in file order."""
+    out = []
+    with open(path) as f:
+        for ln in f:
+            name, a, b, c = ln.rstrip("\n").split("\t")
+            out.append((name, int(a), int(b), int(c)))
+    return out
+
+
+def rebase_pairs(pairs: np.ndarray, first_base_of_reference: int) -> np.ndarray:
+    """Phrase positions are coordinates of the reference sequence; CHIC indexes the merged multi-FASTA, whose first
+    record is the reference (README.md:90).  A match (pos, len) becomes (first_base_of_reference + pos, len); literals
+    (len == 0, pos = byte value) are left alone."""
+    p = np.array(pairs, dtype=np.int64).reshape(-1, 2).copy()
+    p[p[:, 1] > 0, 0] += first_base_of_reference
+    return p
 
 
 if __name__ == "__main__":

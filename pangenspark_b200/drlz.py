@@ -23,6 +23,7 @@ SYMBOLS = [
     "drlz_host_free", "drlz_build_index", "drlz_index_get", "drlz_index_info", "drlz_index_timings",
     "drlz_index_reserve", "drlz_index_buffers", "drlz_index_commit", "drlz_parse", "drlz_parse_batch",
     "drlz_parse_batch_device", "drlz_parse_timings", "drlz_matching_stats", "drlz_copy_to_host", "drlz_submit", "drlz_wait",
+    "drlz_parse_batch_gaps", "drlz_submit_gaps",
 ]
 
 
@@ -74,6 +75,10 @@ def load_library() -> C.CDLL:
         L.drlz_copy_to_host.argtypes = [vp, vp, vp, u64]; L.drlz_copy_to_host.restype = i32
         L.drlz_submit.argtypes = [vp, vp, vp, C.c_uint32, i32, vp, vp, vp, u64, vp, vp]; L.drlz_submit.restype = i32
         L.drlz_wait.argtypes = [vp, u64]; L.drlz_wait.restype = i32
+        L.drlz_parse_batch_gaps.argtypes = [vp, vp, vp, C.c_uint32, i32, vp, vp, vp, u64, vp, vp, u64, vp]
+        L.drlz_parse_batch_gaps.restype = i32
+        L.drlz_submit_gaps.argtypes = [vp, vp, vp, C.c_uint32, i32, vp, vp, vp, u64, vp, vp, u64, vp, vp]
+        L.drlz_submit_gaps.restype = i32
         L.drlz_matching_stats.argtypes = [vp, vp, u64, vp, vp]; L.drlz_matching_stats.restype = i32
         _LIB = L
     return _LIB
@@ -217,6 +222,38 @@ class Drlz:
         if gl is not None:
             gl = [g[: int(m[h])] for h, g in enumerate(gl)]
         return res, m, gl
+
+    def parse_batch_gaps(self, rows, strip_gaps: bool = True, gaps_cap: int | None = None):
+        """parse_batch plus the gap-position side table: returns (pairs list, m[H], list of [runs,2] int64 arrays
+        (first column, length) of every run of '-' per row)."""
+        rows = [_u8(r) for r in rows]
+        H = len(rows)
+        ptrs = (C.c_void_p * max(1, H))(*[r.ctypes.data if r.size else None for r in rows])
+        cols = np.array([r.size for r in rows], dtype=np.uint64)
+        m = np.zeros(max(1, H), dtype=np.uint64)
+        npairs = np.zeros(max(1, H), dtype=np.uint64)
+        ngaps = np.zeros(max(1, H), dtype=np.uint64)
+        cap = max(1024, int(cols.sum()) // 64 + 64 * H)
+        gcap = gaps_cap if gaps_cap is not None else max(1024, int(cols.sum()) // 256 + 64 * H)
+        while True:
+            buf = np.empty(2 * cap, dtype=np.int64)
+            gbuf = np.empty(2 * max(1, gcap), dtype=np.int64)
+            rc = self._lib.drlz_parse_batch_gaps(self._h, ptrs, cols.ctypes.data_as(C.c_void_p), H, int(strip_gaps), None,
+                                                 m.ctypes.data_as(C.c_void_p), buf.ctypes.data_as(C.c_void_p), cap,
+                                                 npairs.ctypes.data_as(C.c_void_p), gbuf.ctypes.data_as(C.c_void_p), gcap,
+                                                 ngaps.ctypes.data_as(C.c_void_p))
+            if rc == -4:
+                cap = max(cap, int(npairs[:H].sum()) + 16)
+                gcap = max(gcap, int(ngaps[:H].sum()) + 16)
+                continue
+            self._ck(rc)
+            break
+        res, gaps, o, go = [], [], 0, 0
+        for h in range(H):
+            c, g = int(npairs[h]), int(ngaps[h])
+            res.append(buf[2 * o: 2 * (o + c)].reshape(-1, 2)); o += c
+            gaps.append(gbuf[2 * go: 2 * (go + g)].reshape(-1, 2)); go += g
+        return res, m[:H].astype(np.int64), gaps
 
     def submit(self, rows, pairs_cap: int, strip_gaps: bool = True):
         """Async form: returns a handle; call .wait() for (pairs list, m).  Buffers are kept alive by the handle."""
