@@ -204,7 +204,7 @@ class Job:
         self.ctx = D.Drlz(self.local)
         self.stream = torch.cuda.Stream()
         self.ctx.set_stream(self.stream.cuda_stream)
-        for key in ("kmer", "chunk", "group_bytes"):
+        for key in ("kmer", "chunk", "group_bytes", "pack_variant", "occ_pack", "tickets", "prefetch"):
             v = os.environ.get("DRLZ_" + key.upper())
             if v:
                 self.ctx.set_option(key, int(v))

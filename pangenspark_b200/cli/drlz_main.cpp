@@ -21,8 +21,8 @@
 //     GPU        drlz_submit: one batch per slot, FIFO worker inside the library, >= 2 in flight     |  concurrently,
 //     I/O pool   pwrite()s <name>.lz and the gapless FASTA part files from the pinned result buffers |  DRLZ_SLOTS deep
 // Environment: DRLZ_DEVICE (default 0), DRLZ_GPUS (default 1; batches go to whichever device has a free slot, each
-// device builds its own index), DRLZ_BATCH_BYTES (default 512 MiB of MSA bytes per batch), DRLZ_SLOTS (default 3),
-// DRLZ_IO_THREADS (default 8 per device, at most the CPUs available), DRLZ_GAPLESS=0 (skip the FASTA part files),
+// device builds its own index), DRLZ_BATCH_BYTES (default 128 MiB of MSA bytes per batch), DRLZ_SLOTS (default 4),
+// DRLZ_IO_THREADS (default: the CPUs available, at most 32), DRLZ_GAPLESS=0 (skip the FASTA part files),
 // DRLZ_MERGED_LZ / DRLZ_MERGED_FA (also write the merged chrNN.lz / chrNN.fa that index_chr.sh:16,20 builds with
 // getmerge; with DRLZ_MERGED_FA also <that>.offsets, the coordinate map CHIC needs: SURVEY 8(f) rank 3),
 // DRLZ_GAPTABLE=1 (<outDir>/<basename>.gaps: int64 LE (column, length) of every run of '-'),
@@ -227,11 +227,12 @@ struct Slot {
     bool failed = false;
 };
 
+// grow-only pinned buffer of `want` elements of `elem` bytes (phrase and gap records are 16 bytes: two int64)
 template <typename T>
-static bool ensure_pinned(T*& p, size_t& cap, size_t want) {
+static bool ensure_pinned(T*& p, size_t& cap, size_t want, size_t elem = sizeof(T)) {
     if (want <= cap) return true;
     if (p) drlz_host_free(p);
-    p = (T*)drlz_host_alloc(want * sizeof(T));
+    p = (T*)drlz_host_alloc(want * elem);
     cap = p ? want : 0;
     return p != nullptr;
 }
@@ -254,12 +255,12 @@ int main(int argc, char** argv) {
     auto env_u64 = [](const char* k, uint64_t dflt) { const char* v = getenv(k); return v && *v ? strtoull(v, nullptr, 10) : dflt; };
     const int dev0 = (int)env_u64("DRLZ_DEVICE", 0);
     int ngpu = (int)env_u64("DRLZ_GPUS", 1); if (ngpu < 1) ngpu = 1;
-    const uint64_t batch_bytes = env_u64("DRLZ_BATCH_BYTES", 512ull << 20);
-    int nslots = (int)env_u64("DRLZ_SLOTS", 3); if (nslots < 2) nslots = 2;
+    const uint64_t batch_bytes = env_u64("DRLZ_BATCH_BYTES", 128ull << 20);
+    int nslots = (int)env_u64("DRLZ_SLOTS", 4); if (nslots < 2) nslots = 2;
     const bool want_gapless = env_u64("DRLZ_GAPLESS", 1) != 0;
     const bool want_gaptable = env_u64("DRLZ_GAPTABLE", 0) != 0;
     unsigned hw = std::thread::hardware_concurrency(); if (!hw) hw = 8;
-    int io_threads = (int)env_u64("DRLZ_IO_THREADS", std::min<uint64_t>(hw, 8ull * ngpu)); if (io_threads < 1) io_threads = 1;
+    int io_threads = (int)env_u64("DRLZ_IO_THREADS", std::min<uint64_t>(hw, 32)); if (io_threads < 1) io_threads = 1;
 
     // staging directories of the hdfs:// mode, removed on every way out
     std::string stage_root;
@@ -332,21 +333,48 @@ int main(int argc, char** argv) {
         if (jobs[i].gz) jobs[i].size = gzip_isize(jobs[i].path);       // inflated size (the slot layout needs it)
     }
     mkdirs(local_out); if (want_gapless) mkdirs(local_gap);
+    // batches: consecutive files of the sorted list, at most batch_bytes each (a bigger row is a batch of its own);
+    // whichever device has a free slot takes the next one
+    std::vector<std::pair<size_t, size_t>> batches;
+    uint64_t slot_bytes = 0, slot_rows = 0;
+    for (size_t i = 0; i < jobs.size();) {
+        size_t e = i; uint64_t acc = 0, padded = 0;
+        while (e < jobs.size() && (e == i || acc + jobs[e].size <= batch_bytes)) { acc += jobs[e].size; padded += ((jobs[e].size + 15) & ~15ull) + 16; ++e; }
+        batches.push_back({i, e});
+        slot_bytes = std::max<uint64_t>(slot_bytes, padded + 16);
+        slot_rows = std::max<uint64_t>(slot_rows, e - i);
+        i = e;
+    }
+    if ((int)(batches.size() / ngpu) + 1 < nslots) nslots = std::max<int>(2, (int)(batches.size() / ngpu) + 1);
 
     printf("Create suffix\n");
     const auto t_index = Clock::now();
     std::vector<drlz_ctx*> ctxs(ngpu, nullptr);
+    std::vector<std::vector<Slot>> all_slots(ngpu);
     std::atomic<int> failed{0};
     {
         std::vector<std::thread> th;
         for (int g = 0; g < ngpu; ++g) th.emplace_back([&, g] {
             if (drlz_create(&ctxs[g], dev0 + g) != DRLZ_OK) { fprintf(stderr, "drlz: no CUDA device %d (there is no CPU fallback)\n", dev0 + g); failed = 1; return; }
+            // the pinned slot buffers are allocated while the index is being built (pinning gigabytes takes as long)
+            std::thread alloc([&, g] {
+                std::vector<Slot> slots(nslots);
+                for (auto& sl : slots)
+                    if (!ensure_pinned(sl.in, sl.in_cap, slot_bytes) || (want_gapless && !ensure_pinned(sl.gl, sl.gl_cap, slot_bytes)) ||
+                        !ensure_pinned(sl.pairs, sl.pairs_cap, slot_bytes / 64 + 1024 * slot_rows, 16) ||
+                        (want_gaptable && !ensure_pinned(sl.gaps, sl.gaps_cap, slot_bytes / 64 + 1024 * slot_rows, 16))) {
+                        fprintf(stderr, "drlz: cannot allocate pinned host memory (%llu bytes per slot)\n", (unsigned long long)slot_bytes); failed = 1; break;
+                    }
+                all_slots[g].swap(slots);
+            });
             int rc = drlz_build_index(ctxs[g], ref.data(), ref.size());
             if (rc != DRLZ_OK) { fprintf(stderr, "drlz: index build failed on device %d: %s\n", dev0 + g, drlz_last_error(ctxs[g])); failed = 1; }
+            alloc.join();
         });
         for (auto& t : th) t.join();
     }
-    if (failed) { for (auto c : ctxs) drlz_destroy(c); return 1; }
+    auto free_slots_all = [&] { for (auto& v : all_slots) for (auto& sl : v) { drlz_host_free(sl.in); drlz_host_free(sl.gl); drlz_host_free(sl.pairs); drlz_host_free(sl.gaps); } };
+    if (failed) { free_slots_all(); for (auto c : ctxs) if (c) drlz_destroy(c); return 1; }
     const double index_s = secs_since(t_index);
     double idx_ms[5] = {0, 0, 0, 0, 0};
     {
@@ -374,7 +402,7 @@ int main(int argc, char** argv) {
         const size_t kRange = 32u << 20;                    // bytes per read / write task
         auto device_pipeline = [&](int g) {
             drlz_ctx* c = ctxs[g];
-            std::vector<Slot> slots(nslots);
+            std::vector<Slot>& slots = all_slots[g];
             std::deque<Slot*> free_slots, in_gpu;
             std::mutex smu; std::condition_variable scv;
             for (auto& s : slots) free_slots.push_back(&s);
@@ -396,7 +424,7 @@ int main(int argc, char** argv) {
                     if (rc == DRLZ_E_NOSPACE) {               // more phrases than the slot's record buffer holds: grow and redo
                         uint64_t need = 16;
                         for (size_t h = 0; h < H; ++h) need += s->np[h];
-                        if (!ensure_pinned(s->pairs, s->pairs_cap, need + need / 8)) rc = DRLZ_E_NOMEM;
+                        if (!ensure_pinned(s->pairs, s->pairs_cap, need + need / 8, 16)) rc = DRLZ_E_NOMEM;
                         else rc = drlz_parse_batch(c, s->rows.data(), s->cols.data(), (uint32_t)H, 1, want_gapless ? s->gptr.data() : nullptr,
                                                    s->m.data(), s->pairs, s->pairs_cap, s->np.data());
                     }
@@ -483,9 +511,9 @@ int main(int argc, char** argv) {
                 s->jobs.clear(); s->failed = false;
                 {
                     std::lock_guard<std::mutex> lk(job_mu);
-                    uint64_t acc = 0;
-                    while (next_job < jobs.size() && (s->jobs.empty() || acc + jobs[next_job].size <= batch_bytes)) {
-                        acc += jobs[next_job].size; s->jobs.push_back(jobs[next_job++]);
+                    if (next_job < batches.size()) {
+                        for (size_t j = batches[next_job].first; j < batches[next_job].second; ++j) s->jobs.push_back(jobs[j]);
+                        ++next_job;
                     }
                 }
                 if (s->jobs.empty()) { std::lock_guard<std::mutex> lk(smu); free_slots.push_back(s); break; }
@@ -497,8 +525,8 @@ int main(int argc, char** argv) {
                 uint64_t total = 0;
                 for (size_t h = 0; h < H; ++h) { s->off[h] = total; total += ((s->jobs[h].size + 15) & ~15ull) + 16; }
                 if (!ensure_pinned(s->in, s->in_cap, total + 16) || (want_gapless && !ensure_pinned(s->gl, s->gl_cap, total + 16)) ||
-                    !ensure_pinned(s->pairs, s->pairs_cap, total / 64 + 1024 * H) ||
-                    (want_gaptable && !ensure_pinned(s->gaps, s->gaps_cap, total / 64 + 1024 * H))) {
+                    !ensure_pinned(s->pairs, s->pairs_cap, total / 64 + 1024 * H, 16) ||
+                    (want_gaptable && !ensure_pinned(s->gaps, s->gaps_cap, total / 64 + 1024 * H, 16))) {
                     fprintf(stderr, "drlz: cannot allocate pinned host memory for a batch of %llu bytes\n", (unsigned long long)total); failed = 1; break;
                 }
                 const auto tr = Clock::now();
@@ -586,13 +614,13 @@ int main(int argc, char** argv) {
             { std::lock_guard<std::mutex> lk(smu); feeder_done = true; }
             scv.notify_all();
             collector.join();
-            for (auto& s : slots) { drlz_host_free(s.in); drlz_host_free(s.gl); drlz_host_free(s.pairs); drlz_host_free(s.gaps); }
         };
         std::vector<std::thread> th;
         for (int g = 0; g < ngpu; ++g) th.emplace_back(device_pipeline, g);
         for (auto& t : th) t.join();
     }
     const double encode_s = secs_since(t_encode);
+    free_slots_all();
     for (auto c : ctxs) drlz_destroy(c);
     if (failed) return 1;
     if (want_gapless) write_file_atomic(local_gap + "/_SUCCESS", "", 0);

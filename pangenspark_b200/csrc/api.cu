@@ -55,7 +55,7 @@ struct drlz_ctx {
     cudaEvent_t ev_stage[12] = {};
     std::string err;
     // options
-    uint64_t x_zeroed = 0; bool keep_x = false; int opt_postzero = 1; int opt_blind_rounds = 2; int opt_occ_pack = 8; uint32_t opt_prefetch = 1200; int opt_k = 0; uint32_t opt_chunk = 8192; uint32_t opt_min_cap = 64; uint32_t opt_foreign_cap = 1u << 20; uint64_t opt_group_bytes = 256ull << 20; int opt_lcp = 0;
+    uint64_t x_zeroed = 0; bool keep_x = false; int opt_postzero = 1; int opt_blind_rounds = 2; int opt_pack_variant = 2; uint32_t opt_prefetch3 = 2; int opt_occ_pack = 8; uint32_t opt_prefetch = 1200; int opt_k = 0; uint32_t opt_chunk = 8192; uint32_t opt_min_cap = 64; uint32_t opt_foreign_cap = 1u << 20; uint64_t opt_group_bytes = 256ull << 20; int opt_lcp = 0;
     // index
     bool have_index = false; uint64_t n = 0; int k = 0; int sa_rounds = 0;
     DevBuf blob, sa, isa, lcp;             // blob = [k-mer table | packed text] (one L2 access-policy window)
@@ -214,6 +214,8 @@ int drlz_set_option(drlz_ctx* c, const char* key, int64_t v) {
     else if (!strcmp(key, "tickets")) c->opt_tickets = v != 0;
     else if (!strcmp(key, "predict")) c->opt_predict = v != 0;
     else if (!strcmp(key, "occ_pack")) c->opt_occ_pack = (int)v;
+    else if (!strcmp(key, "prefetch3")) { if (v < 0 || v > 64) return DRLZ_E_ARG; c->opt_prefetch3 = (uint32_t)v; }
+    else if (!strcmp(key, "pack_variant")) { if (v < 0 || v > 2) return DRLZ_E_ARG; c->opt_pack_variant = (int)v; }
     else if (!strcmp(key, "blind_rounds")) c->opt_blind_rounds = (int)v;
     else if (!strcmp(key, "postzero")) c->opt_postzero = v != 0;
     else if (!strcmp(key, "prefetch")) { if (v < 0 || v > (1 << 20)) return DRLZ_E_ARG; c->opt_prefetch = (uint32_t)v; }
@@ -340,7 +342,14 @@ static int run_device_group(drlz_ctx* c, const uint8_t* rows_dev, const uint64_t
         job.rows = rows_dev; job.row_off = d_row_off; job.cols = d_cols; job.H = H; job.tiles_per_row = T; job.strip = strip;
         job.desc_cnt = c->desc_cnt.as<uint64_t>(); job.desc_exc = c->desc_exc.as<uint64_t>();
         job.tile_counter = c->tile_counter.as<uint32_t>(); job.X = c->X.as<uint64_t>(); job.xoff = d_xoff;
-        job.occ = c->opt_occ_pack; job.prefetch = c->opt_prefetch; job.use_tickets = c->opt_tickets;
+        job.occ = c->opt_occ_pack; job.prefetch = c->opt_pack_variant == 2 ? c->opt_prefetch3 : c->opt_prefetch; job.use_tickets = c->opt_tickets; job.variant = c->opt_pack_variant;
+        job.uniform_cols = 0; job.uniform_stride = 0; job.uniform_off0 = 0;
+        if (H > 0 && cols[0] > 0) {           // an MSA: rows of one length at a constant spacing (the usual case)
+            bool uni = true;
+            const uint64_t st = H > 1 ? row_off[1] - row_off[0] : 0;
+            for (uint32_t h = 0; h < H && uni; ++h) uni = cols[h] == cols[0] && row_off[h] == row_off[0] + (uint64_t)h * st;
+            if (uni) { job.uniform_cols = (uint32_t)cols[0]; job.uniform_stride = st; job.uniform_off0 = row_off[0]; }
+        }
         job.m_out = c->mdev.as<uint64_t>(); job.exc_cnt = c->exccnt.as<uint64_t>();
         job.exc_pos = c->excpos.as<uint32_t>(); job.exc_byte = c->excbyte.as<uint8_t>(); job.exc_stride = exc_stride;
         job.flags = c->flags.as<uint32_t>();
@@ -538,7 +547,7 @@ int drlz_build_index(drlz_ctx* c, const uint8_t* ref, uint64_t n) {
         job.rows = c->stage[0].as<uint8_t>(); job.row_off = dm; job.cols = dm + 1; job.H = 1; job.tiles_per_row = T; job.strip = 0;
         job.desc_cnt = c->desc_cnt.as<uint64_t>(); job.desc_exc = c->desc_exc.as<uint64_t>();
         job.tile_counter = c->tile_counter.as<uint32_t>(); job.X = c->d_text; job.xoff = dm + 2;
-        job.occ = c->opt_occ_pack; job.prefetch = 0; job.use_tickets = 1;
+        job.occ = c->opt_occ_pack; job.prefetch = 0; job.use_tickets = 1; job.variant = c->opt_pack_variant; job.uniform_cols = 0; job.uniform_stride = 0; job.uniform_off0 = 0;
         job.m_out = c->mdev.as<uint64_t>(); job.exc_cnt = c->exccnt.as<uint64_t>();
         job.exc_pos = c->excpos.as<uint32_t>(); job.exc_byte = c->excbyte.as<uint8_t>(); job.exc_stride = 64;
         job.flags = c->flags.as<uint32_t>(); job.gapless = nullptr; job.gapless_off = dm + 3;

@@ -26,6 +26,9 @@ struct PackJob {
     int occ;                      // min CTAs per SM the kernel is compiled for (6 or 8)
     uint32_t prefetch;            // L2 prefetch distance in tiles (0 = off): CTA i prefetches the bytes of tile i + prefetch
     int use_tickets;              // 1: tile ids from the atomic counter; 0: from blockIdx (dispatch order), guarded by a timeout
+    int variant;                  // 0: k_pack (round 1), 1: k_pack2 (lean plain-warp path; exception counts by atomics), 2: k_pack3 (a CTA streams 8 tiles)
+    uint32_t uniform_cols;        // != 0: every row has this many columns and row h starts at rows + uniform_off0 + h * uniform_stride (no per-row loads)
+    uint64_t uniform_stride, uniform_off0;
     uint64_t* X;                  // packed output, zero-filled by the caller
     const uint64_t* xoff;         // [H] word offset of haplotype h inside X (device)
     uint64_t* m_out;              // [H] gapless lengths (device)

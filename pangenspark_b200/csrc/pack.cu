@@ -308,6 +308,509 @@ __global__ void __launch_bounds__(kPackThreads, MINB) k_pack(PackJob job, uint32
     pack_tile(job, s_ticket[1], s_ticket[2], sbits, sm, s_bcast, s_wlast);
 }
 
+// =====================================================================================================================
+// k_pack2 -- the same pass with the common case written for the instruction issue slots it costs.
+//
+// ncu on k_pack (profiles/README.md, round 1): 8.1 thread-instructions per input byte, ALU pipe 2/3 busy, 344 bytes of
+// spills at 32 registers -- the general classification (gaps, foreign bytes, ragged tile ends) sat inline four times in
+// every thread's path.  Here a warp whose 2 KB are plain A/C/G/T -- 97 % of the warps at BASELINE's indel rates -- runs
+// straight-line code: four 128-bit loads, 7 operations per 4 bytes for the exact ACGT test and the codes, one vote, its
+// words shifted onto the output grid with four funnel shifts and stored; no per-lane counts, no scan.  Everything else
+// (a gap or foreign byte anywhere in the warp's 2 KB, the last tile of a row) lives in two __noinline__ functions that
+// re-read the thread's 64 bytes (L1 hits) and keep their registers to themselves.  32-bit positions throughout (rows
+// are shorter than 2^32 - 1024).  The exception count of a row is a plain atomic sum (only tiles that hold a foreign byte
+// look back over the exception descriptors, and a tile without one copies a finished predecessor's prefix when it is
+// there): the last tile of a row no longer walks the whole descriptor row at the tail of the kernel.
+// =====================================================================================================================
+
+// per-lane result of the general classification, kept between the two slow-path calls
+struct SlowLane { uint32_t cnt, exc; };
+
+// 16 bytes of plain bases: codes left aligned in 32 bits.  5 ALU-pipe + 2 FMA-pipe operations per 4 bytes:
+//   t    = bits 2:1 == 10 ('T' among the valid bytes), E = the byte a valid input must equal once its bits 2:1 are
+//          masked away (0x41 for A, C, G; 0x50 for T), acc collects w ^ E unmasked -- the mask 0xF9 is applied once, to
+//          the OR over all 16 words of the thread;
+//   code = [bit 2, bit 1 ^ bit 2] = the low two bits of (w >> 1) ^ (w >> 2) for every byte whose bit 3 is clear, which
+//          holds for A, C, G and T (a byte that fails the test never reaches the output through this path).
+__device__ __forceinline__ uint32_t code_word(uint32_t w, uint32_t& acc) {
+    const uint32_t s1 = w >> 1, s2 = w >> 2;
+    const uint32_t t = s2 & ~s1 & 0x01010101u;
+    acc |= w ^ (t * 15u + 0x41414141u);
+    return ((s1 ^ s2) & 0x03030303u) * 0x40100401u;
+}
+__device__ __forceinline__ uint32_t fast16(const uint4 v, uint32_t& acc) {
+    const uint32_t p0 = code_word(v.x, acc), p1 = code_word(v.y, acc), p2 = code_word(v.z, acc), p3 = code_word(v.w, acc);
+    return top_bytes(p0, p1, p2, p3);
+}
+
+// the thread's 64 bytes again, bounds-checked (bytes at and past `cols` read as zero and do not count)
+__device__ __forceinline__ void load64_checked(const uint8_t* rowp, uint32_t off, uint32_t cols, uint4 (&v)[4], int (&nvalid)[4]) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const uint32_t o = off + 16u * q;
+        v[q] = make_uint4(0, 0, 0, 0);
+        nvalid[q] = 0;
+        if (o < cols) { v[q] = load16(rowp + o); nvalid[q] = cols - o >= 16u ? 16 : (int)(cols - o); }
+    }
+}
+
+// slow path, part 1: kept bases and exceptions of this lane (general classification)
+__device__ __noinline__ SlowLane pack2_slow_count(const uint8_t* rowp, uint32_t off, uint32_t cols, int strip) {
+    uint4 v[4]; int nv[4];
+    load64_checked(rowp, off, cols, v, nv);
+    SlowLane r; r.cnt = 0; r.exc = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        if (!nv[q]) continue;
+        const Seg16 sg = classify16(v[q], nv[q], strip);
+        r.cnt += sg.cnt; r.exc += sg.exc;
+    }
+    return r;
+}
+
+// slow path, part 2: the warp's bases through its bit buffer into the packed output, its exceptions into the row's list.
+//   l       local offset of this lane's first kept base inside the warp
+//   ow      row position (gapless) of the warp's first kept base; Tw kept bases in the warp
+//   e       index of this lane's first exception in the row's list
+__device__ __noinline__ void pack2_slow_emit(int strip, uint64_t* X, uint32_t* ep, uint8_t* eb, uint64_t exc_stride, const uint8_t* rowp,
+                                             uint32_t off, uint32_t cols, uint32_t l, uint64_t ow, uint32_t Tw, uint64_t e, uint32_t nexc,
+                                             uint32_t* sb) {
+    const int lane = threadIdx.x & 31;
+    uint4 v[4]; int nv[4];
+    load64_checked(rowp, off, cols, v, nv);
+    for (int i = lane; i < kWarpBits; i += 32) sb[i] = 0;
+    __syncwarp();
+    uint32_t ll = l;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        if (!nv[q]) continue;
+        const Seg16 sg = classify16(v[q], nv[q], strip);
+        if (sg.cnt) {
+            const uint32_t wi = ll >> 4, sh = (ll & 15u) * 2;
+            atomicOr(&sb[wi], sg.codes >> sh);
+            if (sh && sg.cnt > 16 - (ll & 15u)) atomicOr(&sb[wi + 1], sg.codes << (32 - sh));
+            ll += sg.cnt;
+        }
+    }
+    __syncwarp();
+    if (Tw) flush_bits(sb, X, ow, Tw, lane, 32);
+    if (nexc) {                       // foreign bytes of this lane: (gapless position, byte) into the sorted list of the row
+        uint64_t p = ow + l;
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t w[4] = {v[q].x, v[q].y, v[q].z, v[q].w};
+            for (int b = 0; b < nv[q]; ++b) {
+                const uint32_t byte = (w[b >> 2] >> (8 * (b & 3))) & 255u;
+                if (strip && byte == '-') continue;
+                if (!(byte == 'A' || byte == 'C' || byte == 'G' || byte == 'T')) {
+                    if (e < exc_stride) { ep[e] = (uint32_t)p; eb[e] = (uint8_t)byte; }
+                    ++e;
+                }
+                ++p;
+            }
+        }
+    }
+}
+
+// gapless bytes (the body of the gapless FASTA record, DistributedRLZ.scala:75-80): the warp's kept bytes are staged in
+// shared memory and leave as aligned 16-byte stores (the round-1 kernel wrote them byte by byte from every lane).
+//   gb   the warp's staging buffer (2048 + 16 bytes, 16-byte aligned); n bytes staged; dst = their place in the output
+__device__ __forceinline__ void flush_bytes(const uint8_t* gb, uint8_t* dst, uint32_t n, int lane) {
+    const uint32_t head = min(n, (uint32_t)((16u - (uint32_t)((uintptr_t)dst & 15u)) & 15u));
+    if ((uint32_t)lane < head) dst[lane] = gb[lane];
+    const uint32_t nfull = (n - head) >> 4;
+    const uint32_t* gw = reinterpret_cast<const uint32_t*>(gb);
+    const uint32_t w0 = head >> 2, sel = 0x3210u + 0x1111u * (head & 3u);
+    uint4* d16 = reinterpret_cast<uint4*>(dst + head);
+    for (uint32_t c = lane; c < nfull; c += 32) {
+        const uint32_t* s = gw + w0 + 4 * c;
+        const uint32_t a0 = s[0], a1 = s[1], a2 = s[2], a3 = s[3], a4 = s[4];
+        d16[c] = make_uint4(__byte_perm(a0, a1, sel), __byte_perm(a1, a2, sel), __byte_perm(a2, a3, sel), __byte_perm(a3, a4, sel));
+    }
+    const uint32_t done = head + (nfull << 4);
+    if (done + (uint32_t)lane < n) dst[done + lane] = gb[done + lane];
+}
+__device__ __noinline__ void pack2_slow_gapless(int strip, const uint8_t* rowp, uint32_t off, uint32_t cols, uint32_t l, uint8_t* gb) {
+    uint4 v[4]; int nv[4];
+    load64_checked(rowp, off, cols, v, nv);
+    uint32_t p = l;
+    for (int q = 0; q < 4; ++q) {
+        const uint32_t w[4] = {v[q].x, v[q].y, v[q].z, v[q].w};
+        for (int b = 0; b < nv[q]; ++b) {
+            const uint32_t byte = (w[b >> 2] >> (8 * (b & 3))) & 255u;
+            if (strip && byte == '-') continue;
+            gb[p++] = (uint8_t)byte;
+        }
+    }
+}
+
+static const int kGaplessStage = 2048 + 32;       // bytes of a warp's staging buffer
+
+template <int MINB, bool GAPLESS>
+__global__ void __launch_bounds__(kPackThreads, MINB) k_pack2(PackJob job, uint32_t n_tiles) {
+    __shared__ uint32_t sbits[kPackWarps * kWarpBits];
+    __shared__ __align__(16) uint32_t s_w[kPackWarps];
+    __shared__ uint64_t s_o[2];
+    __shared__ uint64_t s_wlast[kPackWarps];
+    __shared__ uint32_t s_ticket[5];
+    extern __shared__ __align__(16) uint8_t s_gl[];          // GAPLESS: kPackWarps staging buffers
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        const uint32_t id = job.use_tickets ? atomicAdd(job.tile_counter, 1u) : blockIdx.x;
+        s_ticket[0] = id; s_ticket[1] = id % job.H; s_ticket[2] = id / job.H;
+        const uint32_t idp = id + job.prefetch;
+        s_ticket[3] = idp % job.H; s_ticket[4] = (job.prefetch && idp < n_tiles) ? idp / job.H : 0xFFFFFFFFu;
+    }
+    __syncthreads();
+    if (s_ticket[0] >= n_tiles) return;
+    if (s_ticket[4] != 0xFFFFFFFFu && tid < kPackTileBytes / 128) {
+        const uint32_t hp = s_ticket[3];
+        const uint64_t o = (uint64_t)s_ticket[4] * kPackTileBytes + (uint64_t)tid * 128;
+        if (o < job.cols[hp]) asm volatile("prefetch.global.L2 [%0];" ::"l"(job.rows + job.row_off[hp] + o));
+    }
+    const uint32_t h = s_ticket[1], t = s_ticket[2];
+    const uint32_t cols = (uint32_t)job.cols[h];
+    const uint8_t* __restrict__ rowp = job.rows + job.row_off[h];
+    const uint32_t tile_start = t * (uint32_t)kPackTileBytes;          // < 2^32: the host bounds cols by 2^32 - 1024
+    const uint32_t off = tile_start + (uint32_t)tid * 64u;
+    const bool last_tile = t + 1 == job.tiles_per_row;
+
+    // ---- load + classify: a warp of plain bases needs nothing but its codes ------------------------------------------
+    uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0, acc = 0xFFFFFFFFu;
+    if (tile_start + (uint32_t)kPackTileBytes <= cols && tile_start + (uint32_t)kPackTileBytes > tile_start) {
+        const uint4* src = reinterpret_cast<const uint4*>(rowp + off);
+        const uint4 raw0 = src[0], raw1 = src[1], raw2 = src[2], raw3 = src[3];
+        if (GAPLESS) {                 // the bytes themselves are the gapless output of a plain warp: staged right away
+            uint4* g4 = reinterpret_cast<uint4*>(s_gl + warp * kGaplessStage + lane * 64);
+            g4[0] = raw0; g4[1] = raw1; g4[2] = raw2; g4[3] = raw3;
+        }
+        acc = 0;
+        c0 = fast16(raw0, acc); c1 = fast16(raw1, acc); c2 = fast16(raw2, acc); c3 = fast16(raw3, acc);
+    }
+    const bool wclean = __all_sync(0xffffffffu, (acc & 0xF9F9F9F9u) == 0);
+    uint32_t lane_cnt = 64, lane_exc = 0, lane_lo = (uint32_t)lane * 64u, lane_elo = 0, wtot = 2048u;
+    if (!wclean) {
+        const SlowLane sl = pack2_slow_count(rowp, off, cols, job.strip);
+        lane_cnt = sl.cnt; lane_exc = sl.exc;
+        const uint32_t v = sl.cnt | (sl.exc << 16);
+        const uint32_t inc = warp_inclusive_scan<uint32_t, OpSum>(v, OpSum(), lane);
+        wtot = __shfl_sync(0xffffffffu, inc, 31);
+        lane_lo = (inc - v) & 0xFFFFu; lane_elo = (inc - v) >> 16;
+    }
+    if (lane == 0) s_w[warp] = wtot;
+    __syncthreads();
+    const uint4 wa = *reinterpret_cast<const uint4*>(&s_w[0]), wb = *reinterpret_cast<const uint4*>(&s_w[4]);
+    const uint32_t total = wa.x + wa.y + wa.z + wa.w + wb.x + wb.y + wb.z + wb.w;
+    const bool fast = total == (uint32_t)kPackTileBytes;              // every warp plain, full tile
+    uint32_t wbase = (uint32_t)warp * 2048u;
+    if (!fast) {
+        const uint32_t tw[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+        wbase = 0;
+#pragma unroll
+        for (int w = 0; w < kPackWarps; ++w) if (w < warp) wbase += tw[w];
+    }
+    const uint32_t T = total & 0xFFFFu, TE = total >> 16;
+    const uint32_t lw = wbase & 0xFFFFu, lew = wbase >> 16, Tw = wtot & 0xFFFFu;
+
+    // ---- tile offset inside the row: decoupled look-back by warp 0 ---------------------------------------------------
+    if (warp == 0) {
+        uint64_t* dcnt = job.desc_cnt + (uint64_t)h * job.tiles_per_row;
+        uint64_t* dexc = job.desc_exc + (uint64_t)h * job.tiles_per_row;
+        const uint64_t o = lookback(dcnt, t, T, job.flags);
+        uint64_t eo = 0;
+        if (TE) {
+            eo = lookback(dexc, t, TE, job.flags);
+            if (lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(&job.exc_cnt[h]), (unsigned long long)TE);
+        } else if (lane == 0) {
+            // no foreign byte here: pass a finished predecessor's prefix on if it is there, else publish "0 of mine"
+            const uint64_t pv = t ? ld_desc(&dexc[t - 1]) : kDescPrefix;
+            st_desc(&dexc[t], (pv >> 62) == 2 ? pv : kDescAgg);
+        }
+        if (lane == 0) {
+            s_o[0] = o; s_o[1] = eo;
+            if (last_tile) job.m_out[h] = o + T;
+        }
+    }
+    if (fast && lane == 31) s_wlast[warp] = ((uint64_t)c2 << 32) | c3;
+    __syncthreads();
+    if (T == 0) return;
+    const uint64_t ow = s_o[0] + lw;                                   // row position of the warp's first kept base
+
+    if (GAPLESS) {
+        uint8_t* gb = s_gl + warp * kGaplessStage;
+        if (!wclean && lane_cnt) pack2_slow_gapless(job.strip, rowp, off, cols, lane_lo, gb);
+        __syncwarp();
+        if (Tw) flush_bytes(gb, job.gapless + job.gapless_off[h] + ow, Tw, lane);
+    }
+
+    if (wclean) {
+        // The lane owns the warp's local 64-bit words 2*lane and 2*lane+1 = the 32-bit pieces c0..c3; the output grid is
+        // shifted by lead = ow % 32 bases, so output word j = the 64 bits that start 64 - 2*lead bits into local words
+        // (j-1, j).  lead is the same for the whole warp: the half of the funnel is picked by a uniform branch, and every
+        // output half is one funnel shift of two neighbouring pieces.  In a fully plain tile the pieces in front of
+        // lane 0 come from the previous warp through shared memory and only the tile's two edge words are OR-ed into
+        // the zero-filled output; otherwise each plain warp ORs its own two.
+        const uint32_t lead = (uint32_t)ow & 31u;
+        uint32_t pm1 = __shfl_up_sync(0xffffffffu, c3, 1), pm2 = __shfl_up_sync(0xffffffffu, c2, 1);   // pieces in front of c0
+        if (lane == 0) {
+            const uint64_t pw = (fast && warp) ? s_wlast[warp - 1] : 0ull;
+            pm1 = (uint32_t)pw; pm2 = (uint32_t)(pw >> 32);
+        }
+        uint32_t g0h = c0, g0l = c1, g1h = c2, g1l = c3, tail_h = 0, tail_l = 0;
+        if (lead) {
+            const unsigned sr = (2u * lead) & 31u;          // right shift inside a 32-bit piece
+            if (lead < 16) {                                 // less than one piece: output piece k = (piece k-1 : piece k) >> sr
+                g0h = __funnelshift_r(c0, pm1, sr); g0l = __funnelshift_r(c1, c0, sr);
+                g1h = __funnelshift_r(c2, c1, sr);  g1l = __funnelshift_r(c3, c2, sr);
+                tail_h = c3 << (32 - sr);
+            } else {                                         // one piece and more: output piece k = (piece k-2 : piece k-1) >> sr
+                g0h = __funnelshift_r(pm1, pm2, sr); g0l = __funnelshift_r(c0, pm1, sr);
+                g1h = __funnelshift_r(c1, c0, sr);   g1l = __funnelshift_r(c2, c1, sr);
+                tail_h = __funnelshift_r(c3, c2, sr); tail_l = sr ? c3 << (32 - sr) : 0u;
+            }
+        }
+        const uint64_t g0 = ((uint64_t)g0h << 32) | g0l, g1 = ((uint64_t)g1h << 32) | g1l;
+        uint64_t* dst = job.X + job.xoff[h] + (ow >> 5) + 2 * (uint32_t)lane;
+        const bool first_edge = lane == 0 && lead != 0 && !(fast && warp);
+        const bool last_edge = lane == 31 && lead != 0 && !(fast && warp != kPackWarps - 1);
+        if (first_edge) atomicOr(reinterpret_cast<unsigned long long*>(dst), (unsigned long long)g0);
+        else dst[0] = g0;
+        dst[1] = g1;
+        if (last_edge) atomicOr(reinterpret_cast<unsigned long long*>(dst + 2), ((unsigned long long)tail_h << 32) | tail_l);
+        return;
+    }
+    pack2_slow_emit(job.strip, job.X + job.xoff[h], job.exc_pos + (uint64_t)h * job.exc_stride, job.exc_byte + (uint64_t)h * job.exc_stride,
+                    job.exc_stride, rowp, off, cols, lane_lo, ow, Tw, s_o[1] + lew + lane_elo, lane_exc, sbits + warp * kWarpBits);
+}
+
+// =====================================================================================================================
+// k_pack3 -- streaming form: a CTA takes 8 consecutive 16 KB tiles of one row.
+//
+// What bounds the tile-per-CTA kernels once their instructions are cut (k_pack2: 40 % fewer instructions, 3 % less
+// time) is the life cycle of a CTA: ticket -> loads -> classification -> look-back -> stores, ~12 000 cycles per 16 KB
+// with every step waiting for the one before and 8 CTAs per SM to hide it.  Here
+//   phase 1  every warp streams its 8 pieces (2 KB each: warp w of tile k) on its own -- no barrier, the loads of piece
+//            k+1 in flight while piece k is classified -- and leaves the packed codes of each piece in shared memory
+//            (plain piece: one 128-bit store per lane; a piece with a gap or foreign byte: compacted by the slow path);
+//   phase 2  one barrier, one scan over the 64 piece counts, ONE descriptor and one look-back per CTA (per 128 KB);
+//   phase 3  every warp shifts its pieces onto the output grid and stores them.
+// The fixed costs of a CTA are paid once per 128 KB instead of once per 16 KB, and the loads never wait for a look-back.
+// =====================================================================================================================
+static const int kP3Pieces = 8;                                   // tiles per CTA = pieces per warp
+static const uint32_t kP3Bytes = kP3Pieces * kPackTileBytes;      // row bytes per CTA
+static const int kP3Stash = kWarpBits;                            // words per stashed piece (128 + what flush_bits reads past the end)
+
+// slow path of phase 1: the piece compacted into its stash through the general classification; returns the warp's
+// kept bases | exceptions << 16 (warp-uniform).  Called by the whole warp.
+__device__ __noinline__ uint32_t pack3_slow_piece(const uint8_t* rowp, uint32_t off, uint32_t cols, int strip, uint32_t* sb) {
+    const int lane = threadIdx.x & 31;
+    uint4 v[4]; int nv[4];
+    load64_checked(rowp, off, cols, v, nv);
+    Seg16 sg[4];
+    uint32_t cnt = 0, exc = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        sg[q].cnt = 0; sg[q].exc = 0; sg[q].codes = 0;
+        if (nv[q]) sg[q] = classify16(v[q], nv[q], strip);
+        cnt += sg[q].cnt; exc += sg[q].exc;
+    }
+    const uint32_t val = cnt | (exc << 16);
+    const uint32_t inc = warp_inclusive_scan<uint32_t, OpSum>(val, OpSum(), lane);
+    const uint32_t tot = __shfl_sync(0xffffffffu, inc, 31);
+    for (int i = lane; i < kP3Stash; i += 32) sb[i] = 0;
+    __syncwarp();
+    uint32_t l = (inc - val) & 0xFFFFu;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        if (sg[q].cnt) {
+            const uint32_t wi = l >> 4, sh = (l & 15u) * 2;
+            atomicOr(&sb[wi], sg[q].codes >> sh);
+            if (sh && sg[q].cnt > 16 - (l & 15u)) atomicOr(&sb[wi + 1], sg[q].codes << (32 - sh));
+            l += sg[q].cnt;
+        }
+    }
+    __syncwarp();
+    return tot;
+}
+
+// slow path of phase 3: the foreign bytes of a piece into the row's exception list (ow = row position of the piece's
+// first kept base, e0 = index of its first exception).  Called by the whole warp.
+__device__ __noinline__ void pack3_slow_exc(const uint8_t* rowp, uint32_t off, uint32_t cols, int strip, uint32_t* ep, uint8_t* eb,
+                                            uint64_t exc_stride, uint64_t ow, uint64_t e0) {
+    const int lane = threadIdx.x & 31;
+    uint4 v[4]; int nv[4];
+    load64_checked(rowp, off, cols, v, nv);
+    uint32_t cnt = 0, exc = 0;
+    for (int q = 0; q < 4; ++q) {
+        const uint32_t w[4] = {v[q].x, v[q].y, v[q].z, v[q].w};
+        for (int b = 0; b < nv[q]; ++b) {
+            const uint32_t byte = (w[b >> 2] >> (8 * (b & 3))) & 255u;
+            if (strip && byte == '-') continue;
+            ++cnt;
+            if (!(byte == 'A' || byte == 'C' || byte == 'G' || byte == 'T')) ++exc;
+        }
+    }
+    const uint32_t val = cnt | (exc << 16);
+    const uint32_t inc = warp_inclusive_scan<uint32_t, OpSum>(val, OpSum(), lane);
+    uint64_t p = ow + ((inc - val) & 0xFFFFu), e = e0 + ((inc - val) >> 16);
+    if (!exc) return;
+    for (int q = 0; q < 4; ++q) {
+        const uint32_t w[4] = {v[q].x, v[q].y, v[q].z, v[q].w};
+        for (int b = 0; b < nv[q]; ++b) {
+            const uint32_t byte = (w[b >> 2] >> (8 * (b & 3))) & 255u;
+            if (strip && byte == '-') continue;
+            if (!(byte == 'A' || byte == 'C' || byte == 'G' || byte == 'T')) {
+                if (e < exc_stride) { ep[e] = (uint32_t)p; eb[e] = (uint8_t)byte; }
+                ++e;
+            }
+            ++p;
+        }
+    }
+}
+
+template <int MINB>
+__global__ void __launch_bounds__(kPackThreads, MINB) k_pack3(PackJob job, uint32_t n_ctas, uint32_t ctas_per_row) {
+    extern __shared__ __align__(16) uint32_t p3_stash[];               // [kPackWarps][kP3Pieces][kP3Stash]
+    __shared__ uint32_t s_cnt[kP3Pieces * kPackWarps];                 // piece (k, w) at k * 8 + w: kept bases | exceptions << 16
+    __shared__ uint32_t s_pre[kP3Pieces * kPackWarps], s_pre_e[kP3Pieces * kPackWarps];   // exclusive prefixes inside the CTA
+    __shared__ uint64_t s_o[2];
+    __shared__ uint32_t s_ticket[3];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        const uint32_t id = job.use_tickets ? atomicAdd(job.tile_counter, 1u) : blockIdx.x;
+        s_ticket[0] = id; s_ticket[1] = id % job.H; s_ticket[2] = id / job.H;
+    }
+    __syncthreads();
+    if (s_ticket[0] >= n_ctas) return;
+    const uint32_t h = s_ticket[1], c = s_ticket[2];
+    const uint32_t cols = job.uniform_cols ? job.uniform_cols : (uint32_t)job.cols[h];
+    const uint8_t* __restrict__ rowp = job.rows + (job.uniform_cols ? job.uniform_off0 + (uint64_t)h * job.uniform_stride : job.row_off[h]);
+    const uint32_t base = c * kP3Bytes + (uint32_t)warp * 2048u;       // first byte of this warp's piece 0 (< 2^32, as cols is)
+    uint32_t* my = p3_stash + warp * (kP3Pieces * kP3Stash);
+
+    // ---- phase 1: stream the pieces --------------------------------------------------------------------------------
+    // piece k is "full" when all of its 2 KB lie inside the row; (only) full pieces take the plain path
+    // the registers hold piece k+1 while piece k is classified; lanes 0..15 ask L2 for piece k+1+pf (one 128-byte line
+    // each) so that the register loads find their bytes on the chip
+    const uint32_t pf = job.prefetch;
+    auto l2_prefetch = [&](uint32_t pb) {
+        if (lane < 16 && pb < cols && cols - pb > (uint32_t)lane * 128u) asm volatile("prefetch.global.L2 [%0];" ::"l"(rowp + pb + (uint32_t)lane * 128u));
+    };
+    uint4 n0 = make_uint4(0, 0, 0, 0), n1 = n0, n2 = n0, n3 = n0;
+    {
+        const uint32_t pb = base;
+        if (pb < cols && cols - pb >= 2048u) {
+            const uint4* src = reinterpret_cast<const uint4*>(rowp + pb + (uint32_t)lane * 64u);
+            n0 = src[0]; n1 = src[1]; n2 = src[2]; n3 = src[3];
+        }
+        for (uint32_t j = 1; j <= pf && j < (uint32_t)kP3Pieces; ++j) l2_prefetch(base + j * (uint32_t)kPackTileBytes);
+    }
+#pragma unroll 1
+    for (int k = 0; k < kP3Pieces; ++k) {
+        const uint32_t pb = base + (uint32_t)k * (uint32_t)kPackTileBytes;
+        const bool full = pb < cols && cols - pb >= 2048u;
+        const uint4 r0 = n0, r1 = n1, r2 = n2, r3 = n3;
+        {
+            const uint32_t nb = pb + (uint32_t)kPackTileBytes;
+            if (k + 1 < kP3Pieces && nb < cols && cols - nb >= 2048u) {
+                const uint4* src = reinterpret_cast<const uint4*>(rowp + nb + (uint32_t)lane * 64u);
+                n0 = src[0]; n1 = src[1]; n2 = src[2]; n3 = src[3];
+            }
+            if (pf && k + 1 + (int)pf < kP3Pieces) l2_prefetch(nb + pf * (uint32_t)kPackTileBytes);
+        }
+        uint32_t cnt;
+        bool plain = false;
+        if (full) {
+            uint32_t acc = 0;
+            const uint32_t c0 = fast16(r0, acc), c1 = fast16(r1, acc), c2 = fast16(r2, acc), c3 = fast16(r3, acc);
+            plain = __all_sync(0xffffffffu, (acc & 0xF9F9F9F9u) == 0);
+            if (plain) *reinterpret_cast<uint4*>(my + k * kP3Stash + 4 * lane) = make_uint4(c0, c1, c2, c3);
+        }
+        if (plain) cnt = 2048u;
+        else if (pb < cols) cnt = pack3_slow_piece(rowp, pb + (uint32_t)lane * 64u, cols, job.strip, my + k * kP3Stash);
+        else cnt = 0;
+        if (lane == 0) s_cnt[k * kPackWarps + warp] = cnt;
+    }
+    __syncthreads();
+
+    // ---- phase 2: offsets of the 64 pieces inside the CTA, one look-back for the CTA -------------------------------------
+    if (warp == 0) {
+        static_assert(kP3Pieces * kPackWarps == 64, "two pieces per lane in the scan below");
+        const uint32_t v0 = s_cnt[2 * lane], v1 = s_cnt[2 * lane + 1];
+        const uint32_t b0 = v0 & 0xFFFFu, b1 = v1 & 0xFFFFu, e0 = v0 >> 16, e1 = v1 >> 16;
+        const uint32_t sb = b0 + b1, se = e0 + e1;
+        const uint32_t ib = warp_inclusive_scan<uint32_t, OpSum>(sb, OpSum(), lane), ie = warp_inclusive_scan<uint32_t, OpSum>(se, OpSum(), lane);
+        s_pre[2 * lane] = ib - sb; s_pre[2 * lane + 1] = ib - sb + b0;
+        s_pre_e[2 * lane] = ie - se; s_pre_e[2 * lane + 1] = ie - se + e0;
+        const uint32_t T = __shfl_sync(0xffffffffu, ib, 31), TE = __shfl_sync(0xffffffffu, ie, 31);
+        uint64_t* dcnt = job.desc_cnt + (uint64_t)h * ctas_per_row;
+        uint64_t* dexc = job.desc_exc + (uint64_t)h * ctas_per_row;
+        const uint64_t o = lookback(dcnt, c, T, job.flags);
+        uint64_t eo = 0;
+        if (TE) {
+            eo = lookback(dexc, c, TE, job.flags);
+            if (lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(&job.exc_cnt[h]), (unsigned long long)TE);
+        } else if (lane == 0) {
+            const uint64_t pv = c ? ld_desc(&dexc[c - 1]) : kDescPrefix;
+            st_desc(&dexc[c], (pv >> 62) == 2 ? pv : kDescAgg);
+        }
+        if (lane == 0) {
+            s_o[0] = o; s_o[1] = eo;
+            if (c + 1 == ctas_per_row) job.m_out[h] = o + T;
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 3: the pieces onto the output grid --------------------------------------------------------------------
+    uint64_t* X = job.X + job.xoff[h];
+    const uint64_t o_cta = s_o[0];
+#pragma unroll 1
+    for (int k = 0; k < kP3Pieces; ++k) {
+        const uint32_t v = s_cnt[k * kPackWarps + warp];
+        const uint32_t Tw = v & 0xFFFFu;
+        if (!Tw) continue;
+        const uint64_t ow = o_cta + s_pre[k * kPackWarps + warp];
+        const uint32_t* sb = my + k * kP3Stash;
+        if (v == 2048u) {
+            // a plain piece: the lane owns the 32-bit pieces c0..c3 (its 64 bases); see k_pack2 for the funnel
+            const uint4 cc = *reinterpret_cast<const uint4*>(sb + 4 * lane);
+            const uint32_t lead = (uint32_t)ow & 31u;
+            uint32_t pm1 = __shfl_up_sync(0xffffffffu, cc.w, 1), pm2 = __shfl_up_sync(0xffffffffu, cc.z, 1);
+            if (lane == 0) { pm1 = 0; pm2 = 0; }
+            uint32_t g0h = cc.x, g0l = cc.y, g1h = cc.z, g1l = cc.w, tail_h = 0, tail_l = 0;
+            if (lead) {
+                const unsigned sr = (2u * lead) & 31u;
+                if (lead < 16) {
+                    g0h = __funnelshift_r(cc.x, pm1, sr); g0l = __funnelshift_r(cc.y, cc.x, sr);
+                    g1h = __funnelshift_r(cc.z, cc.y, sr); g1l = __funnelshift_r(cc.w, cc.z, sr);
+                    tail_h = cc.w << (32 - sr);
+                } else {
+                    g0h = __funnelshift_r(pm1, pm2, sr); g0l = __funnelshift_r(cc.x, pm1, sr);
+                    g1h = __funnelshift_r(cc.y, cc.x, sr); g1l = __funnelshift_r(cc.z, cc.y, sr);
+                    tail_h = __funnelshift_r(cc.w, cc.z, sr); tail_l = sr ? cc.w << (32 - sr) : 0u;
+                }
+            }
+            const uint64_t g0 = ((uint64_t)g0h << 32) | g0l, g1 = ((uint64_t)g1h << 32) | g1l;
+            uint64_t* dst = X + (ow >> 5) + 2 * (uint32_t)lane;
+            if (lane == 0 && lead) atomicOr(reinterpret_cast<unsigned long long*>(dst), (unsigned long long)g0);
+            else dst[0] = g0;
+            dst[1] = g1;
+            if (lane == 31 && lead) atomicOr(reinterpret_cast<unsigned long long*>(dst + 2), ((unsigned long long)tail_h << 32) | tail_l);
+        } else {
+            flush_bits(sb, X, ow, Tw, lane, 32);
+            if (v >> 16)
+                pack3_slow_exc(rowp, base + (uint32_t)k * (uint32_t)kPackTileBytes + (uint32_t)lane * 64u, cols, job.strip,
+                               job.exc_pos + (uint64_t)h * job.exc_stride, job.exc_byte + (uint64_t)h * job.exc_stride, job.exc_stride,
+                               ow, s_o[1] + s_pre_e[k * kPackWarps + warp]);
+        }
+    }
+}
+
+// exceptions per row are summed by atomics in k_pack2: the overflow test moves here (one thread per row, after the kernel)
+__global__ void k_pack2_finish(PackJob job) {
+    const uint32_t h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h < job.H && job.exc_cnt[h] > job.exc_stride) atomicOr(job.flags, 1u);
+}
+
 // ---- generic alphabets (references with N, soft-masking, IUPAC codes ...): 4 or 8 bits per symbol ----------------
 // Two passes (count, scan, write) with a byte -> code table; slower than k_pack (the MSA bytes are read twice) but
 // alphabet-agnostic.  Bytes outside the reference alphabet become exceptions exactly as in the 2-bit path.
@@ -433,8 +936,32 @@ void launch_pack(const PackJob& job, cudaStream_t s, cudaEvent_t* ev) {
     g_launches += 1;
     const unsigned grid = (unsigned)nt;          // one tile per CTA (4 per ticket measured 18x slower: a tile is published only
                                                  // after its CTA finished the earlier ones, which serialises every row's look-back)
-    if (job.occ >= 8) k_pack<8><<<grid, kPackThreads, 0, s>>>(job, (uint32_t)nt);
-    else k_pack<6><<<grid, kPackThreads, 0, s>>>(job, (uint32_t)nt);
+    if (job.variant == 0) {
+        if (job.occ >= 8) k_pack<8><<<grid, kPackThreads, 0, s>>>(job, (uint32_t)nt);
+        else k_pack<6><<<grid, kPackThreads, 0, s>>>(job, (uint32_t)nt);
+    } else if (job.variant == 2 && !job.gapless) {
+        // k_pack3: one CTA per 8 tiles of a row; its descriptors (one per CTA) live at the head of the tile descriptors
+        const uint32_t cpr = (job.tiles_per_row + kP3Pieces - 1) / kP3Pieces;
+        const uint64_t nc = (uint64_t)job.H * cpr;
+        cudaMemsetAsync(job.exc_cnt, 0, (size_t)job.H * 8, s);
+        const size_t smem = (size_t)kPackWarps * kP3Pieces * kP3Stash * 4;
+        if (job.occ == 5) k_pack3<5><<<(unsigned)nc, kPackThreads, smem, s>>>(job, (uint32_t)nc, cpr);
+        else if (job.occ == 3) k_pack3<3><<<(unsigned)nc, kPackThreads, smem, s>>>(job, (uint32_t)nc, cpr);
+        else k_pack3<4><<<(unsigned)nc, kPackThreads, smem, s>>>(job, (uint32_t)nc, cpr);      // 64 registers: measured best
+        g_launches += 1;
+        k_pack2_finish<<<(job.H + 127) / 128, 128, 0, s>>>(job);
+    } else {
+        cudaMemsetAsync(job.exc_cnt, 0, (size_t)job.H * 8, s);
+        if (job.gapless) {
+            static bool attr_set = false;
+            const size_t smem = (size_t)kPackWarps * kGaplessStage;
+            if (!attr_set) { cudaFuncSetAttribute(k_pack2<6, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
+            k_pack2<6, true><<<grid, kPackThreads, smem, s>>>(job, (uint32_t)nt);
+        } else if (job.occ >= 8) k_pack2<8, false><<<grid, kPackThreads, 0, s>>>(job, (uint32_t)nt);
+        else k_pack2<6, false><<<grid, kPackThreads, 0, s>>>(job, (uint32_t)nt);
+        g_launches += 1;
+        k_pack2_finish<<<(job.H + 127) / 128, 128, 0, s>>>(job);
+    }
     if (ev) cudaEventRecord(ev[2], s);
 }
 

@@ -13,9 +13,12 @@ pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 
 
-@pytest.fixture(scope="module")
-def ctx():
+@pytest.fixture(scope="module", params=[2, 1])
+def ctx(request):
+    """every test runs with both strip/pack kernels: 2 = k_pack3 (a CTA streams 8 tiles; the default), 1 = k_pack2 (a
+    tile per CTA; also the kernel behind the gapless output)"""
     c = D.Drlz(0)
+    c.set_option("pack_variant", request.param)
     yield c
     c.close()
 
@@ -117,6 +120,8 @@ def _check_rows(ctx, d: bytes, rows, sa=None, clean=False):
         sa = orc.sa_build(d)
     lcp = orc.lcp_build(d, sa) if clean else None
     res, m, gl = ctx.parse_batch(rows, strip_gaps=True, want_gapless=True)
+    res2, m2, _ = ctx.parse_batch(rows, strip_gaps=True, want_gapless=False)      # the kernel without the gapless bytes
+    assert (m == m2).all() and all(orc.lz_bytes(a) == orc.lz_bytes(b) for a, b in zip(res, res2))
     for h, r in enumerate(rows):
         x = orc.strip_gaps(r).tobytes()
         a1 = orc.encode_a3(d, sa, lcp, x) if clean else orc.encode_literal(d, sa, x)[0]
