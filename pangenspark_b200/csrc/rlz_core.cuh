@@ -579,9 +579,17 @@ DRLZ_HD void hint_group(const ParseView& pv, int64_t* hint, uint32_t q) {
     uint32_t cur = hv.n_exc ? exc_lower_bound(hv, s) : 0;
     uint64_t stop = stop_after(hv, s, &cur);
     if (stop == s) return;
-    bool open;
-    Match mt = lookup(pv.ix, hv.x, s, (uint32_t)(stop - s), 64u, &open);
-    if (mt.len >= kDiagMinLen) hint[q] = (int64_t)mt.pos - (int64_t)s;
+    // a variant site in the first bases of the chunk leaves the probe without a long match (3 % of the chunks at
+    // BASELINE's rates, which then parse without a prediction at all): two more tries further in -- the hint is a
+    // prediction for the whole chunk, wherever it was taken
+    uint64_t e = s + (1ull << pv.chunk_shift); if (e > hv.m) e = hv.m;
+    for (uint32_t probe = 0; probe < 3; ++probe) {
+        const uint64_t at = s + 96u * probe;
+        if (at >= e || (probe && stop < at + 64)) return;
+        bool open;
+        Match mt = lookup(pv.ix, hv.x, at, (uint32_t)(stop - at), 64u, &open);
+        if (mt.len >= kDiagMinLen) { hint[q] = (int64_t)mt.pos - (int64_t)at; return; }
+    }
 }
 
 // D: mismatch offsets of chunk g along its hinted diagonal (scalar form; the kernel k_diag_w does the same with one
