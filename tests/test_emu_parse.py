@@ -159,3 +159,34 @@ def test_golden():
         assert rc == 0
         for h in range(len(rows)):
             assert orc.lz_bytes(res[h]) == z[f"lz{h}"].tobytes()
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_short_lookups_medium_reference(seed):
+    """lookup_short (the five-load form of the lookup on a variant site) answers only where the table brackets are
+    small, i.e. with a jump table about as large as the reference -- as in production (k = 13 for 48 Mbp), not in the
+    tiny cases above: SNPs, indels, repeats and a suffix of the text that is shorter than the matched prefix"""
+    rng = np.random.default_rng(500 + seed)
+    n = 30_000
+    d = orc.syn_reference(orc.seed_for(1) + seed, n, repeats=0).tobytes()
+    if seed == 1:
+        d = d[:9000] + d[2000:5000] + d[9000:20000] + d[2500:4000] + d[20000:]
+    if seed == 2:
+        d = d + d[100:109]                      # the text ends in a copy of an earlier 9-mer: imitators in the k-mer brackets
+    sa = orc.sa_build(d)
+    rows = []
+    for h in range(4):
+        x = bytearray(d[int(rng.integers(0, 500)):])
+        for _ in range(int(len(x) * (2e-3 if h < 3 else 2e-2))):
+            p = int(rng.integers(0, len(x))); x[p] = b"ACGT"[(b"ACGT".index(x[p:p + 1]) + 1 + int(rng.integers(0, 3))) % 4]
+        for _ in range(6 if h else 0):
+            p = int(rng.integers(0, len(x)))
+            if rng.random() < 0.5: del x[p:p + int(rng.integers(1, 9))]
+            else: x[p:p] = bytes(rng.choice(list(b"ACGT"), size=int(rng.integers(1, 9))).astype(np.uint8))
+        rows.append(bytes(x))
+    rows.append(d)
+    for k, chunk, min_cap in ((8, 256, 64), (9, 1024, 64), (10, 512, 32), (7, 128, 64)):
+        rc, res, m, rounds = emu.parse(d, sa, rows, k, chunk, min_cap, 1 << 20, 1)
+        assert rc == 0
+        for h, r in enumerate(rows):
+            assert res[h].tolist() == orc.encode_literal(d, sa, r)[0].tolist(), (seed, k, chunk, h)
