@@ -9,6 +9,7 @@
 #include <string>
 #include <thread>
 #include <vector>
+#include <nvtx3/nvToolsExt.h>      // header-only NVTX 3: ranges show up in Nsight timelines, cost nothing without a tool attached
 #include "../../include/drlz.h"
 #include "drlz_internal.h"
 #include "scan.cuh"
@@ -238,11 +239,13 @@ void drlz_host_free(void* p) { if (p) cudaFreeHost(p); }
 // device pipeline for one group of rows already resident in device memory
 // ---------------------------------------------------------------------------------------------------
 struct GroupResult { uint64_t total_pairs = 0; };
+struct NvtxRange { explicit NvtxRange(const char* name) { nvtxRangePushA(name); } ~NvtxRange() { nvtxRangePop(); } };
 
 static int run_device_group(drlz_ctx* c, const uint8_t* rows_dev, const uint64_t* row_off, const uint64_t* cols, uint32_t H,
                             int strip, bool want_gapless, uint64_t* m_out, uint64_t* n_pairs, uint64_t* total_pairs,
                             uint64_t* gapless_off_out /*[H], host*/) {
     cudaStream_t s = c->stream;
+    NvtxRange nvtx_group("drlz.group: strip+pack, parse, records");
     const auto t_entry = std::chrono::steady_clock::now();
     *total_pairs = 0;
     if (H == 0) return DRLZ_OK;
@@ -358,7 +361,7 @@ static int run_device_group(drlz_ctx* c, const uint8_t* rows_dev, const uint64_t
         job.gtile_cnt = c->gtile_cnt.as<uint32_t>(); job.gtile_exc = c->gtile_exc.as<uint32_t>();
         job.gtile_off = c->gtile_off.as<uint64_t>(); job.gtile_excoff = c->gtile_excoff.as<uint64_t>();
         job.gscan_tmp = c->gscan_tmp.as<uint64_t>();
-        launch_pack(job, s, &c->ev_stage[2]);                            // ev 2,3,4
+        { NvtxRange r("drlz.pack"); launch_pack(job, s, &c->ev_stage[2]); }                            // ev 2,3,4
         launch_make_hapviews(c->haps.as<HapView>(), c->X.as<uint64_t>(), d_xoff, c->mdev.as<uint64_t>(), c->excpos.as<uint32_t>(),
                              c->excbyte.as<uint8_t>(), c->exccnt.as<uint64_t>(), exc_stride, H, s);
 
@@ -411,7 +414,8 @@ static int run_device_group(drlz_ctx* c, const uint8_t* rows_dev, const uint64_t
         int rounds = 0;
         pb.spec_out = c->out.as<int64_t>(); pb.spec_out_cap = c->out.cap >= 32 ? (c->out.cap - 16) / 16 : 0;
         pb.ev_emitted = c->ev_stage[11]; pb.emitted = false;
-        int prc = parse_stage_count(pb, s, &rounds, &c->ev_stage[5]);   // ev 5,6,7,8 and 9 (after stage A)
+        int prc;
+        { NvtxRange r("drlz.parse: pre-scan, speculative parse, fix-up, marking, emit"); prc = parse_stage_count(pb, s, &rounds, &c->ev_stage[5]); }   // ev 5,6,7,8 and 9 (after stage A)
         CK(c, cudaGetLastError());
         if (prc == 2) {
             if (single_chunk) { c->err = "parse fix-up did not converge"; return DRLZ_E_INTERNAL; }
@@ -483,6 +487,7 @@ int drlz_build_index(drlz_ctx* c, const uint8_t* ref, uint64_t n) {
     if (n > kMaxLen) { c->err = "reference longer than 2^32-1024"; return DRLZ_E_LIMIT; }
     CK(c, cudaSetDevice(c->device));
     cudaStream_t s = c->stream;
+    NvtxRange nvtx_index("drlz.build_index: copy, pack, suffix array, k-mer table, LCP, uniqueness array");
     c->have_index = false;
     cudaEvent_t e[5];
     for (int i = 0; i < 5; ++i) cudaEventCreate(&e[i]);
@@ -742,6 +747,7 @@ static int parse_batch_impl(drlz_ctx* c, const uint8_t* const* rows, const uint6
     std::lock_guard<std::recursive_mutex> lk_(c->mu);
     if (!c->have_index) { c->err = "index not built"; return DRLZ_E_STATE; }
     CK(c, cudaSetDevice(c->device));
+    NvtxRange nvtx_batch("drlz.parse_batch: host rows in, records out");
     for (int i = 0; i < 12; ++i) c->parse_ms[i] = 0;
     // trimmed column counts (Spark's text reader drops the line terminator)
     std::vector<uint64_t> tc(H);

@@ -225,8 +225,10 @@ DRLZ_HD uint32_t cmp_suffix(const uint64_t* __restrict__ X, uint64_t i, const ui
 // and exactly ONE suffix carries them, the call stops there and reports *open = true with len = cap -- the
 // match continues along that unique alignment and its full length is the diagonal run resolved by the caller.
 // If several suffixes share the capped prefix the search is redone uncapped (exact, slower; long exact repeats).
+// probe_only: give up (len = 0) instead of redoing the search uncapped when several suffixes carry the capped pattern --
+// for callers that only want a prediction (k_hint): inside a run of millions of N every uncapped compare streams the run.
 DRLZ_HD Match lookup(const IndexView& ix, const uint64_t* __restrict__ X, uint64_t i64, uint32_t maxlen,
-                     uint32_t cap, bool* open) {
+                     uint32_t cap, bool* open, bool probe_only = false) {
     const int k = ix.k;
     const uint32_t n = (uint32_t)ix.n;
     const uint32_t i = (uint32_t)i64;
@@ -276,7 +278,7 @@ DRLZ_HD Match lookup(const IndexView& ix, const uint64_t* __restrict__ X, uint64
                 // capped: is SA[r] the only suffix carrying the capped pattern?
                 bool multi = false;
                 if (haveN) multi = cmp_suffix_pre(xw, wN, X, i, D, pN, n, plen, &dummy, bl) >= plen;
-                if (multi) { plen = maxlen; continue; }
+                if (multi) { if (probe_only) { mt.len = 0; mt.pos = 0; return mt; } plen = maxlen; continue; }
                 *open = true;
             }
             mt.len = l2; mt.pos = sar; return mt;
@@ -641,7 +643,7 @@ DRLZ_HD void hint_group(const ParseView& pv, int64_t* hint, uint32_t q) {
         const uint64_t at = s + 96u * probe;
         if (at >= e || (probe && stop < at + 64)) return;
         bool open;
-        Match mt = lookup(pv.ix, hv.x, at, (uint32_t)(stop - at), 64u, &open);
+        Match mt = lookup(pv.ix, hv.x, at, (uint32_t)(stop - at), 64u, &open, true);
         if (mt.len >= kDiagMinLen) { hint[q] = (int64_t)mt.pos - (int64_t)at; return; }
     }
 }

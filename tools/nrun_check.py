@@ -1,0 +1,79 @@
+"""The 4-bit generic-alphabet path on a genome-like reference: chr21-sized, ACGT plus N runs as GRCh37 carries them
+(a telomere, a centromere-sized run of `nrun` bases, a few short ones), haplotypes with BASELINE's SNP / indel rates whose
+N runs stay N.  Device-resident throughput next to the 2-bit fast path's, and parity of `check` rows with the oracle.
+
+    python tools/nrun_check.py [n] [H] [nrun]        (GPU box)
+"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+from oracle import oracle as orc  # noqa: E402
+from pangenspark_b200 import drlz as D  # noqa: E402
+
+
+def main():
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 48_000_000
+    H = int(sys.argv[2]) if len(sys.argv) > 2 else 10
+    nrun = int(sys.argv[3]) if len(sys.argv) > 3 else 3_000_000
+    check = int(os.environ.get("NRUN_CHECK_ROWS", 2))
+    seed = orc.seed_for(2)
+    d = orc.syn_reference(seed, n)
+    runs = [(0, min(n // 100, 500_000)), (n // 3, nrun), (n // 2 + 12345, 50_000), (n - n // 50, 30_000), (n // 5, 700)]
+    for a, ln in runs:
+        d[a:a + ln] = ord("N")
+    M = orc.syn_columns(seed, n, 1e-5)
+    stride = (M + 15) // 16 * 16 + 16
+    rows = np.zeros((H, stride), dtype=np.uint8)
+    import ctypes as C
+    orc.lib().syn_rows(seed, d.ctypes.data_as(C.c_void_p), d.size, 1, H, 1e-3, 1e-5, 1e-5, rows.ctypes.data_as(C.c_void_p), stride)
+    # the generator treats N as a base and mutates it: put the N runs back so that the haplotypes carry them whole
+    # (columns of a row = reference positions plus insertion columns; restore by matching against the reference row)
+    ref_row = np.zeros((1, stride), dtype=np.uint8)
+    orc.lib().syn_rows(seed, d.ctypes.data_as(C.c_void_p), d.size, 0, 1, 0.0, 1e-5, 0.0, ref_row.ctypes.data_as(C.c_void_p), stride)
+    is_n = ref_row[0, :M] == ord("N")
+    for h in range(H):
+        rows[h, :M][is_n & (rows[h, :M] != ord("-"))] = ord("N")
+    ctx = D.Drlz(0)
+    t0 = time.time(); ctx.build_index(d); t_first = time.time() - t0
+    ctx.build_index(d)
+    info, it = ctx.index_info(), ctx.index_timings()
+    dev = torch.from_numpy(rows.reshape(-1)).cuda()
+    row_off = np.arange(H, dtype=np.uint64) * np.uint64(stride)
+    cols = np.full(H, M, dtype=np.uint64)
+    for _ in range(2):
+        ptr, npairs, m = ctx.parse_batch_device(dev.data_ptr(), row_off, cols)
+    acc, R = {}, 3
+    for _ in range(R):
+        ptr, npairs, m = ctx.parse_batch_device(dev.data_ptr(), row_off, cols)
+        for a, b in ctx.parse_timings().items():
+            acc[a] = acc.get(a, 0.0) + b / R
+    pairs = ctx.copy_pairs_to_host(ptr, int(npairs.sum()))
+    ok = True
+    if check:
+        sa = orc.sa_build(d)
+        ok = bool((ctx.index_get("sa").astype(np.int64) == sa).all())
+        o = 0
+        for h in range(H):
+            c = int(npairs[h])
+            if h < check:
+                a1, _ = orc.encode_literal(d, sa, orc.strip_gaps(rows[h, :M]))
+                ok = ok and orc.lz_bytes(pairs[o:o + c]) == orc.lz_bytes(a1)
+            o += c
+    out = {"workload": "%.0f Mbp ACGT reference with N runs (longest %.1f Mbp), %d haplotypes, 4-bit symbols" % (n / 1e6, nrun / 1e6, H),
+           "bits": info["bits"], "sigma": info["sigma"], "kmer": info["k"], "index_ms": it["total_ms"], "index_first_call_s": t_first,
+           "sa_rounds": info["sa_rounds"], "gbp_per_s": float(m.sum()) / acc["device_ms"] / 1e6,
+           "kernel_ms": {a: round(b, 3) for a, b in acc.items()}, "phrases": int(npairs.sum()), "parity_rows": check, "ok": ok}
+    print(json.dumps(out))
+    ctx.close()
+    return 0 if ok else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())
