@@ -414,6 +414,9 @@ class Job:
 
 
 def roofline_of(ms, steps, peak, peak_src):
+    """`roofline` of the dominant kernel = the one with the longest average launch, measured by the CUDA events the
+    library records around every kernel of the step; `kernels` lists all of them (the two longest are within a few
+    per cent of each other: k_pack3 moves 82 % of the step's algorithmic bytes, k_spec waits on dependent random loads)."""
     kt, H, M, bases, phrases = ms["kt"], ms["H"], ms["M"], ms["bases"], ms["phrases"]
     Mtot, mtot = float(H) * M, float(bases)
     per_launch = {   # name: (avg ms per launch, algorithmic bytes per launch)
@@ -426,7 +429,7 @@ def roofline_of(ms, steps, peak, peak_src):
     dom = max(per_launch, key=lambda k_: per_launch[k_][0])
     dom_ms, dom_bytes = per_launch[dom]
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
-    traffic, traffic_src = None, None
+    traffic, traffic_src, tj = None, None, {}
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         try:
@@ -435,10 +438,15 @@ def roofline_of(ms, steps, peak, peak_src):
             traffic_src = tj.get("_source", "profiles/traffic.json (hand-kept from the last ncu --set full capture)")
         except Exception:
             traffic = None
+    kernels = {}
+    for name, (kms, kb) in per_launch.items():
+        gbs = kb / (kms * 1e-3) / 1e9 if kms > 0 else 0.0
+        kernels[name] = {"ms": round(kms, 4), "algorithmic_bytes": kb, "achieved": round(gbs, 1), "frac": round(gbs / peak, 4),
+                         "traffic": tj.get(name)}
     alg_step = Mtot + mtot / 2 + 16.0 * phrases            # M + m/4 + m/4 + 16 P
     return {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes,
-            "kernel_ms": dom_ms,
+            "kernel_ms": dom_ms, "kernels": kernels,
             "step": {"algorithmic_bytes": alg_step, "achieved": alg_step / (ms["ms_dev"] * 1e-3) / 1e9,
                      "frac": alg_step / (ms["ms_dev"] * 1e-3) / 1e9 / peak},
             "kernel_ms_per_step": {k_: round(v_ / steps, 4) for k_, v_ in kt.items() if k_.endswith("_ms")}}

@@ -64,6 +64,9 @@ public final class DistributedRLZ {
     public interface Sink {
         void mkdirs(String dir) throws IOException;
         OutputStream create(String path) throws IOException;        // overwrites, like fs.create(path) at DistributedRLZ.scala:257
+        /** {path, size} of every file the glob matches (Spark reads dataGlob from the same file system, drlz.sh:15). */
+        List<String[]> glob(String pattern) throws IOException;
+        java.nio.channels.ReadableByteChannel open(String path) throws IOException;
     }
 
     static final class LocalSink implements Sink {
@@ -71,6 +74,12 @@ public final class DistributedRLZ {
         public OutputStream create(String path) throws IOException {
             return Files.newOutputStream(Path.of(strip(path)), StandardOpenOption.CREATE, StandardOpenOption.WRITE, StandardOpenOption.TRUNCATE_EXISTING);
         }
+        public List<String[]> glob(String pattern) throws IOException {
+            List<String[]> out = new ArrayList<>();
+            for (Path p : expand(strip(pattern))) out.add(new String[] {p.toString(), Long.toString(Files.size(p))});
+            return out;
+        }
+        public java.nio.channels.ReadableByteChannel open(String path) throws IOException { return FileChannel.open(Path.of(strip(path)), StandardOpenOption.READ); }
         private static String strip(String p) { return p.startsWith("file://") ? p.substring(7) : p; }
     }
 
@@ -79,7 +88,7 @@ public final class DistributedRLZ {
         MemorySegment in, gapless, pairs;          // pinned (drlz_host_alloc), sized for one batch
         MemorySegment rowPtrs, glPtrs, cols, m, np, ticket;
         long pairsCap;
-        List<Path> files = new ArrayList<>();
+        List<String[]> files = new ArrayList<>();          // {path, size}
         long[] off;
     }
 
@@ -124,17 +133,18 @@ public final class DistributedRLZ {
             }
             System.out.println("Load suffix\nbroadcasting\nstarted encoding");
 
-            List<Path> inputs = expand(dataGlob);
+            List<String[]> inputs = sink.glob(dataGlob);          // sorted by file name
+            inputs.sort(Comparator.comparing(f -> baseName(f[0])));
             if (inputs.isEmpty()) throw new IOException("Path does not exist: " + dataGlob);      // what Spark says
             sink.mkdirs(outDir);
             sink.mkdirs(gaplessOut);
             // batches of consecutive files, at most batchBytes each
-            List<List<Path>> batches = new ArrayList<>();
+            List<List<String[]>> batches = new ArrayList<>();
             long slotBytes = 0; int slotRows = 1;
             {
-                List<Path> cur = new ArrayList<>(); long acc = 0, padded = 0;
-                for (Path p : inputs) {
-                    long sz = Files.size(p);
+                List<String[]> cur = new ArrayList<>(); long acc = 0, padded = 0;
+                for (String[] p : inputs) {
+                    long sz = Long.parseLong(p[1]);
                     if (!cur.isEmpty() && acc + sz > batchBytes) { batches.add(cur); cur = new ArrayList<>(); acc = 0; padded = 0; }
                     cur.add(p); acc += sz; padded += ((sz + 15) & ~15L) + 16;
                     slotBytes = Math.max(slotBytes, padded + 16); slotRows = Math.max(slotRows, cur.size());
@@ -170,14 +180,16 @@ public final class DistributedRLZ {
                     long at = 0;
                     List<Future<?>> reads = new ArrayList<>();
                     for (int h = 0; h < H; h++) {
-                        final long sz = Files.size(s.files.get(h)), o = at;
-                        final Path p = s.files.get(h);
+                        final long sz = Long.parseLong(s.files.get(h)[1]), o = at;
+                        final String p = s.files.get(h)[0];
                         s.off[h] = o; at += ((sz + 15) & ~15L) + 16;
-                        reads.add(pool.submit(() -> {          // pread straight into the pinned slot
-                            try (FileChannel ch = FileChannel.open(p, StandardOpenOption.READ)) {
-                                ByteBuffer dst = s.in.asSlice(o, sz).asByteBuffer();
-                                long pos = 0;
-                                while (dst.hasRemaining()) { int r = ch.read(dst, pos); if (r < 0) throw new IOException("short read: " + p); pos += r; }
+                        reads.add(pool.submit(() -> {          // straight into the pinned slot
+                            try (java.nio.channels.ReadableByteChannel ch = sink.open(p)) {
+                                long got = 0;
+                                while (got < sz) {             // a ByteBuffer view holds at most 2 GiB
+                                    ByteBuffer dst = s.in.asSlice(o + got, Math.min(sz - got, 1L << 30)).asByteBuffer();
+                                    while (dst.hasRemaining()) { int r = ch.read(dst); if (r < 0) throw new IOException("short read: " + p); got += r; }
+                                }
                             }
                             return null;
                         }));
@@ -211,7 +223,7 @@ public final class DistributedRLZ {
                     final int hh = h; final long po = poff, cnt = s.np.getAtIndex(JAVA_LONG, h), mh = s.m.getAtIndex(JAVA_LONG, h);
                     poff += cnt;
                     mine.add(pool.submit(() -> {
-                        String name = s.files.get(hh).getFileName().toString();
+                        String name = baseName(s.files.get(hh)[0]);
                         // <outDir>/<basename>.lz: the records are already int64 LE (pos, len) -- DistributedRLZ.scala:263-284
                         try (WritableByteChannel out = Channels.newChannel(sink.create(outDir + "/" + name + ".lz"))) {
                             writeAll(out, s.pairs.asSlice(16 * po, 16 * cnt));
@@ -237,6 +249,8 @@ public final class DistributedRLZ {
             destroy.invoke(ctx);
         }
     }
+
+    private static String baseName(String path) { return path.substring(path.lastIndexOf('/') + 1); }
 
     private static void writeAll(WritableByteChannel out, MemorySegment seg) throws IOException {
         long at = 0, n = seg.byteSize();

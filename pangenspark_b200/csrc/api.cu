@@ -575,7 +575,9 @@ int drlz_build_index(drlz_ctx* c, const uint8_t* ref, uint64_t n) {
     (void)off0; (void)m; (void)np; (void)tot;
     cudaEventRecord(e[1], s);
     char ebuf[256]; ebuf[0] = 0;
-    int rc = build_suffix_array(c->d_text, n, bl, c->sa.as<uint32_t>(), c->isa.as<uint32_t>(), s, &c->sa_rounds, ebuf, sizeof ebuf, &c->sa_ws);
+    CK(c, c->lcp.ensure(n * 4 + 8));
+    int rc = build_suffix_array(c->d_text, n, bl, c->sa.as<uint32_t>(), c->isa.as<uint32_t>(), s, &c->sa_rounds, ebuf, sizeof ebuf, &c->sa_ws,
+                                c->lcp.as<uint32_t>());
     if (c->sa_ws.bytes() > (16ull << 30)) {          // whole-genome scale: the parse needs that memory back
         cudaStreamSynchronize(s);
         c->sa_ws.release();
@@ -590,8 +592,9 @@ int drlz_build_index(drlz_ctx* c, const uint8_t* ref, uint64_t n) {
     if (rc != 0) { c->err = "k-mer table build failed"; for (int i = 0; i < 5; ++i) cudaEventDestroy(e[i]); return DRLZ_E_CUDA; }
     cudaEventRecord(e[3], s);
     {   // LCP (kept only on request) and the uniqueness array derived from it
-        CK(c, c->lcp.ensure(n * 4 + 8));
-        rc = build_lcp(c->d_text, n, bl, c->sa.as<uint32_t>(), c->isa.as<uint32_t>(), c->lcp.as<uint32_t>(), s);
+        // no doubling round was needed: every neighbouring pair of suffixes differs inside its first sort key, and the
+        // LCP array came out of the sort (StoreRank); otherwise the Kasai-order kernel computes it
+        rc = c->sa_rounds == 0 ? 0 : build_lcp(c->d_text, n, bl, c->sa.as<uint32_t>(), c->isa.as<uint32_t>(), c->lcp.as<uint32_t>(), s);
         if (rc == 0) rc = build_uniq(n, c->isa.as<uint32_t>(), c->lcp.as<uint32_t>(), c->d_uniq, s);
         if (rc != 0) { c->err = "lcp / uniqueness build failed"; for (int i = 0; i < 5; ++i) cudaEventDestroy(e[i]); return DRLZ_E_CUDA; }
     }

@@ -88,8 +88,10 @@ struct SaWorkspace {
 // Builds SA (uint32[n]) of the packed text and, when isa != null, the inverse.  Returns 0 or a cudaError.
 // bl = log2(bits per symbol) of the packed text
 // ws: scratch kept by the caller (null = allocated and freed inside the call)
+// lcp_from_keys (nullable, uint32[n]): the LCP array as read off the first-round sort keys; final iff *rounds_out == 0
+// (every suffix was distinguished by its first key), otherwise build_lcp must recompute it
 int build_suffix_array(const uint64_t* text, uint64_t n, uint32_t bl, uint32_t* sa, uint32_t* isa, cudaStream_t s,
-                       int* rounds_out, char* err, int errlen, SaWorkspace* ws = nullptr);
+                       int* rounds_out, char* err, int errlen, SaWorkspace* ws = nullptr, uint32_t* lcp_from_keys = nullptr);
 // tab: sigma^k + 1 entries (ix.tab is ignored, ix.text / ix.sa / ix.k / ix.bl / ix.sigma are used)
 // tmp: kmer_table_tmp_bytes(entries) bytes of scratch owned by the caller; the call does not synchronise
 size_t kmer_table_tmp_bytes(uint64_t entries);

@@ -38,12 +38,27 @@ struct LoadHeadIdx {
         return (j == 0 || keys[j] != keys[j - 1]) ? (uint32_t)j : 0u;
     }
 };
-// ISA[sa[j]] = group head; also copies the sorted values into SA
+// ISA[sa[j]] = group head; also copies the sorted values into SA.  With lcp != null the LCP of neighbouring suffixes is
+// read off their sort keys on the way (first S0 symbols + length): exact wherever the two keys differ, which is everywhere
+// once no group is left for the doubling rounds (the caller knows; otherwise build_lcp recomputes the array).
 struct StoreRank {
     const uint32_t* vals; uint32_t* sa; uint32_t* isa;
+    const uint64_t* keys; uint32_t* lcp; uint32_t bl;
     __device__ __forceinline__ void operator()(uint64_t j, uint32_t head) const {
         uint32_t s = vals[j];
         sa[j] = s; isa[s] = head;
+        if (lcp) {
+            uint32_t l = 0;
+            if (j) {
+                const uint32_t s0 = 58u >> bl;
+                const uint64_t keep = ~((1ull << (64 - (s0 << bl))) - 1);
+                const uint64_t a = keys[j - 1], b = keys[j], x = (a ^ b) & keep;
+                const uint32_t la = (uint32_t)(a & 63u), lb = (uint32_t)(b & 63u);
+                l = x ? (uint32_t)(__clzll((long long)x) >> bl) : s0;
+                l = l < la ? l : la; l = l < lb ? l : lb;
+            }
+            lcp[j] = l;
+        }
     }
 };
 // active flag: position j is in a group of size > 1  (keys = sorted keys of the element list, nel elements)
@@ -97,7 +112,7 @@ struct StoreRound {
 static int bits_for(uint64_t v) { int b = 0; while (v) { ++b; v >>= 1; } return b ? b : 1; }
 
 int build_suffix_array(const uint64_t* text, uint64_t n, uint32_t bl, uint32_t* sa, uint32_t* isa_out, cudaStream_t s,
-                       int* rounds_out, char* err, int errlen, SaWorkspace* ws_in) {
+                       int* rounds_out, char* err, int errlen, SaWorkspace* ws_in, uint32_t* lcp_from_keys) {
     int rc = 0;
     if (rounds_out) *rounds_out = 0;
     if (n == 0) return 0;
@@ -129,7 +144,7 @@ int build_suffix_array(const uint64_t* text, uint64_t n, uint32_t bl, uint32_t* 
         k_sa_init_keys<<<nb, T, 0, s>>>(text, n, keys_a, vals_a, bl);
         radix_sort_pairs<uint64_t>(&keys_a, &keys_b, &vals_a, &vals_b, n, 0, 64, hist, scan_tmp, s);
         // ranks = group head index (inclusive running max of head indices); SA = sorted values
-        device_scan<uint32_t, LoadHeadIdx, StoreRank, OpMax, true>(LoadHeadIdx{keys_a}, StoreRank{vals_a, sa, isa}, n,
+        device_scan<uint32_t, LoadHeadIdx, StoreRank, OpMax, true>(LoadHeadIdx{keys_a}, StoreRank{vals_a, sa, isa, keys_a, lcp_from_keys, bl}, n,
                                                                    scan_tmp, OpMax(), 0u, s);
         // active slots
         device_scan<uint32_t, LoadActive, StoreCompact, OpSum, false>(

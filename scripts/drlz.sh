@@ -1,7 +1,9 @@
 #!/usr/bin/env bash
 # Drop-in replacement of the reference's drlz.sh (same arguments: CHR INPATH HDFSURI).
-# Only the launcher line differs: the Spark submit is replaced by the native B200 binary.  With an hdfs:// URI
-# the binary stages outputs locally and uploads them with `hdfs dfs -put` (the mkdirs below are the reference's).
+# Only the launcher line differs: the Spark submit is replaced by the native B200 binary.  With an hdfs:// URI the
+# binary lists and fetches the rows with `hdfs dfs -ls -C` / `-get` when "$INPATH/*.NN" matches nothing locally (Spark
+# read them from HDFS), stages its outputs locally and uploads them with `hdfs dfs -put -f` (the mkdirs below are the
+# reference's).  It exits non-zero when no row matches the glob, like Spark's "Path does not exist".
 CHR=$1
 INPATH=$2
 DRLZOUT=$2drlz
