@@ -65,7 +65,7 @@ int drlz_build_index(drlz_ctx* ctx, const uint8_t* ref, uint64_t n);
 /* copy index arrays to the host.  what: 0 = SA (uint32[n]), 1 = inverse SA (uint32[n]), 2 = LCP (uint32[n],
  * needs option lcp=1), 3 = k-mer table (uint32[sigma^k+1]), 4 = packed text (uint64[ceil(n * bits / 64)]).  */
 int drlz_index_get(drlz_ctx* ctx, int what, void* host_out, uint64_t bytes);
-/* info[0]=n, [1]=k | log2(bits per symbol) << 8 | alphabet size sigma << 16, [2]=prefix-doubling rounds,
+/* info[0]=n, [1]=k | log2(bits per symbol) << 8 | alphabet size sigma << 16 | (long repeats: 1) << 28, [2]=prefix-doubling rounds,
  * [3]=index bytes on device */
 int drlz_index_info(const drlz_ctx* ctx, uint64_t info[4]);
 /* time of the last drlz_build_index in ms (CUDA events on the context stream): [0] total, from before the host->device
@@ -75,7 +75,8 @@ int drlz_index_timings(const drlz_ctx* ctx, double ms[5]);
 /* Multi-GPU: rank 0 builds, the others call drlz_index_reserve(n, info[1] of rank 0) and receive the three
  * buffers by an NCCL broadcast (done by the caller, e.g. torch.distributed) into the device pointers returned by
  * drlz_index_buffers, then call drlz_index_commit.  bufs: [0] packed text + uniqueness array + byte<->code
- * tables, [1] SA, [2] k-mer table.  kinfo = k | log2(bits per symbol) << 8 | alphabet size << 16, exactly
+ * tables, [1] SA (followed by the unsaturated uniqueness array when the reference has repeats of 65535 symbols and more: bit
+ * 28 of kinfo), [2] k-mer table.  kinfo = k | log2(bits per symbol) << 8 | alphabet size << 16 | flags, exactly
  * drlz_index_info's info[1]; a plain k (upper bits 0) means the 2-bit {A,C,G,T} layout. */
 int drlz_index_reserve(drlz_ctx* ctx, uint64_t n, int kinfo);
 int drlz_index_buffers(drlz_ctx* ctx, void* dev_ptrs[3], uint64_t bytes[3]);

@@ -63,6 +63,7 @@ struct drlz_ctx {
     uint64_t* d_text = nullptr; uint32_t* d_tab = nullptr; uint16_t* d_uniq = nullptr; uint8_t* d_lut = nullptr;   // lut = b2c[256], c2b[256]
     size_t blob_bytes = 0, text_bytes = 0, uniq_bytes = 0, tab_bytes = 0;
     uint32_t bl = 1, sigma = 4;        // symbol width (log2 bits) and alphabet size of the index
+    bool has_uniq32 = false;           // some repeat of the reference reaches 65535 symbols: the unsaturated array (behind the SA) is in use
     int opt_predict = 1;
     cudaStream_t l2_stream = nullptr; int opt_l2persist = 0; int opt_occ = 8; int opt_occ_fix = 10; int opt_occ_diag = 12; int opt_tickets = 1; int opt_hint = 1; int opt_diag = 1; uint32_t opt_spec_store = 0;
     double idx_ms[5] = {0, 0, 0, 0, 0};
@@ -70,7 +71,7 @@ struct drlz_ctx {
     SaWorkspace sa_ws;
     DevBuf stage[2], meta_dev, desc_cnt, desc_exc, tile_counter, X, mdev, exccnt, excpos, excbyte,
         flags, haps, gapless, gtile_cnt, gtile_exc, gtile_off, gtile_excoff, gscan_tmp, chunk_hap, first_pos, first_len, run_a, run_b, link_a, link_b, open_i, open_pos, open_len, spec_cnt, spec_exit, alt_entry, alt_cnt, alt_exit, alt_round, alt_own, alt_merge, spec_ph, alt_ph, hint, mm, true_slot, counters, jump_a,
-        jump_b, mark, true_cnt, true_entry, true_off, scan_tmp, hap_pairs, out, ms_a, ms_b, tab_tmp, gap_list, gap_scratch, gap_counter;
+        jump_b, mark, true_cnt, true_entry, true_off, scan_tmp, hap_pairs, out, ms_a, ms_b, tab_tmp, gap_list, gap_scratch, gap_counter, ext, hint_src;
     HostBuf meta_host, small_host, gap_host;
     uint64_t exc_stride_hint = 0;
     // thread safety: every entry point takes `mu` (calls from several threads are serialised on the device)
@@ -172,7 +173,7 @@ void drlz_destroy(drlz_ctx* c) {
                       &c->desc_exc, &c->tile_counter, &c->X, &c->mdev, &c->exccnt, &c->excpos,
                       &c->excbyte, &c->flags, &c->haps, &c->gapless, &c->gtile_cnt, &c->gtile_exc, &c->gtile_off, &c->gtile_excoff, &c->gscan_tmp, &c->chunk_hap, &c->first_pos, &c->first_len, &c->run_a, &c->run_b, &c->link_a, &c->link_b, &c->open_i, &c->open_pos, &c->open_len, &c->spec_cnt, &c->spec_exit,
                       &c->alt_entry, &c->alt_cnt, &c->alt_exit, &c->alt_round, &c->alt_own, &c->alt_merge, &c->spec_ph, &c->alt_ph, &c->hint, &c->mm, &c->true_slot, &c->counters, &c->jump_a, &c->jump_b,
-                      &c->mark, &c->true_cnt, &c->true_entry, &c->true_off, &c->scan_tmp, &c->hap_pairs, &c->out, &c->ms_a, &c->ms_b, &c->tab_tmp, &c->gap_list, &c->gap_scratch, &c->gap_counter};
+                      &c->mark, &c->true_cnt, &c->true_entry, &c->true_off, &c->scan_tmp, &c->hap_pairs, &c->out, &c->ms_a, &c->ms_b, &c->tab_tmp, &c->gap_list, &c->gap_scratch, &c->gap_counter, &c->ext, &c->hint_src};
     for (DevBuf* b : bufs) b->release();
     c->meta_host.release(); c->small_host.release(); c->gap_host.release();
     for (int i = 0; i < 2; ++i) if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]);
@@ -378,6 +379,7 @@ static int run_device_group(drlz_ctx* c, const uint8_t* rows_dev, const uint64_t
         CK(c, c->spec_ph.ensure((size_t)NC * spec_store * 8 + 8)); CK(c, c->alt_ph.ensure(na * kAltStore * 8 + 8));
         CK(c, c->hint.ensure(((size_t)NC / kHintGroup + 2) * 8)); CK(c, c->mm.ensure(((size_t)NC + 1) * kMmStride * 2));
         CK(c, c->true_slot.ensure((size_t)NC * 4 + 4));
+        if (c->has_uniq32) { CK(c, c->ext.ensure((size_t)NC * 4 + 4)); CK(c, c->hint_src.ensure((size_t)NC * 4 + 4)); }
         CK(c, c->alt_round.ensure(na * 4 + 4)); CK(c, c->counters.ensure(sizeof(uint32_t) * (2 + kMaxRounds)));
         CK(c, c->jump_a.ensure(nn * 4 + 4)); CK(c, c->jump_b.ensure(nn * 4 + 4)); CK(c, c->mark.ensure(nn + 4));
         CK(c, c->true_cnt.ensure((size_t)NC * 4 + 4)); CK(c, c->true_entry.ensure((size_t)NC * 4 + 4)); CK(c, c->true_off.ensure((size_t)NC * 8 + 8));
@@ -386,7 +388,7 @@ static int run_device_group(drlz_ctx* c, const uint8_t* rows_dev, const uint64_t
 
         ParseBuffers pb;
         pb.pv.ix = IndexView{c->d_text, c->sa.as<uint32_t>(), c->d_tab, c->n, c->k, c->opt_predict ? c->d_uniq : nullptr,
-                             c->bl, c->sigma, c->d_lut + 256};
+                             c->bl, c->sigma, c->d_lut + 256, (c->opt_predict && c->has_uniq32) ? c->sa.as<uint32_t>() + c->n : nullptr};
         pb.pv.haps = c->haps.as<HapView>(); pb.pv.chunk_hap = c->chunk_hap.as<uint32_t>(); pb.pv.hap_chunk_base = d_base;
         pb.pv.chunk_bases = Ceff; pb.pv.chunk_shift = single_chunk ? 32u : chunk_shift; pb.pv.n_chunks = NC;
         pb.pv.min_cap = single_chunk ? 0xFFFFFFFFu : c->opt_min_cap; pb.pv.foreign_cap = c->opt_foreign_cap;
@@ -402,6 +404,7 @@ static int run_device_group(drlz_ctx* c, const uint8_t* rows_dev, const uint64_t
         pb.pv.spec_store = spec_store; pb.pv.hint = nullptr; pb.pv.mm = nullptr;
         pb.mm = (c->opt_hint && c->opt_diag && !single_chunk) ? c->mm.as<uint16_t>() : nullptr;
         pb.hint = (c->opt_hint && !single_chunk) ? c->hint.as<int64_t>() : nullptr;
+        pb.ext = c->has_uniq32 ? c->ext.as<uint32_t>() : nullptr; pb.hint_src = c->has_uniq32 ? c->hint_src.as<uint32_t>() : nullptr;
         pb.true_slot = c->true_slot.as<uint32_t>();
         pb.pv.counters = c->counters.as<uint32_t>();
         pb.H = H; pb.max_chunks_per_hap = maxc ? maxc : 1; pb.occ = c->opt_occ; pb.occ_fix = c->opt_occ_fix; pb.occ_diag = c->opt_occ_diag; pb.blind_rounds = c->opt_blind_rounds;
@@ -530,7 +533,7 @@ int drlz_build_index(drlz_ctx* c, const uint8_t* ref, uint64_t n) {
     CK(c, alloc_index_blob(c, n, k, sigma, bl));
     CK(c, c->tab_tmp.ensure(kmer_table_tmp_bytes(table_entries(sigma, k))));
     CK(c, cudaMemcpyAsync(c->d_lut, lut, 512, cudaMemcpyHostToDevice, s));
-    CK(c, c->sa.ensure(n * 4 + 4));
+    CK(c, c->sa.ensure(n * 8 + 8));          // suffix array, and behind it the unsaturated uniqueness array (used only if needed)
     CK(c, c->isa.ensure(n * 4 + 4));
     c->n = 0; c->k = 1;
     uint64_t off0 = 0, m = 0, np = 0, tot = 0;
@@ -595,12 +598,14 @@ int drlz_build_index(drlz_ctx* c, const uint8_t* ref, uint64_t n) {
         // no doubling round was needed: every neighbouring pair of suffixes differs inside its first sort key, and the
         // LCP array came out of the sort (StoreRank); otherwise the Kasai-order kernel computes it
         rc = c->sa_rounds == 0 ? 0 : build_lcp(c->d_text, n, bl, c->sa.as<uint32_t>(), c->isa.as<uint32_t>(), c->lcp.as<uint32_t>(), s);
-        if (rc == 0) rc = build_uniq(n, c->isa.as<uint32_t>(), c->lcp.as<uint32_t>(), c->d_uniq, s);
+        if (rc == 0) rc = build_uniq(n, c->isa.as<uint32_t>(), c->lcp.as<uint32_t>(), c->d_uniq, c->sa.as<uint32_t>() + n, c->flags.as<uint32_t>() + 2, s);
         if (rc != 0) { c->err = "lcp / uniqueness build failed"; for (int i = 0; i < 5; ++i) cudaEventDestroy(e[i]); return DRLZ_E_CUDA; }
     }
     cudaEventRecord(e[4], s);
+    CK(c, cudaMemcpyAsync(c->small_host.p, c->flags.as<uint32_t>() + 2, 4, cudaMemcpyDeviceToHost, s));
     CK(c, cudaStreamSynchronize(s));
     CK(c, cudaGetLastError());
+    c->has_uniq32 = *c->small_host.as<uint32_t>() != 0;
     float t;
     cudaEventElapsedTime(&t, e[0], e[4]); c->idx_ms[0] = t;
     cudaEventElapsedTime(&t, e[0], e[1]); c->idx_ms[1] = t;
@@ -634,7 +639,7 @@ int drlz_index_get(drlz_ctx* c, int what, void* host_out, uint64_t bytes) {
 
 int drlz_index_info(const drlz_ctx* c, uint64_t info[4]) {
     if (!c || !info) return DRLZ_E_ARG;
-    info[0] = c->n; info[1] = (uint64_t)c->k | ((uint64_t)c->bl << 8) | ((uint64_t)c->sigma << 16);
+    info[0] = c->n; info[1] = (uint64_t)c->k | ((uint64_t)c->bl << 8) | ((uint64_t)c->sigma << 16) | ((uint64_t)(c->has_uniq32 ? 1 : 0) << 28);
     info[2] = (uint64_t)c->sa_rounds;
     info[3] = c->have_index ? c->blob_bytes + c->n * 4 : 0;
     return DRLZ_OK;
@@ -648,7 +653,8 @@ int drlz_index_timings(const drlz_ctx* c, double ms[5]) {
 
 int drlz_index_reserve(drlz_ctx* c, uint64_t n, int kinfo) {
     int k = kinfo & 0xFF;
-    uint32_t bl = (uint32_t)(kinfo >> 8) & 0xFF, sigma = (uint32_t)kinfo >> 16;
+    uint32_t bl = (uint32_t)(kinfo >> 8) & 0xFF, sigma = ((uint32_t)kinfo >> 16) & 0x1FFu;
+    const bool has32 = ((uint32_t)kinfo >> 28) & 1u;
     if (bl == 0 && sigma == 0) { bl = 1; sigma = 4; }          // plain k: pure-ACGT index
     if (!c || k < 1 || k > 32 || bl < 1 || bl > 3 || sigma < 1 || sigma > 256) return DRLZ_E_ARG;
     std::lock_guard<std::recursive_mutex> lk_(c->mu);
@@ -656,7 +662,8 @@ int drlz_index_reserve(drlz_ctx* c, uint64_t n, int kinfo) {
     CK(c, cudaSetDevice(c->device));
     c->have_index = false;
     CK(c, alloc_index_blob(c, n, k, sigma, bl));
-    CK(c, c->sa.ensure(n * 4 + 4));
+    CK(c, c->sa.ensure(n * 8 + 8));
+    c->has_uniq32 = has32;
     CK(c, cudaMemsetAsync(c->d_text, 0, c->text_bytes, c->stream));
     CK(c, cudaStreamSynchronize(c->stream));
     c->n = n; c->k = k;
@@ -668,7 +675,7 @@ int drlz_index_buffers(drlz_ctx* c, void* dev_ptrs[3], uint64_t bytes[3]) {
     std::lock_guard<std::recursive_mutex> lk_(c->mu);
     if (!c->d_text || !c->d_tab) { c->err = "no index buffers (build or reserve first)"; return DRLZ_E_STATE; }
     dev_ptrs[0] = c->d_text; bytes[0] = c->text_bytes + c->uniq_bytes + 512;   // packed text, uniqueness array, byte<->code tables
-    dev_ptrs[1] = c->sa.p; bytes[1] = c->n * 4;
+    dev_ptrs[1] = c->sa.p; bytes[1] = c->n * (c->has_uniq32 ? 8 : 4);      // suffix array (+ the unsaturated uniqueness array if in use)
     dev_ptrs[2] = c->d_tab; bytes[2] = table_entries(c->sigma, c->k) * 4;
     return DRLZ_OK;
 }

@@ -99,8 +99,9 @@ int build_kmer_table(const IndexView& ix, uint32_t* tab, uint32_t* tmp, cudaStre
 // LCP[j] = lcp(suffix SA[j-1], suffix SA[j]), LCP[0] = 0
 int build_lcp(const uint64_t* text, uint64_t n, uint32_t bl, const uint32_t* sa, const uint32_t* isa, uint32_t* lcp,
               cudaStream_t s);
-// uniq[p] = min(65535, max(LCP[ISA[p]], LCP[ISA[p]+1]))
-int build_uniq(uint64_t n, const uint32_t* isa, const uint32_t* lcp, uint16_t* uniq, cudaStream_t s);
+// uniq[p] = min(65535, max(LCP[ISA[p]], LCP[ISA[p]+1])); uniq32[p] = the same unsaturated; *saturated (device) is set to 1 if
+// any value reached 65535
+int build_uniq(uint64_t n, const uint32_t* isa, const uint32_t* lcp, uint16_t* uniq, uint32_t* uniq32, uint32_t* saturated, cudaStream_t s);
 
 // ---- parse pipeline (parse.cu) -----------------------------------------------------------------
 struct ParseBuffers {
@@ -119,6 +120,8 @@ struct ParseBuffers {
     int blind_rounds;             // fix-up rounds launched without reading the counters back (see parse_stage_count)
     int64_t* hint;                // [ceil(NC / kHintGroup)] diagonal hints (null = no hint pass)
     uint16_t* mm;                 // [NC*kMmStride] mismatch lists (null = no diagonal pre-scan)
+    uint32_t* ext;                // [NC] extents across chunks, hint_src [NC]: scratch of the hint fill (both only used when the index has uniq32)
+    uint32_t* hint_src;
     uint32_t* link_b;             // [NC] second buffers of the list ranking
     uint32_t* run_b;              // [NC]
     uint32_t* jump_a;             // [NC*(kAltSlots+1)]

@@ -816,18 +816,25 @@ __global__ void k_pack2_finish(PackJob job) {
 // alphabet-agnostic.  Bytes outside the reference alphabet become exceptions exactly as in the 2-bit path.
 __global__ void __launch_bounds__(256) k_packg_count(PackJob job) {
     __shared__ uint32_t sm[33];
+    __shared__ uint8_t s_b2c[256];                           // the byte -> code table, once per CTA
+    s_b2c[threadIdx.x] = job.b2c[threadIdx.x];
+    __syncthreads();
     uint32_t h = blockIdx.y, t = blockIdx.x;
     uint64_t cols = job.cols[h];
     uint64_t off = (uint64_t)t * kPackGTileBytes + (uint64_t)threadIdx.x * 16;
     const uint8_t* rowp = job.rows + job.row_off[h];
     uint32_t cnt = 0, exc = 0;
-    for (int b = 0; b < 16; ++b) {
-        uint64_t o = off + b;
-        if (o >= cols) break;
-        uint32_t byte = rowp[o];
-        if (job.strip && byte == '-') continue;
-        ++cnt;
-        if (job.b2c[byte] == 0xFF) ++exc;
+    if (off < cols) {
+        const uint4 q = load16(rowp + off);                  // one 128-bit load per thread (rows are readable up to the next multiple of 16)
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+        const int nv = cols - off >= 16 ? 16 : (int)(cols - off);
+#pragma unroll
+        for (int b = 0; b < 16; ++b) {
+            const uint32_t byte = (w[b >> 2] >> (8 * (b & 3))) & 255u;
+            if (b >= nv || (job.strip && byte == '-')) continue;
+            ++cnt;
+            if (s_b2c[byte] == 0xFF) ++exc;
+        }
     }
     uint32_t total;
     block_exclusive_scan<uint32_t, OpSum>(cnt | (exc << 16), OpSum(), 0u, &total, sm);
@@ -851,23 +858,30 @@ __global__ void k_packg_rows(PackJob job, const uint64_t* total_cnt, const uint6
 __global__ void __launch_bounds__(256) k_packg_write(PackJob job) {
     __shared__ uint8_t scode[kPackGTileBytes];
     __shared__ uint32_t sm[33];
+    __shared__ uint8_t s_b2c[256];
     uint32_t h = blockIdx.y, t = blockIdx.x;
     uint64_t cols = job.cols[h];
     uint64_t tile_start = (uint64_t)t * kPackGTileBytes;
     if (tile_start >= cols) return;
+    s_b2c[threadIdx.x] = job.b2c[threadIdx.x];
+    __syncthreads();
     const uint8_t* rowp = job.rows + job.row_off[h];
     uint64_t off = tile_start + (uint64_t)threadIdx.x * 16;
     uint8_t code[16], raw[16];
     uint32_t cnt = 0, exc = 0;
-    for (int b = 0; b < 16; ++b) {
-        uint64_t o = off + b;
-        if (o >= cols) break;
-        uint32_t byte = rowp[o];
-        if (job.strip && byte == '-') continue;
-        uint32_t c = job.b2c[byte];
-        if (c == 0xFF) { ++exc; }
-        code[cnt] = (uint8_t)c; raw[cnt] = (uint8_t)byte;
-        ++cnt;
+    {
+        const uint4 q = load16(rowp + off);
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+        const int nv = cols - off >= 16 ? 16 : (int)(cols - off);
+#pragma unroll
+        for (int b = 0; b < 16; ++b) {
+            const uint32_t byte = (w[b >> 2] >> (8 * (b & 3))) & 255u;
+            if (b >= nv || (job.strip && byte == '-')) continue;
+            const uint32_t c = s_b2c[byte];
+            if (c == 0xFF) { ++exc; }
+            code[cnt] = (uint8_t)c; raw[cnt] = (uint8_t)byte;
+            ++cnt;
+        }
     }
     uint32_t total;
     uint32_t ex = block_exclusive_scan<uint32_t, OpSum>(cnt | (exc << 16), OpSum(), 0u, &total, sm);

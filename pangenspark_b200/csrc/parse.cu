@@ -50,6 +50,58 @@ __global__ void __launch_bounds__(128) k_hint(ParseView pv, int64_t* hint, uint3
     if (q < nq) DRLZ_WITH_BL(pv, v, hint_group(v, hint, q));
 }
 
+// H, second part: a chunk whose probes found nothing (it starts inside a run of N, or in a long repeat, where no
+// 64-symbol pattern is unique) takes the diagonal of the nearest chunk in front of it in the same haplotype -- inside a
+// run of millions of N the alignment does not change.  "Nearest valid chunk in front" = an inclusive running maximum over
+// (g + 1 if the chunk has a hint of its own, else 0).
+struct LoadHintIdx {
+    const int64_t* hint;
+    __device__ __forceinline__ uint32_t operator()(uint64_t g) const { return hint[g] != kNoDiag ? (uint32_t)g + 1u : 0u; }
+};
+struct StoreHintSrc { uint32_t* src; __device__ __forceinline__ void operator()(uint64_t g, uint32_t v) const { src[g] = v; } };
+__global__ void k_hint_fill(ParseView pv, int64_t* hint, const uint32_t* __restrict__ src) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= pv.n_chunks || hint[g] != kNoDiag) return;
+    const uint32_t f = src[g];                              // 1 + the nearest chunk with a hint (in front of g, or behind it), 0 = none
+    // (reads hint[f - 1], which this kernel never writes: chunks that have a hint return above)
+    if (f && f <= pv.n_chunks && pv.chunk_hap[f - 1] == pv.chunk_hap[g]) hint[g] = hint[f - 1];
+}
+// the same from the other side, for the chunks at the head of a haplotype (a chromosome that begins with a run of N has no
+// chunk in front of it to ask): a right-to-left running minimum over (g + 1 if the chunk has a hint, else "none")
+struct LoadHintIdxRev {
+    const int64_t* hint; uint64_t nc;
+    __device__ __forceinline__ uint32_t operator()(uint64_t e) const { const uint64_t g = nc - 1 - e; return hint[g] != kNoDiag ? (uint32_t)g + 1u : 0xFFFFFFFFu; }
+};
+struct StoreHintSrcRev { uint32_t* src; uint64_t nc; __device__ __forceinline__ void operator()(uint64_t e, uint32_t v) const { src[nc - 1 - e] = v; } };
+
+// ext[]: how far the match along a chunk's diagonal goes, counted through the chunks behind it (rlz_core.cuh: ext_term):
+// a right-to-left segmented sum like the one that ranks the diagonal runs of stage A, with one more sticky bit: a count
+// that ends for no reason (the next chunk was hinted another diagonal) is only a lower bound.
+// element: bits 0..39 symbols, bit 62 inexact, bit 63 "the count ends with this chunk"
+struct OpExtSum {
+    __device__ __forceinline__ uint64_t operator()(uint64_t a, uint64_t b) const {
+        const uint64_t F = 1ull << 63, X = 1ull << 62, M = (1ull << 40) - 1;
+        if (b & F) return b;
+        return (a & F) | ((a | b) & X) | (((a & M) + (b & M)) & M);
+    }
+};
+struct LoadExtRev {
+    ParseView pv; uint64_t nc;
+    __device__ __forceinline__ uint64_t operator()(uint64_t e) const {
+        bool on, exact;
+        const uint32_t v = ext_term(pv, (uint32_t)(nc - 1 - e), &on, &exact);
+        return (uint64_t)v | (on ? 0ull : (1ull << 63)) | ((on || exact) ? 0ull : (1ull << 62));
+    }
+};
+struct StoreExtRev {
+    uint32_t* out; uint64_t nc;
+    __device__ __forceinline__ void operator()(uint64_t e, uint64_t v) const {
+        const uint64_t val = v & ((1ull << 40) - 1);
+        const bool inexact = (v >> 62) & 1ull;
+        out[nc - 1 - e] = val >= 0x7FFFFFFFull ? (0x7FFFFFFFu | kExtInexact) : ((uint32_t)val | (inexact ? kExtInexact : 0u));
+    }
+};
+
 // D: one warp per chunk; lane l compares packed word l of each 1024-base slab (the haplotype side is word aligned
 // because chunks start at multiples of 32 bases), so both streams are read with coalesced 256-byte requests at
 // 32 active lanes -- this is the whole streaming compare of the parse, done once.  Mismatching words are decoded
@@ -388,11 +440,25 @@ int parse_stage_count(ParseBuffers& pb, cudaStream_t s, int* rounds_out, cudaEve
     cudaMemsetAsync(pv.alt_entry, 0xFF, sizeof(uint32_t) * (size_t)NC * kAltSlots, s);
     cudaMemsetAsync(pv.counters, 0, sizeof(uint32_t) * (2 + kMaxRounds), s);
     if (ev) cudaEventRecord(ev[0], s);
+    pv.ext = nullptr;
     if (pv.ix.uniq && pb.hint) {            // H: one 64-base lookup per group of chunks seeds the predicted diagonals
         uint32_t nq = (NC + kHintGroup - 1) / kHintGroup;
         g_launches += 1;
         k_hint<<<(nq + 127) / 128, 128, 0, s>>>(pv, pb.hint, nq);
         pv.hint = pb.hint;
+        // references with repeats beyond the 16-bit range of the uniqueness array (runs of N): chunks without a hint of
+        // their own take the one in front of them
+        const bool long_repeats = pv.ix.uniq32 != nullptr && pb.ext && pb.hint_src && kHintGroup == 1;
+        if (long_repeats) {
+            g_launches += 1;
+            device_scan<uint32_t, LoadHintIdx, StoreHintSrc, OpMax, true>(LoadHintIdx{pb.hint}, StoreHintSrc{pb.hint_src}, NC,
+                                                                          reinterpret_cast<uint32_t*>(pb.scan_tmp), OpMax(), 0u, s);
+            k_hint_fill<<<(NC + 255) / 256, 256, 0, s>>>(pv, pb.hint, pb.hint_src);
+            device_scan<uint32_t, LoadHintIdxRev, StoreHintSrcRev, OpMin, true>(LoadHintIdxRev{pb.hint, NC}, StoreHintSrcRev{pb.hint_src, NC}, NC,
+                                                                                reinterpret_cast<uint32_t*>(pb.scan_tmp), OpMin(), 0xFFFFFFFFu, s);
+            k_hint_fill<<<(NC + 255) / 256, 256, 0, s>>>(pv, pb.hint, pb.hint_src);
+            g_launches += 1;
+        }
         if (pb.mm && pv.chunk_shift >= 5 && pv.chunk_shift <= 15) {   // D: mismatch lists along the hinted diagonals
             pv.mm = pb.mm;
             g_launches += 1;
@@ -401,6 +467,11 @@ int parse_stage_count(ParseBuffers& pb, cudaStream_t s, int* rounds_out, cudaEve
             else if (pb.occ_diag >= 16) k_diag_w<1, 16><<<nb, 128, 0, s>>>(pv);
             else if (pb.occ_diag >= 12) k_diag_w<1, 12><<<nb, 128, 0, s>>>(pv);
             else k_diag_w<1, 10><<<nb, 128, 0, s>>>(pv);
+            if (long_repeats) {                                 // ... and the matches along the diagonals are measured across chunks
+                device_scan<uint64_t, LoadExtRev, StoreExtRev, OpExtSum, true>(LoadExtRev{pv, NC}, StoreExtRev{pb.ext, NC}, NC, pb.scan_tmp,
+                                                                               OpExtSum(), 0ull, s);
+                pv.ext = pb.ext;
+            }
         } else pv.mm = nullptr;
     } else { pv.hint = nullptr; pv.mm = nullptr; }
     if (ev) cudaEventRecord(ev[5], s);

@@ -36,6 +36,10 @@ static inline uint2 make_uint2(uint32_t x, uint32_t y) { uint2 r; r.x = x; r.y =
 
 namespace drlz {
 
+#if !defined(__CUDACC__)
+static uint64_t g_emu_long_hits;          // host harness (tests/emu) only: phrases taken from the extents across chunks
+#endif
+
 static const uint32_t kEmpty = 0xFFFFFFFFu;
 static const int kAltSlots = 3;           // alternative entry records per chunk (see parse pipeline)
 static const int kMaxRounds = 30;
@@ -43,6 +47,7 @@ static const int kHintGroup = 1;          // chunks per diagonal hint (a 64-base
 static const int kMmMax = 14;             // mismatch offsets kept per chunk by the diagonal pre-scan
 static const int kMmStride = 16;          // uint16 per chunk: [count, valid_until, offsets...]
 static const int kAltStore = 4;           // own phrases of an alternative record kept for emission
+static const uint32_t kExtInexact = 0x80000000u;   // ParseView::ext: the count is only a lower bound (see ext_term)
 
 DRLZ_HD int clz64(uint64_t v) {
 #if defined(__CUDA_ARCH__)
@@ -77,6 +82,7 @@ struct IndexView {
     uint32_t bl;            // log2(bits per symbol): 1, 2 or 3
     uint32_t sigma;         // alphabet size (4 when bl == 1)
     const uint8_t* c2b;     // code -> byte (literal phrases)
+    const uint32_t* uniq32; // [n] the same without the 16-bit saturation; only present (non-null) if some repeat reaches 65535 symbols
 };
 
 // key of the first kk symbols of the word xw padded with code 0 to k symbols, and the number of keys sharing that
@@ -431,6 +437,8 @@ struct ParseView {
     uint2* alt_ph;                  // [NC*kAltSlots*kAltStore] own phrases of the alternative records
     uint32_t* counters;             // [0] overflow flag, [1 + r] records created for round r
     uint32_t parsed_rounds;         // fix-up rounds run so far: records registered for a later round are not parsed yet
+    const uint32_t* ext;            // [NC] symbols from the START of chunk g to the first mismatch along its hinted diagonal, counted through
+                                    // the following chunks as long as they lie on the same diagonal (0 = unknown); may be null
 };
 
 DRLZ_HD uint32_t atomic_cas_u32(uint32_t* p, uint32_t cmp, uint32_t val) {
@@ -491,7 +499,7 @@ DRLZ_HD bool list_extent(const uint16_t* mm, uint64_t s, uint64_t i, uint32_t pl
 // mml / hint_g: the chunk's mismatch record and hinted diagonal (mml == nullptr: none).  k_spec keeps its copy of the
 // record in shared memory -- it is read once per predicted phrase, and in L1 it does not survive between two of them.
 DRLZ_HD Match phrase_capped_l(const ParseView& pv, const HapView& hv, uint64_t i, uint32_t* cursor, bool* open, int64_t* diag,
-                              const uint16_t* mml, int64_t hint_g, uint64_t s) {
+                              const uint16_t* mml, int64_t hint_g, uint64_t s, uint32_t g = kEmpty) {
     *open = false;
     uint64_t stop = stop_after(hv, i, cursor);
     if (stop == i) { Match mt; mt.len = 0; mt.pos = hv.exc_byte[*cursor]; return mt; }
@@ -515,6 +523,26 @@ DRLZ_HD Match phrase_capped_l(const ParseView& pv, const HapView& hv, uint64_t i
                     *open = (c == plen && plen < maxlen);
                     return mt;
                 }
+                // Long repeats (N runs of millions of bases, segmental duplications): the match reaches the cap and the
+                // capped pattern is NOT unique (the longest repeat at p is at least as long), so lookup() would search
+                // again uncapped -- streaming the whole repeat in every step of its binary search, from every chunk start
+                // inside it.  The pre-scan knows how far the match along this diagonal really goes (this chunk is clean up
+                // to its end, ext[] counts on through the chunks behind it); if that is longer than the longest repeat at p
+                // it is the unique longest match of the uncapped pattern: what the second pass of lookup() returns.
+                if (c == plen && plen < maxlen && pv.ext && g != kEmpty && g + 1 < pv.n_chunks) {
+                    const uint32_t ur = u != 0xFFFFu ? u : (pv.ix.uniq32 ? pv.ix.uniq32[p] : 0xFFFFFFFFu);
+                    if (ur >= plen && ur != 0xFFFFFFFFu && pv.hint && pv.hint[(g + 1) / kHintGroup] == *diag) {
+                        const uint32_t ex = pv.ext[g + 1];
+                        uint64_t cf = to_end + (uint64_t)(ex & ~kExtInexact);
+                        if (cf > maxlen) cf = maxlen;
+                        if (!(ex & kExtInexact) && cf > ur && cf >= plen) {
+#if !defined(__CUDACC__)
+                            ++g_emu_long_hits;
+#endif
+                            mt.len = (uint32_t)cf; mt.pos = p; return mt;
+                        }
+                    }
+                }
             }
         }
     }
@@ -531,7 +559,7 @@ DRLZ_HD Match phrase_capped(const ParseView& pv, const HapView& hv, uint64_t i, 
                             uint32_t g, uint64_t s) {
     const bool listed = pv.mm && g != kEmpty;
     return phrase_capped_l(pv, hv, i, cursor, open, diag, listed ? pv.mm + (size_t)g * kMmStride : nullptr,
-                           listed ? pv.hint[g / kHintGroup] : kNoDiag, s);
+                           listed ? pv.hint[g / kHintGroup] : kNoDiag, s, g);
 }
 
 // Where an open match (start i, verified len, position pos) continues: the last chunk start j <= i+len.
@@ -686,6 +714,28 @@ DRLZ_HD void diag_scan_chunk(const ParseView& pv, uint32_t g) {
     mm[0] = (uint16_t)cnt; mm[1] = (uint16_t)V;
 }
 
+// one term of ext[]: symbols of chunk g up to its first mismatch along its hinted diagonal (its whole length if there is
+// none), whether the count goes on into chunk g + 1 (same haplotype, same diagonal, nothing in between), and whether a
+// count that ends here ends for a REASON the match cannot outlive -- a mismatch, the end of the haplotype.  If it ends
+// because the next chunk was hinted another diagonal (or none), the match may well go on: the sum is then only a lower
+// bound and carries kExtInexact, and nobody may take it for the length of a phrase.
+DRLZ_HD uint32_t ext_term(const ParseView& pv, uint32_t g, bool* goes_on, bool* exact_end) {
+    *goes_on = false; *exact_end = false;
+    const int64_t dg = pv.hint[g / kHintGroup];
+    const uint32_t h = pv.chunk_hap[g];
+    const HapView& hv = pv.haps[h];
+    const uint64_t s = (uint64_t)(g - pv.hap_chunk_base[h]) << pv.chunk_shift;
+    if (dg == kNoDiag || s >= hv.m) return 0u;
+    uint64_t e = s + (1ull << pv.chunk_shift); if (e > hv.m) e = hv.m;
+    const uint16_t* mm = pv.mm + (size_t)g * kMmStride;
+    const uint32_t len = (uint32_t)(e - s), cnt = mm[0], V = mm[1];
+    if (cnt > 0) { *exact_end = true; return mm[2]; }
+    if (V != len) return V;                                  // (not classified at all: V == 0)
+    if (e == hv.m) { *exact_end = true; return len; }        // the haplotype ends here
+    *goes_on = g + 1 < pv.n_chunks && pv.chunk_hap[g + 1] == h && pv.hint[(g + 1) / kHintGroup] == dg;
+    return len;
+}
+
 // P1 for global chunk g: speculative greedy parse from the chunk's first base with chunk-capped lookups.  Only
 // the last phrase of a chunk can be open (it reaches the chunk end); its total length -- hence the exit of the
 // chunk -- is filled in by resolve_chunk() once the diagonal runs are ranked.  The first phrase doubles as
@@ -709,7 +759,7 @@ DRLZ_HD void spec_parse_chunk(const ParseView& pv, uint32_t g, const uint16_t* m
     int64_t diag = hint_g;
     const uint16_t* mml = !pv.mm ? nullptr : (mm_copy ? mm_copy : pv.mm + (size_t)g * kMmStride);
     while (i < e) {
-        Match mt = phrase_capped_l(pv, hv, i, &cur, &open, &diag, mml, hint_g, s);
+        Match mt = phrase_capped_l(pv, hv, i, &cur, &open, &diag, mml, hint_g, s, g);
         if (i == s) { pv.first_pos[g] = mt.pos; pv.first_len[g] = mt.len; pv.run_len[g] = open ? kEmpty : mt.len; }
         if (cnt < pv.spec_store) pv.spec_ph[(size_t)g * pv.spec_store + cnt] = make_uint2(mt.pos, mt.len);
         ++cnt;

@@ -278,7 +278,8 @@ namespace drlz {
 // ---- uniqueness array: longest repeat starting at each text position --------------------------------------------
 // uniq[p] = min(65535, max(LCP[ISA[p]], LCP[ISA[p]+1])): a match of more than uniq[p] bases that starts at reference
 // position p cannot be matched as long anywhere else (used by the predicted-diagonal path of the parse).
-__global__ void k_uniq(uint64_t n, const uint32_t* __restrict__ isa, const uint32_t* __restrict__ lcp, uint16_t* __restrict__ uniq) {
+__global__ void k_uniq(uint64_t n, const uint32_t* __restrict__ isa, const uint32_t* __restrict__ lcp, uint16_t* __restrict__ uniq,
+                       uint32_t* __restrict__ uniq32, uint32_t* saturated) {
     uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
     uint32_t r = isa[p];
@@ -286,12 +287,15 @@ __global__ void k_uniq(uint64_t n, const uint32_t* __restrict__ isa, const uint3
     uint32_t b = (uint64_t)r + 1 < n ? lcp[r + 1] : 0u;
     uint32_t u = a > b ? a : b;
     uniq[p] = (uint16_t)(u > 65535u ? 65535u : u);
+    uniq32[p] = u;
+    if (u >= 65535u) *saturated = 1u;                       // (every writer stores the same value)
 }
 
-int build_uniq(uint64_t n, const uint32_t* isa, const uint32_t* lcp, uint16_t* uniq, cudaStream_t s) {
+int build_uniq(uint64_t n, const uint32_t* isa, const uint32_t* lcp, uint16_t* uniq, uint32_t* uniq32, uint32_t* saturated, cudaStream_t s) {
+    cudaMemsetAsync(saturated, 0, 4, s);
     if (n == 0) return 0;
     g_launches += 1;
-    k_uniq<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(n, isa, lcp, uniq);
+    k_uniq<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(n, isa, lcp, uniq, uniq32, saturated);
     return (int)cudaGetLastError();
 }
 

@@ -155,7 +155,7 @@ class Drlz:
         a = (C.c_uint64 * 4)()
         self._ck(self._lib.drlz_index_info(self._h, a))
         kinfo = int(a[1])           # k | log2(bits per symbol) << 8 | alphabet size << 16
-        return {"n": int(a[0]), "k": kinfo & 0xFF, "bits": 1 << ((kinfo >> 8) & 0xFF), "sigma": kinfo >> 16, "kinfo": kinfo,
+        return {"n": int(a[0]), "k": kinfo & 0xFF, "bits": 1 << ((kinfo >> 8) & 0xFF), "sigma": (kinfo >> 16) & 0x1FF, "long_repeats": bool((kinfo >> 28) & 1), "kinfo": kinfo,
                 "sa_rounds": int(a[2]), "bytes": int(a[3])}
 
     def index_timings(self):

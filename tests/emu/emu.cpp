@@ -2,6 +2,7 @@
 // on the CPU (sequentially, one "thread" after another) so the chunk-parallel parse logic can be checked
 // against the oracle without a GPU.  It is never linked into libdrlz.so and nothing in the product calls it.
 #include <cstdint>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -61,7 +62,9 @@ static void build_tab(const IndexView& ix, const std::vector<uint32_t>& sa, std:
 extern "C" {
 
 void emu_free(void* p) { free(p); }
+uint64_t emu_long_hits() { return drlz::g_emu_long_hits; }
 
+// use_uniq: 0 = no uniqueness array, 1 = with it, 2 = also the long-repeat machinery (hint fill, extents across chunks)
 // returns 0 ok, 1 reference not ACGT, 2 overflow/unresolved
 int emu_parse(const uint8_t* ref, uint64_t n, const int64_t* sa64, int k, uint32_t chunk, uint32_t min_cap, uint32_t foreign_cap, int use_uniq, int H,
               const uint8_t* const* rows, const uint64_t* cols, int64_t** pairs_out, uint64_t* npairs,
@@ -76,6 +79,7 @@ int emu_parse(const uint8_t* ref, uint64_t n, const int64_t* sa64, int k, uint32
     std::vector<uint32_t> sa(n); for (uint64_t i = 0; i < n; ++i) sa[i] = (uint32_t)sa64[i];
     // uniqueness array: longest repeat starting at p (Kasai LCP on the host; test harness only)
     std::vector<uint16_t> uniq(n + 1, 0);
+    std::vector<uint32_t> uniq32(n + 1, 0);
     {
         std::vector<uint32_t> isa(n), lcp(n + 1, 0);
         for (uint64_t j = 0; j < n; ++j) isa[sa[j]] = (uint32_t)j;
@@ -92,9 +96,11 @@ int emu_parse(const uint8_t* ref, uint64_t n, const int64_t* sa64, int k, uint32
             uint32_t r = isa[p];
             uint32_t u = lcp[r] > lcp[r + 1] ? lcp[r] : lcp[r + 1];
             uniq[p] = (uint16_t)(u > 65535u ? 65535u : u);
+            uniq32[p] = u;
         }
     }
-    IndexView ix{text.data(), sa.data(), nullptr, n, k, use_uniq ? uniq.data() : nullptr, al.bl, al.sigma, al.c2b};
+    IndexView ix{text.data(), sa.data(), nullptr, n, k, use_uniq ? uniq.data() : nullptr, al.bl, al.sigma, al.c2b,
+                 use_uniq ? uniq32.data() : nullptr};
     std::vector<uint32_t> tab; build_tab(ix, sa, tab);
     ix.tab = tab.data();
 
@@ -124,6 +130,7 @@ int emu_parse(const uint8_t* ref, uint64_t n, const int64_t* sa64, int k, uint32
     std::vector<uint2> spec_ph((size_t)NC * spec_store), alt_ph((size_t)NC * kAltSlots * kAltStore);
     std::vector<int64_t> hint(NC / kHintGroup + 1, kNoDiag);
     std::vector<uint16_t> mm((size_t)NC * kMmStride + 16, 0);
+    std::vector<uint32_t> ext;
     ParseView pv{ix, haps.data(), chunk_hap.data(), base.data(), chunk, chunk_shift, NC, min_cap, foreign_cap,
                  first_pos.data(), first_len.data(), run_a.data(), link_a.data(), open_i.data(), open_pos.data(), open_len.data(), spec_cnt.data(), spec_exit.data(),
                  alt_entry.data(), alt_cnt.data(), alt_exit.data(), alt_round.data(), alt_own.data(), alt_merge.data(),
@@ -132,8 +139,35 @@ int emu_parse(const uint8_t* ref, uint64_t n, const int64_t* sa64, int k, uint32
     for (int h = 0; h < H; ++h) if (base[h + 1] - base[h] > maxc0) maxc0 = base[h + 1] - base[h];
     if (use_uniq && chunk_shift >= 5 && chunk_shift <= 15) {
         for (uint32_t q = 0; q * kHintGroup < NC; ++q) hint_group(pv, hint.data(), q);
+        if (use_uniq > 1) {                                  // k_hint_fill: chunks without a hint take the one in front of them (same haplotype)
+            std::vector<int64_t> own(hint);
+            for (uint32_t g = 0; g < NC; ++g) {
+                if (own[g] != kNoDiag) continue;
+                uint32_t f = g;
+                while (f > 0 && own[f] == kNoDiag) --f;
+                if (own[f] != kNoDiag && chunk_hap[f] == chunk_hap[g]) hint[g] = own[f];
+            }
+            own = hint;                                      // second pass, from the other side (haplotypes that begin inside a run)
+            for (uint32_t g = 0; g < NC; ++g) {
+                if (own[g] != kNoDiag) continue;
+                uint32_t f = g;
+                while (f + 1 < NC && own[f] == kNoDiag) ++f;
+                if (own[f] != kNoDiag && chunk_hap[f] == chunk_hap[g]) hint[g] = own[f];
+            }
+        }
         pv.hint = hint.data(); pv.mm = mm.data();
         for (uint32_t g = 0; g < NC; ++g) diag_scan_chunk(pv, g);
+        if (use_uniq > 1) {                                  // ext[]: right-to-left segmented sum of ext_term
+            ext.assign(NC + 1, 0);
+            for (uint32_t g = NC; g-- > 0;) {
+                bool on, exact;
+                const uint32_t v = ext_term(pv, g, &on, &exact);
+                const uint64_t sum = (uint64_t)v + (on ? (uint64_t)(ext[g + 1] & ~kExtInexact) : 0ull);
+                const bool inexact = on ? (ext[g + 1] & kExtInexact) != 0 : !exact;
+                ext[g] = sum >= 0x7FFFFFFFull ? (0x7FFFFFFFu | kExtInexact) : ((uint32_t)sum | (inexact ? kExtInexact : 0u));
+            }
+            pv.ext = ext.data();
+        }
     }
     for (uint32_t g = 0; g < NC; ++g) spec_parse_chunk(pv, g);
     for (uint32_t g = 0; g < NC; ++g) link_chunk(pv, g);
@@ -147,6 +181,10 @@ int emu_parse(const uint8_t* ref, uint64_t n, const int64_t* sa64, int k, uint32
         pv.run_len = ri; pv.link = li;
     }
     for (uint32_t g = 0; g < NC; ++g) resolve_chunk(pv, g);
+    if (getenv("DRLZ_EMU_DEBUG"))
+        for (uint32_t g = 0; g < NC; ++g)
+            fprintf(stderr, "chunk %u s=%u hint=%lld mm=[%u,%u,%u] ext=%u first=(%u,%u) run=%u spec_cnt=%u exit=%u open_i=%u\n", g, g * chunk, (long long)hint[g / kHintGroup],
+                    mm[(size_t)g * kMmStride], mm[(size_t)g * kMmStride + 1], mm[(size_t)g * kMmStride + 2], ext.empty() ? 0u : (ext[g] & 0x7FFFFFFFu), first_pos[g], first_len[g], pv.run_len[g], spec_cnt[g], spec_exit[g], open_i[g]);
     if (counters[0]) return 2;
     {   // A provisional marking pass before any fix-up round has run (what the library does when it launches fewer
         // rounds blind than the input needs): records registered for round 1 are not parsed yet, their counters are

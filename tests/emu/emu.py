@@ -20,6 +20,7 @@ def lib():
         L = C.CDLL(so)
         L.emu_parse.restype = C.c_int
         L.emu_free.argtypes = [C.c_void_p]
+        L.emu_long_hits.restype = C.c_uint64
         _LIB = L
     return _LIB
 
@@ -47,3 +48,8 @@ def parse(ref: bytes, sa: np.ndarray, rows, k: int, chunk: int, min_cap: int = 6
         L.emu_free(outp[h])
         res.append(arr)
     return 0, res, m.astype(np.int64), rounds.value
+
+
+def long_hits() -> int:
+    """phrases the harness took from the extents across chunks so far (long-repeat path of phrase_capped_l)"""
+    return int(lib().emu_long_hits())

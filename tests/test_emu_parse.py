@@ -190,3 +190,30 @@ def test_short_lookups_medium_reference(seed):
         assert rc == 0
         for h, r in enumerate(rows):
             assert res[h].tolist() == orc.encode_literal(d, sa, r)[0].tolist(), (seed, k, chunk, h)
+
+
+def test_long_repeats_hint_fill_and_extents():
+    """Runs far longer than a chunk (N runs, poly-A): chunk starts inside the run have no unique 64-symbol pattern; with
+    use_uniq = 2 they inherit the diagonal of the chunk in front, and the capped-but-not-unique matches take their real
+    length from the extents across chunks (ext[]) instead of the uncapped second pass of the lookup.  Same records as the
+    oracle either way, for aligned runs, a longer and a shorter run in the haplotype, and a SNP right behind the run."""
+    rng = np.random.default_rng(77)
+    left = bytes(rng.choice(list(b"ACGT"), size=3000).astype(np.uint8))
+    right = bytes(rng.choice(list(b"ACGT"), size=4000).astype(np.uint8))
+    for sym in (b"N", b"A"):
+        d = left + sym * 5000 + right + sym * 700 + left[:500]
+        sa = orc.sa_build(d)
+        x0 = bytearray(d)
+        for p in (100, 2500, 8100, 8101, 9000, 12650):
+            x0[p] = b"ACGT"[(b"ACGT".index(bytes(x0[p:p + 1])) + 1) % 4] if x0[p:p + 1] in (b"A", b"C", b"G", b"T") else x0[p]
+        x1 = bytearray(d); x1[8000] = ord("C") if d[8000:8001] != b"C" else ord("G")        # SNP on the first base behind the run
+        rows = [bytes(x0), bytes(x1), d, left + sym * 6000 + right, left + sym * 3500 + right, sym * 2000 + right[:100]]
+        for k, chunk, min_cap in ((5, 256, 64), (6, 1024, 64), (4, 64, 32), (6, 4096, 64)):
+            for mode in (1, 2):
+                before = emu.long_hits()
+                rc, res, m, _ = emu.parse(d, sa, rows, k, chunk, min_cap, 1 << 20, mode)
+                assert rc == 0, (sym, k, chunk, mode, rc)
+                hits = emu.long_hits() - before                  # phrases taken from the extents across chunks
+                assert hits == 0 if mode == 1 else (hits > 0 or chunk >= 4096), (sym, k, chunk, mode, hits)
+                for h, r in enumerate(rows):
+                    assert res[h].tolist() == orc.encode_literal(d, sa, r)[0].tolist(), (sym, k, chunk, mode, h)

@@ -53,7 +53,7 @@ def main():
                     keep[h] = rows[r].copy()
         gen_s = time.time() - t0
         env = dict(os.environ, DRLZ_GPUS=str(gpus), DRLZ_GAPLESS="0", DRLZ_STATS=os.path.join(tmp, "stats.json"))
-        env.setdefault("DRLZ_BATCH_BYTES", str(1 << 30))
+        env.setdefault("DRLZ_BATCH_BYTES", str(256 << 20))       # one chr1-sized row per batch: small pinned slots, short setup
         exe = os.path.join(ROOT, "pangenspark_b200", "bin", "drlz")
         t0 = time.time()
         p = subprocess.run([exe, os.path.join(tmp, "radix"), os.path.join(tmp, "ref.txt"), os.path.join(tmp, "msa", "*.01"), "file:///",
