@@ -869,7 +869,7 @@ __global__ void __launch_bounds__(256) k_packg_write(PackJob job) {
     uint64_t off = tile_start + (uint64_t)threadIdx.x * 16;
     uint8_t code[16], raw[16];
     uint32_t cnt = 0, exc = 0;
-    {
+    if (off < cols) {
         const uint4 q = load16(rowp + off);
         const uint32_t w[4] = {q.x, q.y, q.z, q.w};
         const int nv = cols - off >= 16 ? 16 : (int)(cols - off);
