@@ -48,7 +48,8 @@ int drlz_set_stream(drlz_ctx* ctx, void* cuda_stream);
  *          tuning / A-B switches: "occ", "occ_fix", "occ_diag" (min CTAs per SM of k_spec / k_fix / k_diag_w), "predict" (uniqueness-array
  *          prediction), "hint" + "diag" (per-chunk diagonal hint and mismatch pre-scan), "tickets" (1 = atomic tile tickets in k_pack), "occ_pack" (6 | 8 CTAs per SM k_pack is
  *          compiled for), "prefetch" (L2 prefetch distance of k_pack in tiles, 0 = off),
- *          "spec_store", "l2persist".  None of them changes results. */
+ *          "spec_store", "l2persist", "pack_variant" (2 = k_pack3, 1 = k_pack2), "prefetch3"; "keep_timings" (1: drlz_parse_timings sums over all
+ *          calls since the option was set instead of the last call only).  None of them changes results. */
 int drlz_set_option(drlz_ctx* ctx, const char* key, int64_t value);
 
 /* pinned host memory for the streaming path (cudaHostAlloc); plain malloc memory also works, slower */

@@ -56,7 +56,7 @@ struct drlz_ctx {
     cudaEvent_t ev_stage[12] = {};
     std::string err;
     // options
-    uint64_t x_zeroed = 0; bool keep_x = false; int opt_postzero = 1; int opt_blind_rounds = 2; int opt_pack_variant = 2; uint32_t opt_prefetch3 = 2; int opt_occ_pack = 8; uint32_t opt_prefetch = 1200; int opt_k = 0; uint32_t opt_chunk = 8192; uint32_t opt_min_cap = 64; uint32_t opt_foreign_cap = 1u << 20; uint64_t opt_group_bytes = 256ull << 20; int opt_lcp = 0;
+    uint64_t x_zeroed = 0; bool keep_x = false; int opt_postzero = 1; int opt_keep_timings = 0; int opt_blind_rounds = 2; int opt_pack_variant = 2; uint32_t opt_prefetch3 = 2; int opt_occ_pack = 8; uint32_t opt_prefetch = 1200; int opt_k = 0; uint32_t opt_chunk = 8192; uint32_t opt_min_cap = 64; uint32_t opt_foreign_cap = 1u << 20; uint64_t opt_group_bytes = 256ull << 20; int opt_lcp = 0;
     // index
     bool have_index = false; uint64_t n = 0; int k = 0; int sa_rounds = 0;
     DevBuf blob, sa, isa, lcp;             // blob = [k-mer table | packed text] (one L2 access-policy window)
@@ -216,6 +216,7 @@ int drlz_set_option(drlz_ctx* c, const char* key, int64_t v) {
     else if (!strcmp(key, "tickets")) c->opt_tickets = v != 0;
     else if (!strcmp(key, "predict")) c->opt_predict = v != 0;
     else if (!strcmp(key, "occ_pack")) c->opt_occ_pack = (int)v;
+    else if (!strcmp(key, "keep_timings")) { c->opt_keep_timings = v != 0; for (int i = 0; i < 12; ++i) c->parse_ms[i] = 0; }
     else if (!strcmp(key, "prefetch3")) { if (v < 0 || v > 64) return DRLZ_E_ARG; c->opt_prefetch3 = (uint32_t)v; }
     else if (!strcmp(key, "pack_variant")) { if (v < 0 || v > 2) return DRLZ_E_ARG; c->opt_pack_variant = (int)v; }
     else if (!strcmp(key, "blind_rounds")) c->opt_blind_rounds = (int)v;
@@ -462,7 +463,7 @@ static int run_device_group(drlz_ctx* c, const uint8_t* rows_dev, const uint64_t
         for (int i = 0; i < 10; ++i) { cudaEventElapsedTime(&t, c->ev_stage[iv[i][0]], c->ev_stage[iv[i][1]]); pm[i] += t; }
         pm[10] += rounds; pm[11] += (double)(g_launches - launches0);
         // [2]: host time of this call during which the GPU had nothing of it to run (before the first launch, after the last sync)
-        pm[2] = std::chrono::duration<double, std::milli>(t_first - t_entry).count() +
+        pm[2] = (c->opt_keep_timings ? pm[2] : 0.0) + std::chrono::duration<double, std::milli>(t_first - t_entry).count() +
                 std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_done).count();
         return DRLZ_OK;
     }
@@ -697,7 +698,7 @@ int drlz_parse_batch_device(drlz_ctx* c, const uint8_t* rows_dev, const uint64_t
     std::lock_guard<std::recursive_mutex> lk_(c->mu);
     if (!c->have_index) { c->err = "index not built"; return DRLZ_E_STATE; }
     CK(c, cudaSetDevice(c->device));
-    for (int i = 0; i < 12; ++i) c->parse_ms[i] = 0;
+    if (!c->opt_keep_timings) for (int i = 0; i < 12; ++i) c->parse_ms[i] = 0;
     uint64_t total = 0;
     int rc = run_device_group(c, rows_dev, row_off, cols, H, strip_gaps, false, m_out, n_pairs, &total, nullptr);
     if (rc != DRLZ_OK) return rc;
@@ -758,7 +759,7 @@ static int parse_batch_impl(drlz_ctx* c, const uint8_t* const* rows, const uint6
     if (!c->have_index) { c->err = "index not built"; return DRLZ_E_STATE; }
     CK(c, cudaSetDevice(c->device));
     NvtxRange nvtx_batch("drlz.parse_batch: host rows in, records out");
-    for (int i = 0; i < 12; ++i) c->parse_ms[i] = 0;
+    if (!c->opt_keep_timings) for (int i = 0; i < 12; ++i) c->parse_ms[i] = 0;
     // trimmed column counts (Spark's text reader drops the line terminator)
     std::vector<uint64_t> tc(H);
     for (uint32_t h = 0; h < H; ++h) {
