@@ -470,6 +470,25 @@ def cli_e2e(job, wl, d, ms):
         env = dict(os.environ, DRLZ_GPUS="1", DRLZ_DEVICE=str(job.local), DRLZ_STATS=os.path.join(tmp, "stats.json"))
         cmd = [exe, os.path.join(tmp, "radix"), os.path.join(tmp, "ref.txt"), os.path.join(tmp, "msa", "*.21"), "file:///",
                os.path.join(tmp, "out"), os.path.join(tmp, "gapless")]
+        bases = float(ms["m"][:rows].sum())
+
+        def clear():
+            shutil.rmtree(os.path.join(tmp, "out"), ignore_errors=True)
+            shutil.rmtree(os.path.join(tmp, "gapless"), ignore_errors=True)
+
+        # first the same files through the same pipeline with the device left out (DRLZ_IO_PROBE: reads into the pinned
+        # slots, writes outputs of the same sizes): what the file system of the box gives this process.  It also is the
+        # warm-up of the leg: the first pass over fresh tmpfs pages of a VM is slower than every later one.
+        io = None
+        for _ in range(2):
+            clear()
+            penv = dict(env, DRLZ_IO_PROBE="1", DRLZ_STATS=os.path.join(tmp, "probe.json"))
+            q = subprocess.run(cmd, env=penv, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+            if q.returncode == 0:
+                ps = json.load(open(os.path.join(tmp, "probe.json")))
+                io = {"value": bases / ps["encode_s"] / 1e9, "unit": UNIT, "encode_s": ps["encode_s"], "read_wait_s": ps.get("read_wait_s"),
+                      "write_wait_s": ps.get("write_wait_s")}
+        clear()
         t0 = time.time()
         p = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
         wall = time.time() - t0
@@ -489,12 +508,25 @@ def cli_e2e(job, wl, d, ms):
             ok = ok and b == orc.lz_bytes(ms["res"][h])
         fa = open(os.path.join(tmp, "gapless", "part-00000"), "rb").read()
         ok = ok and fa == b">H%05d.21\n" % wl["h0"] + orc.strip_gaps(ms["rows_arr"][0, :M]).tobytes() + b"\n"
-        bases = float(ms["m"][:rows].sum())
         parse_s = stats.get("encode_s", wall)
+        # the phrases alone (DRLZ_GAPLESS=0: callers that keep the gapless sequences elsewhere): no FASTA to write
+        lz_only = None
+        clear()
+        q = subprocess.run(cmd, env=dict(env, DRLZ_GAPLESS="0", DRLZ_STATS=os.path.join(tmp, "lzonly.json")), stdout=subprocess.PIPE,
+                           stderr=subprocess.PIPE, text=True, timeout=600)
+        if q.returncode == 0:
+            ls = json.load(open(os.path.join(tmp, "lzonly.json")))
+            b = open(os.path.join(tmp, "out", "H%05d.21.lz" % (wl["h0"] + rows - 1)), "rb").read()
+            ok = ok and b == orc.lz_bytes(ms["res"][rows - 1])
+            lz_only = {"value": bases / ls["encode_s"] / 1e9, "unit": UNIT, "encode_s": ls["encode_s"], "read_wait_s": ls.get("read_wait_s"),
+                       "gpu_wait_s": ls.get("gpu_wait_s"), "write_wait_s": ls.get("write_wait_s")}
         return {"value": bases / parse_s / 1e9, "unit": UNIT, "wall_s": wall, "encode_s": parse_s, "rows": rows, "files_ok": bool(ok),
                 "lz_sha256_16": sha, "input_gbs": rows * M / parse_s / 1e9, "stats": stats,
+                "io_ceiling": io, "frac_of_io_ceiling": (bases / parse_s / 1e9 / io["value"]) if io else None, "lz_only": lz_only,
                 "what": "rows as files on tmpfs -> bin/drlz (one GPU) -> .lz and gapless FASTA part files on tmpfs; `value` = bases / "
-                        "seconds of the encode phase (read + copy + parse + write, index build excluded as for `e2e`); wall_s = whole process"}
+                        "seconds of the encode phase (read + copy + parse + write, index build excluded as for `e2e`); wall_s = whole process; "
+                        "io_ceiling = the same files through the same pipeline with the device left out (DRLZ_IO_PROBE=1; run first, twice, "
+                        "also the warm-up of the tmpfs pages); lz_only = the same run with DRLZ_GAPLESS=0 (no FASTA written)"}
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
 

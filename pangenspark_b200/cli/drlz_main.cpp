@@ -222,7 +222,7 @@ struct Slot {
     std::vector<const uint8_t*> rows; std::vector<uint8_t*> gptr; std::vector<uint64_t> cols, m, np, ng;
     std::vector<uint64_t> first_nl, last_body;                  // per row: first '\n', last byte that is not a line terminator (+1)
     std::vector<std::mutex> row_mu;
-    uint64_t ticket = 0;
+    uint64_t ticket = 0, total = 0;                             // total = padded bytes of the batch in `in`
     Latch reads, writes;
     bool failed = false;
 };
@@ -258,6 +258,10 @@ int main(int argc, char** argv) {
     const uint64_t batch_bytes = env_u64("DRLZ_BATCH_BYTES", 128ull << 20);
     int nslots = (int)env_u64("DRLZ_SLOTS", 4); if (nslots < 2) nslots = 2;
     const bool want_gapless = env_u64("DRLZ_GAPLESS", 1) != 0;
+    // DRLZ_IO_PROBE=1: the same pipeline with the device left out -- every batch is read into its pinned slot and
+    // "results" of the same sizes (the raw row as the FASTA body, cols/1024 records) are written; measures what the file
+    // system of the box gives this process (the outputs are NOT a parse)
+    const bool io_probe = env_u64("DRLZ_IO_PROBE", 0) != 0;
     const bool want_gaptable = env_u64("DRLZ_GAPTABLE", 0) != 0;
     unsigned hw = std::thread::hardware_concurrency(); if (!hw) hw = 8;
     int io_threads = (int)env_u64("DRLZ_IO_THREADS", std::min<uint64_t>(hw, 32)); if (io_threads < 1) io_threads = 1;
@@ -399,14 +403,16 @@ int main(int argc, char** argv) {
     size_t next_job = 0;
     {
         Pool pool(io_threads);
-        const size_t kRange = 32u << 20;                    // bytes per read / write task
+        const size_t kRange = (size_t)env_u64("DRLZ_IO_RANGE", 4u << 20);   // bytes per read / write task
         auto device_pipeline = [&](int g) {
             drlz_ctx* c = ctxs[g];
             std::vector<Slot>& slots = all_slots[g];
-            std::deque<Slot*> free_slots, in_gpu;
+            // a slot goes round: free -> reading (pool fills it) -> in_gpu (submitted) -> writing (pool writes its results) -> free;
+            // one thread per arrow, so the reads of batch k+1, the parse of batch k and the writes of batch k-1 overlap
+            std::deque<Slot*> free_slots, reading, in_gpu, writing;
             std::mutex smu; std::condition_variable scv;
             for (auto& s : slots) free_slots.push_back(&s);
-            bool feeder_done = false;
+            bool issuer_done = false, submitter_done = false, collector_done = false;
 
             // collector: waits for the batches in submission order, hands their results to the I/O pool
             std::thread collector([&] {
@@ -414,12 +420,12 @@ int main(int argc, char** argv) {
                     Slot* s;
                     {
                         std::unique_lock<std::mutex> lk(smu);
-                        scv.wait(lk, [&] { return feeder_done || !in_gpu.empty(); });
-                        if (in_gpu.empty()) return;
+                        scv.wait(lk, [&] { return submitter_done || !in_gpu.empty(); });
+                        if (in_gpu.empty()) { collector_done = true; scv.notify_all(); return; }
                         s = in_gpu.front(); in_gpu.pop_front();
                     }
                     const auto tw = Clock::now();
-                    int rc = drlz_wait(c, s->ticket);
+                    int rc = io_probe ? DRLZ_OK : drlz_wait(c, s->ticket);
                     const size_t H = s->jobs.size();
                     if (rc == DRLZ_E_NOSPACE) {               // more phrases than the slot's record buffer holds: grow and redo
                         uint64_t need = 16;
@@ -486,20 +492,82 @@ int main(int argc, char** argv) {
                             goff += s->ng[h];
                         }
                     }
-                    const auto tq = Clock::now();
-                    s->writes.wait();
                     {
                         std::lock_guard<std::mutex> lk(stats.mu);
-                        stats.write_wait_s += secs_since(tq);
                         if (!s->failed) for (size_t h = 0; h < H; ++h) { stats.bases += s->m[h]; stats.pairs += s->np[h]; stats.in_bytes += s->cols[h]; }
                         ++stats.batches;
                     }
+                    { std::lock_guard<std::mutex> lk(smu); writing.push_back(s); }
+                    scv.notify_all();
+                }
+            });
+
+            // releaser: a slot is free again when the pool has written everything that points into it
+            std::thread releaser([&] {
+                for (;;) {
+                    Slot* s;
+                    {
+                        std::unique_lock<std::mutex> lk(smu);
+                        scv.wait(lk, [&] { return collector_done || !writing.empty(); });
+                        if (writing.empty()) return;
+                        s = writing.front(); writing.pop_front();
+                    }
+                    const auto tq = Clock::now();
+                    s->writes.wait();
+                    { std::lock_guard<std::mutex> lk(stats.mu); stats.write_wait_s += secs_since(tq); }
                     { std::lock_guard<std::mutex> lk(smu); free_slots.push_back(s); }
                     scv.notify_all();
                 }
             });
 
-            // feeder: takes the next batch of files, has the pool read them into a free slot, submits the slot
+            // submitter: waits for the reads of the batches in order, checks the rows, hands the slot to the library
+            std::thread submitter([&] {
+                for (;;) {
+                    Slot* s;
+                    {
+                        std::unique_lock<std::mutex> lk(smu);
+                        scv.wait(lk, [&] { return issuer_done || !reading.empty(); });
+                        if (reading.empty()) { submitter_done = true; scv.notify_all(); return; }
+                        s = reading.front(); reading.pop_front();
+                    }
+                    const size_t H = s->jobs.size();
+                    const auto tr = Clock::now();
+                    s->reads.wait();
+                    { std::lock_guard<std::mutex> lk(stats.mu); stats.read_wait_s += secs_since(tr); }
+                    for (size_t h = 0; h < H && !s->failed; ++h) {
+                        // one record per line (Spark read.text); only single-line files are supported
+                        const uint64_t first = std::min<uint64_t>(s->first_nl[h], s->jobs[h].size);
+                        if (s->last_body[h] > first) {
+                            fprintf(stderr, "drlz: %s has more than one line; multi-line rows are unsupported (each line would overwrite the same .lz in the reference)\n", s->jobs[h].path.c_str());
+                            failed = 1; s->failed = true;
+                        }
+                        s->cols[h] = first;
+                    }
+                    int rc = DRLZ_OK;
+                    if (s->failed || failed) rc = DRLZ_E_ARG;          // drain: nothing is submitted after a failure
+                    else if (io_probe) {
+                        for (size_t h = 0; h < H; ++h) {
+                            s->m[h] = s->cols[h]; s->np[h] = s->cols[h] / 1024; s->ng[h] = 0;
+                            if (want_gapless) s->gptr[h] = const_cast<uint8_t*>(s->rows[h]);
+                        }
+                        memset(s->pairs, 0, std::min<size_t>(s->pairs_cap, s->total / 64) * 16);
+                    } else {
+                        rc = want_gaptable
+                            ? drlz_submit_gaps(c, s->rows.data(), s->cols.data(), (uint32_t)H, 1, want_gapless ? s->gptr.data() : nullptr, s->m.data(),
+                                               s->pairs, s->pairs_cap, s->np.data(), s->gaps, s->gaps_cap, s->ng.data(), &s->ticket)
+                            : drlz_submit(c, s->rows.data(), s->cols.data(), (uint32_t)H, 1, want_gapless ? s->gptr.data() : nullptr, s->m.data(),
+                                          s->pairs, s->pairs_cap, s->np.data(), &s->ticket);
+                        if (rc != DRLZ_OK) { fprintf(stderr, "drlz: submit failed: %s\n", drlz_last_error(c)); failed = 1; }
+                    }
+                    {
+                        std::lock_guard<std::mutex> lk(smu);
+                        if (rc == DRLZ_OK) in_gpu.push_back(s); else free_slots.push_back(s);
+                    }
+                    scv.notify_all();
+                }
+            });
+
+            // issuer: takes the next batch of files and a free slot, hands the reads to the pool
             for (;;) {
                 if (failed) break;
                 Slot* s;
@@ -529,7 +597,7 @@ int main(int argc, char** argv) {
                     (want_gaptable && !ensure_pinned(s->gaps, s->gaps_cap, total / 64 + 1024 * H, 16))) {
                     fprintf(stderr, "drlz: cannot allocate pinned host memory for a batch of %llu bytes\n", (unsigned long long)total); failed = 1; break;
                 }
-                const auto tr = Clock::now();
+                s->total = total;
                 for (size_t h = 0; h < H; ++h) {
                     const Job& j = s->jobs[h];
                     uint8_t* dst = s->in + s->off[h];
@@ -590,30 +658,12 @@ int main(int argc, char** argv) {
                         });
                     }
                 }
-                s->reads.wait();
-                { std::lock_guard<std::mutex> lk(stats.mu); stats.read_wait_s += secs_since(tr); }
-                for (size_t h = 0; h < H && !s->failed; ++h) {
-                    // one record per line (Spark read.text); only single-line files are supported
-                    const uint64_t first = std::min<uint64_t>(s->first_nl[h], s->jobs[h].size);
-                    if (s->last_body[h] > first) {
-                        fprintf(stderr, "drlz: %s has more than one line; multi-line rows are unsupported (each line would overwrite the same .lz in the reference)\n", s->jobs[h].path.c_str());
-                        failed = 1; s->failed = true;
-                    }
-                    s->cols[h] = first;
-                }
-                if (s->failed) { std::lock_guard<std::mutex> lk(smu); free_slots.push_back(s); break; }
-                int rc = want_gaptable
-                    ? drlz_submit_gaps(c, s->rows.data(), s->cols.data(), (uint32_t)H, 1, want_gapless ? s->gptr.data() : nullptr, s->m.data(),
-                                       s->pairs, s->pairs_cap, s->np.data(), s->gaps, s->gaps_cap, s->ng.data(), &s->ticket)
-                    : drlz_submit(c, s->rows.data(), s->cols.data(), (uint32_t)H, 1, want_gapless ? s->gptr.data() : nullptr, s->m.data(),
-                                  s->pairs, s->pairs_cap, s->np.data(), &s->ticket);
-                if (rc != DRLZ_OK) { fprintf(stderr, "drlz: submit failed: %s\n", drlz_last_error(c)); failed = 1; std::lock_guard<std::mutex> lk(smu); free_slots.push_back(s); break; }
-                { std::lock_guard<std::mutex> lk(smu); in_gpu.push_back(s); }
+                { std::lock_guard<std::mutex> lk(smu); reading.push_back(s); }
                 scv.notify_all();
             }
-            { std::lock_guard<std::mutex> lk(smu); feeder_done = true; }
+            { std::lock_guard<std::mutex> lk(smu); issuer_done = true; }
             scv.notify_all();
-            collector.join();
+            submitter.join(); collector.join(); releaser.join();
         };
         std::vector<std::thread> th;
         for (int g = 0; g < ngpu; ++g) th.emplace_back(device_pipeline, g);
