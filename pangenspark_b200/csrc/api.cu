@@ -65,7 +65,7 @@ struct drlz_ctx {
     uint32_t bl = 1, sigma = 4;        // symbol width (log2 bits) and alphabet size of the index
     bool has_uniq32 = false;           // some repeat of the reference reaches 65535 symbols: the unsaturated array (behind the SA) is in use
     int opt_predict = 1;
-    cudaStream_t l2_stream = nullptr; int opt_l2persist = 0; int opt_occ = 8; int opt_occ_fix = 10; int opt_occ_diag = 12; int opt_tickets = 1; int opt_hint = 1; int opt_diag = 1; uint32_t opt_spec_store = 0;
+    cudaStream_t l2_stream = nullptr; int opt_l2persist = 0; int opt_occ = 8; int opt_occ_fix = 10; int opt_occ_diag = 12; int opt_spec_sync = 1; int opt_tickets = 1; int opt_hint = 1; int opt_diag = 1; uint32_t opt_spec_store = 0;
     double idx_ms[5] = {0, 0, 0, 0, 0};
     // batch scratch (grow-only)
     SaWorkspace sa_ws;
@@ -210,6 +210,7 @@ int drlz_set_option(drlz_ctx* c, const char* key, int64_t v) {
     else if (!strcmp(key, "occ")) c->opt_occ = (int)v;
     else if (!strcmp(key, "occ_fix")) c->opt_occ_fix = (int)v;
     else if (!strcmp(key, "occ_diag")) c->opt_occ_diag = (int)v;
+    else if (!strcmp(key, "spec_sync")) c->opt_spec_sync = (int)v;
     else if (!strcmp(key, "hint")) c->opt_hint = v != 0;
     else if (!strcmp(key, "diag")) c->opt_diag = v != 0;
     else if (!strcmp(key, "spec_store")) { if (v < 0 || v > 4096) return DRLZ_E_ARG; c->opt_spec_store = (uint32_t)v; }
@@ -407,7 +408,7 @@ static int run_device_group(drlz_ctx* c, const uint8_t* rows_dev, const uint64_t
         pb.hint = (c->opt_hint && !single_chunk) ? c->hint.as<int64_t>() : nullptr;
         pb.ext = c->has_uniq32 ? c->ext.as<uint32_t>() : nullptr; pb.hint_src = c->has_uniq32 ? c->hint_src.as<uint32_t>() : nullptr;
         pb.true_slot = c->true_slot.as<uint32_t>();
-        pb.pv.counters = c->counters.as<uint32_t>();
+        pb.pv.counters = c->counters.as<uint32_t>(); pb.pv.spec_sync = (uint32_t)c->opt_spec_sync;
         pb.H = H; pb.max_chunks_per_hap = maxc ? maxc : 1; pb.occ = c->opt_occ; pb.occ_fix = c->opt_occ_fix; pb.occ_diag = c->opt_occ_diag; pb.blind_rounds = c->opt_blind_rounds;
         pb.jump_a = c->jump_a.as<uint32_t>(); pb.jump_b = c->jump_b.as<uint32_t>(); pb.mark = c->mark.as<uint8_t>();
         pb.true_cnt = c->true_cnt.as<uint32_t>(); pb.true_entry = c->true_entry.as<uint32_t>(); pb.true_off = c->true_off.as<uint64_t>();

@@ -217,6 +217,70 @@ __global__ void __launch_bounds__(128) k_resolve(ParseView pv) {
     uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g < pv.n_chunks) DRLZ_WITH_BL(pv, q, resolve_chunk(q, g));
 }
+// P1 of one chunk per lane, the 32 chunks of a warp in step.  spec_parse_chunk() as it stands in rlz_core.cuh lets every
+// lane run ahead on its own; the lanes then sit in different places of the same code, the warp has one scoreboard, and
+// every dependent miss of every lane is a stall of all 32 (1600 load requests per warp, 8 lanes per instruction).  Here
+// an iteration is: head of the phrase at i (literal / predicted phrase: one read of the uniqueness array) for all
+// lanes; for the lanes that got a phrase, the head of the next one; then the index lookup for all lanes that stand
+// on a variant site.  Same functions, same order per chunk, same phrases: only the interleaving across lanes differs.
+template <typename PV>
+__device__ __forceinline__ void spec_parse_warp(const PV& pv, uint32_t g, bool valid, const uint16_t* mm_copy) {
+    uint32_t h = 0; HapView hv; hv.m = 0; hv.n_exc = 0;
+    uint64_t s = 0, e = 0;
+    bool live = false;
+    if (valid) {
+        h = pv.chunk_hap[g];
+        hv = pv.haps[h];
+        s = (uint64_t)(g - pv.hap_chunk_base[h]) << pv.chunk_shift;
+        e = s + (1ull << pv.chunk_shift); if (e > hv.m) e = hv.m;
+        pv.link[g] = kEmpty;
+        pv.open_i[g] = kEmpty;
+        if (s >= hv.m) {
+            pv.first_pos[g] = 0; pv.first_len[g] = 0; pv.run_len[g] = 0;
+            pv.spec_cnt[g] = 0; pv.spec_exit[g] = (uint32_t)(s > 0xFFFFFFFEull ? 0xFFFFFFFEull : s);
+        } else live = true;
+    }
+    const bool parsed = live;
+    uint64_t i = s; uint32_t cnt = 0;
+    uint32_t cur = (live && hv.n_exc) ? exc_lower_bound(hv, i) : 0;
+    bool open = false;
+    const int64_t hint_g = (valid && pv.hint) ? pv.hint[g / kHintGroup] : kNoDiag;
+    int64_t diag = hint_g;
+    const uint16_t* mml = !pv.mm ? nullptr : mm_copy;
+    auto take = [&](const Match& mt) {
+        if (i == s) { pv.first_pos[g] = mt.pos; pv.first_len[g] = mt.len; pv.run_len[g] = open ? kEmpty : mt.len; }
+        if (cnt < pv.spec_store) pv.spec_ph[(size_t)g * pv.spec_store + cnt] = make_uint2(mt.pos, mt.len);
+        ++cnt;
+        if (open) { pv.open_i[g] = (uint32_t)i; pv.open_pos[g] = mt.pos; pv.open_len[g] = mt.len; live = false; return; }
+        i += mt.len ? mt.len : 1;
+        if (i >= e) live = false;
+    };
+    while (__any_sync(0xffffffffu, live)) {
+        Match mt; uint32_t maxlen = 0, cap = 0;
+        int st = -1;
+        if (live) {
+            st = phrase_head(pv, hv, i, &cur, &open, &diag, mml, hint_g, s, g, &mt, &maxlen, &cap);
+            if (st != kHeadLookup) take(mt);
+        }
+        __syncwarp();
+        if (live && st != kHeadLookup) {
+            st = phrase_head(pv, hv, i, &cur, &open, &diag, mml, hint_g, s, g, &mt, &maxlen, &cap);
+            if (st != kHeadLookup) take(mt);
+        }
+        __syncwarp();
+        if (live && st == kHeadLookup) {
+            mt = phrase_tail(pv, hv, i, maxlen, cap, &open, &diag);
+            take(mt);
+        }
+        __syncwarp();
+    }
+    if (parsed) {
+        pv.spec_cnt[g] = cnt;
+        if (open) pv.spec_exit[g] = kEmpty;                       // resolved later
+        else { pv.spec_exit[g] = (uint32_t)i; register_exit(pv, h, i, 1); }
+    }
+}
+
 template <int MINB>
 __global__ void __launch_bounds__(128, MINB) k_spec(ParseView pv) {
     // every thread keeps its chunk's mismatch record (32 bytes) in shared memory: it is consulted at every predicted
@@ -224,16 +288,19 @@ __global__ void __launch_bounds__(128, MINB) k_spec(ParseView pv) {
     // of the record through L2)
     __shared__ __align__(16) uint16_t smm[128 * kMmStride];
     uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= pv.n_chunks) return;
+    const bool valid = g < pv.n_chunks;
     uint16_t* mine = nullptr;
     if (pv.mm) {
         static_assert(kMmStride == 16, "the record is copied as two 16-byte vectors");
         mine = smm + threadIdx.x * kMmStride;
-        const uint4* src = reinterpret_cast<const uint4*>(pv.mm + (size_t)g * kMmStride);
-        reinterpret_cast<uint4*>(mine)[0] = src[0];
-        reinterpret_cast<uint4*>(mine)[1] = src[1];
+        if (valid) {
+            const uint4* src = reinterpret_cast<const uint4*>(pv.mm + (size_t)g * kMmStride);
+            reinterpret_cast<uint4*>(mine)[0] = src[0];
+            reinterpret_cast<uint4*>(mine)[1] = src[1];
+        }
     }
-    DRLZ_WITH_BL(pv, q, spec_parse_chunk(q, g, mine));
+    if (pv.spec_sync) { DRLZ_WITH_BL(pv, q, spec_parse_warp(q, g, valid, mine)); }
+    else if (valid) DRLZ_WITH_BL(pv, q, spec_parse_chunk(q, g, mine));
 }
 template <int MINB>
 __global__ void __launch_bounds__(128, MINB) k_fix(ParseView pv, uint32_t round) {

@@ -439,6 +439,7 @@ struct ParseView {
     uint32_t parsed_rounds;         // fix-up rounds run so far: records registered for a later round are not parsed yet
     const uint32_t* ext;            // [NC] symbols from the START of chunk g to the first mismatch along its hinted diagonal, counted through
                                     // the following chunks as long as they lie on the same diagonal (0 = unknown); may be null
+    uint32_t spec_sync;             // k_spec: the chunks of a warp parsed in step (phrase heads together, lookups together)
 };
 
 DRLZ_HD uint32_t atomic_cas_u32(uint32_t* p, uint32_t cmp, uint32_t val) {
@@ -498,14 +499,18 @@ DRLZ_HD bool list_extent(const uint16_t* mm, uint64_t s, uint64_t i, uint32_t pl
 
 // mml / hint_g: the chunk's mismatch record and hinted diagonal (mml == nullptr: none).  k_spec keeps its copy of the
 // record in shared memory -- it is read once per predicted phrase, and in L1 it does not survive between two of them.
-DRLZ_HD Match phrase_capped_l(const ParseView& pv, const HapView& hv, uint64_t i, uint32_t* cursor, bool* open, int64_t* diag,
-                              const uint16_t* mml, int64_t hint_g, uint64_t s, uint32_t g = kEmpty) {
+// The phrase at i comes in two halves, so that k_spec can run each with its warp converged: phrase_head() answers the
+// literals at exceptions and the predicted phrases (one read of the uniqueness array), phrase_tail() is the index lookup.
+enum { kHeadLiteral = 0, kHeadPredicted = 1, kHeadLookup = 2 };
+DRLZ_HD int phrase_head(const ParseView& pv, const HapView& hv, uint64_t i, uint32_t* cursor, bool* open, int64_t* diag,
+                        const uint16_t* mml, int64_t hint_g, uint64_t s, uint32_t g, Match* out, uint32_t* maxlen_out, uint32_t* cap_out) {
     *open = false;
     uint64_t stop = stop_after(hv, i, cursor);
-    if (stop == i) { Match mt; mt.len = 0; mt.pos = hv.exc_byte[*cursor]; return mt; }
+    if (stop == i) { out->len = 0; out->pos = hv.exc_byte[*cursor]; return kHeadLiteral; }
     uint32_t maxlen = (uint32_t)(stop - i);
     uint64_t to_end = (((i >> pv.chunk_shift) + 1) << pv.chunk_shift) - i;
     uint32_t cap = to_end > (uint64_t)pv.min_cap ? (to_end > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)to_end) : pv.min_cap;
+    *maxlen_out = maxlen; *cap_out = cap;
     Match mt;
     if (pv.ix.uniq && *diag != kNoDiag) {
         int64_t p64 = (int64_t)i + *diag;
@@ -521,7 +526,7 @@ DRLZ_HD Match phrase_capped_l(const ParseView& pv, const HapView& hv, uint64_t i
                 if (u != 0xFFFFu && c > u) {
                     mt.len = c; mt.pos = p;
                     *open = (c == plen && plen < maxlen);
-                    return mt;
+                    *out = mt; return kHeadPredicted;
                 }
                 // Long repeats (N runs of millions of bases, segmental duplications): the match reaches the cap and the
                 // capped pattern is NOT unique (the longest repeat at p is at least as long), so lookup() would search
@@ -539,13 +544,18 @@ DRLZ_HD Match phrase_capped_l(const ParseView& pv, const HapView& hv, uint64_t i
 #if !defined(__CUDACC__)
                             ++g_emu_long_hits;
 #endif
-                            mt.len = (uint32_t)cf; mt.pos = p; return mt;
+                            mt.len = (uint32_t)cf; mt.pos = p; *out = mt; return kHeadPredicted;
                         }
                     }
                 }
             }
         }
     }
+    return kHeadLookup;
+}
+
+DRLZ_HD Match phrase_tail(const ParseView& pv, const HapView& hv, uint64_t i, uint32_t maxlen, uint32_t cap, bool* open, int64_t* diag) {
+    Match mt;
     // most lookups of the parse stand on a variant site: a match of a dozen symbols somewhere else, which the short form
     // finds in five dependent loads instead of eight
     if (!(pv.ix.bl == 1 && (cap < maxlen ? cap : maxlen) >= kLookShort && lookup_short(pv.ix, get64u(hv.x, (uint32_t)i, 1), &mt)))
@@ -553,6 +563,13 @@ DRLZ_HD Match phrase_capped_l(const ParseView& pv, const HapView& hv, uint64_t i
     if (mt.len == 0) mt.pos = (uint32_t)pv.ix.c2b[base_at(hv.x, i, pv.ix.bl)];
     else if (mt.len >= kDiagMinLen) *diag = (int64_t)mt.pos - (int64_t)i;
     return mt;
+}
+
+DRLZ_HD Match phrase_capped_l(const ParseView& pv, const HapView& hv, uint64_t i, uint32_t* cursor, bool* open, int64_t* diag,
+                              const uint16_t* mml, int64_t hint_g, uint64_t s, uint32_t g = kEmpty) {
+    Match mt; uint32_t maxlen, cap;
+    if (phrase_head(pv, hv, i, cursor, open, diag, mml, hint_g, s, g, &mt, &maxlen, &cap) != kHeadLookup) return mt;
+    return phrase_tail(pv, hv, i, maxlen, cap, open, diag);
 }
 
 DRLZ_HD Match phrase_capped(const ParseView& pv, const HapView& hv, uint64_t i, uint32_t* cursor, bool* open, int64_t* diag,
