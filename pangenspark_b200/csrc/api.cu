@@ -65,13 +65,13 @@ struct drlz_ctx {
     uint32_t bl = 1, sigma = 4;        // symbol width (log2 bits) and alphabet size of the index
     bool has_uniq32 = false;           // some repeat of the reference reaches 65535 symbols: the unsaturated array (behind the SA) is in use
     int opt_predict = 1;
-    cudaStream_t l2_stream = nullptr; int opt_l2persist = 0; int opt_occ = 8; int opt_occ_fix = 10; int opt_occ_diag = 12; int opt_spec_sync = 1; int opt_tickets = 1; int opt_hint = 1; int opt_diag = 1; uint32_t opt_spec_store = 0;
+    cudaStream_t l2_stream = nullptr; int opt_l2persist = 0; int opt_occ = 8; int opt_occ_fix = 10; int opt_occ_diag = 12; int opt_spec_sync = 1; int opt_uniq_coarse = 1; int opt_tickets = 1; int opt_hint = 1; int opt_diag = 1; uint32_t opt_spec_store = 0;
     double idx_ms[5] = {0, 0, 0, 0, 0};
     // batch scratch (grow-only)
     SaWorkspace sa_ws;
     DevBuf stage[2], meta_dev, desc_cnt, desc_exc, tile_counter, X, mdev, exccnt, excpos, excbyte,
         flags, haps, gapless, gtile_cnt, gtile_exc, gtile_off, gtile_excoff, gscan_tmp, chunk_hap, first_pos, first_len, run_a, run_b, link_a, link_b, open_i, open_pos, open_len, spec_cnt, spec_exit, alt_entry, alt_cnt, alt_exit, alt_round, alt_own, alt_merge, spec_ph, alt_ph, hint, mm, true_slot, counters, jump_a,
-        jump_b, mark, true_cnt, true_entry, true_off, scan_tmp, hap_pairs, out, ms_a, ms_b, tab_tmp, gap_list, gap_scratch, gap_counter, ext, hint_src;
+        jump_b, mark, true_cnt, true_entry, true_off, scan_tmp, hap_pairs, out, ms_a, ms_b, tab_tmp, gap_list, gap_scratch, gap_counter, ext, hint_src, uniqc;
     HostBuf meta_host, small_host, gap_host;
     uint64_t exc_stride_hint = 0;
     // thread safety: every entry point takes `mu` (calls from several threads are serialised on the device)
@@ -173,7 +173,7 @@ void drlz_destroy(drlz_ctx* c) {
                       &c->desc_exc, &c->tile_counter, &c->X, &c->mdev, &c->exccnt, &c->excpos,
                       &c->excbyte, &c->flags, &c->haps, &c->gapless, &c->gtile_cnt, &c->gtile_exc, &c->gtile_off, &c->gtile_excoff, &c->gscan_tmp, &c->chunk_hap, &c->first_pos, &c->first_len, &c->run_a, &c->run_b, &c->link_a, &c->link_b, &c->open_i, &c->open_pos, &c->open_len, &c->spec_cnt, &c->spec_exit,
                       &c->alt_entry, &c->alt_cnt, &c->alt_exit, &c->alt_round, &c->alt_own, &c->alt_merge, &c->spec_ph, &c->alt_ph, &c->hint, &c->mm, &c->true_slot, &c->counters, &c->jump_a, &c->jump_b,
-                      &c->mark, &c->true_cnt, &c->true_entry, &c->true_off, &c->scan_tmp, &c->hap_pairs, &c->out, &c->ms_a, &c->ms_b, &c->tab_tmp, &c->gap_list, &c->gap_scratch, &c->gap_counter, &c->ext, &c->hint_src};
+                      &c->mark, &c->true_cnt, &c->true_entry, &c->true_off, &c->scan_tmp, &c->hap_pairs, &c->out, &c->ms_a, &c->ms_b, &c->tab_tmp, &c->gap_list, &c->gap_scratch, &c->gap_counter, &c->ext, &c->hint_src, &c->uniqc};
     for (DevBuf* b : bufs) b->release();
     c->meta_host.release(); c->small_host.release(); c->gap_host.release();
     for (int i = 0; i < 2; ++i) if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]);
@@ -211,6 +211,7 @@ int drlz_set_option(drlz_ctx* c, const char* key, int64_t v) {
     else if (!strcmp(key, "occ_fix")) c->opt_occ_fix = (int)v;
     else if (!strcmp(key, "occ_diag")) c->opt_occ_diag = (int)v;
     else if (!strcmp(key, "spec_sync")) c->opt_spec_sync = (int)v;
+    else if (!strcmp(key, "uniq_coarse")) c->opt_uniq_coarse = (int)v;
     else if (!strcmp(key, "hint")) c->opt_hint = v != 0;
     else if (!strcmp(key, "diag")) c->opt_diag = v != 0;
     else if (!strcmp(key, "spec_store")) { if (v < 0 || v > 4096) return DRLZ_E_ARG; c->opt_spec_store = (uint32_t)v; }
@@ -390,7 +391,8 @@ static int run_device_group(drlz_ctx* c, const uint8_t* rows_dev, const uint64_t
 
         ParseBuffers pb;
         pb.pv.ix = IndexView{c->d_text, c->sa.as<uint32_t>(), c->d_tab, c->n, c->k, c->opt_predict ? c->d_uniq : nullptr,
-                             c->bl, c->sigma, c->d_lut + 256, (c->opt_predict && c->has_uniq32) ? c->sa.as<uint32_t>() + c->n : nullptr};
+                             c->bl, c->sigma, c->d_lut + 256, (c->opt_predict && c->has_uniq32) ? c->sa.as<uint32_t>() + c->n : nullptr,
+                             (c->opt_predict && c->opt_uniq_coarse && c->uniqc.p) ? c->uniqc.as<uint16_t>() : nullptr};
         pb.pv.haps = c->haps.as<HapView>(); pb.pv.chunk_hap = c->chunk_hap.as<uint32_t>(); pb.pv.hap_chunk_base = d_base;
         pb.pv.chunk_bases = Ceff; pb.pv.chunk_shift = single_chunk ? 32u : chunk_shift; pb.pv.n_chunks = NC;
         pb.pv.min_cap = single_chunk ? 0xFFFFFFFFu : c->opt_min_cap; pb.pv.foreign_cap = c->opt_foreign_cap;
@@ -601,6 +603,8 @@ int drlz_build_index(drlz_ctx* c, const uint8_t* ref, uint64_t n) {
         // LCP array came out of the sort (StoreRank); otherwise the Kasai-order kernel computes it
         rc = c->sa_rounds == 0 ? 0 : build_lcp(c->d_text, n, bl, c->sa.as<uint32_t>(), c->isa.as<uint32_t>(), c->lcp.as<uint32_t>(), s);
         if (rc == 0) rc = build_uniq(n, c->isa.as<uint32_t>(), c->lcp.as<uint32_t>(), c->d_uniq, c->sa.as<uint32_t>() + n, c->flags.as<uint32_t>() + 2, s);
+        if (rc == 0 && c->uniqc.ensure(((n >> kUniqBlockShift) + 2) * 2) != cudaSuccess) rc = 1;
+        if (rc == 0) rc = build_uniq_coarse(n, c->d_uniq, c->uniqc.as<uint16_t>(), s);
         if (rc != 0) { c->err = "lcp / uniqueness build failed"; for (int i = 0; i < 5; ++i) cudaEventDestroy(e[i]); return DRLZ_E_CUDA; }
     }
     cudaEventRecord(e[4], s);
@@ -686,6 +690,13 @@ int drlz_index_commit(drlz_ctx* c) {
     if (!c) return DRLZ_E_ARG;
     std::lock_guard<std::recursive_mutex> lk_(c->mu);
     if (!c->d_text || !c->d_tab) return DRLZ_E_STATE;
+    // what is derived from the received buffers is made here: the block maxima of the uniqueness array.  The buffers were
+    // filled by the caller on streams of its own, hence the device-wide synchronisation (once per index).
+    CK(c, cudaSetDevice(c->device));
+    CK(c, cudaDeviceSynchronize());
+    CK(c, c->uniqc.ensure(((c->n >> kUniqBlockShift) + 2) * 2));
+    if (build_uniq_coarse(c->n, c->d_uniq, c->uniqc.as<uint16_t>(), c->stream) != 0) { c->err = "uniqueness summary failed"; return DRLZ_E_CUDA; }
+    CK(c, cudaStreamSynchronize(c->stream));
     c->have_index = true;
     return DRLZ_OK;
 }

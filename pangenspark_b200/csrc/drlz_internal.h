@@ -102,6 +102,7 @@ int build_lcp(const uint64_t* text, uint64_t n, uint32_t bl, const uint32_t* sa,
 // uniq[p] = min(65535, max(LCP[ISA[p]], LCP[ISA[p]+1])); uniq32[p] = the same unsaturated; *saturated (device) is set to 1 if
 // any value reached 65535
 int build_uniq(uint64_t n, const uint32_t* isa, const uint32_t* lcp, uint16_t* uniq, uint32_t* uniq32, uint32_t* saturated, cudaStream_t s);
+int build_uniq_coarse(uint64_t n, const uint16_t* uniq, uint16_t* uniqc, cudaStream_t s);   // max of uniq over blocks of kUniqBlock positions
 
 // ---- parse pipeline (parse.cu) -----------------------------------------------------------------
 struct ParseBuffers {

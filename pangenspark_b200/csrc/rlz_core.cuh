@@ -83,7 +83,9 @@ struct IndexView {
     uint32_t sigma;         // alphabet size (4 when bl == 1)
     const uint8_t* c2b;     // code -> byte (literal phrases)
     const uint32_t* uniq32; // [n] the same without the 16-bit saturation; only present (non-null) if some repeat reaches 65535 symbols
+    const uint16_t* uniqc;  // [ceil(n / kUniqBlock)] max of uniq over blocks of kUniqBlock positions (stays in L2); may be null
 };
+static const uint32_t kUniqBlockShift = 6, kUniqBlock = 1u << kUniqBlockShift;
 
 // key of the first kk symbols of the word xw padded with code 0 to k symbols, and the number of keys sharing that
 // prefix: the table brackets are tab[lokey] and tab[lokey + span]
@@ -132,6 +134,14 @@ DRLZ_HD uint64_t funnel64(uint64_t a, uint64_t b, unsigned sh) {
     const unsigned s = sh & 31;
     const uint32_t w0 = odd ? al : ah, w1 = odd ? bh : al, w2 = odd ? bl_ : bh;
     return ((uint64_t)fsl32(w0, w1, s) << 32) | fsl32(w1, w2, s);
+}
+
+DRLZ_HD void prefetch_l2(const void* p) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+    (void)p;
+#endif
 }
 
 // get64 with a 32-bit position (n, m < 2^32: half the integer work of the 64-bit form).  Always reads the next word
@@ -519,9 +529,22 @@ DRLZ_HD int phrase_head(const ParseView& pv, const HapView& hv, uint64_t i, uint
             uint32_t plen = cap < maxlen ? cap : maxlen;
             uint32_t c;
             bool less;
-            const uint32_t u = pv.ix.uniq[p];                // a DRAM miss as a rule: requested before the list scan, used after it
-            if (!(mml && hint_g == *diag && list_extent(mml, s, i, plen, &c)))
+            // the list first (shared memory): at a listed variant site nothing is predicted, and a read of the uniqueness
+            // array whose answer nobody wants still holds its register -- and the warp -- until it returns
+            const bool listed = mml && hint_g == *diag && list_extent(mml, s, i, plen, &c);
+            if (listed && c == 0) return kHeadLookup;
+            // The test is c > uniq[p], and uniq[p] is a DRAM miss as a rule (2 bytes of a sector at a random place of an
+            // array the size of the reference; k_spec runs at the rate HBM serves such reads).  A phrase of hundreds of
+            // bases against a longest repeat of a dozen: the maximum of uniq over the 64 positions around p, from an array
+            // small enough to stay in L2, nearly always settles it.
+            uint32_t u = pv.ix.uniqc ? pv.ix.uniqc[p >> kUniqBlockShift] : 0xFFFFu;
+            if (!(listed && u != 0xFFFFu && c > u)) u = pv.ix.uniq[p];
+            if (!listed)
                 c = cmp_suffix_w(get64u(hv.x, (uint32_t)i, pv.ix.bl), hv.x, (uint32_t)i, pv.ix.text, p, (uint32_t)pv.ix.n, plen, &less, pv.ix.bl);
+            // The predicted path never touches the haplotype (the mismatch list answers for it), so the lookup at the variant
+            // site behind a predicted phrase would start with a miss on its own pattern: ask for it while the uniqueness
+            // array is still answering (the phrase after this one starts at i + c, whatever it is)
+            if (c < plen) prefetch_l2(hv.x + (((uint32_t)i + c) >> (6 - pv.ix.bl)));
             if (c > 0) {
                 if (u != 0xFFFFu && c > u) {
                     mt.len = c; mt.pos = p;

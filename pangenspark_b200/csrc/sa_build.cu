@@ -299,6 +299,33 @@ int build_uniq(uint64_t n, const uint32_t* isa, const uint32_t* lcp, uint16_t* u
     return (int)cudaGetLastError();
 }
 
+// uniqc[j] = max of uniq over positions [64 j, 64 j + 64): the parse tests c > uniq[p] against it first (rlz_core.cuh)
+__global__ void k_uniq_coarse(uint64_t n, const uint16_t* __restrict__ uniq, uint16_t* __restrict__ uniqc) {
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t a = j << kUniqBlockShift;
+    if (a >= n) return;
+    uint32_t mx = 0;
+    if (a + kUniqBlock <= n) {
+        const uint4* v = reinterpret_cast<const uint4*>(uniq + a);        // 128 bytes, 16-byte aligned (the array is 256-byte aligned)
+#pragma unroll
+        for (int t = 0; t < (int)(kUniqBlock / 8); ++t) {
+            const uint4 q = v[t];
+            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int z = 0; z < 4; ++z) { const uint32_t lo = w[z] & 0xFFFFu, hi = w[z] >> 16; mx = mx > lo ? mx : lo; mx = mx > hi ? mx : hi; }
+        }
+    } else for (uint64_t q = a; q < n; ++q) mx = mx > uniq[q] ? mx : uniq[q];
+    uniqc[j] = (uint16_t)mx;
+}
+
+int build_uniq_coarse(uint64_t n, const uint16_t* uniq, uint16_t* uniqc, cudaStream_t s) {
+    if (n == 0) return 0;
+    const uint64_t nb = (n + kUniqBlock - 1) >> kUniqBlockShift;
+    g_launches += 1;
+    k_uniq_coarse<<<(unsigned)((nb + 255) / 256), 256, 0, s>>>(n, uniq, uniqc);
+    return (int)cudaGetLastError();
+}
+
 }  // namespace drlz
 
 // ---- debug/test entry points (not part of include/drlz.h): exercise the primitives in isolation ----

@@ -99,8 +99,10 @@ int emu_parse(const uint8_t* ref, uint64_t n, const int64_t* sa64, int k, uint32
             uniq32[p] = u;
         }
     }
+    std::vector<uint16_t> uniqc((n >> kUniqBlockShift) + 2, 0);
+    if (use_uniq) for (uint64_t p = 0; p < n; ++p) if (uniq[p] > uniqc[p >> kUniqBlockShift]) uniqc[p >> kUniqBlockShift] = uniq[p];
     IndexView ix{text.data(), sa.data(), nullptr, n, k, use_uniq ? uniq.data() : nullptr, al.bl, al.sigma, al.c2b,
-                 use_uniq ? uniq32.data() : nullptr};
+                 use_uniq ? uniq32.data() : nullptr, use_uniq ? uniqc.data() : nullptr};
     std::vector<uint32_t> tab; build_tab(ix, sa, tab);
     ix.tab = tab.data();
 
