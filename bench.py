@@ -268,7 +268,7 @@ class Job:
         return info, idx_t, bcast_ms, wall_ms
 
     # ---- one workload: device-resident value, end to end, raw copy ceiling ------------------------------------------
-    def measure(self, wl, d, steps, warmup, sampler=None):
+    def measure(self, wl, d, steps, warmup, sampler=None, gapless=True):
         torch, ctx, D, orc = self.torch, self.ctx, self.D, self.orc
         seed = orc.seed_for(wl["cfg"])
         M = orc.syn_columns(seed, wl["n"], wl["p_ins"])
@@ -330,6 +330,55 @@ class Job:
         e2e_val = total_bases / (ms_e2e * 1e-3) / 1e9
         assert [r.shape[0] for r in res] == npairs.tolist() and (m2 == m).all()
 
+        # e2e_gapless: the same call with the gapless sequences copied back too (what the CLI asks for: DistributedRLZ.scala
+        # :66-80 writes them as FASTA) -- the pack kernel's gapless branch and m more bytes device -> host per step
+        e2e_gl = None
+        if gapless and H and not os.environ.get("DRLZ_BENCH_SKIP_GAPLESS"):
+            gl_pin = D.PinnedBuffer(max(1, H) * stride)
+            gl_views = [gl_pin.array[h * stride: h * stride + M] for h in range(H)]
+            with torch.cuda.stream(stream):
+                for _ in range(max(1, warmup - 1)):
+                    res_g, m3, gl = ctx.parse_batch(host_rows, want_gapless=True, pairs_cap=phrases + 1024, out=out_arr, gapless_out=gl_views)
+                self.barrier()
+                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                ev0.record(stream)
+                for _ in range(steps):
+                    res_g, m3, gl = ctx.parse_batch(host_rows, want_gapless=True, pairs_cap=phrases + 1024, out=out_arr, gapless_out=gl_views)
+                ev1.record(stream)
+                self.barrier()
+                ms_gl = self.reduce_max(ev0.elapsed_time(ev1) / steps)
+            assert (m3 == m).all() and gl[0][: int(m[0])].tobytes() == orc.strip_gaps(rows_arr[0, :M]).tobytes()
+            e2e_gl = {"value": total_bases / (ms_gl * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": ms_gl, "h2d_bytes_per_step": int(H * M),
+                      "d2h_bytes_per_step": int(16 * phrases + bases), "d2h_gbs": self.reduce_sum(16.0 * phrases + bases) / (ms_gl * 1e-3) / 1e9}
+            res, m2, _ = ctx.parse_batch(host_rows, pairs_cap=phrases + 1024, out=out_arr)      # `res` views out_arr: restore the plain result
+            # what the box gives both directions at once: the rows host -> device on one stream while as many bytes as the
+            # gapless sequences go device -> host on another (nothing of the library involved)
+            gl_t = torch.from_numpy(gl_pin.array[: H * stride])
+            side = torch.cuda.Stream()
+            dsrc = torch.empty(int(bases), dtype=torch.uint8, device="cuda")
+            torch.cuda.synchronize()
+            self.barrier()
+            ev0, ev1, ev2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            ev0.record(stream)
+            side.wait_event(ev0)
+            for _ in range(steps):
+                with torch.cuda.stream(stream):
+                    dev_rows[: H * stride].copy_(pin_t, non_blocking=True)
+                with torch.cuda.stream(side):
+                    gl_t[: int(bases)].copy_(dsrc, non_blocking=True)
+            ev2.record(side)
+            stream.wait_event(ev2)
+            ev1.record(stream)
+            torch.cuda.synchronize()
+            self.barrier()
+            ms_dup = self.reduce_max(ev0.elapsed_time(ev1) / steps)
+            e2e_gl["duplex_ceiling"] = {"value": total_bases / (ms_dup * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": ms_dup,
+                                        "how": "pinned host -> device copy of the rows and device -> host copy of as many bytes as the gapless sequences, at the same time on two streams, every rank at once"}
+            e2e_gl["frac_of_duplex_ceiling"] = ms_dup / ms_gl
+            del gl_t, dsrc
+            del gl, gl_views
+            gl_pin.free()
+
         # the ceiling of that: nothing but the pinned host->device copy of the same rows, all ranks at once
         with torch.cuda.stream(stream):
             dev_rows[: H * stride].copy_(pin_t, non_blocking=True)
@@ -352,7 +401,7 @@ class Job:
                "frac_of_h2d_ceiling": h2d_gbs / ceil_gbs if ceil_gbs else None,
                "h2d_ceiling_how": "pinned host -> device copy of the same rows on every rank at the same time, nothing else running (whole job, GB/s)"}
         return {"M": M, "stride": stride, "H": H, "rows_arr": rows_arr, "res": res, "m": m, "npairs": npairs, "kt": kt,
-                "ms_dev": ms_dev, "value": value, "total_bases": total_bases, "bases": bases, "phrases": phrases, "e2e": e2e,
+                "ms_dev": ms_dev, "value": value, "total_bases": total_bases, "bases": bases, "phrases": phrases, "e2e": e2e, "e2e_gapless": e2e_gl,
                 "gen_s": gen_s, "_keep": (pin, out_pin, dev_rows)}
 
     # ---- parity gate: every rank, its own rows and its own copy of the index -------------------------------------------
@@ -568,7 +617,7 @@ def run_ours(args):
            "config": {"workload": wl["name"], "l2": "inputs (%.2f GB of MSA rows per GPU) exceed the 126 MB L2; no explicit flush" % (H * M / 1e9),
                       "bases_per_step": ms["total_bases"], "phrases_per_step_rank0": ms["phrases"], "kmer": info["k"],
                       "index": "built once outside the step" + (", NCCL broadcast from rank 0" if world > 1 else "")},
-           "e2e": ms["e2e"], "gpu_launches": int(primary_kt["launches"]),
+           "e2e": ms["e2e"], "e2e_gapless": ms["e2e_gapless"], "gpu_launches": int(primary_kt["launches"]),
            "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
            "index_build": {"total_ms": idx_t["total_ms"], "wall_ms": idx_wall, "sa_ms": idx_t["sa_ms"], "table_ms": idx_t["table_ms"],
                            "pack_ms": idx_t["pack_ms"], "lcp_ms": idx_t["lcp_ms"], "rounds": info["sa_rounds"], "n": info["n"],
@@ -589,7 +638,7 @@ def run_ours(args):
         d3 = orc.syn_reference(orc.seed_for(3), w3["n"])
         info3, idx3, bcast3, wall3 = job.index(d3, warm=False)
         s3 = max(1, min(steps, int(os.environ.get("DRLZ_BENCH_CFG3_STEPS", 3))))
-        m3 = job.measure(w3, d3, s3, 3)
+        m3 = job.measure(w3, d3, s3, 3, gapless=False)
         chk3, _, ok3 = (0, None, True) if skip_cpu else job.parity(w3, d3, m3, 2, want_cpu_baseline=False)
         if not ok3:
             job.close()

@@ -51,8 +51,12 @@ using namespace drlz;
 
 struct drlz_ctx {
     int device = 0;
-    cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
+    cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr, d2h_stream = nullptr;
     cudaEvent_t ev_copied[2] = {nullptr, nullptr};
+    // the gapless sequences of a group go back to the host on their own stream while the next group is parsed: two device
+    // buffers in turn; ev_gl_done[b] = the copies out of buffer b have finished, ev_gl_ready = the group's kernels have
+    cudaEvent_t ev_gl_done[2] = {nullptr, nullptr}, ev_gl_ready = nullptr;
+    int gl_cur = 0; bool gl_pending = false;
     cudaEvent_t ev_stage[12] = {};
     std::string err;
     // options
@@ -71,7 +75,7 @@ struct drlz_ctx {
     SaWorkspace sa_ws;
     DevBuf stage[2], meta_dev, desc_cnt, desc_exc, tile_counter, X, mdev, exccnt, excpos, excbyte,
         flags, haps, gapless, gtile_cnt, gtile_exc, gtile_off, gtile_excoff, gscan_tmp, chunk_hap, first_pos, first_len, run_a, run_b, link_a, link_b, open_i, open_pos, open_len, spec_cnt, spec_exit, alt_entry, alt_cnt, alt_exit, alt_round, alt_own, alt_merge, spec_ph, alt_ph, hint, mm, true_slot, counters, jump_a,
-        jump_b, mark, true_cnt, true_entry, true_off, scan_tmp, hap_pairs, out, ms_a, ms_b, tab_tmp, gap_list, gap_scratch, gap_counter, ext, hint_src, uniqc;
+        jump_b, mark, true_cnt, true_entry, true_off, scan_tmp, hap_pairs, out, ms_a, ms_b, tab_tmp, gap_list, gap_scratch, gap_counter, ext, hint_src, uniqc, gapless_b;
     HostBuf meta_host, small_host, gap_host;
     uint64_t exc_stride_hint = 0;
     // thread safety: every entry point takes `mu` (calls from several threads are serialised on the device)
@@ -151,9 +155,12 @@ int drlz_create(drlz_ctx** out, int device) {
     drlz_ctx* c = new drlz_ctx();
     c->device = device;
     if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return DRLZ_E_CUDA; }
+        cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return DRLZ_E_CUDA; }
     c->stream = c->own_stream;
     for (int i = 0; i < 2; ++i) cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming);
+    for (int i = 0; i < 2; ++i) cudaEventCreateWithFlags(&c->ev_gl_done[i], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->ev_gl_ready, cudaEventDisableTiming);
     for (int i = 0; i < 12; ++i) cudaEventCreate(&c->ev_stage[i]);
     *out = c;
     return DRLZ_OK;
@@ -173,13 +180,16 @@ void drlz_destroy(drlz_ctx* c) {
                       &c->desc_exc, &c->tile_counter, &c->X, &c->mdev, &c->exccnt, &c->excpos,
                       &c->excbyte, &c->flags, &c->haps, &c->gapless, &c->gtile_cnt, &c->gtile_exc, &c->gtile_off, &c->gtile_excoff, &c->gscan_tmp, &c->chunk_hap, &c->first_pos, &c->first_len, &c->run_a, &c->run_b, &c->link_a, &c->link_b, &c->open_i, &c->open_pos, &c->open_len, &c->spec_cnt, &c->spec_exit,
                       &c->alt_entry, &c->alt_cnt, &c->alt_exit, &c->alt_round, &c->alt_own, &c->alt_merge, &c->spec_ph, &c->alt_ph, &c->hint, &c->mm, &c->true_slot, &c->counters, &c->jump_a, &c->jump_b,
-                      &c->mark, &c->true_cnt, &c->true_entry, &c->true_off, &c->scan_tmp, &c->hap_pairs, &c->out, &c->ms_a, &c->ms_b, &c->tab_tmp, &c->gap_list, &c->gap_scratch, &c->gap_counter, &c->ext, &c->hint_src, &c->uniqc};
+                      &c->mark, &c->true_cnt, &c->true_entry, &c->true_off, &c->scan_tmp, &c->hap_pairs, &c->out, &c->ms_a, &c->ms_b, &c->tab_tmp, &c->gap_list, &c->gap_scratch, &c->gap_counter, &c->ext, &c->hint_src, &c->uniqc, &c->gapless_b};
     for (DevBuf* b : bufs) b->release();
     c->meta_host.release(); c->small_host.release(); c->gap_host.release();
     for (int i = 0; i < 2; ++i) if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]);
     for (int i = 0; i < 12; ++i) if (c->ev_stage[i]) cudaEventDestroy(c->ev_stage[i]);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
+    for (int i = 0; i < 2; ++i) if (c->ev_gl_done[i]) cudaEventDestroy(c->ev_gl_done[i]);
+    if (c->ev_gl_ready) cudaEventDestroy(c->ev_gl_ready);
     delete c;
 }
 
@@ -309,7 +319,11 @@ static int run_device_group(drlz_ctx* c, const uint8_t* rows_dev, const uint64_t
     }
     CK(c, c->mdev.ensure((size_t)H * 8)); CK(c, c->exccnt.ensure(((size_t)H + 1) * 8));
     CK(c, c->flags.ensure(16)); CK(c, c->haps.ensure((size_t)H * sizeof(HapView)));
-    if (want_gapless) CK(c, c->gapless.ensure(gbytes + 16));
+    DevBuf& glbuf = c->gl_cur ? c->gapless_b : c->gapless;
+    if (want_gapless) {
+        CK(c, glbuf.ensure(gbytes + 16));
+        CK(c, cudaStreamWaitEvent(c->stream, c->ev_gl_done[c->gl_cur], 0));      // the copies of the group before last out of this buffer
+    }
     if (c->exc_stride_hint < maxcols / 256 + 256) c->exc_stride_hint = maxcols / 256 + 256;
 
     // a group is redone when (a) the fix-up did not converge with chunks (once: one chunk per haplotype, always exact),
@@ -360,7 +374,7 @@ static int run_device_group(drlz_ctx* c, const uint8_t* rows_dev, const uint64_t
         job.m_out = c->mdev.as<uint64_t>(); job.exc_cnt = c->exccnt.as<uint64_t>();
         job.exc_pos = c->excpos.as<uint32_t>(); job.exc_byte = c->excbyte.as<uint8_t>(); job.exc_stride = exc_stride;
         job.flags = c->flags.as<uint32_t>();
-        job.gapless = want_gapless ? c->gapless.as<uint8_t>() : nullptr; job.gapless_off = d_goff;
+        job.gapless = want_gapless ? glbuf.as<uint8_t>() : nullptr; job.gapless_off = d_goff;
         job.bl = c->bl; job.b2c = c->d_lut; job.gtiles_per_row = GT;
         job.gtile_cnt = c->gtile_cnt.as<uint32_t>(); job.gtile_exc = c->gtile_exc.as<uint32_t>();
         job.gtile_off = c->gtile_off.as<uint64_t>(); job.gtile_excoff = c->gtile_excoff.as<uint64_t>();
@@ -771,6 +785,8 @@ static int parse_batch_impl(drlz_ctx* c, const uint8_t* const* rows, const uint6
     if (!c->have_index) { c->err = "index not built"; return DRLZ_E_STATE; }
     CK(c, cudaSetDevice(c->device));
     NvtxRange nvtx_batch("drlz.parse_batch: host rows in, records out");
+    // whatever way out: no copy into the caller's gapless buffers is still in flight when the call returns
+    struct GlGuard { drlz_ctx* c; ~GlGuard() { if (c->gl_pending) { c->gl_pending = false; cudaStreamSynchronize(c->d2h_stream); } } } gl_guard{c};
     if (!c->opt_keep_timings) for (int i = 0; i < 12; ++i) c->parse_ms[i] = 0;
     // trimmed column counts (Spark's text reader drops the line terminator)
     std::vector<uint64_t> tc(H);
@@ -833,10 +849,17 @@ static int parse_batch_impl(drlz_ctx* c, const uint8_t* const* rows, const uint6
             if (total) CK(c, cudaMemcpyAsync(pairs_out + 2 * done_pairs, c->out.p, total * 16, cudaMemcpyDeviceToHost, c->stream));
         } else nospace = true;
         if (want_gl) {
+            // on their own stream: the next group's copy in, its kernels and these copies out run side by side
             uint64_t* sh_m = c->small_host.as<uint64_t>();
+            const uint8_t* glsrc = (c->gl_cur ? c->gapless_b : c->gapless).as<uint8_t>();
+            CK(c, cudaEventRecord(c->ev_gl_ready, c->stream));
+            CK(c, cudaStreamWaitEvent(c->d2h_stream, c->ev_gl_ready, 0));
+            c->gl_pending = true;
             for (uint32_t h = a; h < b; ++h)
                 if (gapless_out[h] && sh_m[h - a])
-                    CK(c, cudaMemcpyAsync(gapless_out[h], c->gapless.as<uint8_t>() + gl_off[h - a], sh_m[h - a], cudaMemcpyDeviceToHost, c->stream));
+                    CK(c, cudaMemcpyAsync(gapless_out[h], glsrc + gl_off[h - a], sh_m[h - a], cudaMemcpyDeviceToHost, c->d2h_stream));
+            CK(c, cudaEventRecord(c->ev_gl_done[c->gl_cur], c->d2h_stream));
+            c->gl_cur ^= 1;
         }
         if (n_gaps) {
             if (strip_gaps) { rc = collect_gap_runs(c, c->stage[gi & 1].as<uint8_t>(), tc.data() + a, b - a, gaps_out, gaps_cap, &done_gaps, n_gaps + a, &nospace); if (rc != DRLZ_OK) return rc; }
@@ -845,6 +868,7 @@ static int parse_batch_impl(drlz_ctx* c, const uint8_t* const* rows, const uint6
         CK(c, cudaStreamSynchronize(c->stream));
         done_pairs += total;
     }
+    if (c->gl_pending) { c->gl_pending = false; CK(c, cudaStreamSynchronize(c->d2h_stream)); }
     if (nospace) { c->err = "pairs_cap or gaps_cap too small"; return DRLZ_E_NOSPACE; }
     return DRLZ_OK;
 }

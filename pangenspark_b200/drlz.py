@@ -188,8 +188,10 @@ class Drlz:
 
     # ---- parse ------------------------------------------------------------------------------------
     def parse_batch(self, rows, strip_gaps: bool = True, want_gapless: bool = False, pairs_cap: int | None = None,
-                    out: np.ndarray | None = None):
-        """rows: list of uint8 arrays / bytes (host).  Returns (list of [np,2] int64 arrays, m[H], gapless list|None)."""
+                    out: np.ndarray | None = None, gapless_out: list | None = None):
+        """rows: list of uint8 arrays / bytes (host).  Returns (list of [np,2] int64 arrays, m[H], gapless list|None).
+        gapless_out: one uint8 array per row (at least as long as the row; e.g. views of pinned memory) to receive the
+        gapless sequences instead of freshly allocated arrays."""
         rows = [_u8(r) for r in rows]
         H = len(rows)
         ptrs = (C.c_void_p * max(1, H))(*[r.ctypes.data if r.size else None for r in rows])
@@ -199,7 +201,9 @@ class Drlz:
         gl = None
         glp = None
         if want_gapless:
-            gl = [np.empty(max(1, r.size), dtype=np.uint8) for r in rows]
+            gl = gapless_out if gapless_out is not None else [np.empty(max(1, r.size), dtype=np.uint8) for r in rows]
+            if len(gl) != H or any(g.size < r.size for g, r in zip(gl, rows)):
+                raise ValueError("gapless_out: one array per row, at least as long as the row")
             glp = (C.c_void_p * max(1, H))(*[g.ctypes.data for g in gl])
         cap = pairs_cap if pairs_cap is not None else max(1024, int(cols.sum()) // 64 + 64 * H)
         while True:
