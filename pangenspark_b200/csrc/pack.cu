@@ -921,6 +921,200 @@ __global__ void __launch_bounds__(256) k_packg_write(PackJob job) {
     }
 }
 
+// =====================================================================================================================
+// k_packg1 -- generic alphabets in one pass.
+//
+// The two-pass kernels above read the rows twice in 4 KB tiles (586 k CTAs of 256 threads per 2.4 GB, twice, with two
+// device scans in between) and keep their codes in dynamically indexed local arrays: 0.37 TB/s.  A reference assembly
+// with N in it -- every real chromosome -- takes this path, so it gets the structure of k_pack2: 16 KB tiles handed out by
+// a ticket (row = id % H), 64 bytes per thread, the tile's place in the row by decoupled look-back over the same
+// descriptors, exception counts by atomics.  Codes come from the 256-entry table in shared memory; every 64-bit word a
+// thread completes on its own (the rule when the tile has no gap column in front of it) is a plain shared-memory store,
+// the others are OR-ed in at their symbol offset; the tile's words then leave shifted onto the output's word grid.
+// =====================================================================================================================
+__device__ __forceinline__ uint32_t comp4(const uint4& v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w)); }
+
+// the block's staged bytes (16-byte aligned, readable 16 bytes past n) to an arbitrarily aligned destination as 16-byte stores
+__device__ __forceinline__ void flush_bytes_block(const uint8_t* gb, uint8_t* dst, uint32_t n, int tid, int nthr) {
+    const uint32_t head = min(n, (uint32_t)((16u - (uint32_t)((uintptr_t)dst & 15u)) & 15u));
+    if ((uint32_t)tid < head) dst[tid] = gb[tid];
+    const uint32_t nfull = (n - head) >> 4;
+    const uint32_t* gw = reinterpret_cast<const uint32_t*>(gb);
+    const uint32_t w0 = head >> 2, sel = 0x3210u + 0x1111u * (head & 3u);
+    uint4* d16 = reinterpret_cast<uint4*>(dst + head);
+    for (uint32_t c = tid; c < nfull; c += nthr) {
+        const uint32_t* q = gw + w0 + 4 * c;
+        const uint32_t a0 = q[0], a1 = q[1], a2 = q[2], a3 = q[3], a4 = q[4];
+        d16[c] = make_uint4(__byte_perm(a0, a1, sel), __byte_perm(a1, a2, sel), __byte_perm(a2, a3, sel), __byte_perm(a3, a4, sel));
+    }
+    const uint32_t done = head + (nfull << 4);
+    if (done + (uint32_t)tid < n) dst[done + tid] = gb[done + tid];
+}
+
+template <int BL>        // log2 of the bits per symbol: 2 or 3
+__global__ void __launch_bounds__(kPackThreads, 4) k_packg1(PackJob job, uint32_t n_tiles) {
+    constexpr int B = 1 << BL, SPW = 64 / B, NG = 64 / SPW;          // bits per symbol, symbols per word, words per 64 input bytes
+    constexpr int NW = kPackTileBytes / SPW;                          // words of a full tile
+    __shared__ uint64_t sw[NW + 2];                                   // [0]: the empty word in front; the tile's words from [1]
+    __shared__ uint8_t s_b2c[256];
+    __shared__ uint32_t sm[33];
+    __shared__ uint64_t s_o[2];
+    __shared__ uint32_t s_ticket[3];
+    extern __shared__ __align__(16) uint8_t s_gl[];                   // gapless output asked for: kPackTileBytes + 32 bytes
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        const uint32_t id = atomicAdd(job.tile_counter, 1u);
+        s_ticket[0] = id; s_ticket[1] = id % job.H; s_ticket[2] = id / job.H;
+    }
+    s_b2c[tid] = job.b2c[tid];
+    for (int i = tid; i < NW + 2; i += kPackThreads) sw[i] = 0;
+    __syncthreads();
+    if (s_ticket[0] >= n_tiles) return;
+    const uint32_t h = s_ticket[1], t = s_ticket[2];
+    const uint32_t cols = (uint32_t)job.cols[h];
+    const uint8_t* __restrict__ rowp = job.rows + job.row_off[h];
+    const uint32_t off = t * (uint32_t)kPackTileBytes + (uint32_t)tid * 64u;     // < 2^32: the host bounds cols by 2^32 - 1024
+    const bool last_tile = t + 1 == job.tiles_per_row;
+    const bool gl_on = job.gapless != nullptr;
+
+    // ---- own 64 bytes: one word per SPW input bytes, kept symbols left aligned ----------------------------------------
+    uint4 v[4]; int nv[4];
+    load64_checked(rowp, off, cols, v, nv);
+    uint64_t gw[NG]; uint32_t gc[NG];
+    uint32_t cnt = 0, exc = 0;
+    // the rule: 64 bytes of the alphabet, no gap column -- every symbol's place in its word is known at compile time
+    bool plain = nv[0] == 16 && nv[1] == 16 && nv[2] == 16 && nv[3] == 16;
+    if (plain && job.strip) {
+        uint32_t any = 0;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const uint32_t x = comp4(v[q >> 2], q & 3) ^ 0x2D2D2D2Du;             // a zero byte = a '-'
+            any |= (x - 0x01010101u) & ~x;
+        }
+        plain = (any & 0x80808080u) == 0;
+    }
+    if (plain) {
+        uint32_t foreign = 0;
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+            uint32_t hi = 0, lw = 0;
+#pragma unroll
+            for (int q = 0; q < SPW; ++q) {
+                const int b = g * SPW + q;
+                const uint32_t code = s_b2c[(comp4(v[b >> 4], (b >> 2) & 3) >> (8 * (b & 3))) & 255u];
+                foreign |= (code + 1u) >> 8;
+                if (q < SPW / 2) hi |= code << (32 - B - B * q); else lw |= code << (32 - B - B * (q - SPW / 2));
+            }
+            gw[g] = ((uint64_t)hi << 32) | lw; gc[g] = SPW;
+        }
+        plain = foreign == 0;
+        if (plain) cnt = 64;
+    }
+    if (!plain)
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {
+        uint64_t w = 0; uint32_t c = 0;
+#pragma unroll
+        for (int q = 0; q < SPW; ++q) {
+            const int b = g * SPW + q;
+            const uint32_t byte = (comp4(v[b >> 4], (b >> 2) & 3) >> (8 * (b & 3))) & 255u;
+            if ((b & 15) < nv[b >> 4] && !(job.strip && byte == '-')) {
+                uint32_t code = s_b2c[byte];
+                if (code == 0xFFu) { ++exc; code = 0; }
+                w |= (uint64_t)code << (64 - B - B * (int)c);
+                ++c;
+            }
+        }
+        gw[g] = w; gc[g] = c; cnt += c;
+    }
+    uint32_t total;
+    const uint32_t ex = block_exclusive_scan<uint32_t, OpSum>(cnt | (exc << 16), OpSum(), 0u, &total, sm);
+    const uint32_t lo = ex & 0xFFFFu, elo = ex >> 16, T = total & 0xFFFFu, TE = total >> 16;
+
+    // ---- the tile's place in the row: look-back by warp 0, while the others fill the word buffer ----------------------
+    if (warp == 0) {
+        uint64_t* dcnt = job.desc_cnt + (uint64_t)h * job.tiles_per_row;
+        uint64_t* dexc = job.desc_exc + (uint64_t)h * job.tiles_per_row;
+        const uint64_t o = lookback(dcnt, t, T, job.flags);
+        uint64_t eo = 0;
+        if (TE) {
+            eo = lookback(dexc, t, TE, job.flags);
+            if (lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(&job.exc_cnt[h]), (unsigned long long)TE);
+        } else if (lane == 0) {
+            const uint64_t pv = t ? ld_desc(&dexc[t - 1]) : kDescPrefix;
+            st_desc(&dexc[t], (pv >> 62) == 2 ? pv : kDescAgg);
+        }
+        if (lane == 0) {
+            s_o[0] = o; s_o[1] = eo;
+            if (last_tile) job.m_out[h] = o + T;
+        }
+    }
+    {
+        uint32_t pos = lo;
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+            const uint32_t c = gc[g];
+            if (!c) continue;
+            const uint32_t wi = 1u + pos / SPW, r = pos % SPW;
+            if (r == 0 && c == (uint32_t)SPW) sw[wi] = gw[g];                     // the whole word is this thread's
+            else {
+                atomicOr(reinterpret_cast<unsigned long long*>(&sw[wi]), (unsigned long long)(gw[g] >> (B * r)));
+                if (r + c > (uint32_t)SPW) atomicOr(reinterpret_cast<unsigned long long*>(&sw[wi + 1]), (unsigned long long)(gw[g] << (64 - B * r)));
+            }
+            pos += c;
+        }
+    }
+    if (gl_on) {                                                      // kept bytes of the tile, in order
+        if (cnt == 64u && (lo & 15u) == 0) {
+            uint4* d = reinterpret_cast<uint4*>(s_gl + lo);
+            d[0] = v[0]; d[1] = v[1]; d[2] = v[2]; d[3] = v[3];
+        } else if (cnt) {
+            uint32_t p = lo;
+            for (int q = 0; q < 4; ++q) {
+                const uint32_t w4[4] = {v[q].x, v[q].y, v[q].z, v[q].w};
+                for (int b = 0; b < nv[q]; ++b) {
+                    const uint32_t byte = (w4[b >> 2] >> (8 * (b & 3))) & 255u;
+                    if (job.strip && byte == '-') continue;
+                    s_gl[p++] = (uint8_t)byte;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (T == 0) return;
+    const uint64_t o = s_o[0];
+
+    if (exc) {                                                        // foreign bytes: (gapless position, byte) into the row's sorted list
+        uint32_t* ep = job.exc_pos + (uint64_t)h * job.exc_stride;
+        uint8_t* eb = job.exc_byte + (uint64_t)h * job.exc_stride;
+        uint64_t e = s_o[1] + elo, p = o + lo;
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t w4[4] = {v[q].x, v[q].y, v[q].z, v[q].w};
+            for (int b = 0; b < nv[q]; ++b) {
+                const uint32_t byte = (w4[b >> 2] >> (8 * (b & 3))) & 255u;
+                if (job.strip && byte == '-') continue;
+                if (s_b2c[byte] == 0xFFu) {
+                    if (e < job.exc_stride) { ep[e] = (uint32_t)p; eb[e] = (uint8_t)byte; }
+                    ++e;
+                }
+                ++p;
+            }
+        }
+    }
+    // ---- the tile's words onto the output's word grid -------------------------------------------------------------------
+    const uint32_t lead = (uint32_t)(o % SPW), sh = B * lead;
+    const uint32_t nwords = (lead + T + SPW - 1) / SPW;
+    uint64_t* X = job.X + job.xoff[h] + o / SPW;
+    for (uint32_t j = tid; j < nwords; j += kPackThreads) {
+        const uint64_t a = sw[j], b = sw[j + 1];                      // the tile's words j - 1 and j
+        const uint64_t val = lead ? (a << (64 - sh)) | (b >> sh) : b;
+        const bool edge = (j == 0 && lead != 0) || (j == nwords - 1 && ((lead + T) % SPW) != 0);
+        if (edge) atomicOr(reinterpret_cast<unsigned long long*>(&X[j]), (unsigned long long)val);
+        else X[j] = val;
+    }
+    if (gl_on) flush_bytes_block(s_gl, job.gapless + job.gapless_off[h] + o, T, tid, kPackThreads);
+}
+
 static void launch_pack_generic(const PackJob& job, cudaStream_t s, cudaEvent_t* ev) {
     dim3 grid(job.gtiles_per_row, job.H);
     uint64_t nt = (uint64_t)job.H * job.gtiles_per_row;
@@ -941,12 +1135,22 @@ static void launch_pack_generic(const PackJob& job, cudaStream_t s, cudaEvent_t*
 
 void launch_pack(const PackJob& job, cudaStream_t s, cudaEvent_t* ev) {
     if (job.H == 0 || job.tiles_per_row == 0) { if (ev) for (int i = 0; i < 3; ++i) cudaEventRecord(ev[i], s); return; }
-    if (job.bl != 1) { launch_pack_generic(job, s, ev); return; }
+    if (job.bl != 1 && job.variant == 0) { launch_pack_generic(job, s, ev); return; }      // the two-pass kernels, kept for comparison
     uint64_t nt = (uint64_t)job.H * job.tiles_per_row;
     cudaMemsetAsync(job.desc_cnt, 0, nt * 8, s);
     cudaMemsetAsync(job.desc_exc, 0, nt * 8, s);
     cudaMemsetAsync(job.tile_counter, 0, 4, s);
     if (ev) { cudaEventRecord(ev[0], s); cudaEventRecord(ev[1], s); }
+    if (job.bl != 1) {
+        cudaMemsetAsync(job.exc_cnt, 0, (size_t)job.H * 8, s);
+        const size_t smem = job.gapless ? (size_t)kPackTileBytes + 32 : 0;
+        g_launches += 2;
+        if (job.bl == 2) k_packg1<2><<<(unsigned)nt, kPackThreads, smem, s>>>(job, (uint32_t)nt);
+        else k_packg1<3><<<(unsigned)nt, kPackThreads, smem, s>>>(job, (uint32_t)nt);
+        k_pack2_finish<<<(job.H + 127) / 128, 128, 0, s>>>(job);
+        if (ev) cudaEventRecord(ev[2], s);
+        return;
+    }
     g_launches += 1;
     const unsigned grid = (unsigned)nt;          // one tile per CTA (4 per ticket measured 18x slower: a tile is published only
                                                  // after its CTA finished the earlier ones, which serialises every row's look-back)

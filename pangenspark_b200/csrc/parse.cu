@@ -517,12 +517,13 @@ int parse_stage_count(ParseBuffers& pb, cudaStream_t s, int* rounds_out, cudaEve
         // their own take the one in front of them
         const bool long_repeats = pv.ix.uniq32 != nullptr && pb.ext && pb.hint_src && kHintGroup == 1;
         if (long_repeats) {
+            // first from behind (a chunk inside a run is placed by what follows the run), then from the front for what is left
             g_launches += 1;
-            device_scan<uint32_t, LoadHintIdx, StoreHintSrc, OpMax, true>(LoadHintIdx{pb.hint}, StoreHintSrc{pb.hint_src}, NC,
-                                                                          reinterpret_cast<uint32_t*>(pb.scan_tmp), OpMax(), 0u, s);
-            k_hint_fill<<<(NC + 255) / 256, 256, 0, s>>>(pv, pb.hint, pb.hint_src);
             device_scan<uint32_t, LoadHintIdxRev, StoreHintSrcRev, OpMin, true>(LoadHintIdxRev{pb.hint, NC}, StoreHintSrcRev{pb.hint_src, NC}, NC,
                                                                                 reinterpret_cast<uint32_t*>(pb.scan_tmp), OpMin(), 0xFFFFFFFFu, s);
+            k_hint_fill<<<(NC + 255) / 256, 256, 0, s>>>(pv, pb.hint, pb.hint_src);
+            device_scan<uint32_t, LoadHintIdx, StoreHintSrc, OpMax, true>(LoadHintIdx{pb.hint}, StoreHintSrc{pb.hint_src}, NC,
+                                                                          reinterpret_cast<uint32_t*>(pb.scan_tmp), OpMax(), 0u, s);
             k_hint_fill<<<(NC + 255) / 256, 256, 0, s>>>(pv, pb.hint, pb.hint_src);
             g_launches += 1;
         }

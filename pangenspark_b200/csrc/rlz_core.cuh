@@ -714,6 +714,24 @@ DRLZ_HD void hint_group(const ParseView& pv, int64_t* hint, uint32_t q) {
         Match mt = lookup(pv.ix, hv.x, at, (uint32_t)(stop - at), 64u, &open, true);
         if (mt.len >= kDiagMinLen) { hint[q] = (int64_t)mt.pos - (int64_t)at; return; }
     }
+    // A chunk that starts inside a run of one symbol (the N runs of a reference assembly) and sees the end of the run:
+    // a match from inside the run is placed by what follows the run, so the probe goes there.  The chunks further inside
+    // the run, which see nothing but the run, inherit this diagonal from behind (k_hint_fill, right to left first).
+    const uint32_t bl = pv.ix.bl, sl = 6 - bl, spw = 1u << sl;
+    const uint64_t w0 = get64u(hv.x, (uint32_t)s, bl);
+    const uint64_t unit = bl == 1 ? 0x5555555555555555ull : (bl == 2 ? 0x1111111111111111ull : 0x0101010101010101ull);
+    const uint64_t rep = (w0 >> (64 - (1u << bl))) * unit;
+    if (w0 != rep) return;
+    uint64_t j = s + spw;
+    while (j < e) {
+        const uint64_t w = get64u(hv.x, (uint32_t)j, bl);
+        if (w != rep) { j += (uint64_t)(clz64(w ^ rep) >> bl); break; }
+        j += spw;
+    }
+    if (j >= e || stop < j + 64) return;
+    bool open;
+    Match mt = lookup(pv.ix, hv.x, j, (uint32_t)(stop - j), 64u, &open, true);
+    if (mt.len >= kDiagMinLen) hint[q] = (int64_t)mt.pos - (int64_t)j;
 }
 
 // D: mismatch offsets of chunk g along its hinted diagonal (scalar form; the kernel k_diag_w does the same with one

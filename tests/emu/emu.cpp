@@ -141,19 +141,19 @@ int emu_parse(const uint8_t* ref, uint64_t n, const int64_t* sa64, int k, uint32
     for (int h = 0; h < H; ++h) if (base[h + 1] - base[h] > maxc0) maxc0 = base[h + 1] - base[h];
     if (use_uniq && chunk_shift >= 5 && chunk_shift <= 15) {
         for (uint32_t q = 0; q * kHintGroup < NC; ++q) hint_group(pv, hint.data(), q);
-        if (use_uniq > 1) {                                  // k_hint_fill: chunks without a hint take the one in front of them (same haplotype)
+        if (use_uniq > 1) {                                  // k_hint_fill: chunks without a hint take the one behind them (same haplotype) ...
             std::vector<int64_t> own(hint);
             for (uint32_t g = 0; g < NC; ++g) {
                 if (own[g] != kNoDiag) continue;
                 uint32_t f = g;
-                while (f > 0 && own[f] == kNoDiag) --f;
+                while (f + 1 < NC && own[f] == kNoDiag) ++f;
                 if (own[f] != kNoDiag && chunk_hap[f] == chunk_hap[g]) hint[g] = own[f];
             }
-            own = hint;                                      // second pass, from the other side (haplotypes that begin inside a run)
+            own = hint;                                      // ... and what is left (the tail of a haplotype) the one in front
             for (uint32_t g = 0; g < NC; ++g) {
                 if (own[g] != kNoDiag) continue;
                 uint32_t f = g;
-                while (f + 1 < NC && own[f] == kNoDiag) ++f;
+                while (f > 0 && own[f] == kNoDiag) --f;
                 if (own[f] != kNoDiag && chunk_hap[f] == chunk_hap[g]) hint[g] = own[f];
             }
         }
