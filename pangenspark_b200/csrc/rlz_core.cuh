@@ -268,7 +268,14 @@ DRLZ_HD Match lookup(const IndexView& ix, const uint64_t* __restrict__ X, uint64
             uint32_t mid = l + ((h - l) >> 1);
             bool less;
             uint32_t pm = SA[mid];
-            uint32_t c = cmp_suffix_w(xw, X, i, D, pm, n, plen, &less, bl);
+            // every suffix between two that share `skip` symbols with the pattern shares them too: inside a long repeat
+            // (the uncapped pass over a run of N) the compares go on where the bounds left off instead of streaming the
+            // repeat again in every step
+            const uint32_t skip = (have_left && have_right) ? (lcp_left < lcp_right ? lcp_left : lcp_right) : 0u;
+            uint32_t c;
+            if (skip >= 64u && skip < plen && skip < n - pm)
+                c = skip + cmp_suffix(X, (uint64_t)i + skip, D, (uint64_t)pm + skip, n, plen - skip, &less, bl);
+            else c = cmp_suffix_w(xw, X, i, D, pm, n, plen, &less, bl);
             if (less) { l = mid + 1; lcp_left = c; have_left = true; }
             else { h = mid; lcp_right = c; have_right = true; sar = pm; }
         }
@@ -338,11 +345,17 @@ DRLZ_HD Match lookup(const IndexView& ix, const uint64_t* __restrict__ X, uint64
 // imitate the prefix through their zero padding and sort in front; a suffix of that bracket that is long enough shares
 // the prefix).  Returns false if it cannot answer (then lookup() does).
 static const int kLookCand = 6;
-static const uint32_t kLookShort = 32;
+static const uint32_t kLookShort = 32;         // symbols of one 2-bit word (wider symbols: 64 >> bl, see lookup_short_len)
+DRLZ_HD uint32_t lookup_short_len(uint32_t bl) { return 64u >> bl; }
+// xw = the pattern's first word (64 >> bl symbols).  Symbols of 2 bits: keys are bit fields; wider symbols (references with
+// N: 4 bits): radix-sigma keys through prefix_keys(), one word holds 16 symbols, so the answer covers matches below 16.
 DRLZ_HD bool lookup_short(const IndexView& ix, uint64_t xw, Match* out) {
     const int k = ix.k;
-    const uint32_t n = (uint32_t)ix.n;
-    const uint64_t key = xw >> (64 - 2 * k);
+    const uint32_t n = (uint32_t)ix.n, bl = ix.bl, wsym = 64u >> bl;
+    if ((uint32_t)k > wsym) return false;
+    uint64_t key, span;
+    if (bl == 1) key = xw >> (64 - 2 * k);
+    else prefix_keys(ix, xw, (uint32_t)k, &key, &span);
     const uint32_t lo = ix.tab[key], hi = ix.tab[key + 1];
     if (hi - lo > (uint32_t)kLookCand - 2u) return false;
     uint32_t best = 0, lcp[kLookCand], sp[kLookCand];
@@ -357,13 +370,13 @@ DRLZ_HD bool lookup_short(const IndexView& ix, uint64_t xw, Match* out) {
     for (int c = 0; c < kLookCand; ++c) {
         lcp[c] = 0;
         if (val[c]) {
-            const uint64_t xr = xw ^ get64u(ix.text, sp[c], 1);
-            const uint32_t l = xr ? (uint32_t)(clz64(xr) >> 1) : 32u, avail = n - sp[c];
+            const uint64_t xr = xw ^ get64u(ix.text, sp[c], bl);
+            const uint32_t l = xr ? (uint32_t)(clz64(xr) >> bl) : wsym, avail = n - sp[c];
             lcp[c] = l < avail ? l : avail;
         }
         if (lcp[c] > best) best = lcp[c];
     }
-    if (best >= kLookShort) return false;
+    if (best >= wsym) return false;
     out->len = best; out->pos = 0;
     if (best == 0) return true;                              // literal; the caller fills in the byte
     if (best >= (uint32_t)k) {                               // the interval lies inside the bracket: entries 1 .. hi - lo of the candidates
@@ -372,8 +385,10 @@ DRLZ_HD bool lookup_short(const IndexView& ix, uint64_t xw, Match* out) {
         for (int c = kLookCand - 2; c >= 1; --c) if (lcp[c] >= best) { out->pos = sp[c]; found = true; }
         return found;
     }
-    const uint64_t lowmask = (1ull << (2 * (k - (int)best))) - 1;
-    const uint32_t a = ix.tab[key & ~lowmask];               // first suffix whose padded k-mer starts with the matched prefix
+    uint64_t pkey;
+    if (bl == 1) pkey = key & ~((1ull << (2 * (k - (int)best))) - 1);
+    else prefix_keys(ix, xw, best, &pkey, &span);
+    const uint32_t a = ix.tab[pkey];                         // first suffix whose padded k-mer starts with the matched prefix
     if (a + 1 >= n) return false;
     const uint32_t p0 = ix.sa[a], p1 = ix.sa[a + 1];
     if (p0 + best <= n) { out->pos = p0; return true; }
@@ -581,7 +596,8 @@ DRLZ_HD Match phrase_tail(const ParseView& pv, const HapView& hv, uint64_t i, ui
     Match mt;
     // most lookups of the parse stand on a variant site: a match of a dozen symbols somewhere else, which the short form
     // finds in five dependent loads instead of eight
-    if (!(pv.ix.bl == 1 && (cap < maxlen ? cap : maxlen) >= kLookShort && lookup_short(pv.ix, get64u(hv.x, (uint32_t)i, 1), &mt)))
+    if (!(pv.ix.bl <= 2 && (cap < maxlen ? cap : maxlen) >= lookup_short_len(pv.ix.bl) &&
+          lookup_short(pv.ix, get64u(hv.x, (uint32_t)i, pv.ix.bl), &mt)))
         mt = lookup(pv.ix, hv.x, i, maxlen, cap, open);
     if (mt.len == 0) mt.pos = (uint32_t)pv.ix.c2b[base_at(hv.x, i, pv.ix.bl)];
     else if (mt.len >= kDiagMinLen) *diag = (int64_t)mt.pos - (int64_t)i;
@@ -728,10 +744,13 @@ DRLZ_HD void hint_group(const ParseView& pv, int64_t* hint, uint32_t q) {
         if (w != rep) { j += (uint64_t)(clz64(w ^ rep) >> bl); break; }
         j += spw;
     }
-    if (j >= e || stop < j + 64) return;
-    bool open;
-    Match mt = lookup(pv.ix, hv.x, j, (uint32_t)(stop - j), 64u, &open, true);
-    if (mt.len >= kDiagMinLen) hint[q] = (int64_t)mt.pos - (int64_t)j;
+    for (uint32_t probe = 0; probe < 3; ++probe) {           // (a variant right behind the run: further in, as above)
+        const uint64_t at = j + 96u * probe;
+        if (at >= e || stop < at + 64) return;
+        bool open;
+        Match mt = lookup(pv.ix, hv.x, at, (uint32_t)(stop - at), 64u, &open, true);
+        if (mt.len >= kDiagMinLen) { hint[q] = (int64_t)mt.pos - (int64_t)at; return; }
+    }
 }
 
 // D: mismatch offsets of chunk g along its hinted diagonal (scalar form; the kernel k_diag_w does the same with one
