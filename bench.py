@@ -67,6 +67,69 @@ def workload_cfg3(rank: int, world: int):
     return {"n": n, "H": b - a, "Htot": Htot, "p_snp": 1e-3, "p_ins": 1e-5, "p_del": 1e-5, "cfg": 3, "h0": a, "name": name}
 
 
+def gen_nrun_workload(orc, n, H, nrun):
+    """A reference assembly as it comes: ACGT with runs of N -- a telomere, a centromere-sized run of `nrun`
+    bases, a few short ones -- and H haplotypes at configs[1] rates whose N runs are the reference's (a panel called
+    against the reference has no variant inside an N region).  Returns (reference bytes, rows [H, stride], M, stride)."""
+    import ctypes as C
+    seed = orc.seed_for(2)
+    d = orc.syn_reference(seed, n)
+    runs = [(0, min(n // 100, 500_000)), (n // 3, nrun), (n // 2 + 12345, 50_000), (n - n // 50, 30_000), (n // 5, 700)]
+    for a, ln in runs:
+        d[a:a + ln] = ord("N")
+    M = orc.syn_columns(seed, n, 1e-5)
+    stride = (M + 15) // 16 * 16 + 16
+    rows = np.zeros((H, stride), dtype=np.uint8)
+    orc.lib().syn_rows(seed, d.ctypes.data_as(C.c_void_p), d.size, 1, H, 1e-3, 1e-5, 1e-5, rows.ctypes.data_as(C.c_void_p), stride)
+    # the generator treats N as a base and mutates it: every haplotype gets the reference's own columns back over the runs
+    ref_row = np.zeros((1, stride), dtype=np.uint8)
+    orc.lib().syn_rows(seed, d.ctypes.data_as(C.c_void_p), d.size, 0, 1, 0.0, 1e-5, 0.0, ref_row.ctypes.data_as(C.c_void_p), stride)
+    is_n = np.flatnonzero(ref_row[0, :M] == ord("N"))
+    breaks = np.flatnonzero(np.diff(is_n) > 16)
+    starts = np.concatenate([[is_n[0]], is_n[breaks + 1]])
+    ends = np.concatenate([is_n[breaks], [is_n[-1]]]) + 1
+    for a, b in zip(starts, ends):
+        rows[:, a:b] = ref_row[0, a:b]
+    return d, rows, M, stride
+
+
+def alphabet_4bit(job, steps):
+    """The generic-alphabet path (4 bits per symbol) on the same scale as the headline: what a reference with N in it --
+    every real chromosome -- gets.  Own context; one row checked against the oracle."""
+    orc, torch, D = job.orc, job.torch, job.D
+    n = int(os.environ.get("DRLZ_BENCH_N", 48_000_000))
+    H = int(os.environ.get("DRLZ_BENCH_4BIT_H", 25))
+    d, rows, M, stride = gen_nrun_workload(orc, n, H, 3_000_000)
+    ctx = D.Drlz(job.local)
+    try:
+        ctx.build_index(d)
+        info, it = ctx.index_info(), ctx.index_timings()
+        dev = torch.from_numpy(rows.reshape(-1)).cuda()
+        row_off = np.arange(H, dtype=np.uint64) * np.uint64(stride)
+        cols = np.full(H, M, dtype=np.uint64)
+        for _ in range(3):
+            ptr, npairs, m = ctx.parse_batch_device(dev.data_ptr(), row_off, cols)
+        ctx.set_option("keep_timings", 1)
+        for _ in range(steps):
+            ptr, npairs, m = ctx.parse_batch_device(dev.data_ptr(), row_off, cols)
+        kt = ctx.parse_timings()
+        ctx.set_option("keep_timings", 0)
+        pairs = ctx.copy_pairs_to_host(ptr, int(npairs.sum()))
+        sa = orc.sa_build(d)
+        ok = bool((ctx.index_get("sa").astype(np.int64) == sa).all())
+        want, _ = orc.encode_literal(d, sa, orc.strip_gaps(rows[0, :M]))
+        ok = ok and orc.lz_bytes(pairs[: int(npairs[0])]) == orc.lz_bytes(want)
+        dev_ms = kt["device_ms"] / steps
+        return {"value": float(m.sum()) / (dev_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": dev_ms, "bits_per_symbol": info["bits"],
+                "sigma": info["sigma"], "kmer": info["k"], "rows": H, "index_ms": it["total_ms"], "sa_rounds": info["sa_rounds"],
+                "kernel_ms_per_step": {k_: round(v_ / steps, 4) for k_, v_ in kt.items() if k_.endswith("_ms")},
+                "parity_checked_rows": 1, "ok": ok,
+                "workload": "%.0f Mbp ACGT reference with runs of N (longest 3 Mbp), %d haplotypes at configs[1] rates; device-resident, "
+                            "sum of the kernels' event times per step" % (n / 1e6, H)}
+    finally:
+        ctx.close()
+
+
 def gen_rows(orc, wl, d, pinned_array=None, rows=None):
     """rows h0..h0+H-1 as [H, stride] uint8 (stride multiple of 16, >= M+16); returns (array, M, stride)"""
     seed = orc.seed_for(wl["cfg"])
@@ -608,6 +671,12 @@ def run_ours(args):
             cli = cli_e2e(job, wl, d, ms)
         except Exception as ex:       # the CLI leg never takes the kernel numbers down with it
             cli = {"error": repr(ex)[:300]}
+    a4 = None
+    if rank == 0 and world == 1 and not os.environ.get("DRLZ_BENCH_SKIP_4BIT"):
+        try:
+            a4 = alphabet_4bit(job, max(3, steps // 2))
+        except Exception as ex:
+            a4 = {"error": repr(ex)[:300]}
     job.barrier()
     primary_kt = ms["kt"]
     H, M = ms["H"], ms["M"]
@@ -617,7 +686,7 @@ def run_ours(args):
            "config": {"workload": wl["name"], "l2": "inputs (%.2f GB of MSA rows per GPU) exceed the 126 MB L2; no explicit flush" % (H * M / 1e9),
                       "bases_per_step": ms["total_bases"], "phrases_per_step_rank0": ms["phrases"], "kmer": info["k"],
                       "index": "built once outside the step" + (", NCCL broadcast from rank 0" if world > 1 else "")},
-           "e2e": ms["e2e"], "e2e_gapless": ms["e2e_gapless"], "gpu_launches": int(primary_kt["launches"]),
+           "e2e": ms["e2e"], "e2e_gapless": ms["e2e_gapless"], "alphabet_4bit": a4, "gpu_launches": int(primary_kt["launches"]),
            "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
            "index_build": {"total_ms": idx_t["total_ms"], "wall_ms": idx_wall, "sa_ms": idx_t["sa_ms"], "table_ms": idx_t["table_ms"],
                            "pack_ms": idx_t["pack_ms"], "lcp_ms": idx_t["lcp_ms"], "rounds": info["sa_rounds"], "n": info["n"],

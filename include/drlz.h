@@ -48,7 +48,8 @@ int drlz_set_stream(drlz_ctx* ctx, void* cuda_stream);
  *          tuning / A-B switches: "occ", "occ_fix", "occ_diag" (min CTAs per SM of k_spec / k_fix / k_diag_w), "predict" (uniqueness-array
  *          prediction), "hint" + "diag" (per-chunk diagonal hint and mismatch pre-scan), "tickets" (1 = atomic tile tickets in k_pack), "occ_pack" (6 | 8 CTAs per SM k_pack is
  *          compiled for), "prefetch" (L2 prefetch distance of k_pack in tiles, 0 = off),
- *          "spec_store", "l2persist", "pack_variant" (2 = k_pack3, 1 = k_pack2), "prefetch3"; "keep_timings" (1: drlz_parse_timings sums over all
+ *          "spec_store", "l2persist", "pack_variant" (2 = k_pack3, 1 = k_pack2, 0 = the round-1 kernels; generic alphabets: 0 = two passes, else k_packg1), "prefetch3",
+ *          "spec_sync" (1 = the chunks of a warp parsed in step), "uniq_coarse" (1 = block maxima of the uniqueness array consulted first); "keep_timings" (1: drlz_parse_timings sums over all
  *          calls since the option was set instead of the last call only).  None of them changes results. */
 int drlz_set_option(drlz_ctx* ctx, const char* key, int64_t value);
 
@@ -78,7 +79,9 @@ int drlz_index_timings(const drlz_ctx* ctx, double ms[5]);
  * drlz_index_buffers, then call drlz_index_commit.  bufs: [0] packed text + uniqueness array + byte<->code
  * tables, [1] SA (followed by the unsaturated uniqueness array when the reference has repeats of 65535 symbols and more: bit
  * 28 of kinfo), [2] k-mer table.  kinfo = k | log2(bits per symbol) << 8 | alphabet size << 16 | flags, exactly
- * drlz_index_info's info[1]; a plain k (upper bits 0) means the 2-bit {A,C,G,T} layout. */
+ * drlz_index_info's info[1]; a plain k (upper bits 0) means the 2-bit {A,C,G,T} layout.  drlz_index_commit waits for the
+ * device (the buffers may have been filled on the caller's streams) and derives what is not broadcast (the block maxima
+ * of the uniqueness array). */
 int drlz_index_reserve(drlz_ctx* ctx, uint64_t n, int kinfo);
 int drlz_index_buffers(drlz_ctx* ctx, void* dev_ptrs[3], uint64_t bytes[3]);
 int drlz_index_commit(drlz_ctx* ctx);

@@ -16,6 +16,7 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 from oracle import oracle as orc  # noqa: E402
 from pangenspark_b200 import drlz as D  # noqa: E402
+import bench  # noqa: E402
 
 
 def main():
@@ -23,27 +24,7 @@ def main():
     H = int(sys.argv[2]) if len(sys.argv) > 2 else 10
     nrun = int(sys.argv[3]) if len(sys.argv) > 3 else 3_000_000
     check = int(os.environ.get("NRUN_CHECK_ROWS", 2))
-    seed = orc.seed_for(2)
-    d = orc.syn_reference(seed, n)
-    runs = [(0, min(n // 100, 500_000)), (n // 3, nrun), (n // 2 + 12345, 50_000), (n - n // 50, 30_000), (n // 5, 700)]
-    for a, ln in runs:
-        d[a:a + ln] = ord("N")
-    M = orc.syn_columns(seed, n, 1e-5)
-    stride = (M + 15) // 16 * 16 + 16
-    rows = np.zeros((H, stride), dtype=np.uint8)
-    import ctypes as C
-    orc.lib().syn_rows(seed, d.ctypes.data_as(C.c_void_p), d.size, 1, H, 1e-3, 1e-5, 1e-5, rows.ctypes.data_as(C.c_void_p), stride)
-    # the generator treats N as a base and mutates it: put the N runs back so that the haplotypes carry them whole
-    # (columns of a row = reference positions plus insertion columns; restore by matching against the reference row)
-    ref_row = np.zeros((1, stride), dtype=np.uint8)
-    orc.lib().syn_rows(seed, d.ctypes.data_as(C.c_void_p), d.size, 0, 1, 0.0, 1e-5, 0.0, ref_row.ctypes.data_as(C.c_void_p), stride)
-    # (a panel called against the reference has no variant inside an N region: every haplotype carries the reference's
-    # columns there, insertion columns included)
-    is_n = np.flatnonzero(ref_row[0, :M] == ord("N"))
-    breaks = np.flatnonzero(np.diff(is_n) > 16)
-    starts = np.concatenate([[is_n[0]], is_n[breaks + 1]]); ends = np.concatenate([is_n[breaks], [is_n[-1]]]) + 1
-    for a, b in zip(starts, ends):
-        rows[:, a:b] = ref_row[0, a:b]
+    d, rows, M, stride = bench.gen_nrun_workload(orc, n, H, nrun)
     ctx = D.Drlz(0)
     t0 = time.time(); ctx.build_index(d); t_first = time.time() - t0
     ctx.build_index(d)
