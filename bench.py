@@ -622,16 +622,23 @@ def cli_e2e(job, wl, d, ms):
         ok = ok and fa == b">H%05d.21\n" % wl["h0"] + orc.strip_gaps(ms["rows_arr"][0, :M]).tobytes() + b"\n"
         parse_s = stats.get("encode_s", wall)
         # the phrases alone (DRLZ_GAPLESS=0: callers that keep the gapless sequences elsewhere): no FASTA to write
-        lz_only = None
-        clear()
-        q = subprocess.run(cmd, env=dict(env, DRLZ_GAPLESS="0", DRLZ_STATS=os.path.join(tmp, "lzonly.json")), stdout=subprocess.PIPE,
-                           stderr=subprocess.PIPE, text=True, timeout=600)
-        if q.returncode == 0:
+        lz_only, lz_runs = None, []
+        for _ in range(3):          # the GPU side of this run is 25 copies of 96 MB: a stall anywhere on the shared box shows (0.07 .. 0.7 s seen)
+            clear()
+            q = subprocess.run(cmd, env=dict(env, DRLZ_GAPLESS="0", DRLZ_STATS=os.path.join(tmp, "lzonly.json")), stdout=subprocess.PIPE,
+                               stderr=subprocess.PIPE, text=True, timeout=600)
+            if q.returncode != 0:
+                continue
             ls = json.load(open(os.path.join(tmp, "lzonly.json")))
             b = open(os.path.join(tmp, "out", "H%05d.21.lz" % (wl["h0"] + rows - 1)), "rb").read()
             ok = ok and b == orc.lz_bytes(ms["res"][rows - 1])
-            lz_only = {"value": bases / ls["encode_s"] / 1e9, "unit": UNIT, "encode_s": ls["encode_s"], "read_wait_s": ls.get("read_wait_s"),
-                       "gpu_wait_s": ls.get("gpu_wait_s"), "write_wait_s": ls.get("write_wait_s")}
+            lz_runs.append(round(bases / ls["encode_s"] / 1e9, 3))
+            if lz_only is None or ls["encode_s"] < lz_only["encode_s"]:
+                lz_only = {"value": bases / ls["encode_s"] / 1e9, "unit": UNIT, "encode_s": ls["encode_s"], "read_wait_s": ls.get("read_wait_s"),
+                           "gpu_wait_s": ls.get("gpu_wait_s"), "write_wait_s": ls.get("write_wait_s")}
+        if lz_only:
+            lz_only["runs"] = lz_runs
+            lz_only["what"] = "best of the runs listed"
         return {"value": bases / parse_s / 1e9, "unit": UNIT, "wall_s": wall, "encode_s": parse_s, "rows": rows, "files_ok": bool(ok),
                 "lz_sha256_16": sha, "input_gbs": rows * M / parse_s / 1e9, "stats": stats,
                 "io_ceiling": io, "frac_of_io_ceiling": (bases / parse_s / 1e9 / io["value"]) if io else None, "lz_only": lz_only,

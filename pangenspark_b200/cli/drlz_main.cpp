@@ -360,6 +360,15 @@ int main(int argc, char** argv) {
         std::vector<std::thread> th;
         for (int g = 0; g < ngpu; ++g) th.emplace_back([&, g] {
             if (drlz_create(&ctxs[g], dev0 + g) != DRLZ_OK) { fprintf(stderr, "drlz: no CUDA device %d (there is no CPU fallback)\n", dev0 + g); failed = 1; return; }
+            if (const char* opts = getenv("DRLZ_OPTIONS")) {           // "key=value,key=value": library options (include/drlz.h), for measurements
+                std::string o(opts);
+                for (size_t a = 0; a < o.size();) {
+                    size_t b = o.find(',', a); if (b == std::string::npos) b = o.size();
+                    const size_t eq = o.find('=', a);
+                    if (eq != std::string::npos && eq < b) drlz_set_option(ctxs[g], o.substr(a, eq - a).c_str(), atoll(o.substr(eq + 1, b - eq - 1).c_str()));
+                    a = b + 1;
+                }
+            }
             // the pinned slot buffers are allocated while the index is being built (pinning gigabytes takes as long)
             std::thread alloc([&, g] {
                 std::vector<Slot> slots(nslots);

@@ -247,19 +247,25 @@ def _gapped_row(rng, d: np.ndarray, events):
         elif kind == "d":
             out.append(np.full(ln, ord("-"), dtype=np.uint8)); i = min(len(d), pos + ln)
         elif kind == "s":
-            out.append(np.array([b"ACGT"[(b"ACGT".index(bytes([d[pos]])) + 1 + int(rng.integers(0, 3))) % 4]], dtype=np.uint8)); i = pos + 1
+            out.append(np.array([b"ACGT"[(b"ACGT".find(bytes([d[pos]])) + 1 + int(rng.integers(0, 3))) % 4]], dtype=np.uint8)); i = pos + 1
         else:
-            out.append(np.array([ord("N")], dtype=np.uint8)); i = pos + 1
+            out.append(np.array([ord("#") if ord("N") in d[:4096] else ord("N")], dtype=np.uint8)); i = pos + 1    # a byte outside the alphabet
     out.append(d[i:])
     return np.concatenate(out)
 
 
-def test_pack_gap_patterns(ctx):
-    """k_pack: gaps, deletions and foreign bytes at and around the borders of the 2 KB warp spans and the 16 KB tiles,
-    gap runs that empty whole warps and whole tiles, rows of different lengths in one batch (tile ids interleave
-    the rows), every alignment of the packed output against the 32-base words."""
+@pytest.mark.parametrize("alphabet", [b"ACGT", b"ACGTN", bytes(range(60, 100))])
+def test_pack_gap_patterns(ctx, alphabet):
+    """k_pack* (2-bit) and k_packg1 (4- and 8-bit symbols): gaps, deletions and foreign bytes at and around the borders
+    of the 64-byte thread spans, the 2 KB warp spans and the 16 KB tiles, gap runs that empty whole warps and whole
+    tiles, rows of different lengths in one batch (tile ids interleave the rows), every alignment of the packed output
+    against the words."""
     rng = np.random.default_rng(77)
     d = orc.syn_reference(orc.seed_for(3), 70_000)
+    if alphabet != b"ACGT":
+        d = rng.choice(list(alphabet), size=70_000).astype(np.uint8)
+        if alphabet == b"ACGTN":
+            d[30_000:30_900] = ord("N")                            # a run of N across a tile border (tile 2 starts at 32768 - gaps)
     ctx.build_index(d)
     sa = orc.sa_build(d)
     rows = []

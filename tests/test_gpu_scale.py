@@ -132,6 +132,16 @@ def test_reference_with_long_n_runs():
     x0 = orc.strip_gaps(rows[0])
     rows.append(np.concatenate([x0[:2_100_000], np.full(1_500_000, ord("N"), np.uint8), x0[3_100_000:]]))   # a longer run than any in the reference
     rows.append(np.concatenate([x0[:2_500_000], x0[2_700_000:]]))                                       # a shorter one
+    # the runs as a panel called against the reference carries them (untouched), with variants right at their edges: a SNP
+    # ten bases behind a run (the probe at the run's end stands on it), deletions in the chunk in front of a run and in
+    # the chunk behind it (the neighbours' diagonals then differ from the one the run's inside needs)
+    y = d.copy()
+    for p in (3_200_010, 5_050_005, 300_003, 1_234_567):
+        y[p] = ord("ACGT"["ACGT".index(chr(y[p])) ^ 1])
+    keep = np.ones(y.size, dtype=bool)
+    for a, b in ((1_999_800, 1_999_805), (3_200_300, 3_200_310), (4_999_000, 4_999_001), (299_000, 299_017)):
+        keep[a:b] = False
+    rows.append(y[keep])
     ctx = D.Drlz(0)
     try:
         ctx.build_index(d)
@@ -140,6 +150,10 @@ def test_reference_with_long_n_runs():
         sa = orc.sa_build(d)
         assert (ctx.index_get("sa").astype(np.int64) == sa).all()
         _check_rows(ctx, d, sa, rows)
+        # rows whose runs are the reference's must not fall into the uncapped search (one such lookup streams the run in
+        # every step of its binary search: milliseconds each, 80 ms in the 50-row run of profiles/README.md item 42)
+        _check_rows(ctx, d, sa, [rows[-1]])
+        assert ctx.parse_timings()["spec_ms"] < 5.0
     finally:
         ctx.close()
 

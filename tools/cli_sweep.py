@@ -43,6 +43,8 @@ def main():
                 env["DRLZ_IO_PROBE"] = "1"
             if len(f) > 3 and f[3] == "nogapless":
                 env["DRLZ_GAPLESS"] = "0"
+            if len(f) > 4:
+                env["DRLZ_OPTIONS"] = f[4].replace(";", ",")
             for rep in range(int(os.environ.get("CLI_SWEEP_REPS", 2))):
                 shutil.rmtree(os.path.join(tmp, "out"), ignore_errors=True)
                 shutil.rmtree(os.path.join(tmp, "gapless"), ignore_errors=True)
