@@ -951,8 +951,8 @@ __device__ __forceinline__ void flush_bytes_block(const uint8_t* gb, uint8_t* ds
     if (done + (uint32_t)tid < n) dst[done + tid] = gb[done + tid];
 }
 
-template <int BL>        // log2 of the bits per symbol: 2 or 3
-__global__ void __launch_bounds__(kPackThreads, 4) k_packg1(PackJob job, uint32_t n_tiles) {
+template <int BL, int MINB>        // log2 of the bits per symbol: 2 or 3; min CTAs per SM
+__global__ void __launch_bounds__(kPackThreads, MINB) k_packg1(PackJob job, uint32_t n_tiles) {
     constexpr int B = 1 << BL, SPW = 64 / B, NG = 64 / SPW;          // bits per symbol, symbols per word, words per 64 input bytes
     constexpr int NW = kPackTileBytes / SPW;                          // words of a full tile
     __shared__ uint64_t sw[NW + 2];                                   // [0]: the empty word in front; the tile's words from [1]
@@ -967,7 +967,7 @@ __global__ void __launch_bounds__(kPackThreads, 4) k_packg1(PackJob job, uint32_
         s_ticket[0] = id; s_ticket[1] = id % job.H; s_ticket[2] = id / job.H;
     }
     s_b2c[tid] = job.b2c[tid];
-    for (int i = tid; i < NW + 2; i += kPackThreads) sw[i] = 0;
+    if (tid == 0) { sw[0] = 0; sw[NW + 1] = 0; }
     __syncthreads();
     if (s_ticket[0] >= n_tiles) return;
     const uint32_t h = s_ticket[1], t = s_ticket[2];
@@ -1027,9 +1027,16 @@ __global__ void __launch_bounds__(kPackThreads, 4) k_packg1(PackJob job, uint32_
         }
         gw[g] = w; gc[g] = c; cnt += c;
     }
-    uint32_t total;
-    const uint32_t ex = block_exclusive_scan<uint32_t, OpSum>(cnt | (exc << 16), OpSum(), 0u, &total, sm);
-    const uint32_t lo = ex & 0xFFFFu, elo = ex >> 16, T = total & 0xFFFFu, TE = total >> 16;
+    // a tile of nothing but plain threads -- the rule -- needs no scan and no cleared word buffer: every thread's place is
+    // known and every word is written whole (3 barriers per tile instead of 6)
+    const bool tile_plain = __syncthreads_and(plain) != 0;
+    uint32_t lo = (uint32_t)tid * 64u, elo = 0, T = (uint32_t)kPackTileBytes, TE = 0;
+    if (!tile_plain) {
+        for (int i = tid; i < NW + 2; i += kPackThreads) sw[i] = 0;
+        uint32_t total;
+        const uint32_t ex = block_exclusive_scan<uint32_t, OpSum>(cnt | (exc << 16), OpSum(), 0u, &total, sm);     // (its barriers order the clearing too)
+        lo = ex & 0xFFFFu; elo = ex >> 16; T = total & 0xFFFFu; TE = total >> 16;
+    }
 
     // ---- the tile's place in the row: look-back by warp 0, while the others fill the word buffer ----------------------
     if (warp == 0) {
@@ -1145,8 +1152,12 @@ void launch_pack(const PackJob& job, cudaStream_t s, cudaEvent_t* ev) {
         cudaMemsetAsync(job.exc_cnt, 0, (size_t)job.H * 8, s);
         const size_t smem = job.gapless ? (size_t)kPackTileBytes + 32 : 0;
         g_launches += 2;
-        if (job.bl == 2) k_packg1<2><<<(unsigned)nt, kPackThreads, smem, s>>>(job, (uint32_t)nt);
-        else k_packg1<3><<<(unsigned)nt, kPackThreads, smem, s>>>(job, (uint32_t)nt);
+        if (job.bl == 2) {
+            if (job.occ == 6) k_packg1<2, 6><<<(unsigned)nt, kPackThreads, smem, s>>>(job, (uint32_t)nt);
+            else if (job.occ == 5) k_packg1<2, 5><<<(unsigned)nt, kPackThreads, smem, s>>>(job, (uint32_t)nt);
+            else if (job.occ == 3) k_packg1<2, 3><<<(unsigned)nt, kPackThreads, smem, s>>>(job, (uint32_t)nt);
+            else k_packg1<2, 4><<<(unsigned)nt, kPackThreads, smem, s>>>(job, (uint32_t)nt);
+        } else k_packg1<3, 4><<<(unsigned)nt, kPackThreads, smem, s>>>(job, (uint32_t)nt);
         k_pack2_finish<<<(job.H + 127) / 128, 128, 0, s>>>(job);
         if (ev) cudaEventRecord(ev[2], s);
         return;

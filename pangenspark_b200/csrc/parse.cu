@@ -531,7 +531,8 @@ int parse_stage_count(ParseBuffers& pb, cudaStream_t s, int* rounds_out, cudaEve
             pv.mm = pb.mm;
             g_launches += 1;
             const unsigned nb = (unsigned)(((uint64_t)NC * 32 + 127) / 128);
-            if (pv.ix.bl != 1) k_diag_w<0, 16><<<nb, 128, 0, s>>>(pv);
+            if (pv.ix.bl == 2) k_diag_w<2, 12><<<nb, 128, 0, s>>>(pv);          // 4-bit symbols: references with N, the real-data path
+            else if (pv.ix.bl != 1) k_diag_w<0, 16><<<nb, 128, 0, s>>>(pv);
             else if (pb.occ_diag >= 16) k_diag_w<1, 16><<<nb, 128, 0, s>>>(pv);
             else if (pb.occ_diag >= 12) k_diag_w<1, 12><<<nb, 128, 0, s>>>(pv);
             else k_diag_w<1, 10><<<nb, 128, 0, s>>>(pv);

@@ -26,6 +26,8 @@ def main():
     check = int(os.environ.get("NRUN_CHECK_ROWS", 2))
     d, rows, M, stride = bench.gen_nrun_workload(orc, n, H, nrun)
     ctx = D.Drlz(0)
+    for kv in filter(None, os.environ.get("NRUN_OPTIONS", "").split(",")):      # library options, e.g. occ_pack=6
+        ctx.set_option(kv.split("=")[0], int(kv.split("=")[1]))
     t0 = time.time(); ctx.build_index(d); t_first = time.time() - t0
     ctx.build_index(d)
     info, it = ctx.index_info(), ctx.index_timings()
