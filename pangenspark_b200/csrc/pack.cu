@@ -1154,9 +1154,9 @@ void launch_pack(const PackJob& job, cudaStream_t s, cudaEvent_t* ev) {
         g_launches += 2;
         if (job.bl == 2) {
             if (job.occ == 6) k_packg1<2, 6><<<(unsigned)nt, kPackThreads, smem, s>>>(job, (uint32_t)nt);
-            else if (job.occ == 5) k_packg1<2, 5><<<(unsigned)nt, kPackThreads, smem, s>>>(job, (uint32_t)nt);
+            else if (job.occ == 4) k_packg1<2, 4><<<(unsigned)nt, kPackThreads, smem, s>>>(job, (uint32_t)nt);
             else if (job.occ == 3) k_packg1<2, 3><<<(unsigned)nt, kPackThreads, smem, s>>>(job, (uint32_t)nt);
-            else k_packg1<2, 4><<<(unsigned)nt, kPackThreads, smem, s>>>(job, (uint32_t)nt);
+            else k_packg1<2, 5><<<(unsigned)nt, kPackThreads, smem, s>>>(job, (uint32_t)nt);      // measured: 3 / 4 / 5 / 6 CTAs per SM = 2.13 / 1.82 / 1.74 / 1.74 ms
         } else k_packg1<3, 4><<<(unsigned)nt, kPackThreads, smem, s>>>(job, (uint32_t)nt);
         k_pack2_finish<<<(job.H + 127) / 128, 128, 0, s>>>(job);
         if (ev) cudaEventRecord(ev[2], s);
