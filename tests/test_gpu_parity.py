@@ -13,10 +13,11 @@ pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 
 
-@pytest.fixture(scope="module", params=[2, 1])
+@pytest.fixture(scope="module", params=[2, 1, 0])
 def ctx(request):
-    """every test runs with both strip/pack kernels: 2 = k_pack3 (a CTA streams 8 tiles; the default), 1 = k_pack2 (a
-    tile per CTA; also the kernel behind the gapless output)"""
+    """every test runs with all strip/pack kernels: 2 = k_pack3 (a CTA streams 8 tiles; the default), 1 = k_pack2 (a
+    tile per CTA; also the kernel behind the gapless output), 0 = the round-1 kernel; generic alphabets: 2 and 1 =
+    k_packg1 (single pass), 0 = the two-pass kernels"""
     c = D.Drlz(0)
     c.set_option("pack_variant", request.param)
     yield c
