@@ -194,7 +194,8 @@ def test_short_lookups_medium_reference(seed):
 
 def test_long_repeats_hint_fill_and_extents():
     """Runs far longer than a chunk (N runs, poly-A): chunk starts inside the run have no unique 64-symbol pattern; with
-    use_uniq = 2 they inherit the diagonal of the chunk in front, and the capped-but-not-unique matches take their real
+    use_uniq = 2 they inherit the diagonal of the chunk behind them (else in front), the chunk that sees the run's end
+    takes its diagonal from a probe behind the run, and the capped-but-not-unique matches take their real
     length from the extents across chunks (ext[]) instead of the uncapped second pass of the lookup.  Same records as the
     oracle either way, for aligned runs, a longer and a shorter run in the haplotype, and a SNP right behind the run."""
     rng = np.random.default_rng(77)
@@ -207,7 +208,13 @@ def test_long_repeats_hint_fill_and_extents():
         for p in (100, 2500, 8100, 8101, 9000, 12650):
             x0[p] = b"ACGT"[(b"ACGT".index(bytes(x0[p:p + 1])) + 1) % 4] if x0[p:p + 1] in (b"A", b"C", b"G", b"T") else x0[p]
         x1 = bytearray(d); x1[8000] = ord("C") if d[8000:8001] != b"C" else ord("G")        # SNP on the first base behind the run
-        rows = [bytes(x0), bytes(x1), d, left + sym * 6000 + right, left + sym * 3500 + right, sym * 2000 + right[:100]]
+        # variants at the edges of a run that is otherwise the reference's: a SNP ten symbols behind it (the probe at the
+        # run's end stands on it), deletions shortly in front of the run and shortly behind it (the neighbouring chunks'
+        # diagonals then differ from the one the inside of the run needs), a deletion inside the run
+        x2 = bytearray(d); x2[8010] = ord("C") if d[8010:8011] != b"C" else ord("G")
+        x3 = bytes(x2[:2900] + x2[2907:8300] + x2[8305:])
+        x4 = d[:5000] + d[5009:]
+        rows = [bytes(x0), bytes(x1), d, left + sym * 6000 + right, left + sym * 3500 + right, sym * 2000 + right[:100], bytes(x2), x3, x4]
         for k, chunk, min_cap in ((5, 256, 64), (6, 1024, 64), (4, 64, 32), (6, 4096, 64)):
             for mode in (1, 2):
                 before = emu.long_hits()
