@@ -719,33 +719,33 @@ DRLZ_HD void hint_group(const ParseView& pv, int64_t* hint, uint32_t q) {
     uint32_t cur = hv.n_exc ? exc_lower_bound(hv, s) : 0;
     uint64_t stop = stop_after(hv, s, &cur);
     if (stop == s) return;
-    // a variant site in the first bases of the chunk leaves the probe without a long match (3 % of the chunks at
-    // BASELINE's rates, which then parse without a prediction at all): two more tries further in -- the hint is a
-    // prediction for the whole chunk, wherever it was taken
     uint64_t e = s + (1ull << pv.chunk_shift); if (e > hv.m) e = hv.m;
-    for (uint32_t probe = 0; probe < 3; ++probe) {
-        const uint64_t at = s + 96u * probe;
-        if (at >= e || (probe && stop < at + 64)) return;
-        bool open;
-        Match mt = lookup(pv.ix, hv.x, at, (uint32_t)(stop - at), 64u, &open, true);
-        if (mt.len >= kDiagMinLen) { hint[q] = (int64_t)mt.pos - (int64_t)at; return; }
-    }
-    // A chunk that starts inside a run of one symbol (the N runs of a reference assembly) and sees the end of the run:
-    // a match from inside the run is placed by what follows the run, so the probe goes there.  The chunks further inside
-    // the run, which see nothing but the run, inherit this diagonal from behind (k_hint_fill, right to left first).
+    // A chunk that starts inside a run of one symbol (the N runs of a reference assembly): a match from inside a run is
+    // placed by what follows the run, so the probe goes behind the run's end if the chunk sees it; the chunks further
+    // inside, which see nothing but the run, get no hint of their own and inherit this diagonal from behind (k_hint_fill,
+    // right to left first).  The end is found by bisection over the chunk's words (first word all run, last word not): a
+    // second run behind the first can mislead it to a later boundary, which is as good a place for a prediction.
     const uint32_t bl = pv.ix.bl, sl = 6 - bl, spw = 1u << sl;
     const uint64_t w0 = get64u(hv.x, (uint32_t)s, bl);
     const uint64_t unit = bl == 1 ? 0x5555555555555555ull : (bl == 2 ? 0x1111111111111111ull : 0x0101010101010101ull);
     const uint64_t rep = (w0 >> (64 - (1u << bl))) * unit;
-    if (w0 != rep) return;
-    uint64_t j = s + spw;
-    while (j < e) {
-        const uint64_t w = get64u(hv.x, (uint32_t)j, bl);
-        if (w != rep) { j += (uint64_t)(clz64(w ^ rep) >> bl); break; }
-        j += spw;
+    uint64_t first = s;
+    if (w0 == rep && e - s >= 2 * spw) {
+        uint64_t a = 0, b = (e - s) / spw - 1;               // words (at s + t * spw) known all-run / known not
+        if (get64u(hv.x, (uint32_t)(s + b * spw), bl) == rep) return;
+        while (b - a > 1) {
+            const uint64_t mid = a + ((b - a) >> 1);
+            if (get64u(hv.x, (uint32_t)(s + mid * spw), bl) == rep) a = mid; else b = mid;
+        }
+        const uint64_t wb = get64u(hv.x, (uint32_t)(s + b * spw), bl);
+        first = s + b * spw + (uint64_t)(clz64(wb ^ rep) >> bl);
+        if (first >= e) return;
     }
-    for (uint32_t probe = 0; probe < 3; ++probe) {           // (a variant right behind the run: further in, as above)
-        const uint64_t at = j + 96u * probe;
+    // a variant site in the first bases leaves the probe without a long match (3 % of the chunks at BASELINE's rates,
+    // which then parse without a prediction at all): two more tries further in -- the hint is a prediction for the whole
+    // chunk, wherever it was taken
+    for (uint32_t probe = 0; probe < 3; ++probe) {
+        const uint64_t at = first + 96u * probe;
         if (at >= e || stop < at + 64) return;
         bool open;
         Match mt = lookup(pv.ix, hv.x, at, (uint32_t)(stop - at), 64u, &open, true);
