@@ -87,6 +87,8 @@ struct IndexView {
 };
 static const uint32_t kUniqBlockShift = 6, kUniqBlock = 1u << kUniqBlockShift;
 
+DRLZ_HD uint32_t fsl32(uint32_t hi, uint32_t lo, unsigned s);
+
 // key of the first kk symbols of the word xw padded with code 0 to k symbols, and the number of keys sharing that
 // prefix: the table brackets are tab[lokey] and tab[lokey + span]
 DRLZ_HD void prefix_keys(const IndexView& ix, uint64_t xw, uint32_t kk, uint64_t* lokey, uint64_t* span) {
@@ -97,10 +99,16 @@ DRLZ_HD void prefix_keys(const IndexView& ix, uint64_t xw, uint32_t kk, uint64_t
         *lokey = kmer & ~lowmask; *span = lowmask + 1;
         return;
     }
-    const uint32_t B = 1u << ix.bl;
-    uint64_t key = 0, sp = 1;
-    for (uint32_t t = 0; t < kk; ++t) key = key * ix.sigma + ((xw >> (64 - B * (t + 1))) & ((1ull << B) - 1));
-    for (uint32_t t = kk; t < (uint32_t)k; ++t) { key *= ix.sigma; sp *= ix.sigma; }
+    // radix-sigma keys in 32-bit arithmetic (the table has at most 2^30 + 1 entries): the next symbol is always the top B
+    // bits of the word, which moves up by one symbol per step (the 64-bit form of this loop was 12 % of k_spec's
+    // instructions on a 4-bit index)
+    const uint32_t B = 1u << ix.bl, sigma = ix.sigma;
+    uint32_t hi = (uint32_t)(xw >> 32), lo = (uint32_t)xw, key = 0, sp = 1;
+    for (uint32_t t = 0; t < kk; ++t) {
+        key = key * sigma + (hi >> (32 - B));
+        hi = fsl32(hi, lo, B); lo <<= B;
+    }
+    for (uint32_t t = kk; t < (uint32_t)k; ++t) { key *= sigma; sp *= sigma; }
     *lokey = key; *span = sp;
 }
 
