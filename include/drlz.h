@@ -65,7 +65,9 @@ void drlz_host_free(void* p);
  * that do not occur in the reference become literal phrases, as in the reference. */
 int drlz_build_index(drlz_ctx* ctx, const uint8_t* ref, uint64_t n);
 /* copy index arrays to the host.  what: 0 = SA (uint32[n]), 1 = inverse SA (uint32[n]), 2 = LCP (uint32[n],
- * needs option lcp=1), 3 = k-mer table (uint32[sigma^k+1]), 4 = packed text (uint64[ceil(n * bits / 64)]).  */
+ * needs option lcp=1), 3 = k-mer table (uint32[sigma^k+1]), 4 = packed text (uint64[ceil(n * bits / 64)]),
+ * 5 = uniqueness array (uint16[n]: the longest repeat that starts at each reference position, saturated at 65535).
+ * The inverse SA is derived from SA on the first request if the build did not need it.  */
 int drlz_index_get(drlz_ctx* ctx, int what, void* host_out, uint64_t bytes);
 /* info[0]=n, [1]=k | log2(bits per symbol) << 8 | alphabet size sigma << 16 | (long repeats: 1) << 28, [2]=prefix-doubling rounds,
  * [3]=index bytes on device */

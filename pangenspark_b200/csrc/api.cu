@@ -63,6 +63,8 @@ struct drlz_ctx {
     uint64_t x_zeroed = 0; bool keep_x = false; int opt_postzero = 1; int opt_keep_timings = 0; int opt_blind_rounds = 2; int opt_pack_variant = 2; uint32_t opt_prefetch3 = 2; int opt_occ_pack = 8; uint32_t opt_prefetch = 1200; int opt_k = 0; uint32_t opt_chunk = 8192; uint32_t opt_min_cap = 64; uint32_t opt_foreign_cap = 1u << 20; uint64_t opt_group_bytes = 256ull << 20; int opt_lcp = 0;
     // index
     bool have_index = false; uint64_t n = 0; int k = 0; int sa_rounds = 0;
+    int opt_l2_fetch = 0, opt_l2_fetch_parse = 0;   // L2 fetch granularity: for the whole device / around the parse kernels only (0 = leave it alone)
+    bool isa_valid = false;                // the inverse suffix array is filled (a build without doubling rounds leaves it out)
     DevBuf blob, sa, isa, lcp;             // blob = [k-mer table | packed text] (one L2 access-policy window)
     uint64_t* d_text = nullptr; uint32_t* d_tab = nullptr; uint16_t* d_uniq = nullptr; uint8_t* d_lut = nullptr;   // lut = b2c[256], c2b[256]
     size_t blob_bytes = 0, text_bytes = 0, uniq_bytes = 0, tab_bytes = 0;
@@ -217,6 +219,15 @@ int drlz_set_option(drlz_ctx* c, const char* key, int64_t v) {
     else if (!strcmp(key, "group_bytes")) { if (v < 0) return DRLZ_E_ARG; c->opt_group_bytes = v ? (uint64_t)v : (256ull << 20); }
     else if (!strcmp(key, "lcp")) c->opt_lcp = v != 0;
     else if (!strcmp(key, "l2persist")) { c->opt_l2persist = v != 0; c->l2_stream = nullptr; }
+    else if (!strcmp(key, "l2_fetch")) {
+        // bytes the L2 fetches from HBM on a miss (cudaLimitMaxL2FetchGranularity: 32 / 64 / 128; a device-wide hint).  The
+        // lookups of the parse read single 32-byte sectors at scattered addresses
+        if (v != 32 && v != 64 && v != 128) return DRLZ_E_ARG;
+        CK(c, cudaSetDevice(c->device));
+        CK(c, cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)v));
+        c->opt_l2_fetch = (int)v;
+    }
+    else if (!strcmp(key, "l2_fetch_parse")) { if (v != 0 && v != 32 && v != 64 && v != 128) return DRLZ_E_ARG; c->opt_l2_fetch_parse = (int)v; }
     else if (!strcmp(key, "occ")) c->opt_occ = (int)v;
     else if (!strcmp(key, "occ_fix")) c->opt_occ_fix = (int)v;
     else if (!strcmp(key, "occ_diag")) c->opt_occ_diag = (int)v;
@@ -436,7 +447,9 @@ static int run_device_group(drlz_ctx* c, const uint8_t* rows_dev, const uint64_t
         pb.spec_out = c->out.as<int64_t>(); pb.spec_out_cap = c->out.cap >= 32 ? (c->out.cap - 16) / 16 : 0;
         pb.ev_emitted = c->ev_stage[11]; pb.emitted = false;
         int prc;
-        { NvtxRange r("drlz.parse: pre-scan, speculative parse, fix-up, marking, emit"); prc = parse_stage_count(pb, s, &rounds, &c->ev_stage[5]); }   // ev 5,6,7,8 and 9 (after stage A)
+        if (c->opt_l2_fetch_parse) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)c->opt_l2_fetch_parse);
+        { NvtxRange r("drlz.parse: pre-scan, speculative parse, fix-up, marking, emit"); prc = parse_stage_count(pb, s, &rounds, &c->ev_stage[5]); }
+        if (c->opt_l2_fetch_parse) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)(c->opt_l2_fetch ? c->opt_l2_fetch : 64));   // ev 5,6,7,8 and 9 (after stage A)
         CK(c, cudaGetLastError());
         if (prc == 2) {
             if (single_chunk) { c->err = "parse fix-up did not converge"; return DRLZ_E_INTERNAL; }
@@ -597,8 +610,10 @@ int drlz_build_index(drlz_ctx* c, const uint8_t* ref, uint64_t n) {
     cudaEventRecord(e[1], s);
     char ebuf[256]; ebuf[0] = 0;
     CK(c, c->lcp.ensure(n * 4 + 8));
+    int fast = 0;
     int rc = build_suffix_array(c->d_text, n, bl, c->sa.as<uint32_t>(), c->isa.as<uint32_t>(), s, &c->sa_rounds, ebuf, sizeof ebuf, &c->sa_ws,
-                                c->lcp.as<uint32_t>());
+                                c->lcp.as<uint32_t>(), c->d_uniq, &fast);
+    c->isa_valid = !fast;
     if (c->sa_ws.bytes() > (16ull << 30)) {          // whole-genome scale: the parse needs that memory back
         cudaStreamSynchronize(s);
         c->sa_ws.release();
@@ -615,8 +630,10 @@ int drlz_build_index(drlz_ctx* c, const uint8_t* ref, uint64_t n) {
     {   // LCP (kept only on request) and the uniqueness array derived from it
         // no doubling round was needed: every neighbouring pair of suffixes differs inside its first sort key, and the
         // LCP array came out of the sort (StoreRank); otherwise the Kasai-order kernel computes it
+        // ... and when no two first keys were equal the uniqueness array came out of it as well (k_sa_finish0; values < 64)
         rc = c->sa_rounds == 0 ? 0 : build_lcp(c->d_text, n, bl, c->sa.as<uint32_t>(), c->isa.as<uint32_t>(), c->lcp.as<uint32_t>(), s);
-        if (rc == 0) rc = build_uniq(n, c->isa.as<uint32_t>(), c->lcp.as<uint32_t>(), c->d_uniq, c->sa.as<uint32_t>() + n, c->flags.as<uint32_t>() + 2, s);
+        if (fast) cudaMemsetAsync(c->flags.as<uint32_t>() + 2, 0, 4, s);
+        else if (rc == 0) rc = build_uniq(n, c->isa.as<uint32_t>(), c->lcp.as<uint32_t>(), c->d_uniq, c->sa.as<uint32_t>() + n, c->flags.as<uint32_t>() + 2, s);
         if (rc == 0 && c->uniqc.ensure(((n >> kUniqBlockShift) + 2) * 2) != cudaSuccess) rc = 1;
         if (rc == 0) rc = build_uniq_coarse(n, c->d_uniq, c->uniqc.as<uint16_t>(), s);
         if (rc != 0) { c->err = "lcp / uniqueness build failed"; for (int i = 0; i < 5; ++i) cudaEventDestroy(e[i]); return DRLZ_E_CUDA; }
@@ -645,10 +662,16 @@ int drlz_index_get(drlz_ctx* c, int what, void* host_out, uint64_t bytes) {
     const void* src = nullptr; uint64_t need = 0;
     switch (what) {
         case 0: src = c->sa.p; need = c->n * 4; break;
-        case 1: src = c->isa.p; need = c->n * 4; if (!c->isa.p) return DRLZ_E_STATE; break;
+        case 1:
+            need = c->n * 4;
+            if (!c->isa_valid) CK(c, c->isa.ensure(c->n * 4 + 4));      // also on the receiving side of a broadcast
+            src = c->isa.p;
+            if (!c->isa_valid) { launch_isa_from_sa(c->sa.as<uint32_t>(), c->n, c->isa.as<uint32_t>(), c->stream); c->isa_valid = true; }   // the build did not need it
+            break;
         case 2: if (!c->opt_lcp || !c->lcp.p) { c->err = "lcp not built (option lcp=1)"; return DRLZ_E_STATE; } src = c->lcp.p; need = c->n * 4; break;
         case 3: src = c->d_tab; need = table_entries(c->sigma, c->k) * 4; break;
         case 4: src = c->d_text; need = ((c->n + (64u >> c->bl) - 1) >> (6 - c->bl)) * 8; break;
+        case 5: src = c->d_uniq; need = c->n * 2; break;
         default: return DRLZ_E_ARG;
     }
     if (bytes < need) { c->err = "host buffer too small"; return DRLZ_E_NOSPACE; }
@@ -684,6 +707,7 @@ int drlz_index_reserve(drlz_ctx* c, uint64_t n, int kinfo) {
     CK(c, alloc_index_blob(c, n, k, sigma, bl));
     CK(c, c->sa.ensure(n * 8 + 8));
     c->has_uniq32 = has32;
+    c->isa_valid = false;
     CK(c, cudaMemsetAsync(c->d_text, 0, c->text_bytes, c->stream));
     CK(c, cudaStreamSynchronize(c->stream));
     c->n = n; c->k = k;

@@ -91,7 +91,11 @@ struct SaWorkspace {
 // lcp_from_keys (nullable, uint32[n]): the LCP array as read off the first-round sort keys; final iff *rounds_out == 0
 // (every suffix was distinguished by its first key), otherwise build_lcp must recompute it
 int build_suffix_array(const uint64_t* text, uint64_t n, uint32_t bl, uint32_t* sa, uint32_t* isa, cudaStream_t s,
-                       int* rounds_out, char* err, int errlen, SaWorkspace* ws = nullptr, uint32_t* lcp_from_keys = nullptr);
+                       int* rounds_out, char* err, int errlen, SaWorkspace* ws = nullptr, uint32_t* lcp_from_keys = nullptr,
+                       uint16_t* uniq_fast = nullptr, int* fast_out = nullptr);
+// uniq_fast + fast_out (both or neither): when the first sort leaves no two equal keys, SA, lcp_from_keys and the uniqueness
+// array uniq_fast[n] are finished in one pass, *fast_out = 1 and ISA IS NOT WRITTEN (launch_isa_from_sa derives it)
+void launch_isa_from_sa(const uint32_t* sa, uint64_t n, uint32_t* isa, cudaStream_t s);
 // tab: sigma^k + 1 entries (ix.tab is ignored, ix.text / ix.sa / ix.k / ix.bl / ix.sigma are used)
 // tmp: kmer_table_tmp_bytes(entries) bytes of scratch owned by the caller; the call does not synchronise
 size_t kmer_table_tmp_bytes(uint64_t entries);

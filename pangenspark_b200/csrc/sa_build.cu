@@ -80,6 +80,52 @@ struct StoreCompact {
     }
 };
 
+// Round 0 without ties (random-like references: every suffix is told apart by its first key).  One pass over the sorted
+// pairs finishes the index arrays that the two scans, the inverse permutation and k_uniq used to produce: SA, the LCP of
+// neighbours read off their keys, and -- scattered through SA instead of gathered through ISA -- the uniqueness array
+// uniq[SA[j]] = max(LCP[j], LCP[j+1]) (< 64, never saturated).  *ties is raised if two neighbouring keys are equal; the
+// caller then takes the general path, which overwrites everything written here.
+__global__ void __launch_bounds__(256) k_sa_finish0(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, uint64_t n,
+                                                    uint32_t bl, uint32_t* __restrict__ sa, uint32_t* __restrict__ lcp,
+                                                    uint16_t* __restrict__ uniq, uint32_t* ties) {
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool tie = false;
+    if (j < n) {
+        const uint32_t s0 = 58u >> bl;
+        const uint64_t keep = ~((1ull << (64 - (s0 << bl))) - 1);
+        const uint64_t b = keys[j];
+        const uint32_t lb = (uint32_t)(b & 63u);
+        uint32_t la_ = 0, ln_ = 0;                      // LCP with the suffix in front, with the one behind
+        if (j) {
+            const uint64_t a = keys[j - 1], x = (a ^ b) & keep;
+            const uint32_t la = (uint32_t)(a & 63u);
+            tie = a == b;
+            uint32_t l = x ? (uint32_t)(__clzll((long long)x) >> bl) : s0;
+            l = l < la ? l : la; la_ = l < lb ? l : lb;
+        }
+        if (j + 1 < n) {
+            const uint64_t c = keys[j + 1], x = (c ^ b) & keep;
+            const uint32_t lc = (uint32_t)(c & 63u);
+            uint32_t l = x ? (uint32_t)(__clzll((long long)x) >> bl) : s0;
+            l = l < lc ? l : lc; ln_ = l < lb ? l : lb;
+        }
+        const uint32_t s = vals[j];
+        sa[j] = s;
+        if (lcp) lcp[j] = la_;
+        uniq[s] = (uint16_t)(la_ > ln_ ? la_ : ln_);
+    }
+    if (__syncthreads_or(tie) && threadIdx.x == 0) *ties = 1u;
+}
+__global__ void k_isa_from_sa(const uint32_t* __restrict__ sa, uint64_t n, uint32_t* __restrict__ isa) {
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) isa[sa[j]] = (uint32_t)j;
+}
+void launch_isa_from_sa(const uint32_t* sa, uint64_t n, uint32_t* isa, cudaStream_t s) {
+    if (!n) return;
+    g_launches += 1;
+    k_isa_from_sa<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(sa, n, isa);
+}
+
 __global__ void k_sa_round_keys(const uint32_t* __restrict__ slots, uint64_t na, const uint32_t* __restrict__ sa,
                                 const uint32_t* __restrict__ isa, uint64_t n, uint64_t h, uint64_t* keys, uint32_t* vals) {
     uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -112,9 +158,11 @@ struct StoreRound {
 static int bits_for(uint64_t v) { int b = 0; while (v) { ++b; v >>= 1; } return b ? b : 1; }
 
 int build_suffix_array(const uint64_t* text, uint64_t n, uint32_t bl, uint32_t* sa, uint32_t* isa_out, cudaStream_t s,
-                       int* rounds_out, char* err, int errlen, SaWorkspace* ws_in, uint32_t* lcp_from_keys) {
+                       int* rounds_out, char* err, int errlen, SaWorkspace* ws_in, uint32_t* lcp_from_keys, uint16_t* uniq_fast,
+                       int* fast_out) {
     int rc = 0;
     if (rounds_out) *rounds_out = 0;
+    if (fast_out) *fast_out = 0;
     if (n == 0) return 0;
     SaWorkspace local;
     SaWorkspace& ws = ws_in ? *ws_in : local;
@@ -143,6 +191,17 @@ int build_suffix_array(const uint64_t* text, uint64_t n, uint32_t bl, uint32_t* 
         g_launches += 1;
         k_sa_init_keys<<<nb, T, 0, s>>>(text, n, keys_a, vals_a, bl);
         radix_sort_pairs<uint64_t>(&keys_a, &keys_b, &vals_a, &vals_b, n, 0, 64, hist, scan_tmp, s);
+        if (uniq_fast && fast_out) {
+            // no two equal keys (the usual outcome on a random-like reference): SA, LCP and the uniqueness array in one pass,
+            // no inverse permutation (api.cu derives it from SA if somebody asks for it)
+            uint32_t* ties = scan_tmp;
+            SA_CK(cudaMemsetAsync(ties, 0, 4, s));
+            g_launches += 1;
+            k_sa_finish0<<<nb, T, 0, s>>>(keys_a, vals_a, n, bl, sa, lcp_from_keys, uniq_fast, ties);
+            SA_CK(cudaMemcpyAsync(tot_host, ties, 4, cudaMemcpyDeviceToHost, s));
+            SA_CK(cudaStreamSynchronize(s));
+            if (*(uint32_t*)tot_host == 0) { *fast_out = 1; SA_CK(cudaGetLastError()); goto done; }
+        }
         // ranks = group head index (inclusive running max of head indices); SA = sorted values
         device_scan<uint32_t, LoadHeadIdx, StoreRank, OpMax, true>(LoadHeadIdx{keys_a}, StoreRank{vals_a, sa, isa, keys_a, lcp_from_keys, bl}, n,
                                                                    scan_tmp, OpMax(), 0u, s);

@@ -168,7 +168,7 @@ class Drlz:
         n, k = info["n"], info["k"]
         spw = 64 // info["bits"]
         kinds = {"sa": (0, np.uint32, n), "isa": (1, np.uint32, n), "lcp": (2, np.uint32, n),
-                 "tab": (3, np.uint32, info["sigma"] ** k + 1), "text": (4, np.uint64, (n + spw - 1) // spw)}
+                 "tab": (3, np.uint32, info["sigma"] ** k + 1), "text": (4, np.uint64, (n + spw - 1) // spw), "uniq": (5, np.uint16, n)}
         code, dt, cnt = kinds[what]
         out = np.empty(cnt, dtype=dt)
         self._ck(self._lib.drlz_index_get(self._h, code, out.ctypes.data_as(C.c_void_p), out.nbytes))

@@ -68,7 +68,13 @@ def _check_index(ctx, d: bytes, k=None):
     if len(d):
         assert (isa[sa] == np.arange(len(d))).all()
         lcp = ctx.index_get("lcp")
-        assert (lcp.astype(np.int64) == orc.lcp_build(d, sa_ref)).all()
+        lcp_ref = orc.lcp_build(d, sa_ref)
+        assert (lcp.astype(np.int64) == lcp_ref).all()
+        # uniqueness array: the longest repeat starting at p = max of the LCPs of its suffix with both SA neighbours
+        nxt = np.concatenate([lcp_ref[1:], [0]])
+        uniq_ref = np.empty(len(d), dtype=np.int64)
+        uniq_ref[sa_ref] = np.minimum(65535, np.maximum(lcp_ref, nxt))
+        assert (ctx.index_get("uniq").astype(np.int64) == uniq_ref).all()
     return sa_ref
 
 

@@ -8,7 +8,7 @@
 //     `mlp` of them in flight per thread (independent), full occupancy; one 4-byte word of every sector is used.
 // Prints sectors/s, the equivalent GB/s at 32 B per sector, and dram__bytes-style traffic is left to ncu.
 // build: nvcc -O2 -gencode arch=compute_100a,code=sm_100a -o tools/bin/random_sectors tools/random_sectors.cu
-// run:   tools/bin/random_sectors [MiB=1024] [per_thread=64] [chain=0|1]
+// run:   tools/bin/random_sectors [MiB=1024] [per_thread=64] [chain=0|1] [l2_fetch_bytes=0|32|64|128]
 //        chain=1: every address depends on the value read before it (one miss in flight per thread, as in a lookup)
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -63,6 +63,17 @@ int main(int argc, char** argv) {
     const size_t mib = argc > 1 ? strtoull(argv[1], nullptr, 10) : 1024;
     const int per_thread = argc > 2 ? atoi(argv[2]) : 64;
     const int chain = argc > 3 ? atoi(argv[3]) : 0;
+    const int fetch = argc > 4 ? atoi(argv[4]) : 0;            // cudaLimitMaxL2FetchGranularity: 32 / 64 / 128 bytes (0 = leave the default)
+    if (fetch) {
+        cudaError_t fe = cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)fetch);
+        size_t got = 0;
+        cudaDeviceGetLimit(&got, cudaLimitMaxL2FetchGranularity);
+        printf("{\"l2_fetch_granularity_requested\": %d, \"set\": \"%s\", \"now\": %zu}\n", fetch, cudaGetErrorString(fe), got);
+    } else {
+        size_t got = 0;
+        cudaDeviceGetLimit(&got, cudaLimitMaxL2FetchGranularity);
+        printf("{\"l2_fetch_granularity_default\": %zu}\n", got);
+    }
     const size_t bytes = mib << 20;
     uint32_t *buf = nullptr, *out = nullptr;
     if (cudaMalloc(&buf, bytes) != cudaSuccess || cudaMalloc(&out, 64) != cudaSuccess) { fprintf(stderr, "cudaMalloc failed\n"); return 1; }
