@@ -287,11 +287,29 @@ int main(int argc, char** argv) {
     std::string local_gap = hdfs ? staging("gapless") : strip_scheme(gapless_dir);
 
     // reference: all lines concatenated (DistributedRLZ.scala:61)
-    std::vector<uint8_t> raw, ref;
+    // ... into pinned memory (drlz_host_alloc): the index build starts with the host->device copy of the reference, and from
+    // pageable memory the driver stages it (3 ms instead of 1 for 48 MB, a quarter of a second at 3.1 Gbp)
+    std::vector<uint8_t> raw;
     if (!read_file(localref, raw)) { fprintf(stderr, "drlz: cannot read %s\n", localref.c_str()); return 1; }
-    ref.reserve(raw.size());
+    struct PinnedRef {
+        uint8_t* p = nullptr; size_t n = 0; bool pinned = true;
+        ~PinnedRef() { if (p) { if (pinned) drlz_host_free(p); else free(p); } }
+        const uint8_t* data() const { return p; }
+        size_t size() const { return n; }
+    } ref;
+    ref.p = (uint8_t*)drlz_host_alloc(raw.size() + 1);
+    if (!ref.p) { ref.pinned = false; ref.p = (uint8_t*)malloc(raw.size() + 1); }      // pageable works too (no device: the build reports it)
+    if (!ref.p) { fprintf(stderr, "drlz: cannot allocate %zu bytes for the reference\n", raw.size()); return 1; }
     size_t nl = 0;
-    for (uint8_t b : raw) { if (b == '\n' || b == '\r') { ++nl; continue; } ref.push_back(b); }
+    for (const uint8_t *t = raw.data(), *e = t + raw.size(); t < e;) {           // stretches between line terminators
+        const uint8_t* a = (const uint8_t*)memchr(t, '\n', (size_t)(e - t));
+        const uint8_t* stop = a ? a : e;
+        const uint8_t* b = (const uint8_t*)memchr(t, '\r', (size_t)(stop - t));
+        if (b) stop = b;
+        memcpy(ref.p + ref.n, t, (size_t)(stop - t)); ref.n += (size_t)(stop - t);
+        if (stop < e) ++nl;
+        t = stop + 1;
+    }
     if (nl > 1) fprintf(stderr, "drlz: warning: %s has %zu line terminators; the reference expects a single-line, header-less file\n",
                         localref.c_str(), nl);
     raw.clear(); raw.shrink_to_fit();

@@ -63,6 +63,7 @@ struct drlz_ctx {
     uint64_t x_zeroed = 0; bool keep_x = false; int opt_postzero = 1; int opt_keep_timings = 0; int opt_blind_rounds = 2; int opt_pack_variant = 2; uint32_t opt_prefetch3 = 2; int opt_occ_pack = 8; uint32_t opt_prefetch = 1200; int opt_k = 0; uint32_t opt_chunk = 8192; uint32_t opt_min_cap = 64; uint32_t opt_foreign_cap = 1u << 20; uint64_t opt_group_bytes = 256ull << 20; int opt_lcp = 0;
     // index
     bool have_index = false; uint64_t n = 0; int k = 0; int sa_rounds = 0;
+    int opt_lcp_ties = 1;                  // LCP after <= 3 doubling rounds from the sort keys + k_lcp_ties (0 = always the Kasai-order kernel)
     int opt_l2_fetch = 0, opt_l2_fetch_parse = 0;   // L2 fetch granularity: for the whole device / around the parse kernels only (0 = leave it alone)
     bool isa_valid = false;                // the inverse suffix array is filled (a build without doubling rounds leaves it out)
     DevBuf blob, sa, isa, lcp;             // blob = [k-mer table | packed text] (one L2 access-policy window)
@@ -219,6 +220,7 @@ int drlz_set_option(drlz_ctx* c, const char* key, int64_t v) {
     else if (!strcmp(key, "group_bytes")) { if (v < 0) return DRLZ_E_ARG; c->opt_group_bytes = v ? (uint64_t)v : (256ull << 20); }
     else if (!strcmp(key, "lcp")) c->opt_lcp = v != 0;
     else if (!strcmp(key, "l2persist")) { c->opt_l2persist = v != 0; c->l2_stream = nullptr; }
+    else if (!strcmp(key, "lcp_ties")) c->opt_lcp_ties = v != 0;
     else if (!strcmp(key, "l2_fetch")) {
         // bytes the L2 fetches from HBM on a miss (cudaLimitMaxL2FetchGranularity: 32 / 64 / 128; a device-wide hint).  The
         // lookups of the parse read single 32-byte sectors at scattered addresses
@@ -631,7 +633,10 @@ int drlz_build_index(drlz_ctx* c, const uint8_t* ref, uint64_t n) {
         // no doubling round was needed: every neighbouring pair of suffixes differs inside its first sort key, and the
         // LCP array came out of the sort (StoreRank); otherwise the Kasai-order kernel computes it
         // ... and when no two first keys were equal the uniqueness array came out of it as well (k_sa_finish0; values < 64)
-        rc = c->sa_rounds == 0 ? 0 : build_lcp(c->d_text, n, bl, c->sa.as<uint32_t>(), c->isa.as<uint32_t>(), c->lcp.as<uint32_t>(), s);
+        // a few rounds: only the pairs inside groups of equal first keys are compared on (k_lcp_ties); the bound on their
+        // LCP (S0 * 2^rounds symbols) keeps that cheap.  Repetitive references (many rounds) take the Kasai-order kernel
+        if (c->sa_rounds >= 1 && c->sa_rounds <= 3 && c->opt_lcp_ties) rc = build_lcp_ties(c->d_text, n, bl, c->sa.as<uint32_t>(), c->lcp.as<uint32_t>(), s);
+        else rc = c->sa_rounds == 0 ? 0 : build_lcp(c->d_text, n, bl, c->sa.as<uint32_t>(), c->isa.as<uint32_t>(), c->lcp.as<uint32_t>(), s);
         if (fast) cudaMemsetAsync(c->flags.as<uint32_t>() + 2, 0, 4, s);
         else if (rc == 0) rc = build_uniq(n, c->isa.as<uint32_t>(), c->lcp.as<uint32_t>(), c->d_uniq, c->sa.as<uint32_t>() + n, c->flags.as<uint32_t>() + 2, s);
         if (rc == 0 && c->uniqc.ensure(((n >> kUniqBlockShift) + 2) * 2) != cudaSuccess) rc = 1;

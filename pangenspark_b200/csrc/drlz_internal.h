@@ -103,6 +103,9 @@ int build_kmer_table(const IndexView& ix, uint32_t* tab, uint32_t* tmp, cudaStre
 // LCP[j] = lcp(suffix SA[j-1], suffix SA[j]), LCP[0] = 0
 int build_lcp(const uint64_t* text, uint64_t n, uint32_t bl, const uint32_t* sa, const uint32_t* isa, uint32_t* lcp,
               cudaStream_t s);
+// the same array from lcp_from_keys of build_suffix_array when only a few doubling rounds ran: the entries equal to S0
+// (pairs with equal first keys) are compared on from symbol S0, all others are already exact
+int build_lcp_ties(const uint64_t* text, uint64_t n, uint32_t bl, const uint32_t* sa, uint32_t* lcp, cudaStream_t s);
 // uniq[p] = min(65535, max(LCP[ISA[p]], LCP[ISA[p]+1])); uniq32[p] = the same unsaturated; *saturated (device) is set to 1 if
 // any value reached 65535
 int build_uniq(uint64_t n, const uint32_t* isa, const uint32_t* lcp, uint16_t* uniq, uint32_t* uniq32, uint32_t* saturated, cudaStream_t s);

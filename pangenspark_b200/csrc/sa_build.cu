@@ -323,6 +323,33 @@ __global__ void k_lcp(const uint64_t* __restrict__ text, uint64_t n, const uint3
     }
 }
 
+// After a few doubling rounds (a random-like reference at whole-genome scale: a handful of equal first keys) the LCP array
+// read off the first-round sort keys (StoreRank) is already exact wherever the two keys differ.  That includes every pair
+// across a group border, whatever the final order inside the groups, because all members of a group carry the same key.
+// Pairs inside a group of equal keys share their first S0 symbols and were written as exactly S0: those, and only those,
+// are compared on from symbol S0.  The caller uses this only when the rounds bound the answer (rounds r => LCP < S0 * 2^r).
+__global__ void k_lcp_ties(const uint64_t* __restrict__ text, uint64_t n, const uint32_t* __restrict__ sa, uint32_t* __restrict__ lcp, uint32_t bl) {
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j == 0 || j >= n) return;
+    const uint32_t s0 = 58u >> bl;
+    if (lcp[j] != s0) return;
+    const uint64_t a = sa[j - 1], b = sa[j];
+    const uint64_t lim = n - (a > b ? a : b);
+    uint64_t hh = s0;
+    while (hh < lim) {
+        const uint64_t xr = get64(text, a + hh, bl) ^ get64(text, b + hh, bl);
+        if (xr) { hh += (uint64_t)(clz64(xr) >> bl); break; }
+        hh += 64u >> bl;
+    }
+    lcp[j] = (uint32_t)(hh > lim ? lim : hh);
+}
+int build_lcp_ties(const uint64_t* text, uint64_t n, uint32_t bl, const uint32_t* sa, uint32_t* lcp, cudaStream_t s) {
+    if (n == 0) return 0;
+    g_launches += 1;
+    k_lcp_ties<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(text, n, sa, lcp, bl);
+    return (int)cudaGetLastError();
+}
+
 int build_lcp(const uint64_t* text, uint64_t n, uint32_t bl, const uint32_t* sa, const uint32_t* isa, uint32_t* lcp, cudaStream_t s) {
     if (n == 0) return 0;
     uint64_t nb = (n + kLcpBlock - 1) / kLcpBlock;

@@ -96,6 +96,24 @@ def test_suffix_array_repeats(ctx):
     assert ctx.index_info()["sa_rounds"] >= 1
 
 
+def test_suffix_array_few_rounds(ctx):
+    """A random-like reference with a few planted repeats of 40..200 bases: one to three doubling rounds, the case in which
+    the LCP array is taken from the first sort keys and only the pairs with equal keys are compared on (k_lcp_ties)."""
+    rng = np.random.default_rng(21)
+    for reps, seg in ((3, 40), (20, 90), (5, 200)):
+        d = rng.choice(list(b"ACGT"), size=300_000).astype(np.uint8)
+        for _ in range(reps):
+            a, b = (int(v) for v in rng.integers(0, d.size - seg, size=2))
+            d[b:b + seg] = d[a:a + seg]
+        d[-35:] = ord("A")                                   # equal keys among the last suffixes as well
+        _check_index(ctx, d.tobytes())
+        rounds = ctx.index_info()["sa_rounds"]
+        assert 1 <= rounds <= 3, rounds
+        ctx.set_option("lcp_ties", 0)                        # the Kasai-order kernel gives the same arrays
+        _check_index(ctx, d.tobytes())
+        ctx.set_option("lcp_ties", 1)
+
+
 def test_kmer_table_and_text(ctx):
     d = orc.syn_reference(orc.seed_for(2), 100_000).tobytes()
     ctx.set_option("kmer", 6)
