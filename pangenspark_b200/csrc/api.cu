@@ -15,6 +15,7 @@
 #include "scan.cuh"
 
 namespace drlz {
+int g_sort_variant = 1;                              // which scatter kernel radix_sort_pairs launches (option sort_variant; process-wide): 1 = k_sort_scatter2
 thread_local unsigned long long g_launches = 0;   // kernels launched by the calling thread (a parse call runs on one thread)
 
 struct DevBuf {
@@ -221,6 +222,7 @@ int drlz_set_option(drlz_ctx* c, const char* key, int64_t v) {
     else if (!strcmp(key, "lcp")) c->opt_lcp = v != 0;
     else if (!strcmp(key, "l2persist")) { c->opt_l2persist = v != 0; c->l2_stream = nullptr; }
     else if (!strcmp(key, "lcp_ties")) c->opt_lcp_ties = v != 0;
+    else if (!strcmp(key, "sort_variant")) { if (v < 0 || v > 2) return DRLZ_E_ARG; g_sort_variant = (int)v; }
     else if (!strcmp(key, "l2_fetch")) {
         // bytes the L2 fetches from HBM on a miss (cudaLimitMaxL2FetchGranularity: 32 / 64 / 128; a device-wide hint).  The
         // lookups of the parse read single 32-byte sectors at scattered addresses

@@ -124,6 +124,114 @@ k_sort_scatter(const K* __restrict__ keys, const uint32_t* __restrict__ vals, K*
     }
 }
 
+// Second form of the scatter (sort_variant 1).  What the profile of the first one shows (ncu, 48 M pairs: 0.58 ms per pass,
+// 2.4 TB/s of DRAM traffic, 23 % issue slots used): a third of the stall samples wait for a MATCH result (16 of them, each
+// consumed at once), a sixth for the values, which are only requested after the keys have left, and the 64-register
+// budget of 4 CTAs per SM spills.  Here all 16 matches are issued back to back before the first one is used, the values
+// are requested as soon as the keys sit in shared memory (they arrive while the keys are being written out), and the
+// output address of a slot is recomputed from a byte array of digits instead of being held in 16 registers.
+template <typename K, int MINB>
+__global__ void __launch_bounds__(kSortThreads, MINB)
+k_sort_scatter2(const K* __restrict__ keys, const uint32_t* __restrict__ vals, K* __restrict__ okeys,
+                uint32_t* __restrict__ ovals, uint64_t n, int shift, const uint32_t* __restrict__ offs,
+                uint32_t ntiles) {
+    __shared__ uint32_t wcnt[kSortWarps][256];
+    __shared__ uint32_t dstart[256];
+    __shared__ uint32_t goff[256];
+    __shared__ uint32_t sm[33];
+    __shared__ K stage[kSortTile];
+    __shared__ uint8_t sdig[kSortTile];       // digit of the key in each slot of the staged tile
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < kSortWarps * 256; i += kSortThreads) (&wcnt[0][0])[i] = 0;
+    const uint64_t tile0 = (uint64_t)blockIdx.x * kSortTile;
+    const uint64_t base = tile0 + (uint64_t)warp * (32 * kSortItems);
+    const uint32_t tile_n = (uint32_t)(n - tile0 < (uint64_t)kSortTile ? n - tile0 : (uint64_t)kSortTile);
+    K key[kSortItems];
+    uint32_t rank[kSortItems];                // first the peer masks, then the ranks, then the slots
+    const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+    for (int k = 0; k < kSortItems; ++k) {
+        const uint64_t i = base + (uint64_t)k * 32 + lane;
+        key[k] = i < n ? keys[i] : (K)0;
+    }
+#pragma unroll
+    for (int k = 0; k < kSortItems; ++k) {
+        const uint64_t i = base + (uint64_t)k * 32 + lane;
+        const unsigned d = i < n ? ((unsigned)(key[k] >> shift) & 255u) : 256u;
+        rank[k] = __match_any_sync(0xffffffffu, d);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kSortItems; ++k) {
+        const uint64_t i = base + (uint64_t)k * 32 + lane;
+        const bool valid = i < n;
+        const unsigned d = (unsigned)(key[k] >> shift) & 255u;
+        const uint32_t peers = rank[k];
+        uint32_t before = 0;
+        if (valid) before = wcnt[warp][d];
+        __syncwarp();
+        rank[k] = before + __popc(peers & lt);
+        if (valid && (peers & lt) == 0) wcnt[warp][d] = before + __popc(peers);
+        __syncwarp();
+    }
+    __syncthreads();
+    {
+        const int t = threadIdx.x;
+        uint32_t run = 0;
+#pragma unroll
+        for (int w = 0; w < kSortWarps; ++w) { uint32_t c = wcnt[w][t]; wcnt[w][t] = run; run += c; }
+        uint32_t total;
+        uint32_t ds = block_exclusive_scan<uint32_t, OpSum>(run, OpSum(), 0u, &total, sm);
+        dstart[t] = ds;
+        goff[t] = offs[(uint64_t)t * ntiles + blockIdx.x];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kSortItems; ++k) {
+        const uint64_t i = base + (uint64_t)k * 32 + lane;
+        if (i < n) {
+            const unsigned d = (unsigned)(key[k] >> shift) & 255u;
+            const uint32_t sl = dstart[d] + wcnt[warp][d] + rank[k];
+            rank[k] = sl;
+            stage[sl] = key[k];
+            sdig[sl] = (uint8_t)d;
+        }
+    }
+    uint32_t val[kSortItems];                 // requested now, used after the keys have been written out
+#pragma unroll
+    for (int k = 0; k < kSortItems; ++k) {
+        const uint64_t i = base + (uint64_t)k * 32 + lane;
+        val[k] = i < n ? vals[i] : 0u;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kSortItems; ++k) {
+        const uint32_t j = (uint32_t)k * kSortThreads + threadIdx.x;
+        if (j < tile_n) {
+            const unsigned d = sdig[j];
+            okeys[goff[d] + (j - dstart[d])] = stage[j];
+        }
+    }
+    __syncthreads();
+    uint32_t* vstage = reinterpret_cast<uint32_t*>(stage);
+#pragma unroll
+    for (int k = 0; k < kSortItems; ++k) {
+        const uint64_t i = base + (uint64_t)k * 32 + lane;
+        if (i < n) vstage[rank[k]] = val[k];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kSortItems; ++k) {
+        const uint32_t j = (uint32_t)k * kSortThreads + threadIdx.x;
+        if (j < tile_n) {
+            const unsigned d = sdig[j];
+            ovals[goff[d] + (j - dstart[d])] = vstage[j];
+        }
+    }
+}
+
+extern int g_sort_variant;                    // 0: k_sort_scatter, 1 / 2: k_sort_scatter2 at 4 / 3 CTAs per SM (api.cu, option sort_variant)
+
 struct SortWorkspace {
     uint32_t* hist;      // 256 * ntiles (+ scan tmp behind it)
     uint32_t* scan_tmp;
@@ -145,7 +253,9 @@ int radix_sort_pairs(K** keys_a, K** keys_b, uint32_t** vals_a, uint32_t** vals_
         k_sort_hist<K><<<ntiles, kSortThreads, 0, s>>>(*keys_a, n, shift, hist, ntiles);
         device_scan<uint32_t, LoadArr<uint32_t, uint32_t>, StoreArr<uint32_t>, OpSum, false>(
             LoadArr<uint32_t, uint32_t>{hist}, StoreArr<uint32_t>{hist}, hn, scan_tmp, OpSum(), 0u, s);
-        k_sort_scatter<K><<<ntiles, kSortThreads, 0, s>>>(*keys_a, *vals_a, *keys_b, *vals_b, n, shift, hist, ntiles);
+        if (g_sort_variant == 1) k_sort_scatter2<K, 4><<<ntiles, kSortThreads, 0, s>>>(*keys_a, *vals_a, *keys_b, *vals_b, n, shift, hist, ntiles);
+        else if (g_sort_variant == 2) k_sort_scatter2<K, 3><<<ntiles, kSortThreads, 0, s>>>(*keys_a, *vals_a, *keys_b, *vals_b, n, shift, hist, ntiles);
+        else k_sort_scatter<K><<<ntiles, kSortThreads, 0, s>>>(*keys_a, *vals_a, *keys_b, *vals_b, n, shift, hist, ntiles);
         K* tk = *keys_a; *keys_a = *keys_b; *keys_b = tk;
         uint32_t* tv = *vals_a; *vals_a = *vals_b; *vals_b = tv;
         ++passes;

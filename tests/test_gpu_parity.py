@@ -38,8 +38,20 @@ def test_scan_primitive():
         assert tot.value == ref[-1]
 
 
-def test_radix_sort_primitive():
+@pytest.mark.parametrize("sort_variant", [0, 1, 2])
+def test_radix_sort_primitive(ctx, sort_variant):
     L = D.load_library()
+    ctx.set_option("sort_variant", sort_variant)           # process-wide: which scatter kernel the sort launches
+    try:
+        _radix_sort_cases(L)
+    finally:
+        ctx.set_option("sort_variant", DEFAULT_SORT_VARIANT)
+
+
+DEFAULT_SORT_VARIANT = 1
+
+
+def _radix_sort_cases(L):
     rng = np.random.default_rng(1)
     for n, bits in ((1, 64), (2, 64), (777, 64), (4096, 64), (4097, 24), (250_000, 64), (1_000_003, 40)):
         keys = rng.integers(0, 2 ** 63, size=n, dtype=np.uint64) * 2 + rng.integers(0, 2, size=n).astype(np.uint64)

@@ -15,7 +15,16 @@ d = orc.syn_reference(orc.seed_for(2), n)
 pin = D.PinnedBuffer(n)
 pin.array[:] = d
 ctx = D.Drlz(0)
-for it in range(3):
-    ctx.build_index(pin.array)
-    print(it, ctx.index_timings(), ctx.index_info(), flush=True)
+variants = [int(v) for v in os.environ.get("SORT_VARIANTS", "").split(",") if v] or [None]
+sa0 = None
+for v in variants:
+    if v is not None:
+        ctx.set_option("sort_variant", v)
+    for it in range(3):
+        ctx.build_index(pin.array)
+        print("sort_variant", v, it, ctx.index_timings(), ctx.index_info(), flush=True)
+    sa = ctx.index_get("sa")
+    if sa0 is None:
+        sa0 = sa
+    print("sort_variant", v, "same SA as the first variant:", bool((sa == sa0).all()), flush=True)
 ctx.close()
