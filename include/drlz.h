@@ -50,7 +50,9 @@ int drlz_set_stream(drlz_ctx* ctx, void* cuda_stream);
  *          compiled for), "prefetch" (L2 prefetch distance of k_pack in tiles, 0 = off),
  *          "spec_store", "l2persist", "pack_variant" (2 = k_pack3, 1 = k_pack2, 0 = the round-1 kernels; generic alphabets: 0 = two passes, else k_packg1), "prefetch3",
  *          "spec_sync" (1 = the chunks of a warp parsed in step), "uniq_coarse" (1 = block maxima of the uniqueness array consulted first); "keep_timings" (1: drlz_parse_timings sums over all
- *          calls since the option was set instead of the last call only).  None of them changes results. */
+ *          calls since the option was set instead of the last call only), "sort_variant" (scatter kernel of the radix sort; process-wide),
+ *          "lcp_ties" (0 = the LCP array always by the Kasai-order kernel), "l2_fetch" / "l2_fetch_parse" (cudaLimitMaxL2FetchGranularity for
+ *          the device / around the parse kernels: 32 | 64 | 128; measured without effect on B200).  None of them changes results. */
 int drlz_set_option(drlz_ctx* ctx, const char* key, int64_t value);
 
 /* pinned host memory for the streaming path (cudaHostAlloc); plain malloc memory also works, slower */
@@ -62,7 +64,8 @@ void drlz_host_free(void* p);
  * Any byte alphabet works, like the reference's byte-wise binary search: a pure {A,C,G,T} reference is packed at
  * 2 bits per base (the measured fast path); otherwise the distinct bytes of the reference get dense, order-
  * preserving codes at 4 bits (<= 16 symbols, e.g. ACGTN + lower case) or 8 bits per symbol.  Haplotype bytes
- * that do not occur in the reference become literal phrases, as in the reference. */
+ * that do not occur in the reference become literal phrases, as in the reference.  The build starts with the host->device
+ * copy of ref: from drlz_host_alloc memory it runs at PCIe speed, from pageable memory the driver stages it (3 x slower). */
 int drlz_build_index(drlz_ctx* ctx, const uint8_t* ref, uint64_t n);
 /* copy index arrays to the host.  what: 0 = SA (uint32[n]), 1 = inverse SA (uint32[n]), 2 = LCP (uint32[n],
  * needs option lcp=1), 3 = k-mer table (uint32[sigma^k+1]), 4 = packed text (uint64[ceil(n * bits / 64)]),
