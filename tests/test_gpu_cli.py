@@ -108,6 +108,30 @@ def test_native_cli_rejects_multiline_rows(tmp_path):
     assert r.returncode == 1 and "more than one line" in r.stderr
 
 
+def test_native_cli_reference_with_line_terminators(tmp_path):
+    """the reference file is the sequence bytes; a trailing newline (or CR LF, or a wrapped file) is dropped
+    with a warning -- `getLines.mkString` in DistributedRLZ.scala:61 does the same to what the parse sees"""
+    from oracle import oracle as orc
+    tmp = str(tmp_path)
+    d, rows = make_dataset(tmp, H=2, n=50_000)
+    raw = bytes(d)
+    sa = orc.sa_build(raw)
+    exe = os.path.join(ROOT, "pangenspark_b200", "bin", "drlz")
+    for k, text in enumerate((raw + b"\n", raw + b"\r\n", raw[:20_000] + b"\n" + raw[20_000:33_333] + b"\r\n" + raw[33_333:] + b"\n")):
+        with open(tmp + "/ref.txt", "wb") as f:
+            f.write(text)
+        out = tmp + "/drlz%d" % k
+        r = subprocess.run([exe, tmp + "/radix", tmp + "/ref.txt", tmp + "/msa/*.01", "", out, tmp + "/gapless%d" % k],
+                           capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr
+        warned = "line terminators" in r.stderr
+        assert not (k == 0 and warned) and not (k == 2 and not warned)      # one trailing newline is the normal case
+        for h in range(2):
+            x = orc.strip_gaps(rows[h]).tobytes()
+            lz = open(os.path.join(out, "H%05d.01.lz" % h), "rb").read()
+            assert lz == orc.lz_bytes(orc.encode_literal(raw, sa, x)[0])
+
+
 def test_native_cli_hdfs_mode(tmp_path):
     from tests.test_stage_scripts import test_cli_hdfs_inputs_through_the_hdfs_command
     test_cli_hdfs_inputs_through_the_hdfs_command(tmp_path)
