@@ -50,7 +50,7 @@ int drlz_set_stream(drlz_ctx* ctx, void* cuda_stream);
  *          compiled for), "prefetch" (L2 prefetch distance of k_pack in tiles, 0 = off),
  *          "spec_store", "l2persist", "pack_variant" (2 = k_pack3, 1 = k_pack2, 0 = the round-1 kernels; generic alphabets: 0 = two passes, else k_packg1), "prefetch3",
  *          "spec_sync" (1 = the chunks of a warp parsed in step), "uniq_coarse" (1 = block maxima of the uniqueness array consulted first); "keep_timings" (1: drlz_parse_timings sums over all
- *          calls since the option was set instead of the last call only), "sort_variant" (scatter kernel of the radix sort; process-wide),
+ *          calls since the option was set instead of the last call only), "sort_variant" / "table_variant" (scatter kernel of the radix sort, one-pass k-mer table; process-wide),
  *          "lcp_ties" (0 = the LCP array always by the Kasai-order kernel), "l2_fetch" / "l2_fetch_parse" (cudaLimitMaxL2FetchGranularity for
  *          the device / around the parse kernels: 32 | 64 | 128; measured without effect on B200).  None of them changes results. */
 int drlz_set_option(drlz_ctx* ctx, const char* key, int64_t value);

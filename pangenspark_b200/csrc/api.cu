@@ -222,6 +222,7 @@ int drlz_set_option(drlz_ctx* c, const char* key, int64_t v) {
     else if (!strcmp(key, "lcp")) c->opt_lcp = v != 0;
     else if (!strcmp(key, "l2persist")) { c->opt_l2persist = v != 0; c->l2_stream = nullptr; }
     else if (!strcmp(key, "lcp_ties")) c->opt_lcp_ties = v != 0;
+    else if (!strcmp(key, "table_variant")) { if (v < 0 || v > 1) return DRLZ_E_ARG; g_table_variant = (int)v; }
     else if (!strcmp(key, "sort_variant")) { if (v < 0 || v > 2) return DRLZ_E_ARG; g_sort_variant = (int)v; }
     else if (!strcmp(key, "l2_fetch")) {
         // bytes the L2 fetches from HBM on a miss (cudaLimitMaxL2FetchGranularity: 32 / 64 / 128; a device-wide hint).  The
@@ -615,8 +616,9 @@ int drlz_build_index(drlz_ctx* c, const uint8_t* ref, uint64_t n) {
     char ebuf[256]; ebuf[0] = 0;
     CK(c, c->lcp.ensure(n * 4 + 8));
     int fast = 0;
+    IndexView tix{c->d_text, c->sa.as<uint32_t>(), nullptr, n, k, nullptr, bl, sigma, c->d_lut + 256};
     int rc = build_suffix_array(c->d_text, n, bl, c->sa.as<uint32_t>(), c->isa.as<uint32_t>(), s, &c->sa_rounds, ebuf, sizeof ebuf, &c->sa_ws,
-                                c->lcp.as<uint32_t>(), c->d_uniq, &fast);
+                                c->lcp.as<uint32_t>(), c->d_uniq, &fast, &tix, c->d_tab, c->tab_tmp.as<uint32_t>());
     c->isa_valid = !fast;
     if (c->sa_ws.bytes() > (16ull << 30)) {          // whole-genome scale: the parse needs that memory back
         cudaStreamSynchronize(s);
@@ -625,10 +627,7 @@ int drlz_build_index(drlz_ctx* c, const uint8_t* ref, uint64_t n) {
     if (rc != 0) { c->err = std::string("suffix array: ") + ebuf; for (int i = 0; i < 5; ++i) cudaEventDestroy(e[i]); return rc == (int)cudaErrorMemoryAllocation ? DRLZ_E_NOMEM : DRLZ_E_CUDA; }
     cudaEventRecord(e[2], s);
 
-    {
-        IndexView tix{c->d_text, c->sa.as<uint32_t>(), nullptr, n, k, nullptr, bl, sigma, c->d_lut + 256};
-        rc = build_kmer_table(tix, c->d_tab, c->tab_tmp.as<uint32_t>(), s);
-    }
+    if (fast != 2) rc = build_kmer_table(tix, c->d_tab, c->tab_tmp.as<uint32_t>(), s);       // 2: written with the suffix array (k_sa_finish0)
     if (rc != 0) { c->err = "k-mer table build failed"; for (int i = 0; i < 5; ++i) cudaEventDestroy(e[i]); return DRLZ_E_CUDA; }
     cudaEventRecord(e[3], s);
     {   // LCP (kept only on request) and the uniqueness array derived from it

@@ -92,12 +92,16 @@ struct SaWorkspace {
 // (every suffix was distinguished by its first key), otherwise build_lcp must recompute it
 int build_suffix_array(const uint64_t* text, uint64_t n, uint32_t bl, uint32_t* sa, uint32_t* isa, cudaStream_t s,
                        int* rounds_out, char* err, int errlen, SaWorkspace* ws = nullptr, uint32_t* lcp_from_keys = nullptr,
-                       uint16_t* uniq_fast = nullptr, int* fast_out = nullptr);
+                       uint16_t* uniq_fast = nullptr, int* fast_out = nullptr, const IndexView* tab_ix = nullptr, uint32_t* tab = nullptr,
+                       uint32_t* tab_tmp = nullptr);
+// tab_ix (k, bl, sigma are read) + tab + tab_tmp (kmer_table_tmp_bytes): in that same pass the k-mer table is written too when its
+// key is a head of the sort key; *fast_out = 2 says so (1: SA / LCP / uniqueness array only, build_kmer_table is still to run)
 // uniq_fast + fast_out (both or neither): when the first sort leaves no two equal keys, SA, lcp_from_keys and the uniqueness
 // array uniq_fast[n] are finished in one pass, *fast_out = 1 and ISA IS NOT WRITTEN (launch_isa_from_sa derives it)
 void launch_isa_from_sa(const uint32_t* sa, uint64_t n, uint32_t* isa, cudaStream_t s);
 // tab: sigma^k + 1 entries (ix.tab is ignored, ix.text / ix.sa / ix.k / ix.bl / ix.sigma are used)
 // tmp: kmer_table_tmp_bytes(entries) bytes of scratch owned by the caller; the call does not synchronise
+extern int g_table_variant;               // sa_build.cu: 1 = the table in one pass (k_tab_build), 0 = fill + mark + scan
 size_t kmer_table_tmp_bytes(uint64_t entries);
 int build_kmer_table(const IndexView& ix, uint32_t* tab, uint32_t* tmp, cudaStream_t s);
 // LCP[j] = lcp(suffix SA[j-1], suffix SA[j]), LCP[0] = 0

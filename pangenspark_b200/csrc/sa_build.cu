@@ -80,16 +80,75 @@ struct StoreCompact {
     }
 };
 
+// ---- the same table in one pass (table_variant 1) ---------------------------------------------------------------
+// Keys are non-decreasing along the suffix array (a proper prefix sorts first and its zero padding is the smallest code),
+// so the entries (key[j-1], key[j]] all equal j: the thread of suffix j writes them, the thread of the last suffix also
+// writes n into everything above its key.  Every table entry is written exactly once -- no fill, no scattered marks, no
+// scan (fill + mark + scan: 1.05 ms and 1.9 GB of traffic for a 268 MB table).  A range is a couple of entries as a rule;
+// ranges above 16 entries are written by the whole warp, one after the other, and those above kTabLongRange (a symbol
+// that hardly occurs, like N, leaves millions of consecutive keys empty) go to a list for k_tab_ranges.
+static const uint32_t kTabLongRange = 1u << 16;
+static const uint32_t kTabListCap = 1u << 15;          // a table has at most 2^30 + 1 entries: at most 2^14 ranges above 2^16
+struct TabRange { uint32_t start, len, value, pad; };
+
+__device__ __forceinline__ void tab_fill_range(uint32_t* __restrict__ tab, uint32_t start, uint32_t len, uint32_t value,
+                                               TabRange* list, uint32_t* list_cnt, int lane) {
+    if (len && len <= 16u) for (uint32_t t = 0; t < len; ++t) tab[start + t] = value;
+    unsigned big = __ballot_sync(0xffffffffu, len > 16u);
+    while (big) {
+        const int src = __ffs(big) - 1;
+        big &= big - 1;
+        const uint32_t st = __shfl_sync(0xffffffffu, start, src), ln = __shfl_sync(0xffffffffu, len, src),
+                       v = __shfl_sync(0xffffffffu, value, src);
+        if (ln > kTabLongRange) {
+            uint32_t slot = 0;
+            if (lane == 0) slot = atomicAdd(list_cnt, 1u);
+            slot = __shfl_sync(0xffffffffu, slot, 0);
+            if (slot < kTabListCap) { if (lane == 0) list[slot] = TabRange{st, ln, v, 0u}; continue; }
+        }
+        for (uint32_t t = (uint32_t)lane; t < ln; t += 32u) tab[st + t] = v;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_tab_ranges(uint32_t* __restrict__ tab, const TabRange* __restrict__ list, const uint32_t* __restrict__ list_cnt) {
+    uint32_t c = *list_cnt;
+    if (c > kTabListCap) c = kTabListCap;
+    const uint32_t stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
+    for (uint32_t e = 0; e < c; ++e) {
+        const TabRange r = list[e];
+        for (uint32_t t = t0; t < r.len; t += stride) tab[r.start + t] = r.value;
+    }
+}
+
 // Round 0 without ties (random-like references: every suffix is told apart by its first key).  One pass over the sorted
 // pairs finishes the index arrays that the two scans, the inverse permutation and k_uniq used to produce: SA, the LCP of
 // neighbours read off their keys, and -- scattered through SA instead of gathered through ISA -- the uniqueness array
 // uniq[SA[j]] = max(LCP[j], LCP[j+1]) (< 64, never saturated).  *ties is raised if two neighbouring keys are equal; the
 // caller then takes the general path, which overwrites everything written here.
+// With tab != null the k-mer table is written on the way: the table key of a suffix is the head of its sort key (k <= S0),
+// so the ranges of tab_fill_range() come from the two keys the thread holds anyway -- no pass over SA, no reads of the text.
 __global__ void __launch_bounds__(256) k_sa_finish0(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, uint64_t n,
                                                     uint32_t bl, uint32_t* __restrict__ sa, uint32_t* __restrict__ lcp,
-                                                    uint16_t* __restrict__ uniq, uint32_t* ties) {
+                                                    uint16_t* __restrict__ uniq, uint32_t* ties,
+                                                    IndexView tix, uint32_t* __restrict__ tab, uint32_t tab_cnt, TabRange* list, uint32_t* list_cnt) {
     const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool tie = false;
+    if (tab) {
+        const uint32_t s0 = 58u >> bl;
+        const uint64_t keep = ~((1ull << (64 - (s0 << bl))) - 1);
+        uint64_t key = 0, prev = 0, span;
+        const bool valid = j < n;
+        if (valid) {
+            prefix_keys(tix, keys[j] & keep, (uint32_t)tix.k, &key, &span);
+            if (j) prefix_keys(tix, keys[j - 1] & keep, (uint32_t)tix.k, &prev, &span);
+        }
+        uint32_t start = 0, len = 0;
+        if (valid && prev <= key) { start = j ? (uint32_t)prev + 1u : 0u; len = (uint32_t)key + 1u - start; }
+        tab_fill_range(tab, start, len, (uint32_t)j, list, list_cnt, threadIdx.x & 31);
+        const bool last = valid && j + 1 == n;
+        start = last ? (uint32_t)key + 1u : 0u; len = last ? tab_cnt - start : 0u;
+        tab_fill_range(tab, start, len, (uint32_t)n, list, list_cnt, threadIdx.x & 31);
+    }
     if (j < n) {
         const uint32_t s0 = 58u >> bl;
         const uint64_t keep = ~((1ull << (64 - (s0 << bl))) - 1);
@@ -159,7 +218,7 @@ static int bits_for(uint64_t v) { int b = 0; while (v) { ++b; v >>= 1; } return 
 
 int build_suffix_array(const uint64_t* text, uint64_t n, uint32_t bl, uint32_t* sa, uint32_t* isa_out, cudaStream_t s,
                        int* rounds_out, char* err, int errlen, SaWorkspace* ws_in, uint32_t* lcp_from_keys, uint16_t* uniq_fast,
-                       int* fast_out) {
+                       int* fast_out, const IndexView* tab_ix, uint32_t* tab, uint32_t* tab_tmp) {
     int rc = 0;
     if (rounds_out) *rounds_out = 0;
     if (fast_out) *fast_out = 0;
@@ -196,11 +255,27 @@ int build_suffix_array(const uint64_t* text, uint64_t n, uint32_t bl, uint32_t* 
             // no inverse permutation (api.cu derives it from SA if somebody asks for it)
             uint32_t* ties = scan_tmp;
             SA_CK(cudaMemsetAsync(ties, 0, 4, s));
+            // the k-mer table in the same pass when its key is a head of the sort key (k symbols <= S0) and the caller wants it
+            uint64_t tab_cnt = 0;
+            IndexView tix{};
+            bool with_tab = tab_ix && tab && tab_tmp && g_table_variant == 1 && (uint32_t)tab_ix->k <= (58u >> bl);
+            if (with_tab) {
+                tix = *tab_ix;
+                tab_cnt = 1;
+                for (int t = 0; t < tix.k; ++t) tab_cnt *= tix.sigma;
+                tab_cnt += 1;
+                if (tab_cnt > 0xFFFFFFFFull) with_tab = false;
+            }
+            uint32_t* list_cnt = with_tab ? tab_tmp : nullptr;
+            TabRange* list = with_tab ? reinterpret_cast<TabRange*>(reinterpret_cast<uint8_t*>(tab_tmp) + 64) : nullptr;
+            if (with_tab) SA_CK(cudaMemsetAsync(list_cnt, 0, 4, s));
             g_launches += 1;
-            k_sa_finish0<<<nb, T, 0, s>>>(keys_a, vals_a, n, bl, sa, lcp_from_keys, uniq_fast, ties);
+            k_sa_finish0<<<nb, T, 0, s>>>(keys_a, vals_a, n, bl, sa, lcp_from_keys, uniq_fast, ties, tix, with_tab ? tab : nullptr, (uint32_t)tab_cnt,
+                                          list, list_cnt);
+            if (with_tab) { g_launches += 1; k_tab_ranges<<<592, 256, 0, s>>>(tab, list, list_cnt); }
             SA_CK(cudaMemcpyAsync(tot_host, ties, 4, cudaMemcpyDeviceToHost, s));
             SA_CK(cudaStreamSynchronize(s));
-            if (*(uint32_t*)tot_host == 0) { *fast_out = 1; SA_CK(cudaGetLastError()); goto done; }
+            if (*(uint32_t*)tot_host == 0) { *fast_out = with_tab ? 2 : 1; SA_CK(cudaGetLastError()); goto done; }
         }
         // ranks = group head index (inclusive running max of head indices); SA = sorted values
         device_scan<uint32_t, LoadHeadIdx, StoreRank, OpMax, true>(LoadHeadIdx{keys_a}, StoreRank{vals_a, sa, isa, keys_a, lcp_from_keys, bl}, n,
@@ -283,12 +358,46 @@ __global__ void k_tab_mark(IndexView ix, uint32_t* tab) {
 struct LoadRev { const uint32_t* tab; uint64_t cnt; __device__ __forceinline__ uint32_t operator()(uint64_t e) const { return tab[cnt - 1 - e]; } };
 struct StoreRev { uint32_t* tab; uint64_t cnt; __device__ __forceinline__ void operator()(uint64_t e, uint32_t v) const { tab[cnt - 1 - e] = v; } };
 
-size_t kmer_table_tmp_bytes(uint64_t entries) { return scan_tmp_elems(entries) * 4 + 64; }
+__global__ void __launch_bounds__(256) k_tab_build(IndexView ix, uint32_t* __restrict__ tab, uint32_t cnt, TabRange* list, uint32_t* list_cnt) {
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const bool valid = j < ix.n;
+    uint64_t key = 0, prev = 0, span;
+    if (valid) {
+        prefix_keys(ix, get64(ix.text, ix.sa[j], ix.bl), (uint32_t)ix.k, &key, &span);
+        if (j) prefix_keys(ix, get64(ix.text, ix.sa[j - 1], ix.bl), (uint32_t)ix.k, &prev, &span);
+    }
+    // (prev, key] <- j ; for the first suffix [0, key] <- 0
+    uint32_t start = 0, len = 0;
+    if (valid && prev <= key) { start = j ? (uint32_t)prev + 1u : 0u; len = (uint32_t)key + 1u - start; }
+    tab_fill_range(tab, start, len, (uint32_t)j, list, list_cnt, lane);
+    // (key of the last suffix, cnt) <- n
+    const bool last = valid && j + 1 == ix.n;
+    start = last ? (uint32_t)key + 1u : 0u; len = last ? cnt - start : 0u;
+    tab_fill_range(tab, start, len, (uint32_t)ix.n, list, list_cnt, lane);
+}
+
+size_t kmer_table_tmp_bytes(uint64_t entries) {
+    const size_t scan = scan_tmp_elems(entries) * 4 + 64, list = (size_t)kTabListCap * sizeof(TabRange) + 64;
+    return scan > list ? scan : list;
+}
+
+int g_table_variant = 1;                   // 1: k_tab_build (one pass), 0: fill + mark + reverse minimum scan (option table_variant; process-wide)
 
 int build_kmer_table(const IndexView& ix, uint32_t* tab, uint32_t* tmp, cudaStream_t s) {
     uint64_t cnt = 1;
     for (int t = 0; t < ix.k; ++t) cnt *= ix.sigma;
     cnt += 1;
+    if (g_table_variant == 1 && cnt <= 0xFFFFFFFFull) {
+        if (ix.n == 0) { cudaMemsetAsync(tab, 0, cnt * 4, s); return (int)cudaGetLastError(); }
+        uint32_t* list_cnt = tmp;                                   // [0]: number of listed ranges, the list 64 bytes behind it
+        TabRange* list = reinterpret_cast<TabRange*>(reinterpret_cast<uint8_t*>(tmp) + 64);
+        cudaMemsetAsync(list_cnt, 0, 4, s);
+        g_launches += 2;
+        k_tab_build<<<(unsigned)((ix.n + 255) / 256), 256, 0, s>>>(ix, tab, (uint32_t)cnt, list, list_cnt);
+        k_tab_ranges<<<592, 256, 0, s>>>(tab, list, list_cnt);
+        return (int)cudaGetLastError();
+    }
     g_launches += 2;
     k_tab_fill<<<(unsigned)((cnt + 255) / 256), 256, 0, s>>>(tab, cnt, (uint32_t)ix.n);
     if (ix.n) k_tab_mark<<<(unsigned)((ix.n + 255) / 256), 256, 0, s>>>(ix, tab);

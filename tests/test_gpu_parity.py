@@ -126,6 +126,52 @@ def test_suffix_array_few_rounds(ctx):
         ctx.set_option("lcp_ties", 1)
 
 
+def test_kmer_table_variants(ctx):
+    """The table written in one pass (table_variant 1: every entry once, long ranges of empty keys by the warp or through
+    the range list) against fill + mark + scan (0), and against its definition: tab[K] = number of suffixes whose
+    zero-padded k-mer key is below K."""
+    rng = np.random.default_rng(5)
+    cases = []
+    cases.append((orc.syn_reference(orc.seed_for(2), 300_000).tobytes(), 0))                       # auto k
+    cases.append((orc.syn_reference(orc.seed_for(2), 5_000).tobytes(), 9))                         # sparse: 262 144 keys for 5 000 suffixes
+    d = orc.syn_reference(orc.seed_for(3), 400_000)
+    d[100_000:180_000] = ord("N"); d[7] = ord("N")
+    cases.append((d.tobytes(), 0))                                                                 # ACGNT, radix-5 keys, millions of empty keys around N
+    cases.append((d.tobytes(), 10))
+    cases.append((bytes(rng.choice(list(bytes(range(40, 90))), size=60_000).astype(np.uint8)), 3))  # 8-bit symbols
+    cases.append((b"A" * 5000, 5))
+    cases.append((b"T" * 100 + b"A", 6))
+    cases.append((b"G", 4))
+    try:
+        for d, k in cases:
+            tabs = []
+            for variant in (0, 1):
+                ctx.set_option("table_variant", variant)
+                ctx.set_option("kmer", k)
+                ctx.build_index(d)
+                tabs.append(ctx.index_get("tab"))
+            assert (tabs[0] == tabs[1]).all(), (len(d), k)
+            info = ctx.index_info()
+            sigma, kk, n = info["sigma"], info["k"], len(d)
+            sa = ctx.index_get("sa").astype(np.int64)
+            alphabet = sorted(set(d))
+            code_of = np.zeros(256, dtype=np.int64)
+            if set(alphabet) <= set(b"ACGT"):
+                code_of[list(b"ACGT")] = np.arange(4)
+            else:
+                code_of[alphabet] = np.arange(len(alphabet))
+            codes = code_of[np.frombuffer(d, dtype=np.uint8)]
+            pad = np.concatenate([codes, np.zeros(kk, dtype=np.int64)])
+            keys = np.zeros(n, dtype=np.int64)
+            for t in range(kk):
+                keys = keys * sigma + pad[sa + t] * (sa + t < n)
+            expect = np.searchsorted(keys, np.arange(sigma ** kk + 1), side="left")
+            assert (tabs[1].astype(np.int64) == expect).all(), (len(d), k)
+    finally:
+        ctx.set_option("table_variant", 1)
+        ctx.set_option("kmer", 0)
+
+
 def test_kmer_table_and_text(ctx):
     d = orc.syn_reference(orc.seed_for(2), 100_000).tobytes()
     ctx.set_option("kmer", 6)
